@@ -1,0 +1,270 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference
+with the zuko/sbi stand-ins of oracle/ref_shims) on seeded inputs, in fp32 and fp64.
+
+TEST INFRASTRUCTURE ONLY; runs in the build container (the reference does not travel to the GPU
+box -- the committed .npz files do).  Usage:
+
+    python oracle/gen_golden.py            # writes every fixture
+    python oracle/gen_golden.py slcp       # only fixtures whose name contains "slcp"
+
+Each fixture holds: the net weights (fp32 as shipped), inputs (theta, x, t grid, dist_cov_est, prior
+parameters, injected noise) and the reference outputs of the section-8(a) rows:
+  scores/prec of `tweedies_approximation` (GAUSS, JAC), `prior_score_fn`, `tweedies_approximation_prior`,
+  `factorized_score` (GAUSS, JAC) and full `ddim` trajectories under replayed noise.
+"""
+from __future__ import annotations
+
+import copy
+import os
+import sys
+from functools import partial
+from unittest import mock
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("D4S_REFERENCE", "/root/reference")
+sys.path[:0] = [os.path.join(HERE, "ref_shims"), REF]
+
+import torch  # noqa: E402
+
+import nse as ref_nse  # noqa: E402
+import pf_nse as ref_pf  # noqa: E402
+import tall_posterior_sampler as ref_tps  # noqa: E402
+import vp_diffused_priors as ref_vp  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+T_GRID = [1.0, 0.9, 0.5, 0.3, 0.29, 0.1, 0.01, 0.001]
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def mlp_arrays(prefix, mlp, out):
+    lin = [mod for mod in mlp if isinstance(mod, torch.nn.Linear)]
+    for i, l in enumerate(lin):
+        out[f"{prefix}.W{i}"] = npy(l.weight).astype(np.float32)
+        out[f"{prefix}.b{i}"] = npy(l.bias).astype(np.float32)
+    out[f"{prefix}.L"] = np.int64(len(lin))
+
+
+def net_arrays(net, out):
+    mlp_arrays("net", net.net, out)
+    if not isinstance(net.embedding_nn_theta, torch.nn.Identity):
+        mlp_arrays("embt", net.embedding_nn_theta, out)
+    if not isinstance(net.embedding_nn_x, torch.nn.Identity):
+        mlp_arrays("embx", net.embedding_nn_x, out)
+    out["freqs"] = npy(net.freqs).astype(np.float64)
+    out["theta_dim"] = np.int64(net.zeros.shape[0])
+    out["n_max"] = np.int64(getattr(net, "n_max", 1))
+    out["pf"] = np.int64(isinstance(net, ref_pf.PF_NSE))
+
+
+def spd_covs(gen, n, m):
+    a = 0.2 * torch.randn(n, m, m, generator=gen)
+    return a @ a.mT + 0.05 * torch.eye(m)
+
+
+class FakeDiagNormal:
+    """Replaces nse.DiagNormal so that `ddim` starts from an injected z0 (nse.py:261)."""
+    z0 = None
+
+    def __init__(self, *a, **k):
+        pass
+
+    def sample(self, shape):
+        return FakeDiagNormal.z0.clone()
+
+
+def run_ddim(net, x, z0, z, **kw):
+    it = iter(z)
+    FakeDiagNormal.z0 = z0
+    with mock.patch.object(ref_nse, "DiagNormal", FakeDiagNormal), \
+            mock.patch("torch.randn_like", side_effect=lambda a: next(it).to(a)):
+        return net.ddim(shape=(z0.shape[0],), x=x, **kw)
+
+
+def make_prior(kind, m, dt, net, low=None, high=None, loc=None, cov=None):
+    if kind == "uniform":
+        low, high = low.to(dt), high.to(dt)
+        prior = torch.distributions.Uniform(low, high, validate_args=False)
+        fn = ref_vp.get_vpdiff_uniform_score(low, high, net)
+    else:
+        loc, cov = loc.to(dt), cov.to(dt)
+        prior = torch.distributions.MultivariateNormal(loc, cov)
+        fn = ref_vp.get_vpdiff_gaussian_score(loc, cov, net)
+    return prior, fn
+
+
+def per_call_case(name, net32, x, prior_kind, prior_params, N, seed, extra_kwargs=None, do_jac=True,
+                  t_grid=T_GRID, traj=None, traj_x=None):
+    """Per-call rows for fp32 and fp64 + optional trajectories."""
+    out = {}
+    net_arrays(net32, out)
+    gen = torch.Generator().manual_seed(seed)
+    m = net32.zeros.shape[0]
+    n = x.shape[0]
+    theta = torch.randn(N, m, generator=gen)
+    cov_est = spd_covs(gen, n, m)
+    out.update(theta=npy(theta), x=npy(x), dist_cov_est=npy(cov_est), t_grid=np.asarray(t_grid, np.float32),
+               prior_kind=np.str_(prior_kind))
+    for k, v in prior_params.items():
+        out[f"prior.{k}"] = npy(v)
+    extra_kwargs = extra_kwargs or {}
+    for k, v in extra_kwargs.items():
+        out[f"kw.{k}"] = npy(v)
+
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        net = copy.deepcopy(net32).to(dt)
+        prior, fn = make_prior(prior_kind, m, dt, net, **prior_params)
+        th, xx, ce = theta.to(dt), x.to(dt), cov_est.to(dt)
+        kw = {k: v.to(dt) for k, v in extra_kwargs.items()}
+        for mode in ("GAUSS", "JAC") if do_jac else ("GAUSS",):
+            fs, sc, pr = [], [], []
+            for tv in t_grid:
+                t = torch.tensor(tv, dtype=torch.float32).to(dt)  # the ddim grid is fp32-valued
+                prec, _, score = net.tweedies_approximator(
+                    x=xx, theta=th, nse=net, t=t, score_fn=partial(net.score, **kw), dist_cov_est=ce, mode=mode)
+                sc.append(npy(score))
+                pr.append(npy(prec[:2]))  # two samples are enough to pin the precisions
+                fs.append(npy(net.factorized_score(th, xx, t, fn, prior, dist_cov_est=ce, cov_mode=mode,
+                                                   prior_type=prior_kind, **kw)))
+            out[f"{tag}.{mode}.factorized_score"] = np.stack(fs)
+            out[f"{tag}.{mode}.prec"] = np.stack(pr)
+            if mode == "GAUSS":
+                out[f"{tag}.scores"] = np.stack(sc)
+        ps, pp = [], []
+        for tv in t_grid:
+            t = torch.tensor(tv, dtype=torch.float32).to(dt)
+            ps.append(npy(fn(th, t)))
+            if float(net.alpha(t)) ** 0.5 > 0.5:  # the reference only evaluates it inside the gate (nse.py:643)
+                pp.append(npy(ref_tps.tweedies_approximation_prior(th, t, fn, nse=net)[0]))
+            else:
+                pp.append(np.full((N, m, m), np.nan, npy(th).dtype))
+        out[f"{tag}.prior_score"] = np.stack(ps)
+        out[f"{tag}.prior_prec"] = np.stack(pp)
+
+    if traj is not None:
+        Nt, steps, eta = traj["N"], traj["steps"], traj["eta"]
+        z0 = torch.randn(Nt, m, generator=gen)
+        z = torch.randn(steps, Nt, m, generator=gen)
+        out.update(traj_z0=npy(z0), traj_z=npy(z), traj_steps=np.int64(steps), traj_eta=np.float64(eta))
+        if traj_x is not None:
+            out["traj_x"] = npy(traj_x)
+        for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            net = copy.deepcopy(net32).to(dt)
+            prior, fn = make_prior(prior_kind, m, dt, net, **prior_params)
+            kw = {k: v.to(dt) for k, v in extra_kwargs.items()}
+            for mode in traj["modes"]:
+                clip = traj.get("clip", (None, None))
+                xt = x if traj_x is None else traj_x  # PF_NSE.ddim splits the raw observations itself
+                kwt = kw if traj_x is None else {}
+                res = run_ddim(net, xt.to(dt), z0.to(dt), z.to(dt), steps=steps, eta=eta, prior=prior,
+                               prior_type=prior_kind, prior_score_fn=fn, dist_cov_est=cov_est.to(dt),
+                               cov_mode=mode, theta_clipping_range=clip, **kwt)
+                out[f"{tag}.{mode}.traj"] = npy(res)
+        if "clip" in traj:
+            out["traj_clip"] = np.asarray(traj["clip"], np.float64)
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, {k: v.shape for k, v in out.items() if hasattr(v, "shape") and "traj" in k})
+
+
+def load_sbibm(task, sub="n_train_30000_bs_256_n_epochs_5000_lr_0.0001", pf=None):
+    d = os.path.join(REF, "results", "sbibm", task, sub)
+    if pf:
+        d = os.path.join(d, pf)
+    net = torch.load(os.path.join(d, "score_network.pkl"), weights_only=False, map_location="cpu")
+    net.net_type = "default"
+    if pf is None:
+        net.tweedies_approximator = ref_tps.tweedies_approximation
+    stats = torch.load(os.path.join(d, "train_means_stds_dict.pkl"), weights_only=False)
+    return net.eval(), stats
+
+
+def sbibm_obs(task, stats, n, log_space=False):
+    x = torch.load(os.path.join(REF, "tasks", "sbibm", "data", task, "reference_observations",
+                                "x_obs_100_num_1.pkl"), weights_only=False)[:n]
+    if log_space:
+        x = torch.log(x)
+    xn = (x - stats["x_train_mean"]) / stats["x_train_std"]
+    return torch.nan_to_num(xn, nan=0.0, posinf=0.0, neginf=0.0).float()  # sbibm_posterior_estimation.py:179-184
+
+
+def slcp_prior(stats):
+    low = (torch.full((5,), -3.0) - stats["theta_train_mean"]) / stats["theta_train_std"] * 2
+    high = (torch.full((5,), 3.0) - stats["theta_train_mean"]) / stats["theta_train_std"] * 2
+    return dict(low=low, high=high)  # sbibm_posterior_estimation.py:188-189
+
+
+def lognormal_prior(stats, loc, scale):
+    loc_n = (loc - stats["theta_train_mean"]) / stats["theta_train_std"]
+    cov = torch.diag_embed(scale.square())
+    cov_n = torch.diag(1 / stats["theta_train_std"]) @ cov @ torch.diag(1 / stats["theta_train_std"])
+    return dict(loc=loc_n, cov=cov_n)  # sbibm_posterior_estimation.py:197-208
+
+
+def main(filt=None):
+    want = lambda name: filt is None or filt in name  # noqa: E731
+    torch.manual_seed(0)
+
+    if want("slcp"):
+        net, st = load_sbibm("slcp")
+        x = sbibm_obs("slcp", st, 6)
+        per_call_case("slcp_n6", net, x, "uniform", slcp_prior(st), N=16, seed=11,
+                      traj=dict(N=24, steps=40, eta=1.0, modes=("GAUSS",)))
+    if want("slcp30"):
+        net, st = load_sbibm("slcp")
+        x = sbibm_obs("slcp", st, 30)
+        per_call_case("slcp30_n30", net, x, "uniform", slcp_prior(st), N=8, seed=12, t_grid=[0.5, 0.1],
+                      traj=dict(N=16, steps=1000, eta=1.0, modes=("GAUSS",)))
+    if want("lv"):
+        net, st = load_sbibm("lotka_volterra")
+        x = sbibm_obs("lotka_volterra", st, 6, log_space=True)
+        pp = lognormal_prior(st, torch.tensor([-0.125, -3.0, -0.125, -3.0]), torch.full((4,), 0.5))
+        per_call_case("lv_n6", net, x, "gaussian", pp, N=16, seed=13,
+                      traj=dict(N=24, steps=40, eta=1.0, modes=("GAUSS",)))
+    if want("sir"):
+        net, st = load_sbibm("sir")
+        x = sbibm_obs("sir", st, 8, log_space=False)
+        pp = lognormal_prior(st, torch.log(torch.tensor([0.4, 0.125])), torch.tensor([0.5, 0.2]))
+        per_call_case("sir_n8", net, x, "gaussian", pp, N=16, seed=14,
+                      traj=dict(N=24, steps=400, eta=0.8, modes=("GAUSS",)))
+    if want("pf"):
+        net, st = load_sbibm("slcp", sub="n_train_10000_bs_256_n_epochs_5000_lr_0.0001", pf="pf_n_max_3")
+        st = dict(st, x_train_mean=st["x_train_mean"][0], x_train_std=st["x_train_std"][0])  # stats are [n_max, d]
+        x = sbibm_obs("slcp", st, 8)
+        xs, ns = net._create_pf_data(x)  # [3,3,8], [3,1]
+        out_x = xs
+        per_call_case("pf_slcp_nmax3_n8", net, out_x, "uniform", slcp_prior(st), N=12, seed=15,
+                      extra_kwargs=dict(n=ns), do_jac=False, t_grid=[0.9, 0.5, 0.1, 0.01],
+                      traj=dict(N=16, steps=30, eta=1.0, modes=("GAUSS",)), traj_x=x)
+    if want("jrnnm"):
+        d = os.path.join(REF, "results", "jrnnm", "4d", "n_train_50000_n_epochs_5000_lr_0.001")
+        net = torch.load(os.path.join(d, "score_network.pkl"), weights_only=False, map_location="cpu").eval()
+        net.net_type = "default"
+        net.tweedies_approximator = ref_tps.tweedies_approximation
+        st = torch.load(os.path.join(d, "train_means_stds_dict.pkl"), weights_only=False)
+        x = torch.load(os.path.join(REF, "results", "jrnnm", "x_obs_100_[135.0, 220.0, 2000.0, 0.0].pkl"),
+                       weights_only=False)[:5]
+        x = ((x - st["x_train_mean"]) / st["x_train_std"]).float()  # jrnnm_posterior_estimation.py:136
+        lo = torch.tensor([10.0, 50.0, 100.0, -20.0])  # tasks/jrnnm/prior.py:4-9
+        hi = torch.tensor([250.0, 500.0, 5000.0, 20.0])
+        low = (lo - st["theta_train_mean"]) / st["theta_train_std"] * 2  # jrnnm_posterior_estimation.py:147-148
+        high = (hi - st["theta_train_mean"]) / st["theta_train_std"] * 2
+        per_call_case("jrnnm4d_n5", net, x, "uniform", dict(low=low, high=high), N=10, seed=16,
+                      t_grid=[0.9, 0.5, 0.29, 0.1, 0.01], traj=dict(N=12, steps=30, eta=1.0, modes=("GAUSS",)))
+    if want("rand"):
+        torch.manual_seed(3)
+        net = ref_nse.NSE(theta_dim=3, x_dim=4, hidden_features=[64, 96]).eval()
+        gen = torch.Generator().manual_seed(6)
+        x = torch.randn(7, 4, generator=gen)
+        per_call_case("rand_m3_n7", net, x, "gaussian", dict(loc=torch.tensor([0.3, -0.2, 0.1]),
+                                                            cov=torch.tensor([[1.0, 0.2, 0.0], [0.2, 0.8, 0.1],
+                                                                              [0.0, 0.1, 1.2]])),
+                      N=9, seed=17, traj=dict(N=9, steps=25, eta=0.5, modes=("GAUSS", "JAC"), clip=(-3.0, 3.0)))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else None)
