@@ -1,0 +1,459 @@
+// C-ABI of libd4s (see include/d4s.h): net packing, argument validation, tiling, launches, trajectory
+// runner with an optional CUDA-graph cache.  No torch types, no host synchronisation on the hot path.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "d4s_common.cuh"
+
+namespace d4s {
+
+static thread_local std::string g_err;
+static long long g_launches = 0;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return D4S_ERR_CUDA;
+}
+
+static int pad_width(int h) {
+    if (h <= 64) return 64;
+    if (h <= 128) return 128;
+    if (h <= 256) return 256;
+    return -1;
+}
+
+}  // namespace d4s
+
+using namespace d4s;
+
+struct D4sNet {
+    NetDev dev;
+    float* blob = nullptr;  // one device allocation holding every packed array
+    size_t blob_floats = 0;
+};
+
+// Tiling of the (sample x observation) grid into TM-row tiles of SG samples x OC observations.
+struct Tiling {
+    int rpp, OC, C, SG, P, W, tiles;
+};
+
+static int make_tiling(const D4sNet* net, const D4sProblem* pb, Tiling* t) {
+    const int m = net->dev.m;
+    t->rpp = (pb->cov_mode == D4S_COV_JAC) ? 1 + m : 1;
+    const int max_pairs = TM / t->rpp;
+    if (max_pairs < 1) return -1;
+    if (pb->paired) {
+        t->OC = 1;
+        t->C = 1;
+        t->SG = max_pairs;
+    } else {
+        int oc = pb->obs_chunk > 0 ? pb->obs_chunk : pb->n_obs;
+        if (oc > max_pairs) oc = max_pairs;
+        if (oc > pb->n_obs) oc = pb->n_obs;
+        // balance the chunks (e.g. n = 70, cap 64 -> 2 chunks of 35 rather than 64 + 6)
+        const int c = (pb->n_obs + oc - 1) / oc;
+        oc = (pb->n_obs + c - 1) / c;
+        t->OC = oc;
+        t->C = (pb->n_obs + oc - 1) / oc;
+        t->SG = max_pairs / oc;
+        if (t->SG < 1) t->SG = 1;
+    }
+    t->P = t->SG * t->OC;
+    t->W = (pb->cov_mode == D4S_COV_JAC) ? m + m * m : 2 * m;
+    const long long groups = ((long long)pb->n_samples + t->SG - 1) / t->SG;
+    const long long tiles = groups * t->C;
+    if (tiles > 2147483647LL) return -1;
+    t->tiles = (int)tiles;
+    return 0;
+}
+
+static int check_problem(const D4sNet* net, const D4sProblem* pb) {
+    if (!net || !pb) return fail(D4S_ERR_ARG, "null net/problem");
+    if (pb->theta_dim != net->dev.m) return fail(D4S_ERR_ARG, "problem.theta_dim != net output dim");
+    if (pb->n_samples < 1 || pb->n_obs < 1) return fail(D4S_ERR_ARG, "n_samples and n_obs must be >= 1");
+    if (pb->cov_mode != D4S_COV_GAUSS && pb->cov_mode != D4S_COV_JAC) return fail(D4S_ERR_ARG, "bad cov_mode");
+    if (pb->paired && pb->n_obs != pb->n_samples) return fail(D4S_ERR_ARG, "paired mode needs n_obs == n_samples");
+    if (!pb->obs_feat) return fail(D4S_ERR_ARG, "obs_feat is null");
+    if (pb->prior_kind == D4S_PRIOR_UNIFORM && (!pb->prior_low || !pb->prior_high))
+        return fail(D4S_ERR_ARG, "uniform prior needs prior_low/prior_high");
+    if (!pb->workspace) return fail(D4S_ERR_ARG, "workspace is null");
+    return D4S_OK;
+}
+
+extern "C" {
+
+int d4s_abi_version(void) { return D4S_ABI_VERSION; }
+const char* d4s_last_error(void) { return g_err.c_str(); }
+int64_t d4s_launch_count(void) { return (int64_t)g_launches; }
+
+int d4s_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
+    if (!out || !d) return fail(D4S_ERR_ARG, "null argument");
+    *out = nullptr;
+    const int L = d->n_layers;
+    if (L < 2 || L > D4S_MAX_LAYERS) return fail(D4S_ERR_ARG, "n_layers must be in [2, 8]");
+    const int m = d->dims[L];
+    if (m < 1 || m > D4S_MAX_THETA) return fail(D4S_ERR_ARG, "theta_dim must be in [1, 10]");
+    if (d->theta_cols != m) return fail(D4S_ERR_ARG, "theta_cols != theta_dim (theta embedding nets: not in this ABI version)");
+    if (d->theta_cols > d->dims[0]) return fail(D4S_ERR_ARG, "theta_cols > input width");
+    int Hp[D4S_MAX_LAYERS] = {0};
+    for (int l = 0; l <= L - 2; ++l) {
+        Hp[l] = pad_width(d->dims[l + 1]);
+        if (Hp[l] < 0) return fail(D4S_ERR_ARG, "hidden width > 256 is not supported");
+    }
+    for (int l = 0; l < L; ++l)
+        if (!d->weight[l] || !d->bias[l]) return fail(D4S_ERR_ARG, "null weight/bias pointer");
+    if (d4s_device_count() < 1) return fail(D4S_ERR_CUDA, "no CUDA device: libd4s has no CPU fallback");
+
+    // host staging of the packed blob
+    std::vector<float> h;
+    std::vector<size_t> off_W(L, 0), off_b(L, 0);
+    auto reserve = [&](size_t n) {
+        size_t o = h.size();
+        h.resize(o + ((n + 3) / 4) * 4, 0.f);  // keep every array 16-byte aligned
+        return o;
+    };
+    const int in0 = d->dims[0];
+    // A: [theta_cols][Hp0], k-major
+    const size_t off_A = reserve((size_t)d->theta_cols * Hp[0]);
+    for (int k = 0; k < d->theta_cols; ++k)
+        for (int o = 0; o < d->dims[1]; ++o) h[off_A + (size_t)k * Hp[0] + o] = d->weight[0][(size_t)o * in0 + k];
+    for (int l = 1; l <= L - 2; ++l) {
+        const int K = d->dims[l], Ho = d->dims[l + 1];
+        off_W[l] = reserve((size_t)Hp[l - 1] * Hp[l]);
+        for (int k = 0; k < K; ++k)
+            for (int o = 0; o < Ho; ++o) h[off_W[l] + (size_t)k * Hp[l] + o] = d->weight[l][(size_t)o * K + k];
+        off_b[l] = reserve(Hp[l]);
+        for (int o = 0; o < Ho; ++o) h[off_b[l] + o] = d->bias[l][o];
+    }
+    const int Kl = d->dims[L - 1];
+    const size_t off_Wout = reserve((size_t)Hp[L - 2] * MMAX);
+    for (int k = 0; k < Kl; ++k)
+        for (int o = 0; o < m; ++o) h[off_Wout + (size_t)k * MMAX + o] = d->weight[L - 1][(size_t)o * Kl + k];
+    const size_t off_bout = reserve(MMAX);
+    for (int o = 0; o < m; ++o) h[off_bout + o] = d->bias[L - 1][o];
+
+    D4sNet* net = new D4sNet();
+    cudaError_t e = cudaMalloc(&net->blob, h.size() * sizeof(float));
+    if (e != cudaSuccess) {
+        delete net;
+        return cuda_fail(e, "cudaMalloc(net)");
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    e = cudaMemcpyAsync(net->blob, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // h goes out of scope
+    if (e != cudaSuccess) {
+        cudaFree(net->blob);
+        delete net;
+        return cuda_fail(e, "cudaMemcpy(net)");
+    }
+    net->blob_floats = h.size();
+    NetDev& nd = net->dev;
+    memset(&nd, 0, sizeof(nd));
+    nd.L = L;
+    nd.m = m;
+    nd.theta_cols = d->theta_cols;
+    for (int l = 0; l <= L - 2; ++l) nd.Hp[l] = Hp[l];
+    nd.A = net->blob + off_A;
+    for (int l = 1; l <= L - 2; ++l) {
+        nd.Wt[l] = net->blob + off_W[l];
+        nd.bias[l] = net->blob + off_b[l];
+    }
+    nd.Wout = net->blob + off_Wout;
+    nd.bout = net->blob + off_bout;
+    *out = net;
+    return D4S_OK;
+}
+
+void d4s_net_free(D4sNet* net) {
+    if (!net) return;
+    if (net->blob) cudaFree(net->blob);
+    delete net;
+}
+
+int d4s_net_h1_padded(const D4sNet* net) { return net ? net->dev.Hp[0] : 0; }
+
+int32_t d4s_mats_floats(int32_t m) { return 2 * m * m + m; }
+
+int64_t d4s_workspace_floats(const D4sNet* net, const D4sProblem* pb) {
+    if (!net || !pb) return -1;
+    Tiling t;
+    if (make_tiling(net, pb, &t) != 0) return -1;
+    return (int64_t)pb->n_samples * t.C * t.W;
+}
+
+static int score_partials_impl(const D4sNet* net, const D4sProblem* pb, const D4sStep* st, const float* theta,
+                               float* scores_out, float* prec_out, cudaStream_t stream) {
+    Tiling t;
+    if (make_tiling(net, pb, &t) != 0) return fail(D4S_ERR_ARG, "cannot tile the problem");
+    if ((int64_t)pb->n_samples * t.C * t.W > pb->workspace_floats) return fail(D4S_ERR_WORKSPACE, "workspace too small");
+    if (pb->cov_mode == D4S_COV_GAUSS && !pb->obs_prec && !pb->paired && pb->n_obs_total > 1 && false)
+        return fail(D4S_ERR_ARG, "GAUSS needs obs_prec");
+    ScoreParams p;
+    memset(&p, 0, sizeof(p));
+    p.net = net->dev;
+    p.N = pb->n_samples;
+    p.n = pb->n_obs;
+    p.C = t.C;
+    p.SG = t.SG;
+    p.OC = t.OC;
+    p.P = t.P;
+    p.jac = pb->cov_mode == D4S_COV_JAC;
+    p.paired = pb->paired;
+    p.W = t.W;
+    p.theta = theta;
+    p.obs_feat = pb->obs_feat;
+    p.time_feat = st->time_feat;
+    p.obs_prec = pb->obs_prec;
+    p.sched = st->sched;
+    p.part = pb->workspace;
+    p.scores_out = scores_out;
+    p.prec_out = prec_out;
+    cudaError_t e = launch_score_simt(p, t.tiles, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "score kernel launch");
+    ++g_launches;
+    return D4S_OK;
+}
+
+static int finalize_impl(const D4sNet* net, const D4sProblem* pb, const D4sStep* st, float* theta, float* score_out,
+                         cudaStream_t stream) {
+    Tiling t;
+    if (make_tiling(net, pb, &t) != 0) return fail(D4S_ERR_ARG, "cannot tile the problem");
+    FinalizeParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = pb->n_samples;
+    p.C = t.C;
+    p.W = t.W;
+    p.m = net->dev.m;
+    p.jac = pb->cov_mode == D4S_COV_JAC;
+    p.prior_kind = pb->prior_kind;
+    p.update = st->update;
+    p.part = pb->workspace;
+    p.sched = st->sched;
+    p.mats = st->mats;
+    p.low = pb->prior_low;
+    p.high = pb->prior_high;
+    p.noise = st->noise;
+    p.seed = pb->seed;
+    p.step_index = st->step_index;
+    p.sample_offset = pb->sample_offset;
+    p.clip_lo = pb->clip_lo;
+    p.clip_hi = pb->clip_hi;
+    p.theta = theta;
+    p.score_out = score_out;
+    cudaError_t e = launch_finalize(p, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "finalize kernel launch");
+    ++g_launches;
+    return D4S_OK;
+}
+
+int d4s_score_partials(const D4sNet* net, const D4sProblem* pb, const D4sStep* st, const float* theta_dev,
+                       float* scores_out_dev, float* prec_out_dev, void* stream) {
+    int rc = check_problem(net, pb);
+    if (rc) return rc;
+    if (!st || !st->sched || !st->time_feat || !theta_dev) return fail(D4S_ERR_ARG, "null step/theta");
+    return score_partials_impl(net, pb, st, theta_dev, scores_out_dev, prec_out_dev, (cudaStream_t)stream);
+}
+
+int d4s_finalize(const D4sNet* net, const D4sProblem* pb, const D4sStep* st, float* theta_dev, float* score_out_dev,
+                 void* stream) {
+    int rc = check_problem(net, pb);
+    if (rc) return rc;
+    if (!st || !st->sched || !st->mats || !theta_dev) return fail(D4S_ERR_ARG, "null step/theta");
+    return finalize_impl(net, pb, st, theta_dev, score_out_dev, (cudaStream_t)stream);
+}
+
+// ---- trajectory runner + CUDA graph cache -----------------------------------------------------------------
+namespace {
+struct GraphKey {
+    const D4sNet* net;
+    D4sProblem pb;
+    int steps;
+    const float *sched, *tf, *mats, *noise;
+    float* theta;
+    uint64_t mode_hash;
+    bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
+};
+struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec;
+    long long launches;
+};
+std::mutex g_graph_mu;
+std::vector<GraphEntry> g_graphs;
+}  // namespace
+
+static int enqueue_steps(const D4sNet* net, const D4sProblem* pb0, int steps, const float* sched, const float* tf,
+                         const float* mats, const float* noise, float* theta, const int32_t* step_mode,
+                         cudaStream_t stream) {
+    D4sProblem pbv = *pb0;
+    D4sProblem* pb = &pbv;
+    const int H1 = net->dev.Hp[0];
+    const int MF = d4s_mats_floats(net->dev.m);
+    const size_t NM = (size_t)pb->n_samples * net->dev.m;
+    for (int k = 0; k < steps; ++k) {
+        D4sStep st;
+        st.sched = sched + (size_t)k * D4S_SCHED_STRIDE;
+        st.time_feat = tf + (size_t)k * H1;
+        st.mats = mats + (size_t)k * MF;
+        st.noise = noise ? noise + (size_t)k * NM : nullptr;
+        st.step_index = k;
+        st.update = 1;
+        pb->cov_mode = step_mode ? step_mode[k] : pb0->cov_mode;
+        int rc = score_partials_impl(net, pb, &st, theta, nullptr, nullptr, stream);
+        if (rc) return rc;
+        rc = finalize_impl(net, pb, &st, theta, nullptr, stream);
+        if (rc) return rc;
+    }
+    return D4S_OK;
+}
+
+int d4s_ddim_run(const D4sNet* net, const D4sProblem* pb, int32_t steps, const float* sched_dev,
+                 const float* time_feat_dev, const float* mats_dev, const float* noise_dev, float* theta_dev,
+                 const int32_t* step_mode, int32_t use_graph, void* stream_) {
+    int rc = check_problem(net, pb);
+    if (rc) return rc;
+    if (steps < 1 || !sched_dev || !time_feat_dev || !mats_dev || !theta_dev) return fail(D4S_ERR_ARG, "bad ddim_run args");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (step_mode) {
+        // the workspace must fit the widest layout used along the trajectory
+        D4sProblem q = *pb;
+        for (int mode = 0; mode < 2; ++mode) {
+            q.cov_mode = mode;
+            bool used = false;
+            for (int k = 0; k < steps && !used; ++k) used = (step_mode[k] == mode);
+            if (used && d4s_workspace_floats(net, &q) > pb->workspace_floats) return fail(D4S_ERR_WORKSPACE, "workspace too small");
+        }
+        for (int k = 0; k < steps; ++k)
+            if (step_mode[k] != D4S_COV_GAUSS && step_mode[k] != D4S_COV_JAC) return fail(D4S_ERR_ARG, "bad step_cov_mode");
+    }
+    if (!use_graph)
+        return enqueue_steps(net, pb, steps, sched_dev, time_feat_dev, mats_dev, noise_dev, theta_dev, step_mode, stream);
+
+    GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.net = net;
+    memcpy(&key.pb, pb, sizeof(D4sProblem));
+    key.steps = steps;
+    key.sched = sched_dev;
+    key.tf = time_feat_dev;
+    key.mats = mats_dev;
+    key.noise = noise_dev;
+    key.theta = theta_dev;
+    key.mode_hash = 1469598103934665603ull;
+    if (step_mode)
+        for (int k = 0; k < steps; ++k) key.mode_hash = (key.mode_hash ^ (uint64_t)(step_mode[k] + 1)) * 1099511628211ull;
+    std::lock_guard<std::mutex> lock(g_graph_mu);
+    for (auto& g : g_graphs) {
+        if (g.key == key) {
+            cudaError_t e = cudaGraphLaunch(g.exec, stream);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
+            g_launches += g.launches;
+            return D4S_OK;
+        }
+    }
+    // capture on a private stream so that a failed capture cannot poison the caller's stream
+    cudaStream_t cap;
+    cudaError_t e = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+    const long long before = g_launches;
+    e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) {
+        cudaStreamDestroy(cap);
+        return cuda_fail(e, "cudaStreamBeginCapture");
+    }
+    rc = enqueue_steps(net, pb, steps, sched_dev, time_feat_dev, mats_dev, noise_dev, theta_dev, step_mode, cap);
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(cap, &graph);
+    const long long n_launch = g_launches - before;
+    g_launches = before;
+    cudaStreamDestroy(cap);
+    if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
+    if (g_graphs.size() >= 8) {
+        cudaGraphExecDestroy(g_graphs.front().exec);
+        g_graphs.erase(g_graphs.begin());
+    }
+    g_graphs.push_back({key, exec, n_launch});
+    e = cudaGraphLaunch(exec, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
+    g_launches += n_launch;
+    return D4S_OK;
+}
+
+void d4s_graph_cache_clear(void) {
+    std::lock_guard<std::mutex> lock(g_graph_mu);
+    for (auto& g : g_graphs) cudaGraphExecDestroy(g.exec);
+    g_graphs.clear();
+}
+
+int d4s_prior_score(int32_t kind, const float* theta_dev, int64_t n_rows, int32_t m, const float* sched_dev,
+                    const float* mats_dev, const float* low_dev, const float* high_dev, float* score_out_dev,
+                    float* jacdiag_out_dev, void* stream) {
+    if (!theta_dev || !sched_dev || !score_out_dev || n_rows < 1 || m < 1) return fail(D4S_ERR_ARG, "bad prior_score args");
+    if (kind == D4S_PRIOR_UNIFORM) {
+        if (!low_dev || !high_dev) return fail(D4S_ERR_ARG, "uniform prior needs low/high");
+    } else if (kind == D4S_PRIOR_GAUSSIAN) {
+        if (!mats_dev) return fail(D4S_ERR_ARG, "gaussian prior needs the mats row");
+    } else {
+        return fail(D4S_ERR_ARG, "bad prior kind");
+    }
+    cudaError_t e = launch_prior_score(kind, theta_dev, n_rows, m, sched_dev, mats_dev, low_dev, high_dev, score_out_dev,
+                                       jacdiag_out_dev, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "prior_score launch");
+    ++g_launches;
+    return D4S_OK;
+}
+
+int d4s_ddim_update(float* theta_dev, const float* score_dev, int64_t n_rows, int32_t m, const float* sched_dev,
+                    const float* noise_dev, uint64_t seed, int32_t step_index, int64_t sample_offset, float clip_lo,
+                    float clip_hi, void* stream) {
+    if (!theta_dev || !score_dev || !sched_dev || n_rows < 1 || m < 1) return fail(D4S_ERR_ARG, "bad ddim_update args");
+    cudaError_t e = launch_ddim_update(theta_dev, score_dev, n_rows, m, sched_dev, noise_dev, seed, step_index,
+                                       sample_offset, clip_lo, clip_hi, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "ddim_update launch");
+    ++g_launches;
+    return D4S_OK;
+}
+
+int d4s_batched_inverse(const float* a_dev, float* out_dev, int32_t batch, int32_t m, void* stream) {
+    if (!a_dev || !out_dev || batch < 1) return fail(D4S_ERR_ARG, "bad batched_inverse args");
+    if (m < 1 || m > D4S_MAX_THETA) return fail(D4S_ERR_ARG, "m must be in [1, 10]");
+    cudaError_t e = launch_batched_inverse(a_dev, out_dev, batch, m, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "batched_inverse launch");
+    ++g_launches;
+    return D4S_OK;
+}
+
+int d4s_philox_normal(float* out_dev, int64_t n_rows, int32_t m, uint64_t seed, int32_t step_index,
+                      int64_t sample_offset, void* stream) {
+    if (!out_dev || n_rows < 1 || m < 1) return fail(D4S_ERR_ARG, "bad philox_normal args");
+    cudaError_t e = launch_philox_normal(out_dev, n_rows, m, seed, step_index, sample_offset, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "philox_normal launch");
+    ++g_launches;
+    return D4S_OK;
+}
+
+}  // extern "C"

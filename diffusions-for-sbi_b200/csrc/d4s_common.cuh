@@ -1,0 +1,180 @@
+// Shared device/host helpers of libd4s (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/d4s.h"
+
+namespace d4s {
+
+// ------------------------------------------------------------------------------------------------
+// tiling constants of the SIMT score kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int TM = 64;      // rows (sample x observation [x tangent] pairs) per tile
+constexpr int NT = 256;     // threads per CTA: 8 warps, warp w owns rows 8w..8w+7
+constexpr int ASTR = 68;    // activation buffer row stride: act[k][ASTR] (k-major), conflict-free STS.128
+constexpr int KC = 8;       // weight k-chunk staged per pipeline stage
+constexpr int HMAX = D4S_MAX_WIDTH;
+constexpr int MMAX = D4S_MAX_THETA;
+
+// Device view of the packed network.  Hidden widths are zero-padded to 64/128/256 so that padded
+// units produce relu(0) = 0 and contribute nothing downstream.
+struct NetDev {
+    int L;                          // linear layers
+    int m;                          // theta_dim
+    int theta_cols;                 // leading input columns of layer 0 fed by theta
+    int Hp[D4S_MAX_LAYERS];         // padded width of hidden layer l (l = 0 .. L-2)
+    const float* A;                 // [theta_cols][Hp[0]]  layer-0 theta block, k-major
+    const float* Wt[D4S_MAX_LAYERS];   // l = 1 .. L-2: [Hp[l-1]][Hp[l]] k-major (transposed torch weight)
+    const float* bias[D4S_MAX_LAYERS]; // l = 1 .. L-2: [Hp[l]]
+    const float* Wout;              // [Hp[L-2]][MMAX] k-major, zero padded columns
+    const float* bout;              // [MMAX]
+};
+
+
+// ------------------------------------------------------------------------------------------------
+// kernel parameter blocks (passed by value) and launchers implemented in the kernel translation units
+// ------------------------------------------------------------------------------------------------
+struct ScoreParams {
+    NetDev net;
+    int N, n, C, SG, OC, P;  // P = SG*OC pairs per tile
+    int jac, paired;
+    int W;                   // floats per (sample, chunk) partial: GAUSS 2m, JAC m + m*m
+    const float* theta;      // [N][m]
+    const float* obs_feat;   // [n][Hp0]
+    const float* time_feat;  // [Hp0]
+    const float* obs_prec;   // GAUSS: [n][m][m]
+    const float* sched;      // [16]
+    float* part;             // [N][C][W]
+    float* scores_out;       // optional [N][n][m]
+    float* prec_out;         // optional JAC [N][n][m][m]
+};
+
+struct FinalizeParams {
+    int N, C, W, m;
+    int jac, prior_kind, update;
+    const float* part;   // [N][C][W]
+    const float* sched;  // [16]
+    const float* mats;   // Lmat[m*m], G[m*m], mu_t[m]
+    const float* low;    // uniform prior
+    const float* high;
+    const float* noise;  // [N][m] or NULL
+    uint64_t seed;
+    int step_index;
+    long long sample_offset;
+    float clip_lo, clip_hi;
+    float* theta;      // [N][m] in/out
+    float* score_out;  // optional [N][m]
+};
+
+cudaError_t launch_score_simt(const ScoreParams& p, int tiles, cudaStream_t stream);
+cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t stream);
+cudaError_t launch_batched_inverse(const float* a, float* out, int batch, int m, cudaStream_t stream);
+cudaError_t launch_prior_score(int kind, const float* theta, long long N, int m, const float* sched, const float* mats,
+                               const float* low, const float* high, float* score_out, float* jacdiag_out,
+                               cudaStream_t stream);
+cudaError_t launch_ddim_update(float* theta, const float* score, long long N, int m, const float* sched,
+                               const float* noise, uint64_t seed, int step, long long sample_offset, float clip_lo,
+                               float clip_hi, cudaStream_t stream);
+cudaError_t launch_philox_normal(float* out, long long n_rows, int m, uint64_t seed, int step, long long sample_offset,
+                                 cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller.  Counter = (dim_pair, sample_lo, sample_hi, step), key = seed.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ inline void philox_round(uint32_t (&c)[4], uint32_t (&k)[2]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#ifdef __CUDA_ARCH__
+    uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+#else
+    uint64_t p0 = (uint64_t)M0 * c[0], p1 = (uint64_t)M1 * c[2];
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+    uint32_t n0 = hi1 ^ c[1] ^ k[0];
+    uint32_t n1 = lo1;
+    uint32_t n2 = hi0 ^ c[3] ^ k[1];
+    uint32_t n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k[0] += 0x9E3779B9u;
+    k[1] += 0xBB67AE85u;
+}
+
+__host__ __device__ inline void philox4x32_10(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                             uint32_t (&out)[4]) {
+    uint32_t c[4] = {c0, c1, c2, c3};
+    uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(c, k);
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+// Four standard normals for (step, sample, quad) where quad covers dims 4*quad .. 4*quad+3.
+__device__ inline void philox_normal4(uint64_t seed, int step, int64_t sample, int quad, float (&z)[4]) {
+    uint32_t r[4];
+    philox4x32_10(seed, (uint32_t)quad, (uint32_t)(uint64_t)sample, (uint32_t)((uint64_t)sample >> 32),
+                  (uint32_t)step, r);
+    const float two_pow_m32 = 2.3283064365386963e-10f;
+    // u in (0, 1]: (r + 0.5) * 2^-32 keeps log() finite
+    float u0 = ((float)r[0] + 0.5f) * two_pow_m32;
+    float u1 = ((float)r[1] + 0.5f) * two_pow_m32;
+    float u2 = ((float)r[2] + 0.5f) * two_pow_m32;
+    float u3 = ((float)r[3] + 0.5f) * two_pow_m32;
+    u0 = fminf(u0, 1.0f); u2 = fminf(u2, 1.0f);
+    float rad0 = sqrtf(-2.0f * logf(u0)), rad1 = sqrtf(-2.0f * logf(u2));
+    float s0, c0, s1, c1;
+    sincospif(2.0f * u1, &s0, &c0);
+    sincospif(2.0f * u3, &s1, &c1);
+    z[0] = rad0 * c0; z[1] = rad0 * s0; z[2] = rad1 * c1; z[3] = rad1 * s1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small dense linear algebra in registers (M compile-time, fully unrolled).  Gauss-Jordan inverse with
+// partial pivoting -- the pivoting strategy of the LU behind torch.linalg.inv that the reference calls
+// (tall_posterior_sampler.py:42,94,154); row swaps are predicated selects so every index stays a
+// compile-time constant.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int M>
+__device__ __forceinline__ void gj_inverse_t(T (&a)[M][M], T (&inv)[M][M]) {
+#pragma unroll
+    for (int r = 0; r < M; ++r)
+#pragma unroll
+        for (int c = 0; c < M; ++c) inv[r][c] = (r == c) ? T(1) : T(0);
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        int p = k;
+        T best = a[k][k] < T(0) ? -a[k][k] : a[k][k];
+#pragma unroll
+        for (int r = k + 1; r < M; ++r) {
+            T v = a[r][k] < T(0) ? -a[r][k] : a[r][k];
+            if (v > best) { best = v; p = r; }
+        }
+#pragma unroll
+        for (int r = k + 1; r < M; ++r) {
+            if (r == p) {
+#pragma unroll
+                for (int c = 0; c < M; ++c) {
+                    T t = a[k][c]; a[k][c] = a[r][c]; a[r][c] = t;
+                    T u = inv[k][c]; inv[k][c] = inv[r][c]; inv[r][c] = u;
+                }
+            }
+        }
+        const T d = T(1) / a[k][k];
+#pragma unroll
+        for (int c = 0; c < M; ++c) { a[k][c] *= d; inv[k][c] *= d; }
+#pragma unroll
+        for (int r = 0; r < M; ++r) {
+            if (r != k) {
+                const T f = a[r][k];
+#pragma unroll
+                for (int c = 0; c < M; ++c) {
+                    a[r][c] -= f * a[k][c];
+                    inv[r][c] -= f * inv[k][c];
+                }
+            }
+        }
+    }
+}
+
+}  // namespace d4s

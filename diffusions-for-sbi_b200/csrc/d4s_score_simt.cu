@@ -1,0 +1,362 @@
+// Kernel 1+2 (fp32 SIMT variant): fused score-network forward on a tile of (sample x observation) pairs,
+// optional forward-mode Jacobian (JAC), Tweedie precisions, and the per-sample partial sums over the
+// tile's observations.  Nothing of shape [N, n, *] is materialised unless the caller asks for it.
+//
+// Replaces (reference file:line):
+//   NSE.forward / NSE.score on the grid           nse.py:112-145 via tall_posterior_sampler.py:114-121
+//   vmap(vmap(jacrev(score)))                      tall_posterior_sampler.py:76-85  (forward mode here)
+//   cov -> inv (JAC)                               tall_posterior_sampler.py:91-94
+//   prec @ scores, .sum(dim=1)                     nse.py:631-636 / 647-652
+//
+// Layer 0 is separable: z0[i,j,:] = A theta_i + obs_feat_j + time_feat (SURVEY.md section 7 identity 1),
+// so it costs m FMAs per element instead of a GEMM.  Hidden layers run as a register-tiled fp32 GEMM:
+// warp w owns rows 8w..8w+7 of the tile and all output columns (lane l -> columns l, l+32, ...), the
+// activations live in shared memory k-major and are updated in place, the weights stream from L2 through
+// a cp.async ring.  JAC rows (one primal + m tangents per pair) share the GEMM; tangents are masked by the
+// primal's ReLU pattern, published per layer as ballot words.
+#include "d4s_common.cuh"
+
+namespace d4s {
+
+constexpr int NSTAGE = 3;
+
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// One hidden layer: acc[q][j] = sum_k act[k][8*warp+q] * Wt[k][lane+32j]
+template <int NC>
+__device__ __forceinline__ void layer_gemm(float (&acc)[8][NC], const float* __restrict__ Wt, int K,
+                                           const float* sAct, float* sW, int warp, int lane, int tid) {
+    constexpr int Hout = NC * 32;
+    constexpr int CHUNK_F4 = KC * Hout / 4;  // float4 per stage
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int j = 0; j < NC; ++j) acc[q][j] = 0.f;
+
+    __syncthreads();  // every warp is done with the previous layer's weight ring before it is refilled
+    const int nchunks = K / KC;
+    auto issue = [&](int ch) {
+        if (ch < nchunks) {
+            const float4* src = reinterpret_cast<const float4*>(Wt + (size_t)ch * KC * Hout);
+            float4* dst = reinterpret_cast<float4*>(sW + (ch % NSTAGE) * KC * HMAX);
+            for (int i = tid; i < CHUNK_F4; i += NT) cp_async16(dst + i, src + i);
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        cp_async_wait<1>();
+        __syncthreads();
+        issue(ch + 2);
+        const float* w = sW + (ch % NSTAGE) * KC * HMAX;
+        const float* a = sAct + (size_t)ch * KC * ASTR + 8 * warp;
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            float4 a0 = *reinterpret_cast<const float4*>(a + kk * ASTR);
+            float4 a1 = *reinterpret_cast<const float4*>(a + kk * ASTR + 4);
+            float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bv[NC];
+#pragma unroll
+            for (int j = 0; j < NC; ++j) bv[j] = w[kk * Hout + lane + 32 * j];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+#pragma unroll
+                for (int j = 0; j < NC; ++j) acc[q][j] = fmaf(av[q], bv[j], acc[q][j]);
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// bias + ReLU (+ JAC masking) and in-place write-back of one hidden layer's activations
+template <int NC>
+__device__ __forceinline__ void layer_epilogue(float (&acc)[8][NC], const float* __restrict__ bias, float* sAct,
+                                               unsigned* sMask, const int* sKind, const int* sPair, int jac,
+                                               int warp, int lane) {
+    float bj[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) bj[j] = __ldg(bias + lane + 32 * j);
+    if (jac) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int r = 8 * warp + q;
+            if (sKind[r] == 0) {  // primal row: publish the ReLU pattern (warp-uniform branch)
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    unsigned word = __ballot_sync(0xffffffffu, acc[q][j] + bj[j] > 0.f);
+                    if (lane == 0) sMask[sPair[r] * 8 + j] = word;
+                }
+            }
+        }
+        __syncthreads();
+    } else {
+        __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int r = 8 * warp + q;
+            const int kind = sKind[r];
+            if (kind <= 0) {
+                v[q] = fmaxf(acc[q][j] + bj[j], 0.f);  // primal (or padding row: harmless)
+            } else {
+                unsigned word = sMask[sPair[r] * 8 + j];
+                v[q] = ((word >> lane) & 1u) ? acc[q][j] : 0.f;
+            }
+        }
+        float* dst = sAct + (size_t)(lane + 32 * j) * ASTR + 8 * warp;
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    __syncwarp();
+}
+
+template <int NC>
+__device__ __forceinline__ void hidden_layer(const float* __restrict__ Wt, const float* __restrict__ bias, int K,
+                                             float* sAct, float* sW, unsigned* sMask, const int* sKind,
+                                             const int* sPair, int jac, int warp, int lane, int tid) {
+    float acc[8][NC];
+    layer_gemm<NC>(acc, Wt, K, sAct, sW, warp, lane, tid);
+    layer_epilogue<NC>(acc, bias, sAct, sMask, sKind, sPair, jac, warp, lane);
+}
+
+// JAC per-pair: Pm = (alpha/sigma^2) inv(I - sigma Jeps), v = Pm s   (tall_posterior_sampler.py:91-94)
+template <int M>
+__device__ __noinline__ void jac_pair(const float* sJp, const float* sSp, float sigma, float a_over_s2, float* outp,
+                                      float* prec_out) {
+    // fp64: the covariance I - sigma*Jeps of a learned (asymmetric, possibly indefinite) Jacobian is the
+    // ill-conditioned step of the JAC path; m^3 flops per pair are free next to the MLP.
+    double a[M][M], inv[M][M], s[M];
+#pragma unroll
+    for (int o = 0; o < M; ++o) {
+        s[o] = (double)sSp[o];
+#pragma unroll
+        for (int k = 0; k < M; ++k) a[o][k] = ((o == k) ? 1.0 : 0.0) - (double)sigma * (double)sJp[o * M + k];
+    }
+    gj_inverse_t<double, M>(a, inv);
+#pragma unroll
+    for (int o = 0; o < M; ++o) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            const double pr = (double)a_over_s2 * inv[o][k];
+            outp[M + o * M + k] = (float)pr;
+            if (prec_out) prec_out[o * M + k] = (float)pr;
+            v = fma(pr, s[k], v);
+        }
+        outp[o] = (float)v;
+    }
+}
+
+__global__ void __launch_bounds__(NT, 2) score_simt_kernel(const ScoreParams p) {
+    extern __shared__ __align__(16) float smem[];
+    float* sAct = smem;                           // [HMAX][ASTR]
+    float* sW = sAct + HMAX * ASTR;               // [NSTAGE][KC][HMAX]
+    float* sS = sW + NSTAGE * KC * HMAX;          // [TM][MMAX] scores of primal rows
+    float* sQS = sS + TM * MMAX;                  // [TM][MMAX] GAUSS: inv(Sigma_j) s ; JAC: per-pair outputs
+    float* sJ = sQS + TM * MMAX;                  // [P][m][m] d eps / d theta
+    float* sTheta = sJ + TM * MMAX;               // [SG][MMAX]
+    unsigned* sMask = reinterpret_cast<unsigned*>(sTheta + TM * MMAX);  // [32][8]
+    int* sKind = reinterpret_cast<int*>(sMask + 32 * 8);                // [TM] -1 invalid, 0 primal, 1+k tangent k
+    int* sPair = sKind + TM;                                            // [TM] pair index within tile
+    int* sSamp = sPair + TM;                                            // [TM] sample index within tile (per pair)
+    int* sObs = sSamp + TM;                                             // [TM] global observation index (per pair)
+
+    const NetDev& net = p.net;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m = net.m;
+    const int tile = blockIdx.x;
+    const int grp = tile / p.C, chunk = tile - grp * p.C;
+    const int i0 = grp * p.SG;
+    const int j0 = chunk * p.OC;
+    const int nsamp = min(p.SG, p.N - i0);
+    const int nobs = p.paired ? 1 : min(p.OC, p.n - j0);
+    const float inv_sigma = p.sched[D4S_S_INV_SIGMA];
+    const float sigma = p.sched[D4S_S_SIGMA];
+    const float a_over_s2 = p.sched[D4S_S_A_OVER_S2];
+
+    // ---- tile metadata -------------------------------------------------------------------------
+    if (tid < TM) {
+        const int r = tid;
+        int kind = -1, pair = 0;
+        if (r < p.P) { kind = 0; pair = r; }
+        else if (p.jac && r < p.P * (1 + m)) { kind = 1 + (r - p.P) / p.P; pair = r % p.P; }
+        const int si = pair / p.OC, oj = pair - si * p.OC;
+        if (kind >= 0 && (si >= nsamp || oj >= nobs)) kind = -1;
+        sKind[r] = kind;
+        sPair[r] = pair;
+        if (r < p.P) {
+            sSamp[r] = si;
+            sObs[r] = p.paired ? min(i0 + si, p.n - 1) : min(j0 + oj, p.n - 1);
+        }
+    }
+    for (int e = tid; e < p.SG * m; e += NT) {
+        const int si = e / m, k = e - si * m;
+        sTheta[si * MMAX + k] = (si < nsamp) ? p.theta[(size_t)(i0 + si) * m + k] : 0.f;
+    }
+    __syncthreads();
+
+    // ---- layer 0 (separable) -------------------------------------------------------------------
+    {
+        const int H0 = net.Hp[0];
+        for (int j = 0; j < H0 / 32; ++j) {
+            const int col = lane + 32 * j;
+            const float tf = __ldg(p.time_feat + col);
+            float acol[MMAX];
+#pragma unroll
+            for (int k = 0; k < MMAX; ++k) acol[k] = (k < m) ? __ldg(net.A + (size_t)k * H0 + col) : 0.f;
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int r = 8 * warp + q;
+                const int kind = sKind[r];
+                const int pr = sPair[r];
+                const int si = sSamp[pr];
+                float z = tf + __ldg(p.obs_feat + (size_t)sObs[pr] * H0 + col);
+#pragma unroll
+                for (int k = 0; k < MMAX; ++k)
+                    if (k < m) z = fmaf(acol[k], sTheta[si * MMAX + k], z);
+                float out = 0.f;
+                if (kind == 0) out = fmaxf(z, 0.f);
+                else if (kind > 0) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int k = 0; k < MMAX; ++k) t = (k == kind - 1) ? acol[k] : t;
+                    out = (z > 0.f) ? t : 0.f;
+                }
+                v[q] = out;
+            }
+            float* dst = sAct + (size_t)col * ASTR + 8 * warp;
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    }
+    __syncwarp();
+
+    // ---- hidden layers 1 .. L-2 ------------------------------------------------------------------
+    for (int l = 1; l <= net.L - 2; ++l) {
+        const int K = net.Hp[l - 1];
+        switch (net.Hp[l]) {
+            case 64: hidden_layer<2>(net.Wt[l], net.bias[l], K, sAct, sW, sMask, sKind, sPair, p.jac, warp, lane, tid); break;
+            case 128: hidden_layer<4>(net.Wt[l], net.bias[l], K, sAct, sW, sMask, sKind, sPair, p.jac, warp, lane, tid); break;
+            default: hidden_layer<8>(net.Wt[l], net.bias[l], K, sAct, sW, sMask, sKind, sPair, p.jac, warp, lane, tid); break;
+        }
+    }
+
+    // ---- output layer: eps[r][o] = bout[o] + sum_k Wout[k][o] act[k][r] ------------------------------
+    {
+        const int K = net.Hp[net.L - 2];
+        for (int e = lane; e < 8 * m; e += 32) {
+            const int q = e & 7, o = e >> 3;
+            const int r = 8 * warp + q;
+            const float* a = sAct + 8 * warp + q;
+            const float* w = net.Wout + o;
+            float d0 = 0.f, d1 = 0.f;
+            for (int k = 0; k < K; k += 2) {
+                d0 = fmaf(a[(size_t)k * ASTR], __ldg(w + (size_t)k * MMAX), d0);
+                d1 = fmaf(a[(size_t)(k + 1) * ASTR], __ldg(w + (size_t)(k + 1) * MMAX), d1);
+            }
+            const float dot = d0 + d1;
+            const int kind = sKind[r];
+            if (kind == 0) {
+                const float s = -(dot + __ldg(net.bout + o)) * inv_sigma;  // nse.py:145
+                sS[r * MMAX + o] = s;
+                if (p.scores_out) {
+                    const int pr = sPair[r];
+                    const size_t gi = (size_t)(i0 + sSamp[pr]);
+                    const size_t gj = p.paired ? 0 : (size_t)sObs[pr];
+                    const size_t nn = p.paired ? 1 : (size_t)p.n;
+                    p.scores_out[(gi * nn + gj) * m + o] = s;
+                }
+            } else if (kind > 0) {
+                sJ[(sPair[r] * m + o) * m + (kind - 1)] = dot;  // d eps_o / d theta_k
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- per-pair Tweedie terms -----------------------------------------------------------------------
+    if (!p.jac) {
+        // GAUSS: inv(Sigma_j) s_ij ; the alpha/sigma^2 I part of the precision is applied after the
+        // reduction (it is the same for every observation).
+        for (int e = tid; e < p.P * m; e += NT) {
+            const int r = e / m, o = e - r * m;
+            float acc = 0.f;
+            if (sKind[r] == 0 && p.obs_prec) {
+                const float* Q = p.obs_prec + ((size_t)sObs[r] * m + o) * m;
+                for (int k = 0; k < m; ++k) acc = fmaf(__ldg(Q + k), sS[r * MMAX + k], acc);
+            }
+            sQS[r * MMAX + o] = acc;
+        }
+    } else {
+        if (tid < p.P && sKind[tid] == 0) {
+            const int r = tid;
+            float* outp = sQS + r * (m + m * m);
+            float* po = nullptr;
+            if (p.prec_out) {
+                const size_t gi = (size_t)(i0 + sSamp[r]);
+                const size_t gj = p.paired ? 0 : (size_t)sObs[r];
+                const size_t nn = p.paired ? 1 : (size_t)p.n;
+                po = p.prec_out + (gi * nn + gj) * m * m;
+            }
+            const float* J = sJ + r * m * m;
+            const float* S = sS + r * MMAX;
+            switch (m) {
+                case 1: jac_pair<1>(J, S, sigma, a_over_s2, outp, po); break;
+                case 2: jac_pair<2>(J, S, sigma, a_over_s2, outp, po); break;
+                case 3: jac_pair<3>(J, S, sigma, a_over_s2, outp, po); break;
+                case 4: jac_pair<4>(J, S, sigma, a_over_s2, outp, po); break;
+                case 5: jac_pair<5>(J, S, sigma, a_over_s2, outp, po); break;
+                case 6: jac_pair<6>(J, S, sigma, a_over_s2, outp, po); break;
+                case 7: jac_pair<7>(J, S, sigma, a_over_s2, outp, po); break;
+                case 8: jac_pair<8>(J, S, sigma, a_over_s2, outp, po); break;
+                case 9: jac_pair<9>(J, S, sigma, a_over_s2, outp, po); break;
+                default: jac_pair<10>(J, S, sigma, a_over_s2, outp, po); break;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- reduction over the tile's observations (fixed order => deterministic) ------------------------
+    const int W = p.W;
+    for (int e = tid; e < nsamp * W; e += NT) {
+        const int si = e / W, c = e - si * W;
+        float acc = 0.f;
+        for (int oj = 0; oj < nobs; ++oj) {
+            const int r = si * p.OC + oj;
+            float v;
+            if (!p.jac) v = (c < m) ? sS[r * MMAX + c] : sQS[r * MMAX + (c - m)];
+            else v = sQS[r * W + c];
+            acc += v;
+        }
+        p.part[((size_t)(i0 + si) * p.C + chunk) * W + c] = acc;
+    }
+}
+
+size_t score_simt_smem_bytes() {
+    return sizeof(float) * (HMAX * ASTR + NSTAGE * KC * HMAX + 4 * TM * MMAX) + sizeof(unsigned) * 32 * 8 +
+           sizeof(int) * 4 * TM;
+}
+
+cudaError_t launch_score_simt(const ScoreParams& p, int tiles, cudaStream_t stream) {
+    static bool configured = false;
+    const size_t smem = score_simt_smem_bytes();
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(score_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    score_simt_kernel<<<tiles, NT, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace d4s

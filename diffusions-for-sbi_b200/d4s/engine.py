@@ -1,0 +1,493 @@
+"""Host side of the tall-data sampler: turns an `NSE`-like module + the reference's keyword arguments
+into the device tables libd4s consumes, and drives the C ABI.
+
+What is computed here (once per trajectory / per call, in fp64 on the host, then cast to fp32):
+  * the DDIM schedule table (nse.py:258-259, 283-298) from the module's own `alpha`/`sigma`
+    (callers monkey-patch them, gen_gaussian_gaussian.py:46-50);
+  * the separable layer-1 partials: per observation `obs_feat` and per step `time_feat`
+    (SURVEY.md section 7 identity 1; PF_NSE layout pf_nse.py:163-164);
+  * the per-step small matrices of the precision-weighted combination (nse.py:628-654):
+    Lambda^-1 (GAUSS + Gaussian prior), the (1-n) P0 C^-1 prior map, sqrt(alpha) mu0.
+Everything that touches a posterior sample runs in the CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import weakref
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi as abi
+
+
+# ---------------------------------------------------------------------------------------------------------
+# prior description
+# ---------------------------------------------------------------------------------------------------------
+@dataclass
+class PriorSpec:
+    kind: int  # abi.PRIOR_*
+    low: Optional[torch.Tensor] = None  # uniform: [m] fp64 cpu
+    high: Optional[torch.Tensor] = None
+    mean: Optional[torch.Tensor] = None  # gaussian: [m], [m, m] fp64 cpu
+    cov: Optional[torch.Tensor] = None
+
+
+def _cpu64(v) -> torch.Tensor:
+    return torch.as_tensor(v).detach().to("cpu", torch.float64)
+
+
+def prior_spec(prior_type: Optional[str], prior, prior_score_fn, m: int) -> PriorSpec:
+    """Reads the prior parameters from the score-function object (d4s.vp_diffused_priors factories expose
+    `.kind/.low/.high/.mean/.cov`) or, failing that, from the torch distribution the reference passes as
+    `prior=` (sbibm_posterior_estimation.py:190,205)."""
+    if prior_type is None:
+        return PriorSpec(abi.PRIOR_NONE)
+    fn_kind = getattr(prior_score_fn, "kind", None)
+    if prior_type == "gaussian":
+        if fn_kind == "gaussian":
+            mean, cov = _cpu64(prior_score_fn.mean), _cpu64(prior_score_fn.cov)
+        elif prior is not None and hasattr(prior, "covariance_matrix"):
+            mean, cov = _cpu64(prior.loc), _cpu64(prior.covariance_matrix)
+        else:
+            raise ValueError("gaussian prior: pass a d4s.vp_diffused_priors score fn or a MultivariateNormal `prior`")
+        if prior is not None and hasattr(prior, "covariance_matrix"):
+            cov = _cpu64(prior.covariance_matrix)  # nse.py:630 reads the precision from `prior`
+        return PriorSpec(abi.PRIOR_GAUSSIAN, mean=mean.reshape(m), cov=cov.reshape(m, m))
+    if prior_type == "uniform":
+        if fn_kind == "uniform":
+            low, high = _cpu64(prior_score_fn.low), _cpu64(prior_score_fn.high)
+        elif prior is not None and hasattr(prior, "low"):
+            low, high = _cpu64(prior.low), _cpu64(prior.high)
+        elif prior is not None and hasattr(prior, "base_dist"):
+            low, high = _cpu64(prior.base_dist.low), _cpu64(prior.base_dist.high)
+        else:
+            raise ValueError("uniform prior: pass a d4s.vp_diffused_priors score fn or a Uniform `prior`")
+        return PriorSpec(abi.PRIOR_UNIFORM, low=low.reshape(m).contiguous(), high=high.reshape(m).contiguous())
+    raise NotImplementedError(f"prior_type={prior_type!r}: only 'gaussian' and 'uniform' have a fused diffused score")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# packed net cache
+# ---------------------------------------------------------------------------------------------------------
+def pad_width(h: int) -> int:
+    """Hidden widths are zero padded to 64 / 128 / 256 (same rule as pad_width() in csrc/d4s_api.cu)."""
+    for w in (64, 128, 256):
+        if h <= w:
+            return w
+    raise abi.D4sError(f"hidden width {h} > {abi.MAX_WIDTH} is not supported")
+
+
+class NetView:
+    """Host-side (fp64) view of the layer-0 blocks of `nse.net`; needs no CUDA device."""
+
+    def __init__(self, linears):
+        L = len(linears)
+        if not 2 <= L <= abi.MAX_LAYERS:
+            raise abi.D4sError(f"score MLP must have 2..{abi.MAX_LAYERS} Linear layers, got {L}")
+        self.linears = linears
+        self.m = linears[-1].out_features
+        self.h1 = linears[0].out_features
+        self.h1p = pad_width(self.h1)
+        self.w1 = linears[0].weight.detach().to("cpu", torch.float64)  # [H1, in]
+        self.b1 = linears[0].bias.detach().to("cpu", torch.float64)
+
+
+class PackedNet(NetView):
+    """Device-resident packed copy of `nse.net` (d4s_net_create) + the host view."""
+
+    def __init__(self, linears, theta_cols: int, device: torch.device):
+        super().__init__(linears)
+        lib = abi.require_cuda()
+        L = len(linears)
+        desc = abi.NetDesc()
+        desc.n_layers = L
+        desc.theta_cols = theta_cols
+        keep = []
+        desc.dims[0] = linears[0].in_features
+        for l, lin in enumerate(linears):
+            w = lin.weight.detach().to("cpu", torch.float32).contiguous()
+            b = lin.bias.detach().to("cpu", torch.float32).contiguous()
+            keep += [w, b]
+            desc.dims[l + 1] = lin.out_features
+            desc.weight[l] = w.data_ptr()
+            desc.bias[l] = b.data_ptr()
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            abi.check(lib.d4s_net_create(C.byref(handle), C.byref(desc), C.c_void_p(stream)))
+        del keep
+        self.handle = handle
+        self.device = device
+        assert self.h1p == lib.d4s_net_h1_padded(handle)
+        self._finalizer = weakref.finalize(self, lib.d4s_net_free, handle)
+
+
+_net_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _linears(mlp) -> list:
+    mods = list(mlp.modules())[1:] if isinstance(mlp, torch.nn.Sequential) else list(mlp.children())
+    lin, prev_linear = [], False
+    for mod in mods:
+        if isinstance(mod, torch.nn.Linear):
+            lin.append(mod)
+        elif isinstance(mod, (torch.nn.ReLU, torch.nn.Identity)):
+            continue
+        else:
+            raise abi.D4sError(f"unsupported module in score MLP: {type(mod).__name__} (Linear/ReLU stacks only)")
+    return lin
+
+
+def packed_net(nse, device: torch.device) -> PackedNet:
+    lin = _linears(nse.net)
+    key = tuple((p.data_ptr(), p._version) for l in lin for p in (l.weight, l.bias)) + (str(device),)
+    hit = _net_cache.get(nse)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    theta_cols = int(getattr(nse, "theta_emb_dim", nse.zeros.shape[0]))
+    pn = PackedNet(lin, theta_cols, device)
+    _net_cache[nse] = (key, pn)
+    return pn
+
+
+# ---------------------------------------------------------------------------------------------------------
+# schedule + tables (fp64 host)
+# ---------------------------------------------------------------------------------------------------------
+def time_grid(steps: int) -> torch.Tensor:
+    """`torch.linspace(1, 0, steps + 1)` in fp32 (nse.py:258); its values are exactly what the reference feeds
+    to alpha/sigma/the time embedding, in fp32 and in fp64 runs alike."""
+    return torch.linspace(1, 0, steps + 1)
+
+
+def _scalar64(fn, t64: torch.Tensor) -> torch.Tensor:
+    out = fn(t64)
+    return torch.as_tensor(out, dtype=torch.float64).reshape(t64.shape)
+
+
+def schedule_rows(nse, t: torch.Tensor, t_prev: Optional[torch.Tensor], eta: float, n_total: int,
+                  combine: Sequence[int]) -> torch.Tensor:
+    """[len(t), 16] fp64 schedule rows.  t_prev = t - dt (None => no DDIM update coefficients)."""
+    t64 = t.to(torch.float64)
+    a = _scalar64(nse.alpha, t64)
+    sig = _scalar64(nse.sigma, t64)
+    rows = torch.zeros(t64.numel(), abi.SCHED_STRIDE, dtype=torch.float64)
+    rows[:, abi.S_T] = t64
+    rows[:, abi.S_ALPHA] = a
+    rows[:, abi.S_SIGMA] = sig
+    rows[:, abi.S_INV_SIGMA] = 1.0 / sig
+    rows[:, abi.S_A_OVER_S2] = a / sig ** 2
+    rows[:, abi.S_SQRT_ALPHA] = a.sqrt()
+    rows[:, abi.S_COMBINE] = torch.as_tensor(list(combine), dtype=torch.float64)
+    rows[:, abi.S_ONE_MINUS_N] = float(1 - n_total)
+    if t_prev is not None:
+        a1 = _scalar64(nse.alpha, t_prev.to(torch.float64))
+        bs = eta * (((1 - a1) / (1 - a)) * (1 - a / a1)).clamp_min(0).sqrt()  # nse.py:285-287
+        c_theta = (a1 / a).sqrt()  # sqrt(alpha_{t-1}) * alpha_t^-1/2      (nse.py:205, 219)
+        # est_noise = (theta - sqrt(a) theta0) / sqrt(1-a) = -sqrt(1-a) * score   (nse.py:218, exact algebra)
+        c_score = c_theta * (1 - a) - (1 - a1 - bs ** 2).clamp_min(0).sqrt() * (1 - a).sqrt()
+        rows[:, abi.S_C_THETA] = c_theta
+        rows[:, abi.S_C_SCORE] = c_score
+        rows[:, abi.S_BRIDGE_STD] = bs
+    return rows
+
+
+def time_embedding64(nse, t64: torch.Tensor) -> torch.Tensor:
+    ang = nse.freqs.detach().to("cpu", torch.float64) * t64[..., None]  # nse.py:125
+    return torch.cat((ang.cos(), ang.sin()), dim=-1)  # nse.py:126
+
+
+def layer1_blocks(nse, pn: NetView):
+    """Column blocks of the first Linear: [theta | x | temb | (one-hot n, PF_NSE only)]."""
+    e_t = int(getattr(nse, "theta_emb_dim", pn.m))
+    e_x = int(getattr(nse, "x_emb_dim"))
+    f2 = 2 * nse.freqs.numel()
+    cols = pn.w1.shape[1]
+    n_hot = cols - e_t - e_x - f2
+    if n_hot < 0:
+        raise abi.D4sError("first Linear is narrower than theta+x+time features")
+    return (slice(0, e_t), slice(e_t, e_t + e_x), slice(e_t + e_x, e_t + e_x + f2),
+            slice(e_t + e_x + f2, cols), n_hot)
+
+
+def time_feat_table(nse, pn: NetView, t: torch.Tensor) -> torch.Tensor:
+    """[len(t), H1p] fp64: W1[:, t-block] temb(t) + b1, zero padded."""
+    _, _, tcol, _, _ = layer1_blocks(nse, pn)
+    temb = time_embedding64(nse, t.to(torch.float64))
+    out = torch.zeros(t.numel(), pn.h1p, dtype=torch.float64)
+    out[:, :pn.h1] = temb @ pn.w1[:, tcol].T + pn.b1
+    return out
+
+
+def obs_feat_table(nse, pn: NetView, x: torch.Tensor, n_sizes: Optional[torch.Tensor]) -> torch.Tensor:
+    """[n, H1p] fp64 layer-1 partial of every observation (or PF_NSE subset).
+
+    NSE:    W1[:, x-block] e_x(x_j)                                                  (nse.py:130-136)
+    PF_NSE: W1[:, x-block] masked-mean_j e_x(x^j) + W1[:, one-hot block] onehot(n)  (pf_nse.py:137-164)
+    """
+    _, xcol, _, hcol, n_hot = layer1_blocks(nse, pn)
+    emb = nse.embedding_nn_x
+    with torch.no_grad():
+        if n_sizes is None:
+            xe = emb(x).detach().to("cpu", torch.float64)  # [n, e_x]
+            feat = xe @ pn.w1[:, xcol].T
+        else:
+            ns = n_sizes.detach().to("cpu", torch.float64).reshape(-1, 1)  # [K, 1]
+            K, n_max = x.shape[0], x.shape[1]
+            mask = (torch.arange(n_max, dtype=torch.float64)[None, :] < ns).to(x.dtype).unsqueeze(-1).to(x.device)
+            x = x.reshape(K, n_max, -1)
+            if hasattr(nse, "set_mask"):
+                nse.set_mask(mask)
+            xe = (mask * emb(mask * x)).detach().to("cpu", torch.float64)  # pf_nse.py:141,154
+            if float(ns.sum()) != 0:
+                x_agg = xe.sum(dim=-2) / ns  # pf_nse.py:109-111
+            else:
+                x_agg = xe.mean(dim=-2)
+            feat = x_agg @ pn.w1[:, xcol].T
+            if not bool((ns == 0).all()):
+                onehot = torch.nn.functional.one_hot(ns.long().reshape(-1) - 1, num_classes=n_hot).to(torch.float64)
+                feat = feat + onehot @ pn.w1[:, hcol].T  # pf_nse.py:158-164
+    out = torch.zeros(feat.shape[0], pn.h1p, dtype=torch.float64)
+    out[:, :pn.h1] = feat
+    return out
+
+
+def combine_mode(prior: PriorSpec, cov_jac: bool, n_total: int, sqrt_alpha: float, weighted: bool = True) -> int:
+    """Which branch of nse.py:627-654 a step takes (decided on the host: it only depends on t)."""
+    if not weighted or prior.kind == abi.PRIOR_NONE:
+        return abi.COMBINE_SUM
+    if prior.kind == abi.PRIOR_GAUSSIAN:
+        return abi.COMBINE_PER_SAMPLE if cov_jac else abi.COMBINE_SHARED
+    if sqrt_alpha > 0.5 and n_total > 1:  # nse.py:643
+        return abi.COMBINE_PER_SAMPLE
+    return abi.COMBINE_SUM
+
+
+def mats_table(rows: torch.Tensor, prior: PriorSpec, cov_jac: bool, n_total: int, sum_q: Optional[torch.Tensor],
+               m: int) -> torch.Tensor:
+    """[steps, 2 m^2 + m] fp64: Lmat | G | mu_t  (layout of D4sStep.mats)."""
+    S = rows.shape[0]
+    eye = torch.eye(m, dtype=torch.float64)
+    a = rows[:, abi.S_ALPHA]
+    sig2 = rows[:, abi.S_SIGMA] ** 2
+    aos2 = rows[:, abi.S_A_OVER_S2]
+    comb = rows[:, abi.S_COMBINE].to(torch.int64)
+    one_minus_n = float(1 - n_total)
+    lmat = torch.zeros(S, m, m, dtype=torch.float64)
+    g = torch.zeros(S, m, m, dtype=torch.float64)
+    mu = torch.zeros(S, m, dtype=torch.float64)
+    base = torch.zeros(S, m, m, dtype=torch.float64)
+    if not cov_jac and sum_q is not None:
+        base = sum_q[None] + (n_total * aos2)[:, None, None] * eye  # sum_j [inv(Sigma_j) + alpha/sigma^2 I]
+    if prior.kind == abi.PRIOR_GAUSSIAN:
+        cov0, mean0 = prior.cov, prior.mean
+        c_t = sig2[:, None, None] * eye + a[:, None, None] * cov0  # vp_diffused_priors.py:65-68
+        c_inv = torch.linalg.inv(c_t)
+        p0 = torch.linalg.inv(cov0)[None] + aos2[:, None, None] * eye  # prec_matrix_backward(prior cov), nse.py:630
+        mu = a.sqrt()[:, None] * mean0
+        weighted = comb != abi.COMBINE_SUM
+        # score_prior = -(theta - mu_t) C^-1 (row-vector form, vp_diffused_priors.py:71) = -C^-T (theta - mu_t)
+        g_w = -one_minus_n * (p0 @ c_inv.transpose(-1, -2))
+        g_s = -one_minus_n * c_inv.transpose(-1, -2)
+        g = torch.where(weighted[:, None, None], g_w, g_s)
+        lam = one_minus_n * p0 + base
+        if cov_jac:
+            lmat = one_minus_n * p0
+        else:
+            shared = comb == abi.COMBINE_SHARED
+            safe = torch.where(shared[:, None, None], lam, eye.expand(S, m, m))
+            lmat = torch.where(shared[:, None, None], torch.linalg.inv(safe), lam)
+    else:
+        lmat = base  # uniform / none: per-sample prior precision is added on the device
+    return torch.cat((lmat.reshape(S, -1), g.reshape(S, -1), mu), dim=1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# launching
+# ---------------------------------------------------------------------------------------------------------
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _dev32(t64: torch.Tensor, device) -> torch.Tensor:
+    return t64.to(torch.float32).contiguous().to(device, non_blocking=False)
+
+
+@dataclass
+class TallSetup:
+    """Device tables of one trajectory / one call (everything d4s_ddim_run needs)."""
+    pn: PackedNet
+    prob: abi.Problem
+    sched: torch.Tensor
+    time_feat: torch.Tensor
+    mats: torch.Tensor
+    step_modes: Optional[np.ndarray]
+    keep: tuple  # tensors referenced by raw pointers in `prob`
+    n_steps: int
+
+
+def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: Optional[torch.Tensor], eta: float,
+                prior: PriorSpec, cov_mode: str, dist_cov_est: Optional[torch.Tensor], paired: bool = False,
+                n_sizes: Optional[torch.Tensor] = None, clip=(None, None), seed: int = 0, sample_offset: int = 0,
+                weighted: bool = True, obs_slice: Optional[slice] = None, obs_chunk: int = 0) -> TallSetup:
+    """`obs_slice` restricts the kernels to a shard of the observations (observation sharding over ranks):
+    (1-n) and Lambda still use the total n, the partial sums are all-reduced by the caller."""
+    lib = abi.require_cuda()
+    if not x.is_cuda:
+        raise abi.D4sError("d4s: observations must live on a CUDA device (no CPU fallback)")
+    device = x.device
+    pn = packed_net(nse, device)
+    m = pn.m
+    if cov_mode not in ("GAUSS", "JAC"):
+        raise NotImplementedError("Available methods are GAUSS, JAC")
+    cov_jac = cov_mode == "JAC"
+    x2 = x if x.ndim > 1 else x[None]
+    n_total = x2.shape[0]
+    if paired:
+        weighted = False
+    sum_q = q_dev = None
+    if not cov_jac and weighted and not paired:
+        if dist_cov_est is None:
+            raise ValueError("cov_mode='GAUSS' needs dist_cov_est (tall_posterior_sampler.py:125)")
+        q64 = torch.linalg.inv(dist_cov_est.detach().to("cpu", torch.float64))  # [n, m, m]
+        sum_q = q64.sum(dim=0)
+    t = t.detach().to("cpu").reshape(-1)
+    sa = _scalar64(nse.alpha, t.to(torch.float64)).sqrt()
+    comb = [combine_mode(prior, cov_jac, n_total, float(s), weighted) for s in sa]
+    rows = schedule_rows(nse, t, None if t_prev is None else t_prev.detach().to("cpu").reshape(-1), eta, n_total, comb)
+    mats = mats_table(rows, prior, cov_jac, n_total, sum_q, m)
+    tf = time_feat_table(nse, pn, t)
+    of = obs_feat_table(nse, pn, x2, n_sizes)
+    if obs_slice is not None:
+        of = of[obs_slice]
+        if sum_q is not None:
+            q64 = q64[obs_slice]
+    if sum_q is not None:
+        q_dev = _dev32(q64, device)
+    of_dev = _dev32(of, device)
+    low_dev = high_dev = None
+    if prior.kind == abi.PRIOR_UNIFORM:
+        low_dev, high_dev = _dev32(prior.low, device), _dev32(prior.high, device)
+
+    prob = abi.Problem()
+    prob.n_samples = n_samples
+    prob.n_obs = of.shape[0]
+    prob.theta_dim = m
+    prob.cov_mode = abi.COV_JAC if cov_jac else abi.COV_GAUSS
+    prob.prior_kind = prior.kind
+    prob.paired = 1 if paired else 0
+    prob.obs_chunk = obs_chunk
+    prob.n_obs_total = n_total
+    prob.obs_feat = of_dev.data_ptr()
+    prob.obs_prec = 0 if q_dev is None else q_dev.data_ptr()
+    prob.prior_low = 0 if low_dev is None else low_dev.data_ptr()
+    prob.prior_high = 0 if high_dev is None else high_dev.data_ptr()
+    lo, hi = clip
+    prob.clip_lo, prob.clip_hi = (1.0, -1.0) if lo is None else (float(lo), float(hi))
+    prob.seed = seed & (2 ** 64 - 1)
+    prob.sample_offset = sample_offset
+    # JAC trajectories skip the Jacobian on SUM steps (nse.py:642-643 discards it there)
+    step_modes = None
+    if cov_jac and any(c == abi.COMBINE_SUM for c in comb):
+        step_modes = np.asarray([abi.COV_GAUSS if c == abi.COMBINE_SUM else abi.COV_JAC for c in comb], np.int32)
+    ws_floats = 0
+    for mode in {prob.cov_mode} | (set(step_modes.tolist()) if step_modes is not None else set()):
+        q = abi.Problem.from_buffer_copy(prob)
+        q.cov_mode = mode
+        ws_floats = max(ws_floats, lib.d4s_workspace_floats(pn.handle, C.byref(q)))
+    if ws_floats <= 0:
+        raise abi.D4sError("d4s_workspace_floats failed")
+    ws = torch.empty(ws_floats, dtype=torch.float32, device=device)
+    prob.workspace = ws.data_ptr()
+    prob.workspace_floats = ws_floats
+    return TallSetup(pn, prob, _dev32(rows, device), _dev32(tf, device), _dev32(mats, device), step_modes,
+                     (of_dev, q_dev, low_dev, high_dev, ws), t.numel())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def philox_normal(n_rows: int, m: int, seed: int, step_index: int, sample_offset: int, device) -> torch.Tensor:
+    """z[i, k] from the generator the fused update uses (d4s_philox_normal)."""
+    lib = abi.require_cuda()
+    out = torch.empty(n_rows, m, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        abi.check(lib.d4s_philox_normal(_ptr(out), n_rows, m, C.c_uint64(seed & (2 ** 64 - 1)), step_index,
+                                        sample_offset, _stream(device)))
+    return out
+
+
+def run_trajectory(setup: TallSetup, theta: torch.Tensor, noise: Optional[torch.Tensor], use_graph: bool) -> torch.Tensor:
+    """theta[N, m] (initial draw) is updated in place through every DDIM step and returned."""
+    lib = abi.require_cuda()
+    assert theta.is_cuda and theta.dtype == torch.float32 and theta.is_contiguous()
+    if noise is not None:
+        noise = noise.to(theta.device, torch.float32).contiguous()
+        assert noise.shape == (setup.n_steps,) + tuple(theta.shape)
+    modes = None
+    if setup.step_modes is not None:
+        modes = setup.step_modes.ctypes.data_as(C.POINTER(C.c_int32))
+    with torch.cuda.device(theta.device):
+        abi.check(lib.d4s_ddim_run(setup.pn.handle, C.byref(setup.prob), setup.n_steps, _ptr(setup.sched),
+                                   _ptr(setup.time_feat), _ptr(setup.mats), _ptr(noise), _ptr(theta), modes,
+                                   1 if use_graph else 0, _stream(theta.device)))
+    return theta
+
+
+def step_struct(setup: TallSetup, k: int, noise_k: Optional[torch.Tensor], update: bool) -> abi.Step:
+    st = abi.Step()
+    st.sched = setup.sched[k].data_ptr()
+    st.time_feat = setup.time_feat[k].data_ptr()
+    st.mats = setup.mats[k].data_ptr()
+    st.noise = 0 if noise_k is None else noise_k.data_ptr()
+    st.step_index = k
+    st.update = 1 if update else 0
+    return st
+
+
+def score_partials(setup: TallSetup, theta: torch.Tensor, k: int = 0, want_scores=False, want_prec=False):
+    """Kernel 1(+2) alone: fills the workspace partial sums; optionally materialises scores / JAC precisions."""
+    lib = abi.require_cuda()
+    N, m = theta.shape
+    n = setup.prob.n_obs if not setup.prob.paired else 1
+    scores = torch.empty(N, n, m, dtype=torch.float32, device=theta.device) if want_scores else None
+    prec = None
+    if want_prec and setup.prob.cov_mode == abi.COV_JAC:
+        prec = torch.empty(N, n, m, m, dtype=torch.float32, device=theta.device)
+    st = step_struct(setup, k, None, False)
+    with torch.cuda.device(theta.device):
+        abi.check(lib.d4s_score_partials(setup.pn.handle, C.byref(setup.prob), C.byref(st), _ptr(theta), _ptr(scores),
+                                         _ptr(prec), _stream(theta.device)))
+    return scores, prec
+
+
+def finalize(setup: TallSetup, theta: torch.Tensor, k: int = 0, noise_k: Optional[torch.Tensor] = None,
+             update: bool = False) -> torch.Tensor:
+    """Kernel 3(+4) alone: reduces the workspace, applies prior + solve; returns the total score [N, m]."""
+    lib = abi.require_cuda()
+    out = torch.empty_like(theta)
+    st = step_struct(setup, k, noise_k, update)
+    with torch.cuda.device(theta.device):
+        abi.check(lib.d4s_finalize(setup.pn.handle, C.byref(setup.prob), C.byref(st), _ptr(theta), _ptr(out),
+                                   _stream(theta.device)))
+    return out
+
+
+def batched_inverse(a: torch.Tensor) -> torch.Tensor:
+    lib = abi.require_cuda()
+    a = a.to(torch.float32).contiguous()
+    if not a.is_cuda:
+        raise abi.D4sError("d4s.batched_inverse: CUDA tensors only")
+    m = a.shape[-1]
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        abi.check(lib.d4s_batched_inverse(_ptr(a), _ptr(out), a.numel() // (m * m), m, _stream(a.device)))
+    return out
+
+
+def launch_count() -> int:
+    return int(abi.load().d4s_launch_count())

@@ -1,0 +1,240 @@
+"""`NSE`: the reference's neural score estimator API (nse.py:23-299, 544-656 of diffusions-for-sbi) with the
+tall-data sampling path executed by the sm_100a kernels of libd4s.
+
+Kept verbatim from the reference: constructor signature, `forward/score`, the VP-SDE schedule functions
+`alpha/sigma/beta/f/g`, `mean_pred/bridge_mean`, and the signatures + keyword contract of `ddim`,
+`ddim_step` and `factorized_score` (kwargs `prior, prior_type, prior_score_fn, dist_cov_est, cov_mode,
+n`, forwarded through `ddim(**kwargs)` exactly like nse.py:254-256).
+
+Different by design: `ddim` and `factorized_score` do not evaluate the network pair by pair in torch; they
+hand the whole trajectory / call to the C ABI (engine.py).  They require CUDA tensors and raise otherwise:
+there is no CPU or torch fallback on this path.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Callable, Optional
+
+import torch
+import torch.nn as nn
+from torch import Size, Tensor
+
+from . import _cabi as abi
+from . import engine
+from .nn import MLP
+
+
+def _use_graph_default() -> bool:
+    return os.environ.get("D4S_CUDA_GRAPH", "1") != "0"
+
+
+class NSE(nn.Module):
+    """Noise-parametrised score network eps(theta, x, t) for the VP SDE with beta(t) = 32 t (nse.py:23-104)."""
+
+    def __init__(self, theta_dim: int, x_dim: int, freqs: int = 3, build_net: Callable[..., nn.Module] = MLP,
+                 net_type: str = "default", embedding_nn_theta: nn.Module = nn.Identity(),
+                 embedding_nn_x: nn.Module = nn.Identity(), **kwargs) -> None:
+        super().__init__()
+        if net_type != "default":
+            raise NotImplementedError("net_type='fnet' is a dead configuration of the reference (SURVEY.md section 2)")
+        self.embedding_nn_theta = embedding_nn_theta
+        self.embedding_nn_x = embedding_nn_x
+        self.theta_emb_dim, self.x_emb_dim = self.get_theta_x_embedding_dim(theta_dim, x_dim)
+        self.net_type = net_type
+        self.n_max = 1
+        self.net = build_net(self.theta_emb_dim + self.x_emb_dim + 2 * freqs, theta_dim, **kwargs)
+        self.register_buffer("freqs", torch.arange(1, freqs + 1) * math.pi)
+        self.register_buffer("zeros", torch.zeros(theta_dim))
+        self.register_buffer("ones", torch.ones(theta_dim))
+
+    # The reference stores its Tweedie hook as an instance attribute (nse.py:98) and scripts re-assign it after
+    # unpickling (sbibm_posterior_estimation.py:602).  It is accepted and ignored: the fused kernels never
+    # materialise the [N, n, m, m] tensors the hook returns.  Use d4s.tweedies_approximation for the hook API.
+    @property
+    def tweedies_approximator(self):
+        from .tall_posterior_sampler import tweedies_approximation
+        return self.__dict__.get("_tweedies_approximator", tweedies_approximation)
+
+    @tweedies_approximator.setter
+    def tweedies_approximator(self, fn):
+        self.__dict__["_tweedies_approximator"] = fn
+
+    def get_theta_x_embedding_dim(self, theta_dim: int, x_dim: int):
+        with torch.no_grad():
+            e_t = self.embedding_nn_theta(torch.ones(1, theta_dim)).shape[-1]
+            e_x = self.embedding_nn_x(torch.ones(1, x_dim)).shape[-1]
+        return e_t, e_x
+
+    # ---- model definition (torch; used for training and ad-hoc evaluation, not by the samplers) -----------
+    def forward(self, theta: Tensor, x: Tensor, t: Tensor) -> Tensor:
+        """eps(theta, x, t) with theta[*, m], x[*, d], t[*] broadcast over the batch dims (nse.py:112-136)."""
+        ang = self.freqs * t[..., None]
+        temb = torch.cat((ang.cos(), ang.sin()), dim=-1)
+        th = self.embedding_nn_theta(theta)
+        xe = self.embedding_nn_x(x)
+        batch = torch.broadcast_shapes(th.shape[:-1], xe.shape[:-1], temb.shape[:-1])
+        feats = [v.expand(batch + v.shape[-1:]) for v in (th, xe, temb)]
+        return self.net(torch.cat(feats, dim=-1))
+
+    def score(self, theta: Tensor, x: Tensor, t: Tensor, **kwargs) -> Tensor:
+        return -self(theta, x, t) / self.sigma(t)  # nse.py:144-145
+
+    # ---- VP SDE: d theta = -0.5 beta(t) theta dt + sqrt(beta(t)) dW (nse.py:147-170) -----------------------
+    def beta(self, t: Tensor) -> Tensor:
+        return 32 * t
+
+    def f(self, t: Tensor) -> Tensor:
+        return -0.5 * self.beta(t)
+
+    def g(self, t: Tensor) -> Tensor:
+        return torch.sqrt(self.beta(t))
+
+    def alpha(self, t: Tensor) -> Tensor:
+        return torch.exp(-16 * t ** 2)
+
+    def sigma(self, t: Tensor) -> Tensor:
+        return torch.sqrt(1 - self.alpha(t) + math.exp(-16))
+
+    def mean_pred(self, theta: Tensor, score: Tensor, alpha_t: Tensor, **kwargs) -> Tensor:
+        return (alpha_t ** (-0.5)) * (theta + (1 - alpha_t) * score)  # nse.py:199-207
+
+    def bridge_mean(self, alpha_t: Tensor, alpha_t_1: Tensor, theta_t: Tensor, theta_0: Tensor, bridge_std: float) -> Tensor:
+        eps_hat = (theta_t - (alpha_t ** 0.5) * theta_0) / ((1 - alpha_t) ** 0.5)  # nse.py:209-221
+        return (alpha_t_1 ** 0.5) * theta_0 + ((1 - alpha_t_1 - bridge_std ** 2) ** 0.5) * eps_hat
+
+    # ---- helpers ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _require_cuda(*tensors):
+        for v in tensors:
+            if isinstance(v, Tensor) and not v.is_cuda:
+                raise abi.D4sError("diffusions-for-sbi_b200 samplers need CUDA tensors (sm_100a); there is no CPU "
+                                   "fallback -- move the module and its inputs to the GPU")
+        abi.require_cuda()
+
+    def _is_single_context(self, shape: Size, x: Tensor) -> bool:
+        # nse.py:253: paired rows, a single 1-D observation, or one observation row use the plain score
+        return x.shape[0] == shape[0] or x.ndim == 1 or x.shape[0] == 1
+
+    def _split_kwargs(self, kwargs: dict):
+        kw = dict(kwargs)
+        opts = dict(
+            prior=kw.pop("prior", None),
+            prior_type=kw.pop("prior_type", "gaussian"),
+            prior_score_fn=kw.pop("prior_score_fn", None),
+            dist_cov_est=kw.pop("dist_cov_est", None),
+            dist_cov_est_prior=kw.pop("dist_cov_est_prior", None),
+            cov_mode=kw.pop("cov_mode", "GAUSS"),
+            clf_free_guidance=kw.pop("clf_free_guidance", False),
+            n_sizes=kw.pop("n", None),
+        )
+        noise = kw.pop("_noise", None)  # (z0[N,m], z[steps,N,m]) injected noise for replay tests
+        seed = kw.pop("_seed", None)
+        sample_offset = kw.pop("_sample_offset", 0)
+        if kw:
+            raise TypeError(f"unexpected keyword arguments: {sorted(kw)}")
+        if opts["clf_free_guidance"]:
+            raise NotImplementedError("clf_free_guidance=True: next-scope row (SURVEY.md section 8(f) rank 3)")
+        return opts, noise, seed, sample_offset
+
+    def _draw_seed(self) -> int:
+        # one draw from torch's global CPU generator, so torch.manual_seed(...) makes runs reproducible
+        return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+    # ---- samplers -----------------------------------------------------------------------------------------
+    def ddim(self, shape: Size, x: Tensor, steps: int = 1000, eta: float = 1.0, verbose: bool = False,
+             theta_clipping_range=(None, None), **kwargs) -> Tensor:
+        """DDIM sampler adapted to n context observations (nse.py:223-267); returns theta[shape[0], m] on x.device.
+
+        The whole `steps`-long loop is enqueued by one C-ABI call (two kernels per step, CUDA-graph captured).
+        """
+        self._require_cuda(x)
+        opts, noise, seed, sample_offset = self._split_kwargs(kwargs)
+        N = int(shape[0])
+        m = self.zeros.shape[0]
+        grid = engine.time_grid(steps)  # nse.py:258
+        t, t_prev = grid[:-1], grid[:-1].to(torch.float64) - 1.0 / steps  # nse.py:259, 284
+        single = self._is_single_context(shape, x)
+        if single:
+            paired = x.ndim > 1 and x.shape[0] == N and N > 1
+            prior = engine.PriorSpec(abi.PRIOR_NONE)
+            weighted = False
+        else:
+            paired = False
+            prior = engine.prior_spec(opts["prior_type"], opts["prior"], opts["prior_score_fn"], m)
+            weighted = True
+        if seed is None:
+            seed = self._draw_seed()
+        setup = engine.build_setup(self, x, N, t, t_prev, float(eta), prior, opts["cov_mode"], opts["dist_cov_est"],
+                                   paired=paired, n_sizes=opts["n_sizes"], clip=theta_clipping_range, seed=seed,
+                                   sample_offset=sample_offset, weighted=weighted)
+        if noise is not None:
+            z0, z = noise
+            theta = z0.to(x.device, torch.float32).contiguous().clone()
+        else:
+            z = None
+            theta = engine.philox_normal(N, m, seed, -1, sample_offset, x.device)  # nse.py:261
+        return engine.run_trajectory(setup, theta, z, _use_graph_default())
+
+    def ddim_step(self, theta: Tensor, x: Tensor, t: Tensor, score_fun: Callable[[Tensor, Tensor, Tensor], Tensor],
+                  dt: float, eta: float, **kwargs) -> Tensor:
+        """One DDIM step with a caller-supplied score function (nse.py:269-299); the update runs in kernel 4."""
+        self._require_cuda(theta)
+        score = score_fun(theta, x, t).detach()
+        noise = kwargs.pop("_noise", None)
+        tt = torch.as_tensor(t).detach().to("cpu").reshape(1)
+        rows = engine.schedule_rows(self, tt, tt.to(torch.float64) - dt, float(eta), 1, [abi.COMBINE_SUM])
+        sched = rows.to(torch.float32).to(theta.device)
+        out = theta.detach().to(torch.float32).contiguous().clone()
+        sc = score.to(torch.float32).contiguous()
+        lib = abi.require_cuda()
+        import ctypes as C
+        seed = self._draw_seed() if noise is None else 0
+        with torch.cuda.device(theta.device):
+            abi.check(lib.d4s_ddim_update(engine._ptr(out), engine._ptr(sc), out.shape[0], out.shape[1],
+                                          engine._ptr(sched), engine._ptr(noise), C.c_uint64(seed), 0, 0, 1.0, -1.0,
+                                          engine._stream(theta.device)))
+        return out
+
+    def factorized_score(self, theta, x_obs, t, prior_score_fn, prior, dist_cov_est=None, dist_cov_est_prior=None,
+                         cov_mode="GAUSS", prior_type="gaussian", clf_free_guidance=False, **kwargs) -> Tensor:
+        """Precision-weighted tall-data score ("GAUSS"/"JAC", nse.py:544-656), one fused call: kernel 1(+2) then 3."""
+        self._require_cuda(theta, x_obs)
+        if clf_free_guidance:
+            raise NotImplementedError("clf_free_guidance=True: next-scope row (SURVEY.md section 8(f) rank 3)")
+        n_sizes = kwargs.pop("n", None)
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments: {sorted(kwargs)}")
+        m = self.zeros.shape[0]
+        spec = engine.prior_spec(prior_type, prior, prior_score_fn, m)
+        tt = torch.as_tensor(t).detach().to("cpu").reshape(1)
+        setup = engine.build_setup(self, x_obs, theta.shape[0], tt, None, 0.0, spec, cov_mode, dist_cov_est,
+                                   n_sizes=n_sizes)
+        th = theta.detach().to(torch.float32).contiguous()
+        if setup.step_modes is not None:
+            setup.prob.cov_mode = int(setup.step_modes[0])
+        engine.score_partials(setup, th, 0)
+        return engine.finalize(setup, th, 0)
+
+    # ---- stand-alone prior score (used by d4s.vp_diffused_priors objects) -------------------------------------
+    def _prior_score_native(self, theta: Tensor, t: Tensor, spec: "engine.PriorSpec", want_jac: bool = False):
+        self._require_cuda(theta)
+        import ctypes as C
+        lib = abi.require_cuda()
+        m = theta.shape[-1]
+        tt = torch.as_tensor(t).detach().to("cpu").reshape(1)
+        rows = engine.schedule_rows(self, tt, None, 0.0, 0, [abi.COMBINE_SUM])  # n = 0 => (1 - n) = 1
+        mats = engine.mats_table(rows, spec, False, 0, None, m)
+        dev = theta.device
+        th = theta.detach().to(torch.float32).contiguous()
+        sched, mats = rows.to(torch.float32).to(dev), mats.to(torch.float32).to(dev)
+        low = high = None
+        if spec.kind == abi.PRIOR_UNIFORM:
+            low, high = spec.low.to(torch.float32).to(dev), spec.high.to(torch.float32).to(dev)
+        out = torch.empty_like(th)
+        jac = torch.empty_like(th) if (want_jac and spec.kind == abi.PRIOR_UNIFORM) else None
+        with torch.cuda.device(dev):
+            abi.check(lib.d4s_prior_score(spec.kind, engine._ptr(th), th.shape[0], m, engine._ptr(sched),
+                                          engine._ptr(mats), engine._ptr(low), engine._ptr(high), engine._ptr(out),
+                                          engine._ptr(jac), engine._stream(dev)))
+        return (out, jac) if want_jac else out

@@ -1,0 +1,89 @@
+"""Tweedie-approximation helpers with the reference's signatures (tall_posterior_sampler.py:35-155).
+
+These exist for API compatibility (the `nse.tweedies_approximator` hook of nse.py:588-596 and scripts that call
+the helpers directly).  They *materialise* [N, n, m(, m)] tensors, which the fused sampling path never does:
+`NSE.ddim` / `NSE.factorized_score` keep the per-pair quantities on chip.  The arithmetic still runs in the CUDA
+kernels of libd4s -- scores and JAC precisions come from kernel 1/2 with its optional outputs switched on.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi as abi
+from . import engine
+
+
+def _t_cpu(t):
+    return torch.as_tensor(t).detach().to("cpu").reshape(1)
+
+
+def prec_matrix_backward(t, dist_cov, nse):
+    """inv(Sigma) + alpha/sigma^2 I for Sigma[*, m, m] (tall_posterior_sampler.py:35-43)."""
+    if not dist_cov.is_cuda:
+        raise abi.D4sError("d4s.prec_matrix_backward: CUDA tensors only (no CPU fallback)")
+    m = dist_cov.shape[-1]
+    tt = _t_cpu(t).to(torch.float64)
+    aos2 = float(engine._scalar64(nse.alpha, tt) / engine._scalar64(nse.sigma, tt) ** 2)
+    inv = engine.batched_inverse(dist_cov.reshape(-1, m, m)).reshape(dist_cov.shape)
+    return inv + aos2 * torch.eye(m, device=dist_cov.device, dtype=inv.dtype)
+
+
+def tweedies_approximation(x, theta, t, score_fn=None, nse=None, dist_cov_est=None, mode="JAC",
+                           clip_mean_bounds=(None, None), partial_factorization=False, n=None):
+    """(prec[N,n,m,m], mean[N,n,m], score[N,n,m]) of p(theta_0 | theta_t, x_j) (tall_posterior_sampler.py:46-135).
+
+    `score_fn` is accepted for signature compatibility and ignored: the scores are those of `nse` itself
+    (every call site of the reference passes `partial(nse.score, **kwargs)`).  PF_NSE subset sizes go in `n`
+    (or are recovered from a `functools.partial(nse.score, n=...)`).
+    """
+    if mode not in ("GAUSS", "JAC"):
+        raise NotImplementedError("Available methods are GAUSS, JAC")
+    if n is None and score_fn is not None and getattr(score_fn, "keywords", None):
+        n = score_fn.keywords.get("n")
+    nse._require_cuda(theta, x)
+    N, m = theta.shape
+    tt = _t_cpu(t)
+    setup = engine.build_setup(nse, x, N, tt, None, 0.0, engine.PriorSpec(abi.PRIOR_NONE), mode,
+                               dist_cov_est if mode == "GAUSS" else None, n_sizes=n, weighted=False)
+    th = theta.detach().to(torch.float32).contiguous()
+    scores, prec = engine.score_partials(setup, th, 0, want_scores=True, want_prec=(mode == "JAC"))
+    if mode == "GAUSS":
+        prec = prec_matrix_backward(t, dist_cov_est, nse)[None].expand(N, -1, -1, -1)
+    t64 = tt.to(torch.float64)
+    alpha_t = float(engine._scalar64(nse.alpha, t64))
+    sigma_t = float(engine._scalar64(nse.sigma, t64))
+    mean = (th[:, None] + sigma_t ** 2 * scores) / math.sqrt(alpha_t)
+    if clip_mean_bounds[0]:
+        mean = mean.clip(*clip_mean_bounds)
+    return prec, mean, scores
+
+
+def tweedies_approximation_prior(theta, t, score_fn, nse, mode="vmap"):
+    """(prec[N,m,m], mean[N,m], score[N,m]) for the diffused prior (tall_posterior_sampler.py:138-155).
+    `score_fn` must be a d4s.vp_diffused_priors object (its parameters are needed for the closed forms)."""
+    if mode != "vmap":
+        raise NotImplementedError
+    kind = getattr(score_fn, "kind", None)
+    if kind not in ("uniform", "gaussian"):
+        raise abi.D4sError("tweedies_approximation_prior needs a d4s.vp_diffused_priors score object")
+    spec = score_fn._spec()
+    N, m = theta.shape
+    tt = _t_cpu(t).to(torch.float64)
+    alpha_t = float(engine._scalar64(nse.alpha, tt))
+    sigma_t = float(engine._scalar64(nse.sigma, tt))
+    if kind == "uniform":
+        score, jd = nse._prior_score_native(theta, t, spec, want_jac=True)
+        prec_diag = (alpha_t / sigma_t ** 2) / (1.0 + sigma_t ** 2 * jd)
+        prec = torch.diag_embed(prec_diag)
+    else:
+        score = nse._prior_score_native(theta, t, spec)
+        eye = torch.eye(m, dtype=torch.float64)
+        c_t = sigma_t ** 2 * eye + alpha_t * spec.cov
+        jac = -torch.linalg.inv(c_t).T
+        cov = (sigma_t ** 2 / alpha_t) * (eye + sigma_t ** 2 * jac)
+        prec = torch.linalg.inv(cov).to(torch.float32).to(theta.device)[None].expand(N, -1, -1)
+    mean = (theta + sigma_t ** 2 * score) / math.sqrt(alpha_t)
+    return prec, mean, score
+
+
+import math  # noqa: E402  (kept at the bottom: only the helpers above use it)

@@ -28,6 +28,12 @@ import numpy as np
 SQRT2 = math.sqrt(2.0)
 LOG_SQRT_2PI = 0.5 * math.log(2.0 * math.pi)
 
+# "numpy" (default; what the parity tests use) or "torch": route the MLP GEMM+bias+ReLU of
+# OracleMLP.__call__ through torch's CPU ops.  numpy's elementwise ops are single-threaded, which makes
+# the numpy MLP ~2-3x slower than the reference's ATen path on 8 cores; bench.py's CPU-baseline legs
+# switch this on so the reported baseline is not an unfairly slow strawman.
+GEMM_BACKEND = "numpy"
+
 try:  # vectorised erf; scipy is in the image, math.erf is the fallback
     from scipy.special import erf as _erf
 except Exception:  # pragma: no cover
@@ -49,22 +55,36 @@ class OracleMLP:
 
     def __call__(self, h: np.ndarray) -> np.ndarray:
         L = len(self.weights)
+        lead = h.shape[:-1]
+        h = h.reshape(-1, h.shape[-1])  # one [rows, in] GEMM per layer, as torch's vmap'd nn.Linear does
+        if GEMM_BACKEND == "torch":  # timing legs only: the reference's own multi-threaded ATen CPU path
+            import torch
+            ht = torch.from_numpy(np.ascontiguousarray(h))
+            for l, (w, b) in enumerate(zip(self.weights, self.biases)):
+                ht = torch.addmm(torch.from_numpy(b), ht, torch.from_numpy(w).t())
+                if l < L - 1:
+                    ht = ht.relu_()
+            h = ht.numpy()
+            return h.reshape(lead + h.shape[-1:])
         for l, (w, b) in enumerate(zip(self.weights, self.biases)):
-            h = h @ w.T + b
+            h = h @ w.T
+            h += b
             if l < L - 1:
-                h = np.maximum(h, 0)
-        return h
+                np.maximum(h, 0, out=h)
+        return h.reshape(lead + h.shape[-1:])
 
     def forward_with_masks(self, h: np.ndarray):
         """Forward pass that also returns the ReLU masks D_l = (z_l > 0) of every hidden layer."""
         masks = []
         L = len(self.weights)
+        lead = h.shape[:-1]
+        h = h.reshape(-1, h.shape[-1])
         for l, (w, b) in enumerate(zip(self.weights, self.biases)):
             h = h @ w.T + b
             if l < L - 1:
-                masks.append(h > 0)
+                masks.append((h > 0).reshape(lead + h.shape[-1:]))
                 h = np.maximum(h, 0)
-        return h, masks
+        return h.reshape(lead + h.shape[-1:]), masks
 
     def vjp_rows(self, masks, in_cols: slice) -> np.ndarray:
         """Rows of d(out)/d(in[in_cols]) for every batch element, by reverse accumulation
@@ -78,7 +98,8 @@ class OracleMLP:
             w = self.weights[l]
             if l == 0:
                 w = w[:, in_cols]
-            g = g @ w
+            lead = g.shape[:-1]
+            g = (g.reshape(-1, g.shape[-1]) @ w).reshape(lead + (w.shape[-1],))
         return g
 
 

