@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""Benchmark of the tall-data DDIM posterior sampler (BASELINE.json metric: posterior samples/s, DDIM GAUSS/JAC).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--cov-mode GAUSS|JAC] [--n-obs 30]
+
+A bench "step" is ONE complete `NSE.ddim` trajectory (default: BASELINE config 2 = sbibm SLCP shape, theta=5,
+x=8, MLP 19->256^3->5, n_obs=30, 1000 posterior samples per GPU, 1000 DDIM steps, eta=1, GAUSS, uniform prior;
+synthetic observations and random-init weights).  Rank r of N samples its own 1000 posterior samples
+(samples shard with no communication => "scaling": "weak"); value = all ranks' samples / max-over-ranks time.
+
+value        device-resident: tables/inputs in HBM, CUDA events around d4s_ddim_run only.
+e2e          NSE.ddim(...) through the public API with HOST inputs (pinned), H2D + table build + D2H inside.
+roofline     score kernel (kernel 1): algorithmic flops per launch / average launch duration, vs the measured
+             bf16 tensor peak of MEASURED_PEAKS.json (the SIMT fp32 path cannot approach it).
+cpu_baseline the oracle port (numpy + torch-CPU GEMMs, all host threads) on a bounded sample of DDIM steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "diffusions-for-sbi_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+SHAPES = {  # BASELINE.json configs
+    "slcp": dict(m=5, d=8, hidden=(256, 256, 256), prior="uniform"),
+    "lotka_volterra": dict(m=4, d=20, hidden=(256, 256, 256), prior="gaussian"),
+    "sir": dict(m=2, d=10, hidden=(256, 256, 256), prior="gaussian"),
+    "stress": dict(m=10, d=10, hidden=(256, 256, 256), prior="gaussian"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--task", default="slcp", choices=sorted(SHAPES))
+    ap.add_argument("--cov-mode", default="GAUSS", choices=["GAUSS", "JAC"])
+    ap.add_argument("--n-obs", type=int, default=30)
+    ap.add_argument("--samples", type=int, default=1000, help="posterior samples per GPU")
+    ap.add_argument("--ddim-steps", type=int, default=None, help="default 1000 (GAUSS) / 400 (JAC)")
+    ap.add_argument("--cpu-sample-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    """Synthetic inputs of the task's shape: seeded, identical on every rank."""
+    sh = SHAPES[args.task]
+    m, d, n = sh["m"], sh["d"], args.n_obs
+    rng = np.random.default_rng(0)
+    widths = [m + d + 6, *sh["hidden"], m]  # freqs = 3 (nse.py:27)
+    weights, biases = [], []
+    for a_, b_ in zip(widths[:-1], widths[1:]):  # nn.Linear default init: U(-1/sqrt(in), 1/sqrt(in))
+        k_ = 1.0 / np.sqrt(a_)
+        weights.append(rng.uniform(-k_, k_, size=(b_, a_)).astype(np.float32))
+        biases.append(rng.uniform(-k_, k_, size=(b_,)).astype(np.float32))
+    x = np.random.default_rng(1).standard_normal((n, d)).astype(np.float32)
+    a = 0.2 * np.random.default_rng(2).standard_normal((n, m, m))
+    cov = (a @ a.transpose(0, 2, 1) + 0.05 * np.eye(m)).astype(np.float32)
+    if sh["prior"] == "uniform":
+        prior = dict(low=np.full(m, -3.46, np.float32), high=np.full(m, 3.46, np.float32))
+    else:
+        prior = dict(mean=np.zeros(m, np.float32), cov=np.eye(m, dtype=np.float32))
+    ddim_steps = args.ddim_steps or (1000 if args.cov_mode == "GAUSS" else 400)
+    eta = 1.0 if ddim_steps == 1000 else 0.8 if ddim_steps == 400 else 0.5  # sbibm_posterior_estimation.py:330-334
+    return dict(weights=weights, biases=biases, x=x, cov=cov, prior=prior, m=m, d=d, n=n, ddim_steps=ddim_steps,
+                eta=eta, prior_kind=sh["prior"], hidden=sh["hidden"])
+
+
+def build_nse(w, dev):
+    """d4s.NSE of the task's architecture holding the synthetic weights."""
+    import torch
+    import d4s
+    nse = d4s.NSE(w["m"], w["d"], freqs=3, hidden_features=list(w["hidden"]))
+    lin = [mod for mod in nse.net if isinstance(mod, torch.nn.Linear)]
+    with torch.no_grad():
+        for l, wt, b in zip(lin, w["weights"], w["biases"]):
+            l.weight.copy_(torch.as_tensor(wt))
+            l.bias.copy_(torch.as_tensor(b))
+    return nse.to(dev).eval()
+
+
+def oracle_objects(w):
+    """The same net / prior as oracle objects -- used ONLY by the CPU-baseline legs."""
+    from oracle import d4s_oracle as orc
+    onet = orc.OracleNet(w["m"], w["d"], (np.arange(1, 4) * np.pi).astype(np.float32),
+                         orc.OracleMLP([a.copy() for a in w["weights"]], [b.copy() for b in w["biases"]]),
+                         dtype=np.float32)
+    if w["prior_kind"] == "uniform":
+        oprior = orc.UniformPrior(w["prior"]["low"].astype(np.float64), w["prior"]["high"].astype(np.float64))
+    else:
+        oprior = orc.GaussianPrior(w["prior"]["mean"].astype(np.float64), w["prior"]["cov"].astype(np.float64))
+    return orc, onet, oprior
+
+
+def flops_per_pair(w):
+    dims = [w["m"] + w["d"] + 6, *w["hidden"], w["m"]]
+    return 2 * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+
+
+def config_dict(args, w, world):
+    return {"workload": f"sbibm {args.task} shape: theta={w['m']}, x={w['d']}, MLP {w['m'] + w['d'] + 6}->"
+                        f"{'x'.join(map(str, w['hidden']))}->{w['m']}, n_obs={w['n']}, {args.samples} posterior "
+                        f"samples per GPU, DDIM {w['ddim_steps']} steps eta={w['eta']}, {args.cov_mode}, "
+                        f"{w['prior_kind']} prior; one bench step = one full trajectory",
+            "n_obs": w["n"], "samples_per_gpu": args.samples, "ddim_steps": w["ddim_steps"], "cov_mode": args.cov_mode,
+            "parallelism": f"samples sharded over {world} GPU(s), no collective",
+            "l2": "256 MiB buffer written between timed trajectories (L2 flush)"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU baseline = oracle port on the host cores (bounded sample of DDIM steps)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(args, w, n_ddim_steps, repeats=1):
+    """posterior samples/s of the oracle port, extrapolated from `n_ddim_steps` DDIM steps spread over the
+    trajectory (the cost per step is t-independent except for the alpha-gate of nse.py:643)."""
+    import torch
+    orc, onet, oprior = oracle_objects(w)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    orc.GEMM_BACKEND = "torch"
+    N = args.samples
+    rng = np.random.default_rng(3)
+    theta = rng.standard_normal((N, w["m"])).astype(np.float32)
+    grid = orc.time_grid(w["ddim_steps"])[:-1]
+    idx = np.linspace(0, len(grid) - 1, n_ddim_steps).round().astype(int)
+    z = rng.standard_normal((N, w["m"])).astype(np.float32)
+
+    def one(tv):
+        s = orc.factorized_score(onet, theta, w["x"], np.float32(tv), oprior, w["cov"], args.cov_mode, w["prior_kind"])
+        return orc.ddim_step(onet, theta, s, np.float32(tv), 1 / w["ddim_steps"], w["eta"], z)
+
+    one(grid[idx[0]])  # warm-up
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for k in idx:
+            one(grid[k])
+        dt = (time.perf_counter() - t0) / len(idx)
+        best = dt if best is None else min(best, dt)
+    rate = N / (best * w["ddim_steps"])
+    return rate, cores, best
+
+
+def run_reference(args):
+    w = workload(args)
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for _ in range(args.warmup):
+        cpu_oracle_rate(args, w, 2)
+    rates, per_step = [], []
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        r, cores, dt = cpu_oracle_rate(args, w, max(2, args.cpu_sample_steps // 2))
+        rates.append(r)
+        per_step.append(dt)
+    value = float(np.median(rates))
+    sample = (f"{max(2, args.cpu_sample_steps // 2)} of {w['ddim_steps']} DDIM steps per bench step (N={args.samples}, "
+              f"n_obs={w['n']}), extrapolated linearly; oracle port, torch-CPU GEMM backend")
+    line = {"impl": "reference", "metric": "posterior samples/sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(np.median(per_step)) * w["ddim_steps"] * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, w, 1),
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t_all}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks sampler (recipe line of B200_PROFILING.md)
+# ---------------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import d4s
+    from d4s import _cabi as abi
+    from d4s import engine
+
+    w = workload(args)
+    N, m, n = args.samples, w["m"], w["n"]
+    nse = build_nse(w, dev)
+    # host (pinned) copies of the inputs for the e2e leg
+    x_h = torch.as_tensor(w["x"]).pin_memory()
+    cov_h = torch.as_tensor(w["cov"]).pin_memory()
+    if w["prior_kind"] == "uniform":
+        lo_h = torch.as_tensor(w["prior"]["low"]).pin_memory()
+        hi_h = torch.as_tensor(w["prior"]["high"]).pin_memory()
+    else:
+        mu_h = torch.as_tensor(w["prior"]["mean"]).pin_memory()
+        pc_h = torch.as_tensor(w["prior"]["cov"]).pin_memory()
+
+    def make_prior():
+        if w["prior_kind"] == "uniform":
+            lo, hi = lo_h.to(dev, non_blocking=True), hi_h.to(dev, non_blocking=True)
+            return torch.distributions.Uniform(lo, hi, validate_args=False), d4s.get_vpdiff_uniform_score(lo, hi, nse)
+        mu, pc = mu_h.to(dev, non_blocking=True), pc_h.to(dev, non_blocking=True)
+        return (torch.distributions.MultivariateNormal(mu, pc, validate_args=False),
+                d4s.get_vpdiff_gaussian_score(mu, pc, nse))
+
+    out_h = torch.empty(N, m).pin_memory()
+    seed0 = 1234
+
+    def e2e_step(it):
+        """The call a user makes: host inputs -> NSE.ddim -> samples back on the host."""
+        x = x_h.to(dev, non_blocking=True)
+        cov = cov_h.to(dev, non_blocking=True)
+        prior, fn = make_prior()
+        th = nse.ddim((N,), x, steps=w["ddim_steps"], eta=w["eta"], prior=prior, prior_type=w["prior_kind"],
+                      prior_score_fn=fn, dist_cov_est=cov, cov_mode=args.cov_mode, _seed=seed0 + it,
+                      _sample_offset=rank * N)
+        out_h.copy_(th, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_h
+
+    # device-resident leg: tables built once, only d4s_ddim_run in the timed region
+    x_d, cov_d = x_h.to(dev), cov_h.to(dev)
+    prior, fn = make_prior()
+    spec = engine.prior_spec(w["prior_kind"], prior, fn, m)
+    grid = engine.time_grid(w["ddim_steps"])
+    setup = engine.build_setup(nse, x_d, N, grid[:-1], grid[:-1].double() - 1.0 / w["ddim_steps"], w["eta"], spec,
+                               args.cov_mode, cov_d, seed=seed0, sample_offset=rank * N)
+    theta0 = engine.philox_normal(N, m, seed0, -1, rank * N, dev)
+    theta = theta0.clone()
+    h2d = sum(t.numel() * 4 for t in (x_h, cov_h)) + sum(t.numel() * 4 for t in (setup.sched, setup.time_feat, setup.mats)) \
+        + sum(t.numel() * 4 for t in setup.keep[:4] if t is not None)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn_step, k):
+        flush.fill_(float(k))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn_step(k)
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    def dev_step(k):
+        theta.copy_(theta0)
+        engine.run_trajectory(setup, theta, None, True)
+
+    for k in range(args.warmup):
+        dev_step(k)
+        e2e_step(k)
+    barrier()
+    clocks = Clocks(local)
+    clocks.start()
+    l0 = engine.launch_count()
+    barrier()
+    ms_dev = [timed(dev_step, k) for k in range(args.steps)]
+    barrier()
+    launches = engine.launch_count() - l0
+    ms_e2e = []
+    for k in range(args.steps):
+        flush.fill_(float(k))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_step(k)
+        ms_e2e.append((time.perf_counter() - t0) * 1e3)
+    barrier()
+    clk = clocks.stop()
+    assert torch.isfinite(theta).all(), "non-finite samples"
+
+    # dominant kernel alone: average launch duration of kernel 1 with CUDA events on the launching stream
+    reps = 200
+    engine.score_partials(setup, theta, 0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(reps):
+        engine.score_partials(setup, theta, (k * 7) % w["ddim_steps"])
+    e1.record()
+    e1.synchronize()
+    k1_ms = e0.elapsed_time(e1) / reps
+    e0.record()
+    for k in range(reps):
+        engine.finalize(setup, theta, (k * 7) % w["ddim_steps"])
+    e1.record()
+    e1.synchronize()
+    k3_ms = e0.elapsed_time(e1) / reps
+
+    tot_dev = torch.tensor([sum(ms_dev), sum(ms_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot_dev, op=dist.ReduceOp.MAX)
+    tot_dev = tot_dev.cpu().tolist()
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops", 1590.0)
+        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)" if peaks else "fallback 1590"
+        rpp = (1 + m) if args.cov_mode == "JAC" else 1
+        flops = float(N) * n * flops_per_pair(w) * rpp
+        ach = flops / (k1_ms * 1e-3) / 1e12
+        ms_step = tot_dev[0] / args.steps
+        value = N * world / (ms_step * 1e-3)
+        e2e_val = N * world / (tot_dev[1] / args.steps * 1e-3)
+        line = {"metric": "posterior samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_dict(args, w, world),
+                "clocks": clk,
+                "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(N * m * 4), "ms_per_step": tot_dev[1] / args.steps},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                             "traffic": None, "kernel": "score_simt_kernel (fp32 SIMT)", "peak_source": peak_src,
+                             "flops_per_launch": flops, "launch_ms": k1_ms, "finalize_launch_ms": k3_ms,
+                             "share_of_step": k1_ms * w["ddim_steps"] / ms_step},
+                "us_per_ddim_step": ms_step * 1e3 / w["ddim_steps"]}
+        if not args.no_cpu_baseline:
+            rate, cores, dt = cpu_oracle_rate(args, w, args.cpu_sample_steps)
+            line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_sample_steps} of {w['ddim_steps']} DDIM steps at N={N}, "
+                                              f"n_obs={n}, extrapolated linearly; oracle port with torch-CPU GEMMs",
+                                    "ms_per_ddim_step": dt * 1e3}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

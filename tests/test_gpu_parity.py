@@ -193,7 +193,8 @@ def test_paired_and_single_observation_ddim(dev):
     xp = rng.standard_normal((N, 4))
     ref = orc.ddim_single(onet, xp, z0, z, steps, 0.5)
     out = nse.ddim((N,), _t(xp, dev), steps=steps, eta=0.5, _noise=noise)
-    assert np.abs(out.cpu().numpy() - ref).max() < TRAJ_TOL
+    # a random-init net gives no contraction: |theta| grows to ~1e3, so the tolerance is relative
+    assert np.abs(out.cpu().numpy() - ref).max() < TRAJ_TOL * max(1.0, np.abs(ref).max()) * 1e-1
     x1 = rng.standard_normal(4)
     ref = orc.ddim_single(onet, x1, z0, z, steps, 0.5, clip=(-1.0, 1.0))
     for xx in (x1, x1[None]):
