@@ -12,6 +12,10 @@ namespace d4s {
 
 static thread_local std::string g_err;
 static long long g_launches = 0;
+static int g_opt_path = 0;      // 0 auto, 1 SIMT per-step kernels only, 2 require the tcgen05 trajectory kernel
+static int g_opt_swap = 0;      // debug: swap LBO/SBO in the UMMA descriptors
+static int g_opt_tc_steps = 0;  // > 0: DDIM steps per tcgen05 launch (0 = whole trajectory in one launch)
+static int* g_err_flag = nullptr;
 
 static int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -20,6 +24,20 @@ static int fail(int code, const std::string& msg) {
 static int cuda_fail(cudaError_t e, const char* what) {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
     return D4S_ERR_CUDA;
+}
+
+static uint16_t f32_to_bf16_rn(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+    u += 0x7fffu + ((u >> 16) & 1u);  // round to nearest even
+    return (uint16_t)(u >> 16);
+}
+static float bf16_to_f32(uint16_t b) {
+    uint32_t u = (uint32_t)b << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
 }
 
 static int pad_width(int h) {
@@ -147,6 +165,30 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
         for (int o = 0; o < m; ++o) h[off_Wout + (size_t)k * MMAX + o] = d->weight[L - 1][(size_t)o * Kl + k];
     const size_t off_bout = reserve(MMAX);
     for (int o = 0; o < m; ++o) h[off_bout + o] = d->bias[L - 1][o];
+    // tcgen05 path: output layer in torch layout [m][Kp], hidden layers as bf16 hi/lo UMMA operand images
+    const size_t off_WoutT = reserve((size_t)m * Hp[L - 2]);
+    for (int o = 0; o < m; ++o)
+        for (int k = 0; k < Kl; ++k) h[off_WoutT + (size_t)o * Hp[L - 2] + k] = d->weight[L - 1][(size_t)o * Kl + k];
+    std::vector<size_t> off_img(L, 0);
+    for (int l = 1; l <= L - 2; ++l) {
+        const int K = d->dims[l], Ho = d->dims[l + 1], Kp = Hp[l - 1], Np = Hp[l];
+        const size_t bytes = (size_t)(Kp / 16) * Np * 64;
+        off_img[l] = reserve(bytes / 4);
+        uint16_t* img = reinterpret_cast<uint16_t*>(h.data() + off_img[l]);
+        for (int ks = 0; ks < Kp / 16; ++ks)
+            for (int hf = 0; hf < 2; ++hf)
+                for (int nn = 0; nn < Np; ++nn)
+                    for (int e = 0; e < 8; ++e) {
+                        const int k = ks * 16 + hf * 8 + e;
+                        const float w = (nn < Ho && k < K) ? d->weight[l][(size_t)nn * K + k] : 0.f;
+                        const uint16_t hi = f32_to_bf16_rn(w);
+                        const uint16_t lo = f32_to_bf16_rn(w - bf16_to_f32(hi));
+                        const size_t base = ((size_t)ks * Np * 64) / 2;  // in uint16 units
+                        const size_t idx = (size_t)hf * Np * 8 + (size_t)nn * 8 + e;
+                        img[base + idx] = hi;
+                        img[base + (size_t)Np * 16 + idx] = lo;
+                    }
+    }
 
     D4sNet* net = new D4sNet();
     cudaError_t e = cudaMalloc(&net->blob, h.size() * sizeof(float));
@@ -176,6 +218,8 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
     }
     nd.Wout = net->blob + off_Wout;
     nd.bout = net->blob + off_bout;
+    nd.WoutT = net->blob + off_WoutT;
+    for (int l = 1; l <= L - 2; ++l) nd.wimg[l] = reinterpret_cast<const uint8_t*>(net->blob + off_img[l]);
     *out = net;
     return D4S_OK;
 }
@@ -323,6 +367,78 @@ static int enqueue_steps(const D4sNet* net, const D4sProblem* pb0, int steps, co
     return D4S_OK;
 }
 
+// Returns 0 when the trajectory was enqueued on the fused tcgen05 kernel, 1 when the problem is not eligible
+// (caller falls back to the per-step SIMT kernels), < 0 on error.
+static int try_traj_tc(const D4sNet* net, const D4sProblem* pb, int steps, const float* sched, const float* tf,
+                       const float* mats, const float* noise, float* theta, const int32_t* step_mode,
+                       cudaStream_t stream) {
+    const NetDev& nd = net->dev;
+    bool eligible = g_opt_path != 1 && pb->cov_mode == D4S_COV_GAUSS && !pb->paired && nd.L >= 3;
+    if (step_mode)
+        for (int k = 0; k < steps && eligible; ++k) eligible = (step_mode[k] == D4S_COV_GAUSS);
+    if (!eligible) {
+        if (g_opt_path == 2) return fail(D4S_ERR_ARG, "tcgen05 path required but the problem is not eligible");
+        return 1;
+    }
+    TrajParams p;
+    memset(&p, 0, sizeof(p));
+    p.net = nd;
+    p.N = pb->n_samples;
+    p.n = pb->n_obs;
+    int oc = pb->obs_chunk > 0 ? pb->obs_chunk : pb->n_obs;
+    if (oc > 128) oc = 128;
+    if (oc > pb->n_obs) oc = pb->n_obs;
+    const int c = (pb->n_obs + oc - 1) / oc;
+    oc = (pb->n_obs + c - 1) / c;
+    p.OC = oc;
+    p.C = (pb->n_obs + oc - 1) / oc;
+    p.SG = 128 / oc;
+    if (p.SG > 8) p.SG = 8;
+    if (p.SG < 1) p.SG = 1;
+    p.P = p.SG * p.OC;
+    p.swap_lbo_sbo = g_opt_swap;
+    p.obs_feat = pb->obs_feat;
+    p.obs_prec = pb->obs_prec;
+    p.sched = sched;
+    p.time_feat = tf;
+    p.mats = mats;
+    p.noise = noise;
+    p.theta = theta;
+    FinalizeParams& f = p.fin;
+    f.N = pb->n_samples;
+    f.C = 1;
+    f.W = 2 * nd.m;
+    f.m = nd.m;
+    f.jac = 0;
+    f.prior_kind = pb->prior_kind;
+    f.update = 1;
+    f.low = pb->prior_low;
+    f.high = pb->prior_high;
+    f.seed = pb->seed;
+    f.sample_offset = pb->sample_offset;
+    f.clip_lo = pb->clip_lo;
+    f.clip_hi = pb->clip_hi;
+    if (!g_err_flag) {
+        if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaMalloc(flag)");
+        cudaMemset(g_err_flag, 0, sizeof(int));
+    }
+    p.error_flag = g_err_flag;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int groups = (p.N + p.SG - 1) / p.SG;
+    const int ctas = groups < sms ? groups : sms;
+    const int per = g_opt_tc_steps > 0 ? g_opt_tc_steps : steps;
+    for (int s0 = 0; s0 < steps; s0 += per) {
+        p.step_begin = s0;
+        p.step_end = s0 + per < steps ? s0 + per : steps;
+        cudaError_t e = launch_traj_tc(p, ctas, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "tcgen05 trajectory kernel launch");
+        ++g_launches;
+    }
+    return 0;
+}
+
 int d4s_ddim_run(const D4sNet* net, const D4sProblem* pb, int32_t steps, const float* sched_dev,
                  const float* time_feat_dev, const float* mats_dev, const float* noise_dev, float* theta_dev,
                  const int32_t* step_mode, int32_t use_graph, void* stream_) {
@@ -341,6 +457,10 @@ int d4s_ddim_run(const D4sNet* net, const D4sProblem* pb, int32_t steps, const f
         }
         for (int k = 0; k < steps; ++k)
             if (step_mode[k] != D4S_COV_GAUSS && step_mode[k] != D4S_COV_JAC) return fail(D4S_ERR_ARG, "bad step_cov_mode");
+    }
+    {
+        const int tc = try_traj_tc(net, pb, steps, sched_dev, time_feat_dev, mats_dev, noise_dev, theta_dev, step_mode, stream);
+        if (tc <= 0) return tc;  // 0 = launched on the tcgen05 path, < 0 = error
     }
     if (!use_graph)
         return enqueue_steps(net, pb, steps, sched_dev, time_feat_dev, mats_dev, noise_dev, theta_dev, step_mode, stream);
@@ -435,6 +555,16 @@ int d4s_ddim_update(float* theta_dev, const float* score_dev, int64_t n_rows, in
                                        sample_offset, clip_lo, clip_hi, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "ddim_update launch");
     ++g_launches;
+    return D4S_OK;
+}
+
+int d4s_set_option(const char* key, int32_t value) {
+    if (!key) return fail(D4S_ERR_ARG, "null option key");
+    const std::string k(key);
+    if (k == "path") g_opt_path = value;
+    else if (k == "swap_lbo_sbo") g_opt_swap = value;
+    else if (k == "tc_steps_per_launch") g_opt_tc_steps = value;
+    else return fail(D4S_ERR_ARG, "unknown option: " + k);
     return D4S_OK;
 }
 

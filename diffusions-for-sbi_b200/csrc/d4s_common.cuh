@@ -29,6 +29,8 @@ struct NetDev {
     const float* bias[D4S_MAX_LAYERS]; // l = 1 .. L-2: [Hp[l]]
     const float* Wout;              // [Hp[L-2]][MMAX] k-major, zero padded columns
     const float* bout;              // [MMAX]
+    const float* WoutT;             // [m][Hp[L-2]] output layer, torch layout (tcgen05 path epilogue)
+    const uint8_t* wimg[D4S_MAX_LAYERS];  // l = 1 .. L-2: bf16 hi/lo UMMA images, [Hp[l-1]/16][hi | lo][2][Hp[l]][8]
 };
 
 
@@ -66,6 +68,25 @@ struct FinalizeParams {
     float* theta;      // [N][m] in/out
     float* score_out;  // optional [N][m]
 };
+
+// fused tcgen05 trajectory kernel (d4s_traj_tc.cu)
+struct TrajParams {
+    NetDev net;
+    int N, n, C, SG, OC, P;
+    int step_begin, step_end;
+    int swap_lbo_sbo;        // debug: exchange the two descriptor strides
+    const float* obs_feat;   // [n][Hp0]
+    const float* obs_prec;   // [n][m][m] or NULL
+    const float* sched;      // [steps][16]
+    const float* time_feat;  // [steps][Hp0]
+    const float* mats;       // [steps][2 m^2 + m]
+    const float* noise;      // [steps][N][m] or NULL
+    FinalizeParams fin;      // constant part of the per-step finalize parameters
+    float* theta;            // [N][m] in/out
+    int* error_flag;
+};
+cudaError_t launch_traj_tc(const TrajParams& p, int n_ctas, cudaStream_t stream);
+int traj_tc_smem_bytes();
 
 cudaError_t launch_score_simt(const ScoreParams& p, int tiles, cudaStream_t stream);
 cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t stream);

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D4S_ABI_VERSION 5
+#define D4S_ABI_VERSION 6
 
 #define D4S_OK 0
 #define D4S_ERR_ARG -1      /* bad argument / unsupported shape */
@@ -157,6 +157,10 @@ D4S_API int d4s_ddim_run(const D4sNet* net, const D4sProblem* prob, int32_t step
                  const float* time_feat_dev, const float* mats_dev, const float* noise_dev, float* theta_dev,
                  const int32_t* step_cov_mode_host, int32_t use_graph, void* stream);
 D4S_API void d4s_graph_cache_clear(void);
+/* Library options: "path" = 0 auto | 1 per-step fp32 SIMT kernels only | 2 require the fused tcgen05 trajectory
+ * kernel (bf16x3 split on the tensor cores; GAUSS, tall grid); "tc_steps_per_launch" = DDIM steps per tcgen05
+ * launch (0 = whole trajectory in one launch); "swap_lbo_sbo" = descriptor debug switch. */
+D4S_API int d4s_set_option(const char* key, int32_t value);
 
 /* ---- stand-alone pieces of kernel 3/4 (API parity with the reference's public helpers) ---------------- */
 /* prior_score_fn(theta, t) of vp_diffused_priors.py:20-46 (uniform: also d score / d theta, the diagonal
