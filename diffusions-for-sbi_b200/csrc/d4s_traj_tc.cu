@@ -42,7 +42,9 @@ constexpr int OFF_BASE = OFF_HALF + TC_M * MMAX * 4;          // float [SG_MAX][
 constexpr int OFF_ACC = OFF_BASE + TC_SG_MAX * 256 * 4;       // float [SG_MAX][2*MMAX]
 constexpr int OFF_THETA = OFF_ACC + TC_SG_MAX * 2 * MMAX * 4; // float [SG_MAX][MMAX]
 constexpr int OFF_WOUT = OFF_THETA + TC_SG_MAX * MMAX * 4;    // float [MMAX][256] output layer (torch layout)
-constexpr int OFF_BAR = OFF_WOUT + MMAX * 256 * 4;            // mbarriers
+constexpr int OFF_NOISE = OFF_WOUT + MMAX * 256 * 4;          // float [SG_MAX][MMAX] DDIM noise of the current step
+constexpr int OFF_PRIOR = OFF_NOISE + TC_SG_MAX * MMAX * 4;   // float [SG_MAX][2][MMAX] uniform-prior score / derivative
+constexpr int OFF_BAR = OFF_PRIOR + TC_SG_MAX * 2 * MMAX * 4; // mbarriers
 constexpr int OFF_TMEM = OFF_BAR + (2 * TC_NSTG + 2) * 8;
 constexpr int TC_SMEM_BYTES = OFF_TMEM + 16;
 
@@ -145,17 +147,17 @@ __device__ __forceinline__ int a_off(int r, int kg) { return (kg >> 1) * 4096 + 
 
 template <int M>
 __device__ __noinline__ void finalize_one(const FinalizeParams& fp, const float* part, float* theta, const float* noise,
-                                          long long gs, const double* pre) {
+                                          long long gs, const float* pre) {
     double loc[2 * M];
     if (pre) {
 #pragma unroll
-        for (int k = 0; k < M; ++k) { loc[k] = pre[k]; loc[M + k] = pre[MMAX + k]; }
+        for (int k = 0; k < M; ++k) { loc[k] = (double)pre[k]; loc[M + k] = (double)pre[MMAX + k]; }
     }
     finalize_sample<M>(fp, part, theta, nullptr, noise, gs, pre ? loc : nullptr);
 }
 
 __device__ __forceinline__ void finalize_dispatch(int m, const FinalizeParams& fp, const float* part, float* theta,
-                                                  const float* noise, long long gs, const double* pre) {
+                                                  const float* noise, long long gs, const float* pre) {
     switch (m) {
         case 1: finalize_one<1>(fp, part, theta, noise, gs, pre); break;
         case 2: finalize_one<2>(fp, part, theta, noise, gs, pre); break;
@@ -181,7 +183,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
     float* sAcc = reinterpret_cast<float*>(smem + OFF_ACC);
     float* sTheta = reinterpret_cast<float*>(smem + OFF_THETA);
     float* sWout = reinterpret_cast<float*>(smem + OFF_WOUT);
-    double* sPrior = reinterpret_cast<double*>(smem + OFF_HALF);  // [SG][2][MMAX] doubles, aliases sHalf (dead by then)
+    float* sNoise = reinterpret_cast<float*>(smem + OFF_NOISE);
+    float* sPrior = reinterpret_cast<float*>(smem + OFF_PRIOR);
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
     const uint32_t bar0 = smem_u32(smem + OFF_BAR);
     auto bar_full = [&](int s) { return bar0 + 8u * s; };
@@ -278,7 +281,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
         const int q = warp & 3, ch = warp >> 2;
         const int row = 32 * q + lane;  // the TMEM lane / tile row this thread owns in the epilogues
         unsigned d_cnt = 0;
+        const bool uni = (p.fin.prior_kind == D4S_PRIOR_UNIFORM);
         const int Kout = net.Hp[L - 2];
+        // rows of the tile that hold no (sample, observation) pair stay zero for the whole kernel
+        for (int e = tid; e < 2 * TC_A_BYTES / 16; e += 256) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
         for (int e = tid; e < m * Kout; e += 256) sWout[(e / Kout) * 256 + (e % Kout)] = __ldg(net.WoutT + e);
         for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
             const int i0 = g * p.SG;
@@ -313,47 +319,81 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     const int j0 = chunk * p.OC;
                     const int nobs = min(p.OC, p.n - j0);
                     // ---- layer 0: act0[r][col] = relu(base[si][col] + obs_feat[j][col]) -> bf16 hi/lo A images -----------
+                    // item = (observation oj, k-group kg): one 32-byte read of obs_feat serves the rows of all SG samples;
+                    // all global loads of a thread are issued before their first use.
                     {
-                        const int r = tid & 127;
-                        const int si = r / p.OC, oj = r - si * p.OC;
-                        const bool valid = (r < p.P) && (si < nsamp) && (oj < nobs);
-                        const float* urow = p.obs_feat + (size_t)min(j0 + oj, p.n - 1) * H0;
-                        const float* brow = sBase + min(si, TC_SG_MAX - 1) * 256;
-                        // 4 k-groups per iteration: all global loads are issued before the first use
-                        for (int kg0 = tid >> 7; kg0 < H0 / 8; kg0 += 8) {
-                            float4 u[4][2];
+                        const int nkg = H0 / 8;
+                        const int items = p.OC * nkg;
+                        constexpr int IPT = 4;  // items per thread per pass
+                        for (int it0 = 0; it0 < items; it0 += 256 * IPT) {
+                            float4 u[IPT][2];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int kg = kg0 + 2 * j;
-                                if (valid && kg < H0 / 8) {
-                                    u[j][0] = __ldg(reinterpret_cast<const float4*>(urow + 8 * kg));
-                                    u[j][1] = __ldg(reinterpret_cast<const float4*>(urow + 8 * kg + 4));
+                            for (int j = 0; j < IPT; ++j) {
+                                const int item = it0 + j * 256 + tid;
+                                const int kg = item / p.OC, oj = item - kg * p.OC;
+                                if (item < items && oj < nobs) {
+                                    const float* up = p.obs_feat + (size_t)(j0 + oj) * H0 + 8 * kg;
+                                    u[j][0] = __ldg(reinterpret_cast<const float4*>(up));
+                                    u[j][1] = __ldg(reinterpret_cast<const float4*>(up + 4));
                                 } else {
                                     u[j][0] = u[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                                 }
                             }
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int kg = kg0 + 2 * j;
-                                if (kg >= H0 / 8) break;
-                                float v[8];
-                                if (valid) {
-                                    const float4 b0 = *reinterpret_cast<const float4*>(brow + 8 * kg);
-                                    const float4 b1 = *reinterpret_cast<const float4*>(brow + 8 * kg + 4);
-                                    v[0] = fmaxf(u[j][0].x + b0.x, 0.f); v[1] = fmaxf(u[j][0].y + b0.y, 0.f);
-                                    v[2] = fmaxf(u[j][0].z + b0.z, 0.f); v[3] = fmaxf(u[j][0].w + b0.w, 0.f);
-                                    v[4] = fmaxf(u[j][1].x + b1.x, 0.f); v[5] = fmaxf(u[j][1].y + b1.y, 0.f);
-                                    v[6] = fmaxf(u[j][1].z + b1.z, 0.f); v[7] = fmaxf(u[j][1].w + b1.w, 0.f);
-                                } else {
+                            for (int j = 0; j < IPT; ++j) {
+                                const int item = it0 + j * 256 + tid;
+                                if (item >= items) break;
+                                const int kg = item / p.OC, oj = item - kg * p.OC;
+                                const bool ovalid = oj < nobs;
+                                for (int si = 0; si < p.SG; ++si) {
+                                    float v[8];
+                                    if (ovalid && si < nsamp) {
+                                        const float* brow = sBase + si * 256 + 8 * kg;
+                                        const float4 b0 = *reinterpret_cast<const float4*>(brow);
+                                        const float4 b1 = *reinterpret_cast<const float4*>(brow + 4);
+                                        v[0] = fmaxf(u[j][0].x + b0.x, 0.f); v[1] = fmaxf(u[j][0].y + b0.y, 0.f);
+                                        v[2] = fmaxf(u[j][0].z + b0.z, 0.f); v[3] = fmaxf(u[j][0].w + b0.w, 0.f);
+                                        v[4] = fmaxf(u[j][1].x + b1.x, 0.f); v[5] = fmaxf(u[j][1].y + b1.y, 0.f);
+                                        v[6] = fmaxf(u[j][1].z + b1.z, 0.f); v[7] = fmaxf(u[j][1].w + b1.w, 0.f);
+                                    } else {
 #pragma unroll
-                                    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                                        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                                    }
+                                    store_split8(v, sAhi, sAlo, a_off(si * p.OC + oj, kg));
                                 }
-                                store_split8(v, sAhi, sAlo, a_off(r, kg));
                             }
                         }
+                        // rows beyond the SG*OC pairs of the tile are never written: zero them once per kernel (below)
                     }
                     fence_proxy_async();
                     mbar_arrive(bar_a);
+
+                    // ---- theta-only work of this step, hidden behind the first tensor-core layer -----------------------------
+                    if (chunk == 0) {
+                        if (uni && tid < nsamp * m) {  // erf/exp of the diffused-uniform score: one thread per (sample, dim)
+                            const int si = tid / m, k = tid - si * m;
+                            double s0, jac;
+                            uniform_prior_terms((double)sTheta[si * MMAX + k], (double)__ldg(p.fin.low + k),
+                                                (double)__ldg(p.fin.high + k), (double)__ldg(sched + D4S_S_SQRT_ALPHA),
+                                                (double)__ldg(sched + D4S_S_SIGMA), s0, jac);
+                            sPrior[si * 2 * MMAX + k] = (float)s0;
+                            sPrior[si * 2 * MMAX + MMAX + k] = (float)jac;
+                        }
+                        const int nq = (m + 3) / 4;
+                        if (tid >= 128 && tid < 128 + nsamp * nq) {  // DDIM noise: one thread per (sample, 4 dims)
+                            const int e = tid - 128, si = e / nq, qd = e - si * nq;
+                            float z[4] = {0.f, 0.f, 0.f, 0.f};
+                            if (p.noise) {
+                                const float* nz = p.noise + ((size_t)step * p.N + (i0 + si)) * m;
+                                for (int k = 0; k < 4; ++k)
+                                    if (4 * qd + k < m) z[k] = __ldg(nz + 4 * qd + k);
+                            } else {
+                                philox_normal4(p.fin.seed, step, p.fin.sample_offset + i0 + si, qd, z);
+                            }
+                            for (int k = 0; k < 4; ++k)
+                                if (4 * qd + k < MMAX) sNoise[si * MMAX + 4 * qd + k] = z[k];
+                        }
+                    }
 
                     // ---- hidden layers on the tensor core; epilogues here ----------------------------------------------------
                     float po[MMAX];  // output-layer partial dot products of this thread's row / column half
@@ -362,60 +402,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     for (int l = 1; l <= L - 2; ++l) {
                         const int Nn = net.Hp[l];
                         const bool last = (l == L - 2);
+                        const int half_cols = Nn >> 1;
+                        const int nblk = half_cols / 32;
+                        const float* bias_l = net.bias[l] + ch * half_cols;
+                        float4 bcur[8], bnxt[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) bcur[e] = __ldg(reinterpret_cast<const float4*>(bias_l) + e);  // hidden behind the MMA
                         mbar_wait(bar_d, d_cnt & 1u, p.error_flag);
                         ++d_cnt;
                         tc_fence_after();
-                        const int half_cols = Nn >> 1;
-                        const int nblk = half_cols / 32;
-                        for (int cb = 0; cb < nblk; cb += 2) {
-                            const bool two = (cb + 1 < nblk);
-                            uint32_t d[2][32];
-                            tc_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(ch * half_cols + 32 * cb), d[0]);
-                            if (two)
-                                tc_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(ch * half_cols + 32 * (cb + 1)), d[1]);
+                        for (int cb = 0; cb < nblk; ++cb) {
+                            const int col0 = ch * half_cols + 32 * cb;
+                            uint32_t d[32];
+                            tc_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, d);
+                            if (cb + 1 < nblk) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e)
+                                    bnxt[e] = __ldg(reinterpret_cast<const float4*>(bias_l + 32 * (cb + 1)) + e);
+                            }
                             tc_wait_ld();
+                            float a[32];
 #pragma unroll
-                            for (int b = 0; b < 2; ++b) {
-                                if (b == 1 && !two) break;
-                                const int col0 = ch * half_cols + 32 * (cb + b);
-                                const float* bias = net.bias[l] + col0;
-                                float a[32];
+                            for (int e = 0; e < 8; ++e) {
+                                a[4 * e] = fmaxf(__uint_as_float(d[4 * e]) + bcur[e].x, 0.f);
+                                a[4 * e + 1] = fmaxf(__uint_as_float(d[4 * e + 1]) + bcur[e].y, 0.f);
+                                a[4 * e + 2] = fmaxf(__uint_as_float(d[4 * e + 2]) + bcur[e].z, 0.f);
+                                a[4 * e + 3] = fmaxf(__uint_as_float(d[4 * e + 3]) + bcur[e].w, 0.f);
+                            }
+                            if (!last) {
 #pragma unroll
-                                for (int e = 0; e < 32; e += 4) {
-                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + e));
-                                    a[e] = fmaxf(__uint_as_float(d[b][e]) + b4.x, 0.f);
-                                    a[e + 1] = fmaxf(__uint_as_float(d[b][e + 1]) + b4.y, 0.f);
-                                    a[e + 2] = fmaxf(__uint_as_float(d[b][e + 2]) + b4.z, 0.f);
-                                    a[e + 3] = fmaxf(__uint_as_float(d[b][e + 3]) + b4.w, 0.f);
+                                for (int k8 = 0; k8 < 4; ++k8) {
+                                    float v[8];
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) v[e] = a[8 * k8 + e];
+                                    store_split8(v, sAhi, sAlo, a_off(row, (col0 >> 3) + k8));
                                 }
-                                if (!last) {
+                            } else {
+                                // output layer in fp32: po[o] += sum_c act[c] * Wout[o][c]   (Wout in smem, broadcast reads)
 #pragma unroll
-                                    for (int k8 = 0; k8 < 4; ++k8) {
-                                        float v[8];
+                                for (int o = 0; o < MMAX; ++o) {
+                                    if (o < m) {
+                                        const float* w = sWout + o * 256 + col0;
+                                        float acc = po[o];
 #pragma unroll
-                                        for (int e = 0; e < 8; ++e) v[e] = a[8 * k8 + e];
-                                        store_split8(v, sAhi, sAlo, a_off(row, (col0 >> 3) + k8));
-                                    }
-                                } else {
-                                    // output layer in fp32: po[o] += sum_c act[c] * Wout[o][c]   (Wout in smem, broadcast reads)
-#pragma unroll
-                                    for (int o = 0; o < MMAX; ++o) {
-                                        if (o < m) {
-                                            const float* w = sWout + o * 256 + col0;
-                                            float acc = po[o];
-#pragma unroll
-                                            for (int e = 0; e < 32; e += 4) {
-                                                const float4 w4 = *reinterpret_cast<const float4*>(w + e);
-                                                acc = fmaf(a[e], w4.x, acc);
-                                                acc = fmaf(a[e + 1], w4.y, acc);
-                                                acc = fmaf(a[e + 2], w4.z, acc);
-                                                acc = fmaf(a[e + 3], w4.w, acc);
-                                            }
-                                            po[o] = acc;
+                                        for (int e = 0; e < 32; e += 4) {
+                                            const float4 w4 = *reinterpret_cast<const float4*>(w + e);
+                                            acc = fmaf(a[e], w4.x, acc);
+                                            acc = fmaf(a[e + 1], w4.y, acc);
+                                            acc = fmaf(a[e + 2], w4.z, acc);
+                                            acc = fmaf(a[e + 3], w4.w, acc);
                                         }
+                                        po[o] = acc;
                                     }
                                 }
                             }
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) bcur[e] = bnxt[e];
                         }
                         if (!last) {
                             fence_proxy_async();
@@ -465,16 +507,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     compute_bar();
                 }  // chunks
                 // ---- finalize: prior, Lambda solve, DDIM update (theta stays in smem) ---------------------------------------------
-                const bool uni = (p.fin.prior_kind == D4S_PRIOR_UNIFORM);
-                if (uni && tid < nsamp * m) {  // erf/exp of the diffused-uniform score: one thread per (sample, dim)
-                    const int si = tid / m, k = tid - si * m;
-                    double s0, jac;
-                    uniform_prior_terms((double)sTheta[si * MMAX + k], (double)__ldg(p.fin.low + k), (double)__ldg(p.fin.high + k),
-                                        (double)__ldg(sched + D4S_S_SQRT_ALPHA), (double)__ldg(sched + D4S_S_SIGMA), s0, jac);
-                    sPrior[si * 2 * MMAX + k] = s0;
-                    sPrior[si * 2 * MMAX + MMAX + k] = jac;
-                }
-                compute_bar();
                 if (tid < nsamp) {
                     FinalizeParams fp = p.fin;
                     fp.C = 1;
@@ -482,9 +514,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     fp.sched = sched;
                     fp.mats = p.mats + (size_t)step * (2 * m * m + m);
                     fp.step_index = step;
-                    const float* nz = p.noise ? p.noise + ((size_t)step * p.N + (i0 + tid)) * m : nullptr;
-                    finalize_dispatch(m, fp, sAcc + tid * 2 * m, sTheta + tid * MMAX, nz, fp.sample_offset + i0 + tid,
-                                      uni ? sPrior + tid * 2 * MMAX : nullptr);
+                    finalize_dispatch(m, fp, sAcc + tid * 2 * m, sTheta + tid * MMAX, sNoise + tid * MMAX,
+                                      fp.sample_offset + i0 + tid, uni ? sPrior + tid * 2 * MMAX : nullptr);
                 }
                 compute_bar();
             }  // steps
