@@ -16,6 +16,8 @@ static int g_opt_path = 0;      // 0 auto, 1 SIMT per-step kernels only, 2 requi
 static int g_opt_swap = 0;      // debug: swap LBO/SBO in the UMMA descriptors
 static int g_opt_tc_steps = 0;  // > 0: DDIM steps per tcgen05 launch (0 = whole trajectory in one launch)
 static int* g_err_flag = nullptr;
+static int g_opt_profile = 0;
+static long long* g_prof = nullptr;
 
 static int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -423,6 +425,13 @@ static int try_traj_tc(const D4sNet* net, const D4sProblem* pb, int steps, const
         cudaMemset(g_err_flag, 0, sizeof(int));
     }
     p.error_flag = g_err_flag;
+    if (g_opt_profile) {
+        if (!g_prof) {
+            if (cudaMalloc(&g_prof, 16 * sizeof(long long)) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaMalloc(prof)");
+        }
+        cudaMemsetAsync(g_prof, 0, 16 * sizeof(long long), stream);
+        p.prof = g_prof;
+    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -564,7 +573,16 @@ int d4s_set_option(const char* key, int32_t value) {
     if (k == "path") g_opt_path = value;
     else if (k == "swap_lbo_sbo") g_opt_swap = value;
     else if (k == "tc_steps_per_launch") g_opt_tc_steps = value;
+    else if (k == "profile") g_opt_profile = value;
     else return fail(D4S_ERR_ARG, "unknown option: " + k);
+    return D4S_OK;
+}
+
+int d4s_get_profile(int64_t* out16) {
+    if (!out16) return fail(D4S_ERR_ARG, "null output");
+    if (!g_prof) return fail(D4S_ERR_ARG, "profiling was not enabled (d4s_set_option(\"profile\", 1))");
+    cudaError_t e = cudaMemcpy(out16, g_prof, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(prof)");
     return D4S_OK;
 }
 

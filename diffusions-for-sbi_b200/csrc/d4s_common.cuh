@@ -84,6 +84,7 @@ struct TrajParams {
     FinalizeParams fin;      // constant part of the per-step finalize parameters
     float* theta;            // [N][m] in/out
     int* error_flag;
+    long long* prof;         // optional [16] phase cycle counters (CTA 0)
 };
 cudaError_t launch_traj_tc(const TrajParams& p, int n_ctas, cudaStream_t stream);
 int traj_tc_smem_bytes();

@@ -15,7 +15,9 @@
 // Replaces the same reference lines as kernels 1-4 (nse.py:263-298, 544-656; tall_posterior_sampler.py:95-128).
 //
 // Warp roles: warps 0-7 compute/epilogue (TMEM lane quarter = warp % 4, column half = warp / 4),
-//             warp 8 = TMA producer (one lane), warp 9 = TMEM allocator + MMA issuer (one lane).
+//             warp 8 = TMA producer (one lane), warp 9 = TMEM allocator + MMA issuer (one lane),
+//             warp 10 = scalar helper: per-step schedule/matrix rows -> smem, fp64 diffused-prior terms, Philox noise
+//             (everything that depends only on theta at the start of the step, off the critical path).
 #include <cuda_bf16.h>
 
 #include "d4s_finalize_core.cuh"
@@ -23,30 +25,39 @@
 namespace d4s {
 
 constexpr int TC_M = 128;                      // tile rows = TMEM lanes
-constexpr int TC_CW = 8;                       // compute warps
-constexpr int TC_THREADS = (TC_CW + 2) * 32;   // 320
+constexpr int TC_CW = 16;                      // compute warps
+constexpr int TC_THREADS = (TC_CW + 3) * 32;   // 608: + TMA producer, MMA issuer, scalar helper
+constexpr int TC_CT = TC_CW * 32;              // compute threads
 constexpr int TC_NSTG = 4;                     // weight ring stages
 constexpr int TC_STAGE_BYTES = 256 * 64;       // one K=16 step of W_hi | W_lo for N <= 256
 constexpr int TC_A_BYTES = (256 / 16) * 4096;  // 64 KB: act[128 x 256] bf16 in K16-step images
-constexpr int TC_SG_MAX = 8;                   // samples per tile (layer-0 staging buffer)
+constexpr int TC_SG_MAX = 8;                   // samples per tile (warp w < SG sums sample w)
+constexpr int TC_MATS_MAX = 2 * MMAX * MMAX + MMAX + 2;
 constexpr long long SPIN_LIMIT_CYCLES = 4000000000LL;  // ~2 s: bounded mbarrier waits trap instead of hanging
 
 // ---- shared memory carve-up (bytes) ---------------------------------------------------------------------------
 constexpr int OFF_AHI = 0;
 constexpr int OFF_ALO = OFF_AHI + TC_A_BYTES;
 constexpr int OFF_RING = OFF_ALO + TC_A_BYTES;
-constexpr int OFF_S = OFF_RING + TC_NSTG * TC_STAGE_BYTES;   // float [128][MMAX] scores
-constexpr int OFF_QS = OFF_S + TC_M * MMAX * 4;               // float [128][MMAX] inv(Sigma_j) s
-constexpr int OFF_HALF = OFF_QS + TC_M * MMAX * 4;            // float [128][MMAX] output-layer partials (upper half)
-constexpr int OFF_BASE = OFF_HALF + TC_M * MMAX * 4;          // float [SG_MAX][256] layer-0 per-sample part
-constexpr int OFF_ACC = OFF_BASE + TC_SG_MAX * 256 * 4;       // float [SG_MAX][2*MMAX]
-constexpr int OFF_THETA = OFF_ACC + TC_SG_MAX * 2 * MMAX * 4; // float [SG_MAX][MMAX]
-constexpr int OFF_WOUT = OFF_THETA + TC_SG_MAX * MMAX * 4;    // float [MMAX][256] output layer (torch layout)
-constexpr int OFF_NOISE = OFF_WOUT + MMAX * 256 * 4;          // float [SG_MAX][MMAX] DDIM noise of the current step
-constexpr int OFF_PRIOR = OFF_NOISE + TC_SG_MAX * MMAX * 4;   // float [SG_MAX][2][MMAX] uniform-prior score / derivative
-constexpr int OFF_BAR = OFF_PRIOR + TC_SG_MAX * 2 * MMAX * 4; // mbarriers
+constexpr int OFF_S = OFF_RING + TC_NSTG * TC_STAGE_BYTES;    // float [128][MMAX] scores (also the half-exchange buffer)
+constexpr int OFF_QS = OFF_S + TC_M * MMAX * 4;                // float [128][MMAX] inv(Sigma_j) s
+constexpr int OFF_BASE = OFF_QS + TC_M * MMAX * 4;             // float [SG_MAX][256] layer-0 per-sample part
+constexpr int OFF_WOUT = OFF_BASE + TC_SG_MAX * 256 * 4;       // float [MMAX][256] output layer (torch layout)
+constexpr int OFF_ACC = OFF_WOUT + MMAX * 256 * 4;             // float [SG_MAX][2*MMAX] sums over observations
+constexpr int OFF_THETA = OFF_ACC + TC_SG_MAX * 2 * MMAX * 4;  // float [SG_MAX][MMAX]
+constexpr int OFF_NOISE = OFF_THETA + TC_SG_MAX * MMAX * 4;    // float [SG_MAX][MMAX] DDIM noise of the step
+constexpr int OFF_PRIOR = OFF_NOISE + TC_SG_MAX * MMAX * 4;    // float [SG_MAX][2][MMAX] uniform-prior score, derivative
+constexpr int OFF_SCHED = OFF_PRIOR + TC_SG_MAX * 2 * MMAX * 4;  // float [16] schedule row of the step
+constexpr int OFF_MATS = OFF_SCHED + 16 * 4;                   // float [TC_MATS_MAX] Lmat | G | mu_t of the step
+constexpr int OFF_BOUT = OFF_MATS + TC_MATS_MAX * 4;           // float [MMAX + 2]
+constexpr int OFF_ROWS = OFF_BOUT + (MMAX + 2) * 4;            // uint8 [128] sample of row, uint8 [128] observation of row
+constexpr int OFF_MINV = OFF_ROWS + 256;                       // float [SG_MAX][MMAX*MMAX] per-sample inverse of Lambda_i
+constexpr int OFF_G = OFF_MINV + TC_SG_MAX * MMAX * MMAX * 4;  // float [SG_MAX][MMAX] prior term of the step
+constexpr int OFF_BAR = OFF_G + TC_SG_MAX * MMAX * 4;          // mbarriers
 constexpr int OFF_TMEM = OFF_BAR + (2 * TC_NSTG + 2) * 8;
 constexpr int TC_SMEM_BYTES = OFF_TMEM + 16;
+static_assert(TC_SMEM_BYTES <= 232448, "shared memory budget (227 KB per CTA) exceeded");
+static_assert(OFF_BAR % 8 == 0 && OFF_SCHED % 16 == 0, "alignment");
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -114,7 +125,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
 
 // UMMA shared-memory descriptor, K-major, no swizzle ("interleave"): 8x16B core matrices, 128 B each.
 //   lbo = byte distance between the two K halves of a K=16 step, sbo = byte distance between 8-row groups.
@@ -127,16 +147,25 @@ __device__ __forceinline__ uint32_t umma_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 }
 
-// splits 8 fp32 activations into bf16 hi / lo and stores the two 16-byte K-groups
+// named barriers: 1 = compute warps only; 2 = theta of the step is final (compute arrive, helper sync);
+//                 3 = helper results ready (helper arrive, compute sync)
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// Splits 8 fp32 activations into bf16 hi / lo and stores the two 16-byte K-groups.  hi = RN_bf16(v) by Veltkamp
+// splitting (c = v * (2^16 + 1); hi = c - (c - v): three FMA-pipe ops, no conversion-unit instruction), lo = v - hi
+// exactly, truncated to bf16 when packed (its dropped bits are < 2^-17 |v|).  Packing is one PRMT per pair.
 __device__ __forceinline__ void store_split8(const float (&v)[8], uint8_t* a_hi, uint8_t* a_lo, int byte_off) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-        const float2 hf = __bfloat1622float2(h);
-        const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
-        hi[e] = *reinterpret_cast<const uint32_t*>(&h);
-        lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+        const float x0 = v[2 * e], x1 = v[2 * e + 1];
+        // __f*_rn intrinsics are never contracted into FMAs (contraction would defeat the splitting)
+        const float c0 = __fmul_rn(x0, 65537.0f), c1 = __fmul_rn(x1, 65537.0f);
+        const float h0 = __fsub_rn(c0, __fsub_rn(c0, x0)), h1 = __fsub_rn(c1, __fsub_rn(c1, x1));
+        const float l0 = __fsub_rn(x0, h0), l1 = __fsub_rn(x1, h1);
+        hi[e] = __byte_perm(__float_as_uint(h0), __float_as_uint(h1), 0x7632);
+        lo[e] = __byte_perm(__float_as_uint(l0), __float_as_uint(l1), 0x7632);
     }
     *reinterpret_cast<uint4*>(a_hi + byte_off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(a_lo + byte_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -145,30 +174,44 @@ __device__ __forceinline__ void store_split8(const float (&v)[8], uint8_t* a_hi,
 // byte offset of (row r, k-group kg of 8 columns) inside an A image: K16 step = kg/2, half = kg%2
 __device__ __forceinline__ int a_off(int r, int kg) { return (kg >> 1) * 4096 + (kg & 1) * 2048 + r * 16; }
 
+// Optional phase timing (d4s_set_option("profile", 1)): thread 0 of CTA 0 accumulates clock64() deltas per phase.
+#define PROF_MARK(slot)                                                     \
+    do {                                                                    \
+        if (prof_on) {                                                      \
+            const long long now_ = clock64();                               \
+            p.prof[slot] += now_ - prof_t;                                  \
+            prof_t = now_;                                                  \
+        }                                                                   \
+    } while (0)
+
+// Helper warp: per-sample Lambda_i = Lbase + (1-n) diag(p0_i) and its inverse, in fp64 (nse.py:647-654 builds and
+// solves this system; here the inverse is prepared off the critical path, the solve is a mat-vec in the tail).
 template <int M>
-__device__ __noinline__ void finalize_one(const FinalizeParams& fp, const float* part, float* theta, const float* noise,
-                                          long long gs, const float* pre) {
-    double loc[2 * M];
-    if (pre) {
+__device__ __noinline__ void lambda_inverse(const float* lbase, const float* p0, double one_minus_n, float* out) {
+    double a[M][M], inv[M][M];
 #pragma unroll
-        for (int k = 0; k < M; ++k) { loc[k] = (double)pre[k]; loc[M + k] = (double)pre[MMAX + k]; }
-    }
-    finalize_sample<M>(fp, part, theta, nullptr, noise, gs, pre ? loc : nullptr);
+    for (int r = 0; r < M; ++r)
+#pragma unroll
+        for (int c = 0; c < M; ++c) a[r][c] = (double)lbase[r * M + c] + ((r == c) ? one_minus_n * (double)p0[r] : 0.0);
+    gj_inverse_t<double, M>(a, inv);
+#pragma unroll
+    for (int r = 0; r < M; ++r)
+#pragma unroll
+        for (int c = 0; c < M; ++c) out[r * M + c] = (float)inv[r][c];
 }
 
-__device__ __forceinline__ void finalize_dispatch(int m, const FinalizeParams& fp, const float* part, float* theta,
-                                                  const float* noise, long long gs, const float* pre) {
+__device__ __forceinline__ void lambda_inverse_dispatch(int m, const float* lbase, const float* p0, double omn, float* out) {
     switch (m) {
-        case 1: finalize_one<1>(fp, part, theta, noise, gs, pre); break;
-        case 2: finalize_one<2>(fp, part, theta, noise, gs, pre); break;
-        case 3: finalize_one<3>(fp, part, theta, noise, gs, pre); break;
-        case 4: finalize_one<4>(fp, part, theta, noise, gs, pre); break;
-        case 5: finalize_one<5>(fp, part, theta, noise, gs, pre); break;
-        case 6: finalize_one<6>(fp, part, theta, noise, gs, pre); break;
-        case 7: finalize_one<7>(fp, part, theta, noise, gs, pre); break;
-        case 8: finalize_one<8>(fp, part, theta, noise, gs, pre); break;
-        case 9: finalize_one<9>(fp, part, theta, noise, gs, pre); break;
-        default: finalize_one<10>(fp, part, theta, noise, gs, pre); break;
+        case 1: lambda_inverse<1>(lbase, p0, omn, out); break;
+        case 2: lambda_inverse<2>(lbase, p0, omn, out); break;
+        case 3: lambda_inverse<3>(lbase, p0, omn, out); break;
+        case 4: lambda_inverse<4>(lbase, p0, omn, out); break;
+        case 5: lambda_inverse<5>(lbase, p0, omn, out); break;
+        case 6: lambda_inverse<6>(lbase, p0, omn, out); break;
+        case 7: lambda_inverse<7>(lbase, p0, omn, out); break;
+        case 8: lambda_inverse<8>(lbase, p0, omn, out); break;
+        case 9: lambda_inverse<9>(lbase, p0, omn, out); break;
+        default: lambda_inverse<10>(lbase, p0, omn, out); break;
     }
 }
 
@@ -178,13 +221,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
     uint8_t* sAlo = smem + OFF_ALO;
     float* sS = reinterpret_cast<float*>(smem + OFF_S);
     float* sQS = reinterpret_cast<float*>(smem + OFF_QS);
-    float* sHalf = reinterpret_cast<float*>(smem + OFF_HALF);
     float* sBase = reinterpret_cast<float*>(smem + OFF_BASE);
+    float* sWout = reinterpret_cast<float*>(smem + OFF_WOUT);
     float* sAcc = reinterpret_cast<float*>(smem + OFF_ACC);
     float* sTheta = reinterpret_cast<float*>(smem + OFF_THETA);
-    float* sWout = reinterpret_cast<float*>(smem + OFF_WOUT);
     float* sNoise = reinterpret_cast<float*>(smem + OFF_NOISE);
     float* sPrior = reinterpret_cast<float*>(smem + OFF_PRIOR);
+    float* sSched = reinterpret_cast<float*>(smem + OFF_SCHED);
+    float* sMats = reinterpret_cast<float*>(smem + OFF_MATS);
+    float* sBout = reinterpret_cast<float*>(smem + OFF_BOUT);
+    float* sMinv = reinterpret_cast<float*>(smem + OFF_MINV);
+    float* sG = reinterpret_cast<float*>(smem + OFF_G);
+    uint8_t* sRowSi = smem + OFF_ROWS;
+    uint8_t* sRowOj = smem + OFF_ROWS + 128;
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
     const uint32_t bar0 = smem_u32(smem + OFF_BAR);
     auto bar_full = [&](int s) { return bar0 + 8u * s; };
@@ -197,6 +246,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
     const int m = net.m, L = net.L;
     const int H0 = net.Hp[0];
     const int n_groups = (p.N + p.SG - 1) / p.SG;
+    const int mats_floats = 2 * m * m + m;
+    constexpr int NB23 = TC_CT + 32;  // participants of named barriers 2 and 3
 
     if (tid == 0) {
         for (int s = 0; s < TC_NSTG; ++s) {
@@ -211,6 +262,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(256));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
+    // constant tables: output layer, its bias, row -> (sample, observation) maps, zeroed operand images
+    for (int e = tid; e < 2 * TC_A_BYTES / 16; e += TC_THREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
+    {
+        const int Kout = net.Hp[L - 2];
+        for (int e = tid; e < m * Kout; e += TC_THREADS) sWout[(e / Kout) * 256 + (e % Kout)] = __ldg(net.WoutT + e);
+        if (tid < MMAX) sBout[tid] = (tid < m) ? __ldg(net.bout + tid) : 0.f;
+        if (tid < TC_M) {
+            const int si = tid / p.OC, oj = tid - si * p.OC;
+            sRowSi[tid] = (uint8_t)(tid < p.P ? si : 255);
+            sRowOj[tid] = (uint8_t)(tid < p.P ? oj : 255);
+        }
+    }
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -250,10 +314,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                 for (int l = 1; l <= L - 2; ++l) {
                     const int K = net.Hp[l - 1], Nn = net.Hp[l];
                     const uint32_t idesc = umma_idesc(Nn);
-                    const uint32_t b_lbo = p.swap_lbo_sbo ? 128u : (uint32_t)Nn * 16u;
-                    const uint32_t b_sbo = p.swap_lbo_sbo ? (uint32_t)Nn * 16u : 128u;
-                    const uint32_t a_lbo = p.swap_lbo_sbo ? 128u : 2048u;
-                    const uint32_t a_sbo = p.swap_lbo_sbo ? 2048u : 128u;
+                    const uint32_t b_lbo = (uint32_t)Nn * 16u, b_sbo = 128u;  // K halves N*16 B apart, 8-row groups 128 B
+                    const uint32_t a_lbo = 2048u, a_sbo = 128u;
                     mbar_wait(bar_a, a_cnt & 1u, p.error_flag);
                     ++a_cnt;
                     tc_fence_after();
@@ -276,31 +338,100 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                 }
             }
         }
-    } else {
-        // ================= compute warps ==================================================================================
-        const int q = warp & 3, ch = warp >> 2;
-        const int row = 32 * q + lane;  // the TMEM lane / tile row this thread owns in the epilogues
-        unsigned d_cnt = 0;
+    } else if (warp == TC_CW + 2) {
+        // ================= scalar helper: everything that only needs theta at the start of the step =================
         const bool uni = (p.fin.prior_kind == D4S_PRIOR_UNIFORM);
-        const int Kout = net.Hp[L - 2];
-        // rows of the tile that hold no (sample, observation) pair stay zero for the whole kernel
-        for (int e = tid; e < 2 * TC_A_BYTES / 16; e += 256) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
-        for (int e = tid; e < m * Kout; e += 256) sWout[(e / Kout) * 256 + (e % Kout)] = __ldg(net.WoutT + e);
+        const int nq = (m + 3) / 4;
         for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
             const int i0 = g * p.SG;
             const int nsamp = min(p.SG, p.N - i0);
-            for (int e = tid; e < TC_SG_MAX * MMAX; e += 256) {
+            for (int step = p.step_begin; step < p.step_end; ++step) {
+                bar_sync(2, NB23);  // theta of this step is final; last step's consumers are done with our buffers
+                const float* sched = p.sched + (size_t)step * D4S_SCHED_STRIDE;
+                if (lane < D4S_SCHED_STRIDE) sSched[lane] = __ldg(sched + lane);
+                const float* mrow = p.mats + (size_t)step * mats_floats;
+                for (int e = lane; e < mats_floats; e += 32) sMats[e] = __ldg(mrow + e);
+                __syncwarp();
+                const int combine = (int)sSched[D4S_S_COMBINE];
+                const double omn = (double)sSched[D4S_S_ONE_MINUS_N], aos2 = (double)sSched[D4S_S_A_OVER_S2];
+                const bool per_sample = (combine == D4S_COMBINE_PER_SAMPLE);
+                if (uni) {  // erf/exp of the diffused-uniform score in fp64: one lane per (sample, dim)
+                    const double sa = (double)sSched[D4S_S_SQRT_ALPHA], sg = (double)sSched[D4S_S_SIGMA];
+                    for (int e = lane; e < nsamp * m; e += 32) {
+                        const int si = e / m, k = e - si * m;
+                        double s0, jac;
+                        uniform_prior_terms((double)sTheta[si * MMAX + k], (double)__ldg(p.fin.low + k),
+                                            (double)__ldg(p.fin.high + k), sa, sg, s0, jac);
+                        if (per_sample) {
+                            const double p0 = aos2 / (1.0 + sg * sg * jac);  // inv(sigma^2/alpha (1 + sigma^2 J0))
+                            sPrior[si * MMAX + k] = (float)p0;
+                            sG[si * MMAX + k] = (float)(omn * p0 * s0);
+                        } else {
+                            sG[si * MMAX + k] = (float)(omn * s0);
+                        }
+                    }
+                } else if (p.fin.prior_kind == D4S_PRIOR_GAUSSIAN) {  // g = G (theta - mu_t), G from the step's matrix row
+                    const float* G = sMats + m * m;
+                    const float* mu = sMats + 2 * m * m;
+                    for (int e = lane; e < nsamp * m; e += 32) {
+                        const int si = e / m, r = e - si * m;
+                        double acc = 0.0;
+                        for (int c = 0; c < m; ++c) acc = fma((double)G[r * m + c], (double)sTheta[si * MMAX + c] - (double)mu[c], acc);
+                        sG[si * MMAX + r] = (float)acc;
+                    }
+                } else {
+                    for (int e = lane; e < TC_SG_MAX * MMAX; e += 32) sG[e] = 0.f;
+                }
+                __syncwarp();
+                if (per_sample && lane < nsamp) {
+                    if (uni) {
+                        lambda_inverse_dispatch(m, sMats, sPrior + lane * MMAX, omn, sMinv + lane * MMAX * MMAX);
+                    } else {  // no per-sample prior precision: invert the step's Lambda as it is
+                        for (int k = 0; k < m; ++k) sPrior[lane * MMAX + k] = 0.f;
+                        lambda_inverse_dispatch(m, sMats, sPrior + lane * MMAX, 0.0, sMinv + lane * MMAX * MMAX);
+                    }
+                }
+                for (int e = lane; e < nsamp * nq; e += 32) {  // DDIM noise: one lane per (sample, 4 dims)
+                    const int si = e / nq, qd = e - si * nq;
+                    float z[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (p.noise) {
+                        const float* nz = p.noise + ((size_t)step * p.N + (i0 + si)) * m;
+                        for (int k = 0; k < 4; ++k)
+                            if (4 * qd + k < m) z[k] = __ldg(nz + 4 * qd + k);
+                    } else {
+                        philox_normal4(p.fin.seed, step, p.fin.sample_offset + i0 + si, qd, z);
+                    }
+                    for (int k = 0; k < 4; ++k)
+                        if (4 * qd + k < MMAX) sNoise[si * MMAX + 4 * qd + k] = z[k];
+                }
+                __syncwarp();
+                bar_arrive(3, NB23);
+            }
+        }
+    } else {
+        // ================= compute warps ==================================================================================
+        const int q = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column quarter
+        const int row = 32 * q + lane;           // the TMEM lane / tile row this thread owns in the epilogues
+        unsigned d_cnt = 0;
+        const bool prof_on = (p.prof != nullptr) && blockIdx.x == 0 && tid == 0;
+        long long prof_t = prof_on ? clock64() : 0;
+        const bool uni = (p.fin.prior_kind == D4S_PRIOR_UNIFORM);
+        const int nkg = H0 / 8;
+        for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+            const int i0 = g * p.SG;
+            const int nsamp = min(p.SG, p.N - i0);
+            for (int e = tid; e < TC_SG_MAX * MMAX; e += TC_CT) {
                 const int si = e / MMAX, k = e - si * MMAX;
                 sTheta[e] = (si < nsamp && k < m) ? p.theta[(size_t)(i0 + si) * m + k] : 0.f;
             }
             compute_bar();
             for (int step = p.step_begin; step < p.step_end; ++step) {
-                const float* sched = p.sched + (size_t)step * D4S_SCHED_STRIDE;
-                const float inv_sigma = __ldg(sched + D4S_S_INV_SIGMA);
+                bar_arrive(2, NB23);  // theta is final: the helper warp may start on this step
+                const float inv_sigma = __ldg(p.sched + (size_t)step * D4S_SCHED_STRIDE + D4S_S_INV_SIGMA);
                 // ---- layer-0 per-sample part: base[si][col] = time_feat[col] + sum_k A[k][col] theta[si][k] ----------
                 {
                     const float* tf = p.time_feat + (size_t)step * H0;
-                    for (int col = tid; col < H0; col += 256) {
+                    for (int col = tid; col < H0; col += TC_CT) {
                         float acol[MMAX];
 #pragma unroll
                         for (int k = 0; k < MMAX; ++k) acol[k] = (k < m) ? __ldg(net.A + (size_t)k * H0 + col) : 0.f;
@@ -315,36 +446,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     }
                 }
                 compute_bar();
+                PROF_MARK(0);  // per-sample layer-0 part
                 for (int chunk = 0; chunk < p.C; ++chunk) {
                     const int j0 = chunk * p.OC;
                     const int nobs = min(p.OC, p.n - j0);
                     // ---- layer 0: act0[r][col] = relu(base[si][col] + obs_feat[j][col]) -> bf16 hi/lo A images -----------
-                    // item = (observation oj, k-group kg): one 32-byte read of obs_feat serves the rows of all SG samples;
-                    // all global loads of a thread are issued before their first use.
-                    {
-                        const int nkg = H0 / 8;
-                        const int items = p.OC * nkg;
-                        constexpr int IPT = 4;  // items per thread per pass
-                        for (int it0 = 0; it0 < items; it0 += 256 * IPT) {
-                            float4 u[IPT][2];
+                    // warp w owns k-groups w, w+16; lanes run over the observations: one 32-byte read of obs_feat
+                    // serves the rows of all SG samples, and every global load is issued before its first use.
+                    for (int oj = lane; oj < p.OC; oj += 32) {
+                        const bool ovalid = oj < nobs;
+                        const float* up = p.obs_feat + (size_t)(j0 + (ovalid ? oj : 0)) * H0;
+                        float4 u[2][2];
 #pragma unroll
-                            for (int j = 0; j < IPT; ++j) {
-                                const int item = it0 + j * 256 + tid;
-                                const int kg = item / p.OC, oj = item - kg * p.OC;
-                                if (item < items && oj < nobs) {
-                                    const float* up = p.obs_feat + (size_t)(j0 + oj) * H0 + 8 * kg;
-                                    u[j][0] = __ldg(reinterpret_cast<const float4*>(up));
-                                    u[j][1] = __ldg(reinterpret_cast<const float4*>(up + 4));
-                                } else {
-                                    u[j][0] = u[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                }
+                        for (int j = 0; j < 2; ++j) {
+                            const int kg = warp + 16 * j;
+                            if (ovalid && kg < nkg) {
+                                u[j][0] = __ldg(reinterpret_cast<const float4*>(up + 8 * kg));
+                                u[j][1] = __ldg(reinterpret_cast<const float4*>(up + 8 * kg + 4));
+                            } else {
+                                u[j][0] = u[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                             }
+                        }
 #pragma unroll
-                            for (int j = 0; j < IPT; ++j) {
-                                const int item = it0 + j * 256 + tid;
-                                if (item >= items) break;
-                                const int kg = item / p.OC, oj = item - kg * p.OC;
-                                const bool ovalid = oj < nobs;
+                        for (int j = 0; j < 2; ++j) {
+                            const int kg = warp + 16 * j;
+                            if (kg < nkg) {
                                 for (int si = 0; si < p.SG; ++si) {
                                     float v[8];
                                     if (ovalid && si < nsamp) {
@@ -363,37 +489,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                                 }
                             }
                         }
-                        // rows beyond the SG*OC pairs of the tile are never written: zero them once per kernel (below)
                     }
                     fence_proxy_async();
                     mbar_arrive(bar_a);
-
-                    // ---- theta-only work of this step, hidden behind the first tensor-core layer -----------------------------
-                    if (chunk == 0) {
-                        if (uni && tid < nsamp * m) {  // erf/exp of the diffused-uniform score: one thread per (sample, dim)
-                            const int si = tid / m, k = tid - si * m;
-                            double s0, jac;
-                            uniform_prior_terms((double)sTheta[si * MMAX + k], (double)__ldg(p.fin.low + k),
-                                                (double)__ldg(p.fin.high + k), (double)__ldg(sched + D4S_S_SQRT_ALPHA),
-                                                (double)__ldg(sched + D4S_S_SIGMA), s0, jac);
-                            sPrior[si * 2 * MMAX + k] = (float)s0;
-                            sPrior[si * 2 * MMAX + MMAX + k] = (float)jac;
-                        }
-                        const int nq = (m + 3) / 4;
-                        if (tid >= 128 && tid < 128 + nsamp * nq) {  // DDIM noise: one thread per (sample, 4 dims)
-                            const int e = tid - 128, si = e / nq, qd = e - si * nq;
-                            float z[4] = {0.f, 0.f, 0.f, 0.f};
-                            if (p.noise) {
-                                const float* nz = p.noise + ((size_t)step * p.N + (i0 + si)) * m;
-                                for (int k = 0; k < 4; ++k)
-                                    if (4 * qd + k < m) z[k] = __ldg(nz + 4 * qd + k);
-                            } else {
-                                philox_normal4(p.fin.seed, step, p.fin.sample_offset + i0 + si, qd, z);
-                            }
-                            for (int k = 0; k < 4; ++k)
-                                if (4 * qd + k < MMAX) sNoise[si * MMAX + 4 * qd + k] = z[k];
-                        }
-                    }
+                    PROF_MARK(1);  // layer 0
 
                     // ---- hidden layers on the tensor core; epilogues here ----------------------------------------------------
                     float po[MMAX];  // output-layer partial dot products of this thread's row / column half
@@ -402,28 +501,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     for (int l = 1; l <= L - 2; ++l) {
                         const int Nn = net.Hp[l];
                         const bool last = (l == L - 2);
-                        const int half_cols = Nn >> 1;
-                        const int nblk = half_cols / 32;
-                        const float* bias_l = net.bias[l] + ch * half_cols;
-                        float4 bcur[8], bnxt[8];
+                        const int qcols = Nn >> 2;  // columns of this warp's quarter: 64 / 32 / 16
+                        const int nblk = qcols / 16;
+                        const float* bias_l = net.bias[l] + cq * qcols;
+                        float4 bcur[4], bnxt[4];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) bcur[e] = __ldg(reinterpret_cast<const float4*>(bias_l) + e);  // hidden behind the MMA
+                        for (int e = 0; e < 4; ++e) bcur[e] = __ldg(reinterpret_cast<const float4*>(bias_l) + e);  // hidden behind the MMA
                         mbar_wait(bar_d, d_cnt & 1u, p.error_flag);
                         ++d_cnt;
                         tc_fence_after();
+                        PROF_MARK(3);  // waiting for the tensor core
                         for (int cb = 0; cb < nblk; ++cb) {
-                            const int col0 = ch * half_cols + 32 * cb;
-                            uint32_t d[32];
-                            tc_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, d);
+                            const int col0 = cq * qcols + 16 * cb;
+                            uint32_t d[16];
+                            tc_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, d);
                             if (cb + 1 < nblk) {
 #pragma unroll
-                                for (int e = 0; e < 8; ++e)
-                                    bnxt[e] = __ldg(reinterpret_cast<const float4*>(bias_l + 32 * (cb + 1)) + e);
+                                for (int e = 0; e < 4; ++e)
+                                    bnxt[e] = __ldg(reinterpret_cast<const float4*>(bias_l + 16 * (cb + 1)) + e);
                             }
                             tc_wait_ld();
-                            float a[32];
+                            float a[16];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
+                            for (int e = 0; e < 4; ++e) {
                                 a[4 * e] = fmaxf(__uint_as_float(d[4 * e]) + bcur[e].x, 0.f);
                                 a[4 * e + 1] = fmaxf(__uint_as_float(d[4 * e + 1]) + bcur[e].y, 0.f);
                                 a[4 * e + 2] = fmaxf(__uint_as_float(d[4 * e + 2]) + bcur[e].z, 0.f);
@@ -431,7 +531,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                             }
                             if (!last) {
 #pragma unroll
-                                for (int k8 = 0; k8 < 4; ++k8) {
+                                for (int k8 = 0; k8 < 2; ++k8) {
                                     float v[8];
 #pragma unroll
                                     for (int e = 0; e < 8; ++e) v[e] = a[8 * k8 + e];
@@ -445,7 +545,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                                         const float* w = sWout + o * 256 + col0;
                                         float acc = po[o];
 #pragma unroll
-                                        for (int e = 0; e < 32; e += 4) {
+                                        for (int e = 0; e < 16; e += 4) {
                                             const float4 w4 = *reinterpret_cast<const float4*>(w + e);
                                             acc = fmaf(a[e], w4.x, acc);
                                             acc = fmaf(a[e + 1], w4.y, acc);
@@ -457,69 +557,125 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                                 }
                             }
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) bcur[e] = bnxt[e];
+                            for (int e = 0; e < 4; ++e) bcur[e] = bnxt[e];
                         }
                         if (!last) {
                             fence_proxy_async();
                             tc_fence_before();
                             mbar_arrive(bar_a);
                         }
+                        PROF_MARK(4);  // epilogues
                     }
-                    // single-hidden-layer nets (L == 2) have no tensor-core layer: output layer straight from layer 0
-                    // is not supported here (the host routes them to the SIMT path).
 
-                    // ---- scores: combine the two column halves, s = -(eps + b)/sigma ----------------------------------------
-                    if (ch == 1) {
+                    // ---- scores: combine the four column quarters (tree through sS / sQS), s = -(eps + b)/sigma ---------------
+                    if (cq == 1 || cq == 3) {
+                        float* dst = (cq == 1) ? sS : sQS;
 #pragma unroll
                         for (int o = 0; o < MMAX; ++o)
-                            if (o < m) sHalf[row * MMAX + o] = po[o];
+                            if (o < m) dst[row * MMAX + o] = po[o];
                     }
                     tc_fence_before();
                     compute_bar();
-                    if (ch == 0) {
+                    if (cq == 0 || cq == 2) {
+                        const float* src = (cq == 0) ? sS : sQS;
 #pragma unroll
                         for (int o = 0; o < MMAX; ++o)
-                            if (o < m) sS[row * MMAX + o] = -(po[o] + sHalf[row * MMAX + o] + __ldg(net.bout + o)) * inv_sigma;
+                            if (o < m) po[o] += src[row * MMAX + o];
                     }
                     compute_bar();
-                    // ---- inv(Sigma_j) s per pair -----------------------------------------------------------------------------
-                    for (int e = tid; e < p.P * m; e += 256) {
-                        const int r = e / m, o = e - r * m;
-                        const int si = r / p.OC, oj = r - si * p.OC;
-                        float acc = 0.f;
-                        if (p.obs_prec && si < nsamp && oj < nobs) {
-                            const float* Q = p.obs_prec + ((size_t)(j0 + oj) * m + o) * m;
-                            for (int k = 0; k < m; ++k) acc = fmaf(__ldg(Q + k), sS[r * MMAX + k], acc);
+                    if (cq == 2) {
+#pragma unroll
+                        for (int o = 0; o < MMAX; ++o)
+                            if (o < m) sS[row * MMAX + o] = po[o];
+                    }
+                    compute_bar();
+                    if (cq == 0) {
+#pragma unroll
+                        for (int o = 0; o < MMAX; ++o)
+                            if (o < m) sS[row * MMAX + o] = -(po[o] + sS[row * MMAX + o] + sBout[o]) * inv_sigma;
+                    }
+                    compute_bar();
+                    PROF_MARK(5);  // scores
+                    // ---- per-sample sums over the chunk's observations: warp -> sample, lane -> observation ------------------------
+                    // S1 = sum_j s_ij, S2 = sum_j inv(Sigma_j) s_ij; butterfly reduction over lanes (fixed order => deterministic)
+                    if (warp < nsamp) {
+                        float s1[MMAX], s2[MMAX];
+#pragma unroll
+                        for (int o = 0; o < MMAX; ++o) s1[o] = s2[o] = 0.f;
+                        for (int oj = lane; oj < nobs; oj += 32) {
+                            const float* srow = sS + (warp * p.OC + oj) * MMAX;
+                            float sv[MMAX];
+#pragma unroll
+                            for (int k = 0; k < MMAX; ++k) sv[k] = (k < m) ? srow[k] : 0.f;
+#pragma unroll
+                            for (int o = 0; o < MMAX; ++o) s1[o] += sv[o];
+                            if (p.obs_prec) {
+                                const float* Q = p.obs_prec + (size_t)(j0 + oj) * m * m;
+#pragma unroll
+                                for (int o = 0; o < MMAX; ++o) {
+                                    if (o < m) {
+                                        float acc = s2[o];
+#pragma unroll
+                                        for (int k = 0; k < MMAX; ++k)
+                                            if (k < m) acc = fmaf(__ldg(Q + o * m + k), sv[k], acc);
+                                        s2[o] = acc;
+                                    }
+                                }
+                            }
                         }
-                        sQS[r * MMAX + o] = acc;
-                    }
-                    compute_bar();
-                    // ---- sums over the chunk's observations (fixed order) ------------------------------------------------------
-                    for (int e = tid; e < nsamp * 2 * m; e += 256) {
-                        const int si = e / (2 * m), c = e - si * 2 * m;
-                        float acc = (chunk == 0) ? 0.f : sAcc[si * 2 * m + c];
-                        for (int oj = 0; oj < nobs; ++oj) {
-                            const int r = si * p.OC + oj;
-                            acc += (c < m) ? sS[r * MMAX + c] : sQS[r * MMAX + (c - m)];
+#pragma unroll
+                        for (int o = 0; o < MMAX; ++o) {
+                            if (o < m) {
+#pragma unroll
+                                for (int sh = 16; sh > 0; sh >>= 1) {
+                                    s1[o] += __shfl_xor_sync(0xffffffffu, s1[o], sh);
+                                    s2[o] += __shfl_xor_sync(0xffffffffu, s2[o], sh);
+                                }
+                            }
                         }
-                        sAcc[si * 2 * m + c] = acc;
+                        if (lane == 0) {
+#pragma unroll
+                            for (int o = 0; o < MMAX; ++o) {
+                                if (o < m) {
+                                    float* acc = sAcc + warp * 2 * m;
+                                    acc[o] = (chunk == 0 ? 0.f : acc[o]) + s1[o];
+                                    acc[m + o] = (chunk == 0 ? 0.f : acc[m + o]) + s2[o];
+                                }
+                            }
+                        }
                     }
                     compute_bar();
+                    PROF_MARK(6);  // inv(Sigma) s + sums over observations
                 }  // chunks
                 // ---- finalize: prior, Lambda solve, DDIM update (theta stays in smem) ---------------------------------------------
-                if (tid < nsamp) {
-                    FinalizeParams fp = p.fin;
-                    fp.C = 1;
-                    fp.W = 2 * m;
-                    fp.sched = sched;
-                    fp.mats = p.mats + (size_t)step * (2 * m * m + m);
-                    fp.step_index = step;
-                    finalize_dispatch(m, fp, sAcc + tid * 2 * m, sTheta + tid * MMAX, sNoise + tid * MMAX,
-                                      fp.sample_offset + i0 + tid, uni ? sPrior + tid * 2 * MMAX : nullptr);
+                bar_sync(3, NB23);  // schedule/matrix rows, prior terms and noise of this step are in smem
+                PROF_MARK(2);       // (time spent waiting for the helper warp, normally zero)
+                if (warp < nsamp && lane < m) {  // warp -> sample, lane -> theta component; fp32, everything in smem
+                    const int si = warp, r = lane;
+                    const int combine = (int)sSched[D4S_S_COMBINE];
+                    const float* acc = sAcc + si * 2 * m;
+                    float out;
+                    if (combine == D4S_COMBINE_SUM) {
+                        out = sG[si * MMAX + r] + acc[r];  // (1-n) s0 + sum_j s_ij   (nse.py:642)
+                    } else {
+                        const float aos2 = sSched[D4S_S_A_OVER_S2];
+                        const float* Minv = (combine == D4S_COMBINE_SHARED) ? sMats : sMinv + si * MMAX * MMAX;
+                        float o = 0.f;
+                        for (int c = 0; c < m; ++c) {
+                            const float w = fmaf(aos2, acc[c], acc[m + c]) + sG[si * MMAX + c];  // nse.py:631-636 / 647-652
+                            o = fmaf(Minv[r * m + c], w, o);
+                        }
+                        out = o;  // Lambda^-1 w   (nse.py:638 / 654)
+                    }
+                    float v = sSched[D4S_S_C_THETA] * sTheta[si * MMAX + r] + sSched[D4S_S_C_SCORE] * out +
+                              sSched[D4S_S_BRIDGE_STD] * sNoise[si * MMAX + r];  // nse.py:289-298
+                    if (p.fin.clip_lo <= p.fin.clip_hi) v = fminf(fmaxf(v, p.fin.clip_lo), p.fin.clip_hi);
+                    sTheta[si * MMAX + r] = v;
                 }
                 compute_bar();
+                PROF_MARK(7);  // finalize
             }  // steps
-            for (int e = tid; e < nsamp * m; e += 256) {
+            for (int e = tid; e < nsamp * m; e += TC_CT) {
                 const int si = e / m, k = e - si * m;
                 p.theta[(size_t)(i0 + si) * m + k] = sTheta[si * MMAX + k];
             }

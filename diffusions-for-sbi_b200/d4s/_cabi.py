@@ -13,7 +13,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libd4s.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_LAYERS = 8
 MAX_THETA = 10
 MAX_WIDTH = 256
@@ -30,7 +30,7 @@ S_T, S_ALPHA, S_SIGMA, S_INV_SIGMA, S_A_OVER_S2, S_C_THETA, S_C_SCORE, S_BRIDGE_
 EXPORTS = [
     "d4s_abi_version", "d4s_last_error", "d4s_device_count", "d4s_net_create", "d4s_net_free",
     "d4s_net_h1_padded", "d4s_workspace_floats", "d4s_mats_floats", "d4s_score_partials", "d4s_finalize",
-    "d4s_ddim_run", "d4s_graph_cache_clear", "d4s_set_option", "d4s_prior_score", "d4s_ddim_update", "d4s_batched_inverse", "d4s_philox_normal", "d4s_launch_count",
+    "d4s_ddim_run", "d4s_graph_cache_clear", "d4s_set_option", "d4s_get_profile", "d4s_prior_score", "d4s_ddim_update", "d4s_batched_inverse", "d4s_philox_normal", "d4s_launch_count",
 ]
 
 
@@ -114,6 +114,7 @@ def load():
             "d4s_ddim_run": (C.c_int, [vp, C.POINTER(Problem), i32, vp, vp, vp, vp, vp, C.POINTER(i32), i32, vp]),
             "d4s_graph_cache_clear": (None, []),
             "d4s_set_option": (C.c_int, [C.c_char_p, i32]),
+            "d4s_get_profile": (C.c_int, [C.POINTER(i64)]),
             "d4s_prior_score": (C.c_int, [i32, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]),
             "d4s_ddim_update": (C.c_int, [vp, vp, i64, i32, vp, vp, u64, i32, i64, C.c_float, C.c_float, vp]),
             "d4s_batched_inverse": (C.c_int, [vp, vp, i32, i32, vp]),
@@ -133,6 +134,17 @@ def load():
 def set_option(key: str, value: int):
     """Library switches (see d4s_set_option in include/d4s.h): path, tc_steps_per_launch, swap_lbo_sbo."""
     check(load().d4s_set_option(key.encode(), int(value)))
+
+
+PROFILE_PHASES = ["layer0_sample_part", "layer0", "prior_noise", "tensor_wait", "epilogues", "scores",
+                  "prec_and_sums", "finalize"]
+
+
+def get_profile():
+    """Phase cycle counters of the last profiled tcgen05 launch (CTA 0): dict phase -> cycles."""
+    buf = (C.c_int64 * 16)()
+    check(load().d4s_get_profile(buf))
+    return {name: int(buf[i]) for i, name in enumerate(PROFILE_PHASES)}
 
 
 def check(rc: int):

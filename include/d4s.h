@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D4S_ABI_VERSION 6
+#define D4S_ABI_VERSION 7
 
 #define D4S_OK 0
 #define D4S_ERR_ARG -1      /* bad argument / unsupported shape */
@@ -161,6 +161,10 @@ D4S_API void d4s_graph_cache_clear(void);
  * kernel (bf16x3 split on the tensor cores; GAUSS, tall grid); "tc_steps_per_launch" = DDIM steps per tcgen05
  * launch (0 = whole trajectory in one launch); "swap_lbo_sbo" = descriptor debug switch. */
 D4S_API int d4s_set_option(const char* key, int32_t value);
+/* "profile" = 1 makes CTA 0 of the tcgen05 kernel accumulate clock64() cycles per phase; this call synchronises and
+ * copies the 16 counters of the last launch: 0 layer-0 sample part, 1 layer 0, 2 prior+noise, 3 tensor-core wait,
+ * 4 epilogues, 5 scores, 6 inv(Sigma) s + sums, 7 finalize. */
+D4S_API int d4s_get_profile(int64_t* out16);
 
 /* ---- stand-alone pieces of kernel 3/4 (API parity with the reference's public helpers) ---------------- */
 /* prior_score_fn(theta, t) of vp_diffused_priors.py:20-46 (uniform: also d score / d theta, the diagonal

@@ -48,3 +48,12 @@ print(f"swap={swap} N={N} n={n} steps={steps} hidden={hidden}: |tc-simt|max={flo
       f"|simt-oracle|={np.abs(ref.cpu().numpy() - orc_out).max() / scale:.3e} "
       f"|tc-oracle|={np.abs(out.cpu().numpy() - orc_out).max() / scale:.3e} (rel to {scale:.2f})")
 
+
+if os.environ.get("D4S_PROFILE"):
+    abi.set_option("profile", 1)
+    out = nse.ddim((N,), xt, **kw)
+    torch.cuda.synchronize()
+    prof = abi.get_profile()
+    tot = sum(prof.values())
+    groups = -(-N // max(1, min(8, 128 // min(n, 128)))) 
+    print("phase cycles (CTA 0):", {k: f"{v} ({100 * v / tot:.1f}%)" for k, v in prof.items()}, "total", tot)
