@@ -466,10 +466,10 @@ def score_partials(setup: TallSetup, theta: torch.Tensor, k: int = 0, want_score
 
 
 def finalize(setup: TallSetup, theta: torch.Tensor, k: int = 0, noise_k: Optional[torch.Tensor] = None,
-             update: bool = False) -> torch.Tensor:
+             update: bool = False, want_score: bool = True) -> Optional[torch.Tensor]:
     """Kernel 3(+4) alone: reduces the workspace, applies prior + solve; returns the total score [N, m]."""
     lib = abi.require_cuda()
-    out = torch.empty_like(theta)
+    out = torch.empty_like(theta) if want_score else None
     st = step_struct(setup, k, noise_k, update)
     with torch.cuda.device(theta.device):
         abi.check(lib.d4s_finalize(setup.pn.handle, C.byref(setup.prob), C.byref(st), _ptr(theta), _ptr(out),
