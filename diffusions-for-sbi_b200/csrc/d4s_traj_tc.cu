@@ -85,9 +85,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
+    unsigned polls = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > SPIN_LIMIT_CYCLES) {  // a protocol bug must not hang the GPU: fail loudly instead
-            if (err) atomicExch(err, 1);
+        if ((++polls & 255u) == 0u && clock64() - t0 > SPIN_LIMIT_CYCLES) {
+            if (err) atomicExch(err, 1);  // a protocol bug must not hang the GPU: fail loudly instead
             __trap();
         }
     }
@@ -417,6 +418,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
         long long prof_t = prof_on ? clock64() : 0;
         const bool uni = (p.fin.prior_kind == D4S_PRIOR_UNIFORM);
         const int nkg = H0 / 8;
+        // layer-0 theta block: thread `tid` owns column tid of A for the whole kernel (registers)
+        float acol[MMAX];
+#pragma unroll
+        for (int k = 0; k < MMAX; ++k) acol[k] = (k < m && tid < H0) ? __ldg(net.A + (size_t)k * H0 + tid) : 0.f;
+        float tf_next = (tid < H0 && n_steps > 0) ? __ldg(p.time_feat + (size_t)p.step_begin * H0 + tid) : 0.f;
         for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
             const int i0 = g * p.SG;
             const int nsamp = min(p.SG, p.N - i0);
@@ -429,20 +435,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                 bar_arrive(2, NB23);  // theta is final: the helper warp may start on this step
                 const float inv_sigma = __ldg(p.sched + (size_t)step * D4S_SCHED_STRIDE + D4S_S_INV_SIGMA);
                 // ---- layer-0 per-sample part: base[si][col] = time_feat[col] + sum_k A[k][col] theta[si][k] ----------
-                {
-                    const float* tf = p.time_feat + (size_t)step * H0;
-                    for (int col = tid; col < H0; col += TC_CT) {
-                        float acol[MMAX];
+                if (tid < H0) {
+                    const float t0 = tf_next;
+                    const int nstep = (step + 1 < p.step_end) ? step + 1 : p.step_begin;  // (next group restarts the grid)
+                    tf_next = __ldg(p.time_feat + (size_t)nstep * H0 + tid);  // consumed one step later: latency hidden
+                    for (int si = 0; si < p.SG; ++si) {
+                        float z = t0;
 #pragma unroll
-                        for (int k = 0; k < MMAX; ++k) acol[k] = (k < m) ? __ldg(net.A + (size_t)k * H0 + col) : 0.f;
-                        const float t0 = __ldg(tf + col);
-                        for (int si = 0; si < p.SG; ++si) {
-                            float z = t0;
-#pragma unroll
-                            for (int k = 0; k < MMAX; ++k)
-                                if (k < m) z = fmaf(acol[k], sTheta[si * MMAX + k], z);
-                            sBase[si * 256 + col] = z;
-                        }
+                        for (int k = 0; k < MMAX; ++k)
+                            if (k < m) z = fmaf(acol[k], sTheta[si * MMAX + k], z);
+                        sBase[si * 256 + tid] = z;
                     }
                 }
                 compute_bar();
@@ -596,53 +598,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     }
                     compute_bar();
                     PROF_MARK(5);  // scores
-                    // ---- per-sample sums over the chunk's observations: warp -> sample, lane -> observation ------------------------
-                    // S1 = sum_j s_ij, S2 = sum_j inv(Sigma_j) s_ij; butterfly reduction over lanes (fixed order => deterministic)
-                    if (warp < nsamp) {
-                        float s1[MMAX], s2[MMAX];
-#pragma unroll
-                        for (int o = 0; o < MMAX; ++o) s1[o] = s2[o] = 0.f;
+                    // ---- per-sample sums over the chunk's observations --------------------------------------------------------------
+                    // item = (sample si, component c < 2m): S1[c] = sum_j s_ij[c] (c < m), S2[c-m] = sum_j (inv(Sigma_j) s_ij)[c-m];
+                    // a warp takes one item at a time, its lanes run over the observations, one butterfly per item
+                    // (fixed order => deterministic).
+                    for (int item = warp; item < nsamp * 2 * m; item += TC_CW) {
+                        const int si = item / (2 * m), c = item - si * 2 * m;
+                        float acc = 0.f;
                         for (int oj = lane; oj < nobs; oj += 32) {
-                            const float* srow = sS + (warp * p.OC + oj) * MMAX;
-                            float sv[MMAX];
+                            const float* srow = sS + (si * p.OC + oj) * MMAX;
+                            if (c < m) {
+                                acc += srow[c];
+                            } else if (p.obs_prec) {
+                                const float* Q = p.obs_prec + ((size_t)(j0 + oj) * m + (c - m)) * m;
 #pragma unroll
-                            for (int k = 0; k < MMAX; ++k) sv[k] = (k < m) ? srow[k] : 0.f;
-#pragma unroll
-                            for (int o = 0; o < MMAX; ++o) s1[o] += sv[o];
-                            if (p.obs_prec) {
-                                const float* Q = p.obs_prec + (size_t)(j0 + oj) * m * m;
-#pragma unroll
-                                for (int o = 0; o < MMAX; ++o) {
-                                    if (o < m) {
-                                        float acc = s2[o];
-#pragma unroll
-                                        for (int k = 0; k < MMAX; ++k)
-                                            if (k < m) acc = fmaf(__ldg(Q + o * m + k), sv[k], acc);
-                                        s2[o] = acc;
-                                    }
-                                }
+                                for (int k = 0; k < MMAX; ++k)
+                                    if (k < m) acc = fmaf(__ldg(Q + k), srow[k], acc);
                             }
                         }
 #pragma unroll
-                        for (int o = 0; o < MMAX; ++o) {
-                            if (o < m) {
-#pragma unroll
-                                for (int sh = 16; sh > 0; sh >>= 1) {
-                                    s1[o] += __shfl_xor_sync(0xffffffffu, s1[o], sh);
-                                    s2[o] += __shfl_xor_sync(0xffffffffu, s2[o], sh);
-                                }
-                            }
-                        }
-                        if (lane == 0) {
-#pragma unroll
-                            for (int o = 0; o < MMAX; ++o) {
-                                if (o < m) {
-                                    float* acc = sAcc + warp * 2 * m;
-                                    acc[o] = (chunk == 0 ? 0.f : acc[o]) + s1[o];
-                                    acc[m + o] = (chunk == 0 ? 0.f : acc[m + o]) + s2[o];
-                                }
-                            }
-                        }
+                        for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+                        if (lane == 0) sAcc[si * 2 * m + c] = (chunk == 0 ? 0.f : sAcc[si * 2 * m + c]) + acc;
                     }
                     compute_bar();
                     PROF_MARK(6);  // inv(Sigma) s + sums over observations
