@@ -129,7 +129,18 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
     if (L < 2 || L > D4S_MAX_LAYERS) return fail(D4S_ERR_ARG, "n_layers must be in [2, 8]");
     const int m = d->dims[L];
     if (m < 1 || m > D4S_MAX_THETA) return fail(D4S_ERR_ARG, "theta_dim must be in [1, 10]");
-    if (d->theta_cols != m) return fail(D4S_ERR_ARG, "theta_cols != theta_dim (theta embedding nets: not in this ABI version)");
+    const int EL = d->emb_layers;
+    if (EL < 0 || EL > D4S_MAX_LAYERS) return fail(D4S_ERR_ARG, "emb_layers must be in [0, 8]");
+    if (EL == 0 && d->theta_cols != m) return fail(D4S_ERR_ARG, "theta_cols != theta_dim without a theta embedding net");
+    if (EL > 0) {
+        if (d->emb_dims[0] != m) return fail(D4S_ERR_ARG, "theta embedding input width != theta_dim");
+        if (d->emb_dims[EL] != d->theta_cols) return fail(D4S_ERR_ARG, "theta embedding output width != theta_cols");
+        for (int l = 0; l <= EL; ++l)
+            if (d->emb_dims[l] < 1 || d->emb_dims[l] > D4S_MAX_WIDTH) return fail(D4S_ERR_ARG, "theta embedding width out of range");
+        for (int l = 0; l < EL; ++l)
+            if (!d->emb_weight[l] || !d->emb_bias[l]) return fail(D4S_ERR_ARG, "null embedding weight/bias pointer");
+    }
+    if (d->theta_cols < 1 || d->theta_cols > D4S_MAX_WIDTH) return fail(D4S_ERR_ARG, "theta_cols out of range");
     if (d->theta_cols > d->dims[0]) return fail(D4S_ERR_ARG, "theta_cols > input width");
     int Hp[D4S_MAX_LAYERS] = {0};
     for (int l = 0; l <= L - 2; ++l) {
@@ -160,6 +171,15 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
             for (int o = 0; o < Ho; ++o) h[off_W[l] + (size_t)k * Hp[l] + o] = d->weight[l][(size_t)o * K + k];
         off_b[l] = reserve(Hp[l]);
         for (int o = 0; o < Ho; ++o) h[off_b[l] + o] = d->bias[l][o];
+    }
+    std::vector<size_t> off_eW(D4S_MAX_LAYERS, 0), off_eb(D4S_MAX_LAYERS, 0);
+    for (int l = 0; l < EL; ++l) {  // theta embedding, k-major
+        const int K = d->emb_dims[l], Ho = d->emb_dims[l + 1];
+        off_eW[l] = reserve((size_t)K * Ho);
+        for (int k = 0; k < K; ++k)
+            for (int o = 0; o < Ho; ++o) h[off_eW[l] + (size_t)k * Ho + o] = d->emb_weight[l][(size_t)o * K + k];
+        off_eb[l] = reserve(Ho);
+        for (int o = 0; o < Ho; ++o) h[off_eb[l] + o] = d->emb_bias[l][o];
     }
     const int Kl = d->dims[L - 1];
     const size_t off_Wout = reserve((size_t)Hp[L - 2] * MMAX);
@@ -221,6 +241,12 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
     nd.Wout = net->blob + off_Wout;
     nd.bout = net->blob + off_bout;
     nd.WoutT = net->blob + off_WoutT;
+    nd.emb_L = EL;
+    for (int l = 0; l <= EL && EL > 0; ++l) nd.emb_dims[l] = d->emb_dims[l];
+    for (int l = 0; l < EL; ++l) {
+        nd.emb_Wt[l] = net->blob + off_eW[l];
+        nd.emb_bias[l] = net->blob + off_eb[l];
+    }
     for (int l = 1; l <= L - 2; ++l) nd.wimg[l] = reinterpret_cast<const uint8_t*>(net->blob + off_img[l]);
     *out = net;
     return D4S_OK;
@@ -236,18 +262,30 @@ int d4s_net_h1_padded(const D4sNet* net) { return net ? net->dev.Hp[0] : 0; }
 
 int32_t d4s_mats_floats(int32_t m) { return 2 * m * m + m; }
 
-int64_t d4s_workspace_floats(const D4sNet* net, const D4sProblem* pb) {
+int64_t d4s_partials_floats(const D4sNet* net, const D4sProblem* pb) {
     if (!net || !pb) return -1;
     Tiling t;
     if (make_tiling(net, pb, &t) != 0) return -1;
     return (int64_t)pb->n_samples * t.C * t.W;
 }
 
+// workspace = [partial sums N*C*W] [base_pre N*H1p] [tan_pre N*m*H1p]  (the last two only with a theta embedding net)
+int64_t d4s_workspace_floats(const D4sNet* net, const D4sProblem* pb) {
+    const int64_t part = d4s_partials_floats(net, pb);
+    if (part < 0) return -1;
+    int64_t extra = 0;
+    if (net->dev.emb_L > 0) {
+        extra = (int64_t)pb->n_samples * net->dev.Hp[0];
+        if (pb->cov_mode == D4S_COV_JAC) extra += (int64_t)pb->n_samples * net->dev.m * net->dev.Hp[0];
+    }
+    return part + extra;
+}
+
 static int score_partials_impl(const D4sNet* net, const D4sProblem* pb, const D4sStep* st, const float* theta,
                                float* scores_out, float* prec_out, cudaStream_t stream) {
     Tiling t;
     if (make_tiling(net, pb, &t) != 0) return fail(D4S_ERR_ARG, "cannot tile the problem");
-    if ((int64_t)pb->n_samples * t.C * t.W > pb->workspace_floats) return fail(D4S_ERR_WORKSPACE, "workspace too small");
+    if (d4s_workspace_floats(net, pb) > pb->workspace_floats) return fail(D4S_ERR_WORKSPACE, "workspace too small");
     if (pb->cov_mode == D4S_COV_GAUSS && !pb->obs_prec && !pb->paired && pb->n_obs_total > 1 && false)
         return fail(D4S_ERR_ARG, "GAUSS needs obs_prec");
     ScoreParams p;
@@ -270,6 +308,15 @@ static int score_partials_impl(const D4sNet* net, const D4sProblem* pb, const D4
     p.part = pb->workspace;
     p.scores_out = scores_out;
     p.prec_out = prec_out;
+    if (net->dev.emb_L > 0) {  // kernel 0: embedded theta -> layer-0 sample part (+ JAC tangent seeds)
+        float* base_pre = pb->workspace + (size_t)pb->n_samples * t.C * t.W;
+        float* tan_pre = p.jac ? base_pre + (size_t)pb->n_samples * net->dev.Hp[0] : nullptr;
+        cudaError_t e0 = launch_theta_embed(net->dev, theta, pb->n_samples, p.jac, base_pre, tan_pre, stream);
+        if (e0 != cudaSuccess) return cuda_fail(e0, "theta embedding kernel launch");
+        ++g_launches;
+        p.base_pre = base_pre;
+        p.tan_pre = tan_pre;
+    }
     cudaError_t e = launch_score_simt(p, t.tiles, stream);
     if (e != cudaSuccess) return cuda_fail(e, "score kernel launch");
     ++g_launches;
@@ -375,7 +422,7 @@ static int try_traj_tc(const D4sNet* net, const D4sProblem* pb, int steps, const
                        const float* mats, const float* noise, float* theta, const int32_t* step_mode,
                        cudaStream_t stream) {
     const NetDev& nd = net->dev;
-    bool eligible = g_opt_path != 1 && pb->cov_mode == D4S_COV_GAUSS && !pb->paired && nd.L >= 3;
+    bool eligible = g_opt_path != 1 && pb->cov_mode == D4S_COV_GAUSS && !pb->paired && nd.L >= 3 && nd.emb_L == 0;
     if (step_mode)
         for (int k = 0; k < steps && eligible; ++k) eligible = (step_mode[k] == D4S_COV_GAUSS);
     if (!eligible) {

@@ -30,6 +30,11 @@ struct NetDev {
     const float* Wout;              // [Hp[L-2]][MMAX] k-major, zero padded columns
     const float* bout;              // [MMAX]
     const float* WoutT;             // [m][Hp[L-2]] output layer, torch layout (tcgen05 path epilogue)
+    // optional theta-embedding MLP (nse.py:129): emb_L linear layers, k-major fp32, widths as given (<= 256)
+    int emb_L;
+    int emb_dims[D4S_MAX_LAYERS + 1];
+    const float* emb_Wt[D4S_MAX_LAYERS];    // [in][out]
+    const float* emb_bias[D4S_MAX_LAYERS];  // [out]
     const uint8_t* wimg[D4S_MAX_LAYERS];  // l = 1 .. L-2: bf16 hi/lo UMMA images, [Hp[l-1]/16][hi | lo][2][Hp[l]][8]
 };
 
@@ -43,6 +48,8 @@ struct ScoreParams {
     int jac, paired;
     int W;                   // floats per (sample, chunk) partial: GAUSS 2m, JAC m + m*m
     const float* theta;      // [N][m]
+    const float* base_pre;   // optional [N][Hp0]: A e_theta(theta_i) from the embedding kernel (else A theta_i in-kernel)
+    const float* tan_pre;    // optional [N][m][Hp0]: A d e_theta / d theta_k (JAC tangent seeds)
     const float* obs_feat;   // [n][Hp0]
     const float* time_feat;  // [Hp0]
     const float* obs_prec;   // GAUSS: [n][m][m]
@@ -89,6 +96,8 @@ struct TrajParams {
 cudaError_t launch_traj_tc(const TrajParams& p, int n_ctas, cudaStream_t stream);
 int traj_tc_smem_bytes();
 
+cudaError_t launch_theta_embed(const NetDev& net, const float* theta, int N, int jac, float* base_pre, float* tan_pre,
+                               cudaStream_t stream);
 cudaError_t launch_score_simt(const ScoreParams& p, int tiles, cudaStream_t stream);
 cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t stream);
 cudaError_t launch_batched_inverse(const float* a, float* out, int batch, int m, cudaStream_t stream);

@@ -208,12 +208,13 @@ __global__ void __launch_bounds__(NT, 2) score_simt_kernel(const ScoreParams p) 
     // ---- layer 0 (separable) -------------------------------------------------------------------
     {
         const int H0 = net.Hp[0];
+        const bool pre = (p.base_pre != nullptr);  // theta goes through an embedding MLP (separate kernel)
         for (int j = 0; j < H0 / 32; ++j) {
             const int col = lane + 32 * j;
             const float tf = __ldg(p.time_feat + col);
             float acol[MMAX];
 #pragma unroll
-            for (int k = 0; k < MMAX; ++k) acol[k] = (k < m) ? __ldg(net.A + (size_t)k * H0 + col) : 0.f;
+            for (int k = 0; k < MMAX; ++k) acol[k] = (!pre && k < m) ? __ldg(net.A + (size_t)k * H0 + col) : 0.f;
             float v[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -221,16 +222,25 @@ __global__ void __launch_bounds__(NT, 2) score_simt_kernel(const ScoreParams p) 
                 const int kind = sKind[r];
                 const int pr = sPair[r];
                 const int si = sSamp[pr];
+                const size_t gi = (size_t)min(i0 + si, p.N - 1);
                 float z = tf + __ldg(p.obs_feat + (size_t)sObs[pr] * H0 + col);
+                if (pre) {
+                    z += __ldg(p.base_pre + gi * H0 + col);
+                } else {
 #pragma unroll
-                for (int k = 0; k < MMAX; ++k)
-                    if (k < m) z = fmaf(acol[k], sTheta[si * MMAX + k], z);
+                    for (int k = 0; k < MMAX; ++k)
+                        if (k < m) z = fmaf(acol[k], sTheta[si * MMAX + k], z);
+                }
                 float out = 0.f;
                 if (kind == 0) out = fmaxf(z, 0.f);
                 else if (kind > 0) {
                     float t = 0.f;
+                    if (pre) {
+                        t = __ldg(p.tan_pre + (gi * m + (kind - 1)) * H0 + col);
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < MMAX; ++k) t = (k == kind - 1) ? acol[k] : t;
+                        for (int k = 0; k < MMAX; ++k) t = (k == kind - 1) ? acol[k] : t;
+                    }
                     out = (z > 0.f) ? t : 0.f;
                 }
                 v[q] = out;
@@ -340,6 +350,73 @@ __global__ void __launch_bounds__(NT, 2) score_simt_kernel(const ScoreParams p) 
         }
         p.part[((size_t)(i0 + si) * p.C + chunk) * W + c] = acc;
     }
+}
+
+// ---- kernel 0: theta-embedding MLP (JR-NMM nets, nse.py:129) + projection on the layer-0 theta block -------------------
+// One CTA per posterior sample.  Rows: the primal e(theta_i) and, for JAC, the m tangents d e / d theta_k (forward
+// mode, masked by the primal's ReLU pattern).  Output: base_pre[i][col] = sum_f A[f][col] e_f,
+// tan_pre[i][k][col] = sum_f A[f][col] d e_f / d theta_k.
+__global__ void __launch_bounds__(256) theta_embed_kernel(const NetDev net, const float* __restrict__ theta, int N, int jac,
+                                                         float* __restrict__ base_pre, float* __restrict__ tan_pre) {
+    __shared__ float act[2][1 + MMAX][HMAX];  // ping-pong activations: row 0 primal, rows 1..m tangents
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const int m = net.m, rows = jac ? 1 + m : 1;
+    if (i >= N) return;
+    for (int e = tid; e < (1 + MMAX) * HMAX; e += blockDim.x) {
+        const int r = e / HMAX, c = e - r * HMAX;
+        float v = 0.f;
+        if (c < m) v = (r == 0) ? theta[(size_t)i * m + c] : ((c == r - 1) ? 1.f : 0.f);  // tangent seeds = unit vectors
+        act[0][r][c] = v;
+    }
+    __syncthreads();
+    int cur = 0;
+    for (int l = 0; l < net.emb_L; ++l) {
+        const int K = net.emb_dims[l], Nn = net.emb_dims[l + 1];
+        const bool relu = (l < net.emb_L - 1);
+        for (int o = tid; o < Nn; o += blockDim.x) {
+            float acc[1 + MMAX];
+#pragma unroll
+            for (int r = 0; r < 1 + MMAX; ++r) acc[r] = 0.f;
+            for (int k = 0; k < K; ++k) {
+                const float w = __ldg(net.emb_Wt[l] + (size_t)k * Nn + o);
+#pragma unroll
+                for (int r = 0; r < 1 + MMAX; ++r)
+                    if (r < rows) acc[r] = fmaf(w, act[cur][r][k], acc[r]);
+            }
+            const float z = acc[0] + __ldg(net.emb_bias[l] + o);
+            const bool on = !relu || z > 0.f;
+            act[cur ^ 1][0][o] = relu ? fmaxf(z, 0.f) : z;
+#pragma unroll
+            for (int r = 1; r < 1 + MMAX; ++r)
+                if (r < rows) act[cur ^ 1][r][o] = on ? acc[r] : 0.f;
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    const int F = net.theta_cols, H0 = net.Hp[0];
+    for (int col = tid; col < H0; col += blockDim.x) {
+        float acc[1 + MMAX];
+#pragma unroll
+        for (int r = 0; r < 1 + MMAX; ++r) acc[r] = 0.f;
+        for (int f = 0; f < F; ++f) {
+            const float a = __ldg(net.A + (size_t)f * H0 + col);
+#pragma unroll
+            for (int r = 0; r < 1 + MMAX; ++r)
+                if (r < rows) acc[r] = fmaf(a, act[cur][r][f], acc[r]);
+        }
+        base_pre[(size_t)i * H0 + col] = acc[0];
+        if (jac) {
+#pragma unroll
+            for (int r = 1; r < 1 + MMAX; ++r)
+                if (r < rows) tan_pre[((size_t)i * m + (r - 1)) * H0 + col] = acc[r];
+        }
+    }
+}
+
+cudaError_t launch_theta_embed(const NetDev& net, const float* theta, int N, int jac, float* base_pre, float* tan_pre,
+                               cudaStream_t stream) {
+    theta_embed_kernel<<<N, 256, 0, stream>>>(net, theta, N, jac, base_pre, tan_pre);
+    return cudaGetLastError();
 }
 
 size_t score_simt_smem_bytes() {

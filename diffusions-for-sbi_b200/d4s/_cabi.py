@@ -13,7 +13,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libd4s.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_LAYERS = 8
 MAX_THETA = 10
 MAX_WIDTH = 256
@@ -29,7 +29,7 @@ S_T, S_ALPHA, S_SIGMA, S_INV_SIGMA, S_A_OVER_S2, S_C_THETA, S_C_SCORE, S_BRIDGE_
 
 EXPORTS = [
     "d4s_abi_version", "d4s_last_error", "d4s_device_count", "d4s_net_create", "d4s_net_free",
-    "d4s_net_h1_padded", "d4s_workspace_floats", "d4s_mats_floats", "d4s_score_partials", "d4s_finalize",
+    "d4s_net_h1_padded", "d4s_workspace_floats", "d4s_partials_floats", "d4s_mats_floats", "d4s_score_partials", "d4s_finalize",
     "d4s_ddim_run", "d4s_graph_cache_clear", "d4s_set_option", "d4s_get_profile", "d4s_prior_score", "d4s_ddim_update", "d4s_batched_inverse", "d4s_philox_normal", "d4s_launch_count",
 ]
 
@@ -45,6 +45,10 @@ class NetDesc(C.Structure):
         ("theta_cols", C.c_int32),
         ("weight", C.c_void_p * MAX_LAYERS),
         ("bias", C.c_void_p * MAX_LAYERS),
+        ("emb_layers", C.c_int32),
+        ("emb_dims", C.c_int32 * (MAX_LAYERS + 1)),
+        ("emb_weight", C.c_void_p * MAX_LAYERS),
+        ("emb_bias", C.c_void_p * MAX_LAYERS),
     ]
 
 
@@ -108,6 +112,7 @@ def load():
             "d4s_net_free": (None, [vp]),
             "d4s_net_h1_padded": (C.c_int, [vp]),
             "d4s_workspace_floats": (i64, [vp, C.POINTER(Problem)]),
+            "d4s_partials_floats": (i64, [vp, C.POINTER(Problem)]),
             "d4s_mats_floats": (i32, [i32]),
             "d4s_score_partials": (C.c_int, [vp, C.POINTER(Problem), C.POINTER(Step), vp, vp, vp, vp]),
             "d4s_finalize": (C.c_int, [vp, C.POINTER(Problem), C.POINTER(Step), vp, vp, vp]),

@@ -99,7 +99,7 @@ class NetView:
 class PackedNet(NetView):
     """Device-resident packed copy of `nse.net` (d4s_net_create) + the host view."""
 
-    def __init__(self, linears, theta_cols: int, device: torch.device):
+    def __init__(self, linears, theta_cols: int, device: torch.device, emb_linears=()):
         super().__init__(linears)
         lib = abi.require_cuda()
         L = len(linears)
@@ -115,6 +115,14 @@ class PackedNet(NetView):
             desc.dims[l + 1] = lin.out_features
             desc.weight[l] = w.data_ptr()
             desc.bias[l] = b.data_ptr()
+        desc.emb_layers = len(emb_linears)
+        for l, lin in enumerate(emb_linears):
+            w = lin.weight.detach().to("cpu", torch.float32).contiguous()
+            b = lin.bias.detach().to("cpu", torch.float32).contiguous()
+            keep += [w, b]
+            desc.emb_dims[l], desc.emb_dims[l + 1] = lin.in_features, lin.out_features
+            desc.emb_weight[l] = w.data_ptr()
+            desc.emb_bias[l] = b.data_ptr()
         handle = C.c_void_p()
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device).cuda_stream
@@ -144,12 +152,14 @@ def _linears(mlp) -> list:
 
 def packed_net(nse, device: torch.device) -> PackedNet:
     lin = _linears(nse.net)
-    key = tuple((p.data_ptr(), p._version) for l in lin for p in (l.weight, l.bias)) + (str(device),)
+    emb = nse.embedding_nn_theta
+    emb_lin = [] if isinstance(emb, torch.nn.Identity) else _linears(emb)
+    key = tuple((p.data_ptr(), p._version) for l in lin + emb_lin for p in (l.weight, l.bias)) + (str(device),)
     hit = _net_cache.get(nse)
     if hit is not None and hit[0] == key:
         return hit[1]
     theta_cols = int(getattr(nse, "theta_emb_dim", nse.zeros.shape[0]))
-    pn = PackedNet(lin, theta_cols, device)
+    pn = PackedNet(lin, theta_cols, device, emb_lin)
     _net_cache[nse] = (key, pn)
     return pn
 

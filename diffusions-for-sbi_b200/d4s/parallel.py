@@ -89,7 +89,7 @@ def ddim_obs_sharded(nse, shape, x: torch.Tensor, steps: int = 1000, eta: float 
         mode = int(setup.step_modes[k]) if setup.step_modes is not None else setup.prob.cov_mode
         setup.prob.cov_mode = mode
         engine.score_partials(setup, theta, k)
-        n_floats = lib.d4s_workspace_floats(setup.pn.handle, C.byref(setup.prob))
+        n_floats = lib.d4s_partials_floats(setup.pn.handle, C.byref(setup.prob))
         dist.all_reduce(ws[:n_floats], group=group)  # NCCL sum of the [N, C, W] partial sums
         engine.finalize(setup, theta, k, noise_k=None if z is None else z[k], update=True, want_score=False)
     return theta

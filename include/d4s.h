@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D4S_ABI_VERSION 7
+#define D4S_ABI_VERSION 8
 
 #define D4S_OK 0
 #define D4S_ERR_ARG -1      /* bad argument / unsupported shape */
@@ -84,6 +84,13 @@ typedef struct {
     int32_t theta_cols;                  /* leading input columns fed by (embedded) theta */
     const float* weight[D4S_MAX_LAYERS]; /* HOST pointers, [dims[l+1], dims[l]] row-major (torch layout) */
     const float* bias[D4S_MAX_LAYERS];   /* HOST pointers, [dims[l+1]] */
+    /* optional embedding MLP of theta (nse.py:31,129 `embedding_nn_theta`, a Linear/ReLU stack like the main net):
+     * emb_layers == 0 means nn.Identity (then theta_cols == theta_dim); otherwise emb_dims[0] == theta_dim and
+     * emb_dims[emb_layers] == theta_cols.  Widths <= 256. */
+    int32_t emb_layers;
+    int32_t emb_dims[D4S_MAX_LAYERS + 1];
+    const float* emb_weight[D4S_MAX_LAYERS];
+    const float* emb_bias[D4S_MAX_LAYERS];
 } D4sNetDesc;
 
 /* Everything that is constant along one trajectory / one factorized_score call. */
@@ -131,6 +138,8 @@ D4S_API int d4s_net_h1_padded(const D4sNet* net);
 
 /* ---- sizes -------------------------------------------------------------------------------------- */
 D4S_API int64_t d4s_workspace_floats(const D4sNet* net, const D4sProblem* prob);
+/* floats of the leading partial-sum block [N, C, W] of the workspace (what observation sharding all-reduces) */
+D4S_API int64_t d4s_partials_floats(const D4sNet* net, const D4sProblem* prob);
 D4S_API int32_t d4s_mats_floats(int32_t theta_dim);
 
 /* ---- kernel 1+2: score network on the (sample x observation) grid, Tweedie precisions, partial sums.

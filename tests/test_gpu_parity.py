@@ -13,7 +13,7 @@ from oracle import d4s_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-CASES = [c for c in gio.names() if "jrnnm" not in c]  # theta-embedding nets: next scope row
+CASES = gio.names()
 REL_TOL = 1e-4
 TRAJ_TOL = 1e-3
 

@@ -11,7 +11,7 @@ from d4s import engine
 from d4s_helpers import nse_from_oracle
 from oracle import d4s_oracle as orc
 
-CASES = [c for c in gio.names() if "jrnnm" not in c]
+CASES = gio.names()
 
 
 def _spec(g):
@@ -24,8 +24,9 @@ def _spec(g):
 
 def emulate_scores(onet, nse, view, theta, x, tf_row, of, inv_sigma):
     """kernel 1: separable layer 0 + hidden layers + output layer on the (sample x obs) grid."""
-    A = view.w1[:, :onet.theta_dim].numpy()  # theta block
-    z = (theta @ A.T)[:, None, :] + of[None, :, :view.h1] + tf_row[None, None, :view.h1]
+    feat = theta if onet.emb_theta is None else onet.emb_theta(theta)  # kernel 0: theta-embedding MLP
+    A = view.w1[:, :feat.shape[-1]].numpy()  # theta block
+    z = (feat @ A.T)[:, None, :] + of[None, :, :view.h1] + tf_row[None, None, :view.h1]
     h = np.maximum(z, 0)
     ws, bs = onet.net.weights, onet.net.biases
     for l in range(1, len(ws) - 1):
