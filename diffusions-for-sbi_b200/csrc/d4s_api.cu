@@ -62,7 +62,13 @@ struct D4sNet {
 // Tiling of the (sample x observation) grid into TM-row tiles of SG samples x OC observations.
 struct Tiling {
     int rpp, OC, C, SG, P, W, tiles;
+    int Cws;  // chunks in the workspace layout [N][Cws][W]: 1 when the tcgen05 kernel reduces over chunks itself
+    bool tc;  // the tcgen05 kernel evaluates this problem (GAUSS, tall grid, >= 2 hidden layers, no theta embedding)
 };
+
+static bool tc_eligible(const D4sNet* net, const D4sProblem* pb) {
+    return g_opt_path != 1 && pb->cov_mode == D4S_COV_GAUSS && !pb->paired && net->dev.L >= 3 && net->dev.emb_L == 0;
+}
 
 static int make_tiling(const D4sNet* net, const D4sProblem* pb, Tiling* t) {
     const int m = net->dev.m;
@@ -91,6 +97,8 @@ static int make_tiling(const D4sNet* net, const D4sProblem* pb, Tiling* t) {
     const long long tiles = groups * t->C;
     if (tiles > 2147483647LL) return -1;
     t->tiles = (int)tiles;
+    t->tc = tc_eligible(net, pb);
+    t->Cws = t->tc ? 1 : t->C;
     return 0;
 }
 
@@ -227,6 +235,10 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
         return cuda_fail(e, "cudaMemcpy(net)");
     }
     net->blob_floats = h.size();
+    if (!g_err_flag) {  // allocated eagerly: cudaMalloc is not allowed later inside a stream capture
+        if (cudaMalloc(&g_err_flag, sizeof(int)) == cudaSuccess) cudaMemset(g_err_flag, 0, sizeof(int));
+        else g_err_flag = nullptr;
+    }
     NetDev& nd = net->dev;
     memset(&nd, 0, sizeof(nd));
     nd.L = L;
@@ -266,19 +278,83 @@ int64_t d4s_partials_floats(const D4sNet* net, const D4sProblem* pb) {
     if (!net || !pb) return -1;
     Tiling t;
     if (make_tiling(net, pb, &t) != 0) return -1;
-    return (int64_t)pb->n_samples * t.C * t.W;
+    return (int64_t)pb->n_samples * t.Cws * t.W;
 }
 
 // workspace = [partial sums N*C*W] [base_pre N*H1p] [tan_pre N*m*H1p]  (the last two only with a theta embedding net)
 int64_t d4s_workspace_floats(const D4sNet* net, const D4sProblem* pb) {
-    const int64_t part = d4s_partials_floats(net, pb);
-    if (part < 0) return -1;
+    if (!net || !pb) return -1;
+    Tiling t;
+    if (make_tiling(net, pb, &t) != 0) return -1;
+    const int64_t part = (int64_t)pb->n_samples * t.C * t.W;  // room for either kernel's layout
     int64_t extra = 0;
     if (net->dev.emb_L > 0) {
         extra = (int64_t)pb->n_samples * net->dev.Hp[0];
         if (pb->cov_mode == D4S_COV_JAC) extra += (int64_t)pb->n_samples * net->dev.m * net->dev.Hp[0];
     }
     return part + extra;
+}
+
+// Fills the parameter block of the fused tcgen05 kernel (tile geometry, tables, finalize constants).
+static int fill_traj_params(const D4sNet* net, const D4sProblem* pb, const float* sched, const float* tf, const float* mats,
+                            const float* noise, float* theta, TrajParams* out, int* n_ctas, cudaStream_t stream) {
+    const NetDev& nd = net->dev;
+    TrajParams& p = *out;
+    memset(&p, 0, sizeof(p));
+    p.net = nd;
+    p.N = pb->n_samples;
+    p.n = pb->n_obs;
+    int oc = pb->obs_chunk > 0 ? pb->obs_chunk : pb->n_obs;
+    if (oc > 128) oc = 128;
+    if (oc > pb->n_obs) oc = pb->n_obs;
+    const int c = (pb->n_obs + oc - 1) / oc;
+    oc = (pb->n_obs + c - 1) / c;
+    p.OC = oc;
+    p.C = (pb->n_obs + oc - 1) / oc;
+    p.SG = 128 / oc;
+    if (p.SG > 8) p.SG = 8;
+    if (p.SG < 1) p.SG = 1;
+    p.P = p.SG * p.OC;
+    p.swap_lbo_sbo = g_opt_swap;
+    p.obs_feat = pb->obs_feat;
+    p.obs_prec = pb->obs_prec;
+    p.sched = sched;
+    p.time_feat = tf;
+    p.mats = mats;
+    p.noise = noise;
+    p.theta = theta;
+    FinalizeParams& f = p.fin;
+    f.N = pb->n_samples;
+    f.C = 1;
+    f.W = 2 * nd.m;
+    f.m = nd.m;
+    f.jac = 0;
+    f.prior_kind = pb->prior_kind;
+    f.update = 1;
+    f.low = pb->prior_low;
+    f.high = pb->prior_high;
+    f.seed = pb->seed;
+    f.sample_offset = pb->sample_offset;
+    f.clip_lo = pb->clip_lo;
+    f.clip_hi = pb->clip_hi;
+    if (!g_err_flag) {
+        if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaMalloc(flag)");
+        cudaMemset(g_err_flag, 0, sizeof(int));
+    }
+    p.error_flag = g_err_flag;
+    if (g_opt_profile) {
+        if (!g_prof) {
+            if (cudaMalloc(&g_prof, 16 * sizeof(long long)) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaMalloc(prof)");
+        }
+        cudaMemsetAsync(g_prof, 0, 16 * sizeof(long long), stream);
+        p.prof = g_prof;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int groups = (p.N + p.SG - 1) / p.SG;
+    *n_ctas = groups < sms ? groups : sms;
+    return D4S_OK;
 }
 
 static int score_partials_impl(const D4sNet* net, const D4sProblem* pb, const D4sStep* st, const float* theta,
@@ -288,6 +364,21 @@ static int score_partials_impl(const D4sNet* net, const D4sProblem* pb, const D4
     if (d4s_workspace_floats(net, pb) > pb->workspace_floats) return fail(D4S_ERR_WORKSPACE, "workspace too small");
     if (pb->cov_mode == D4S_COV_GAUSS && !pb->obs_prec && !pb->paired && pb->n_obs_total > 1 && false)
         return fail(D4S_ERR_ARG, "GAUSS needs obs_prec");
+    if (t.tc && !scores_out && !prec_out) {
+        // tcgen05 kernel in export mode: one step, sums over all observation chunks written as [N][1][2m]
+        TrajParams tp;
+        int ctas = 0;
+        int rc = fill_traj_params(net, pb, st->sched, st->time_feat, st->mats, nullptr, const_cast<float*>(theta), &tp, &ctas,
+                                  stream);
+        if (rc) return rc;
+        tp.step_begin = 0;
+        tp.step_end = 1;
+        tp.part_out = pb->workspace;
+        cudaError_t e = launch_traj_tc(tp, ctas, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "tcgen05 kernel launch (export mode)");
+        ++g_launches;
+        return D4S_OK;
+    }
     ScoreParams p;
     memset(&p, 0, sizeof(p));
     p.net = net->dev;
@@ -305,7 +396,7 @@ static int score_partials_impl(const D4sNet* net, const D4sProblem* pb, const D4
     p.time_feat = st->time_feat;
     p.obs_prec = pb->obs_prec;
     p.sched = st->sched;
-    p.part = pb->workspace;
+    p.part = t.tc ? nullptr : pb->workspace;  // a materialising call on a tcgen05-eligible problem leaves no partial sums
     p.scores_out = scores_out;
     p.prec_out = prec_out;
     if (net->dev.emb_L > 0) {  // kernel 0: embedded theta -> layer-0 sample part (+ JAC tangent seeds)
@@ -330,7 +421,7 @@ static int finalize_impl(const D4sNet* net, const D4sProblem* pb, const D4sStep*
     FinalizeParams p;
     memset(&p, 0, sizeof(p));
     p.N = pb->n_samples;
-    p.C = t.C;
+    p.C = t.Cws;
     p.W = t.W;
     p.m = net->dev.m;
     p.jac = pb->cov_mode == D4S_COV_JAC;
@@ -421,8 +512,7 @@ static int enqueue_steps(const D4sNet* net, const D4sProblem* pb0, int steps, co
 static int try_traj_tc(const D4sNet* net, const D4sProblem* pb, int steps, const float* sched, const float* tf,
                        const float* mats, const float* noise, float* theta, const int32_t* step_mode,
                        cudaStream_t stream) {
-    const NetDev& nd = net->dev;
-    bool eligible = g_opt_path != 1 && pb->cov_mode == D4S_COV_GAUSS && !pb->paired && nd.L >= 3 && nd.emb_L == 0;
+    bool eligible = tc_eligible(net, pb);
     if (step_mode)
         for (int k = 0; k < steps && eligible; ++k) eligible = (step_mode[k] == D4S_COV_GAUSS);
     if (!eligible) {
@@ -430,60 +520,9 @@ static int try_traj_tc(const D4sNet* net, const D4sProblem* pb, int steps, const
         return 1;
     }
     TrajParams p;
-    memset(&p, 0, sizeof(p));
-    p.net = nd;
-    p.N = pb->n_samples;
-    p.n = pb->n_obs;
-    int oc = pb->obs_chunk > 0 ? pb->obs_chunk : pb->n_obs;
-    if (oc > 128) oc = 128;
-    if (oc > pb->n_obs) oc = pb->n_obs;
-    const int c = (pb->n_obs + oc - 1) / oc;
-    oc = (pb->n_obs + c - 1) / c;
-    p.OC = oc;
-    p.C = (pb->n_obs + oc - 1) / oc;
-    p.SG = 128 / oc;
-    if (p.SG > 8) p.SG = 8;
-    if (p.SG < 1) p.SG = 1;
-    p.P = p.SG * p.OC;
-    p.swap_lbo_sbo = g_opt_swap;
-    p.obs_feat = pb->obs_feat;
-    p.obs_prec = pb->obs_prec;
-    p.sched = sched;
-    p.time_feat = tf;
-    p.mats = mats;
-    p.noise = noise;
-    p.theta = theta;
-    FinalizeParams& f = p.fin;
-    f.N = pb->n_samples;
-    f.C = 1;
-    f.W = 2 * nd.m;
-    f.m = nd.m;
-    f.jac = 0;
-    f.prior_kind = pb->prior_kind;
-    f.update = 1;
-    f.low = pb->prior_low;
-    f.high = pb->prior_high;
-    f.seed = pb->seed;
-    f.sample_offset = pb->sample_offset;
-    f.clip_lo = pb->clip_lo;
-    f.clip_hi = pb->clip_hi;
-    if (!g_err_flag) {
-        if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaMalloc(flag)");
-        cudaMemset(g_err_flag, 0, sizeof(int));
-    }
-    p.error_flag = g_err_flag;
-    if (g_opt_profile) {
-        if (!g_prof) {
-            if (cudaMalloc(&g_prof, 16 * sizeof(long long)) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaMalloc(prof)");
-        }
-        cudaMemsetAsync(g_prof, 0, 16 * sizeof(long long), stream);
-        p.prof = g_prof;
-    }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int groups = (p.N + p.SG - 1) / p.SG;
-    const int ctas = groups < sms ? groups : sms;
+    int ctas = 0;
+    int rc = fill_traj_params(net, pb, sched, tf, mats, noise, theta, &p, &ctas, stream);
+    if (rc) return rc;
     const int per = g_opt_tc_steps > 0 ? g_opt_tc_steps : steps;
     for (int s0 = 0; s0 < steps; s0 += per) {
         p.step_begin = s0;

@@ -90,6 +90,7 @@ struct TrajParams {
     const float* noise;      // [steps][N][m] or NULL
     FinalizeParams fin;      // constant part of the per-step finalize parameters
     float* theta;            // [N][m] in/out
+    float* part_out;         // export mode (per-step API / observation sharding): [N][2m] sums S1 | S2, no update
     int* error_flag;
     long long* prof;         // optional [16] phase cycle counters (CTA 0)
 };

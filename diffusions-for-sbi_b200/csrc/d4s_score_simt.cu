@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(NT, 2) score_simt_kernel(const ScoreParams p) 
             else v = sQS[r * W + c];
             acc += v;
         }
-        p.part[((size_t)(i0 + si) * p.C + chunk) * W + c] = acc;
+        if (p.part) p.part[((size_t)(i0 + si) * p.C + chunk) * W + c] = acc;
     }
 }
 

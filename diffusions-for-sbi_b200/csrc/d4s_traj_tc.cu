@@ -348,6 +348,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
             const int nsamp = min(p.SG, p.N - i0);
             for (int step = p.step_begin; step < p.step_end; ++step) {
                 bar_sync(2, NB23);  // theta of this step is final; last step's consumers are done with our buffers
+                if (p.part_out) {  // export mode: the caller reduces over ranks and finalizes; nothing to prepare
+                    bar_arrive(3, NB23);
+                    continue;
+                }
                 const float* sched = p.sched + (size_t)step * D4S_SCHED_STRIDE;
                 if (lane < D4S_SCHED_STRIDE) sSched[lane] = __ldg(sched + lane);
                 const float* mrow = p.mats + (size_t)step * mats_floats;
@@ -626,7 +630,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                 // ---- finalize: prior, Lambda solve, DDIM update (theta stays in smem) ---------------------------------------------
                 bar_sync(3, NB23);  // schedule/matrix rows, prior terms and noise of this step are in smem
                 PROF_MARK(2);       // (time spent waiting for the helper warp, normally zero)
-                if (warp < nsamp && lane < m) {  // warp -> sample, lane -> theta component; fp32, everything in smem
+                if (p.part_out) {
+                    for (int e = tid; e < nsamp * 2 * m; e += TC_CT) p.part_out[(size_t)i0 * 2 * m + e] = sAcc[e];
+                } else if (warp < nsamp && lane < m) {  // warp -> sample, lane -> theta component; fp32, everything in smem
                     const int si = warp, r = lane;
                     const int combine = (int)sSched[D4S_S_COMBINE];
                     const float* acc = sAcc + si * 2 * m;
@@ -651,9 +657,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                 compute_bar();
                 PROF_MARK(7);  // finalize
             }  // steps
-            for (int e = tid; e < nsamp * m; e += TC_CT) {
-                const int si = e / m, k = e - si * m;
-                p.theta[(size_t)(i0 + si) * m + k] = sTheta[si * MMAX + k];
+            if (!p.part_out) {
+                for (int e = tid; e < nsamp * m; e += TC_CT) {
+                    const int si = e / m, k = e - si * m;
+                    p.theta[(size_t)(i0 + si) * m + k] = sTheta[si * MMAX + k];
+                }
             }
             compute_bar();
         }  // groups

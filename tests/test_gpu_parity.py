@@ -67,9 +67,18 @@ def test_jac_precisions(name, dev):
         assert orc.rel_l2(sc.cpu().numpy(), g["f64.scores"][k]) < 2e-5
 
 
+@pytest.fixture(params=[0, 1], ids=["auto", "simt"])
+def kernel_path(request):
+    """0 = automatic (tcgen05 bf16x3 kernel where eligible), 1 = fp32 SIMT kernels only."""
+    from d4s import _cabi as abi
+    abi.set_option("path", request.param)
+    yield request.param
+    abi.set_option("path", 0)
+
+
 @pytest.mark.parametrize("name", CASES)
 @pytest.mark.parametrize("mode", ["GAUSS", "JAC"])
-def test_factorized_score(name, mode, dev):
+def test_factorized_score(name, mode, dev, kernel_path):
     g, onet, nse, prior, fn, ptype, kw = _setup(name, dev)
     if f"f64.{mode}.factorized_score" not in g:
         pytest.skip("PF+JAC has no reference behaviour (SURVEY.md 8(a) a11)")
@@ -161,7 +170,7 @@ def _d4s_prior(oprior, nse, dev):
 
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: f"m{s[0]}_n{s[3]}_N{s[4]}_{s[5]}")
 @pytest.mark.parametrize("mode", ["GAUSS", "JAC"])
-def test_factorized_score_vs_oracle(shape, mode, dev):
+def test_factorized_score_vs_oracle(shape, mode, dev, kernel_path):
     from d4s_helpers import nse_from_oracle
     m, d, hidden, n, N, pkind = shape
     if mode == "JAC" and N * n > 4000:
