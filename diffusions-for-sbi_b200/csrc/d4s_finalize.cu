@@ -83,9 +83,16 @@ __global__ void ddim_update_kernel(float* __restrict__ theta, const float* __res
                                    int step, long long sample_offset, float clip_lo, float clip_hi) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const double c_theta = (double)sched[D4S_S_C_THETA], c_score = (double)sched[D4S_S_C_SCORE];
+    const double c_theta = (double)sched[D4S_S_C_THETA];
+    double c_score = (double)sched[D4S_S_C_SCORE];
+    const double tame = (double)sched[D4S_S_TAME];
+    if (tame > 0.0) {  // tamed ULA (nse.py:336)
+        double nrm = 0.0;
+        for (int k = 0; k < m; ++k) nrm = fma((double)score[i * m + k], (double)score[i * m + k], nrm);
+        c_score = tame / (1.0 + tame * sqrt(nrm));
+    }
     const float bstd = sched[D4S_S_BRIDGE_STD];
-    const bool clip = clip_lo <= clip_hi;
+    const bool clip = clip_lo <= clip_hi && sched[D4S_S_CLIP] != 0.f;
     for (int qd = 0; qd < (m + 3) / 4; ++qd) {
         float z[4] = {0.f, 0.f, 0.f, 0.f};
         if (!noise && bstd != 0.f) philox_normal4(seed, step, sample_offset + i, qd, z);

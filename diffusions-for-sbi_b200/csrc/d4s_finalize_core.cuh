@@ -162,7 +162,7 @@ __device__ __forceinline__ void finalize_sample(const FinalizeParams& p, const f
     double out[M];
     if (combine == D4S_COMBINE_SUM) {
 #pragma unroll
-        for (int k = 0; k < M; ++k) out[k] = g[k] + (p.jac ? 0.0 : S1[k]);
+        for (int k = 0; k < M; ++k) out[k] = g[k] + (p.jac ? 0.0 : (double)p.sched[D4S_S_S1_WEIGHT] * S1[k]);
     } else {
         double w[M];
 #pragma unroll
@@ -188,7 +188,15 @@ __device__ __forceinline__ void finalize_sample(const FinalizeParams& p, const f
 
     // ---- DDIM update: theta' = c_theta theta + c_score score + bridge_std z -----------------------------
     if (p.update) {
-        const double c_theta = (double)p.sched[D4S_S_C_THETA], c_score = (double)p.sched[D4S_S_C_SCORE];
+        const double c_theta = (double)p.sched[D4S_S_C_THETA];
+        double c_score = (double)p.sched[D4S_S_C_SCORE];
+        const double tame = (double)p.sched[D4S_S_TAME];
+        if (tame > 0.0) {  // tamed ULA step (nse.py:336): eps / (1 + eps ||g||)
+            double nrm = 0.0;
+#pragma unroll
+            for (int k = 0; k < M; ++k) nrm = fma(out[k], out[k], nrm);
+            c_score = tame / (1.0 + tame * sqrt(nrm));
+        }
         const float bstd = p.sched[D4S_S_BRIDGE_STD];
         float z[(M + 3) / 4 * 4];
         if (noise) {
@@ -205,7 +213,7 @@ __device__ __forceinline__ void finalize_sample(const FinalizeParams& p, const f
 #pragma unroll
             for (int k = 0; k < M; ++k) z[k] = 0.f;
         }
-        const bool clip = p.clip_lo <= p.clip_hi;
+        const bool clip = (p.clip_lo <= p.clip_hi) && p.sched[D4S_S_CLIP] != 0.f;
 #pragma unroll
         for (int k = 0; k < M; ++k) {
             float v = (float)(c_theta * (double)th[k] + c_score * out[k] + (double)bstd * (double)z[k]);

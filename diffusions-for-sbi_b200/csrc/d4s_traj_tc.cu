@@ -632,27 +632,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                 PROF_MARK(2);       // (time spent waiting for the helper warp, normally zero)
                 if (p.part_out) {
                     for (int e = tid; e < nsamp * 2 * m; e += TC_CT) p.part_out[(size_t)i0 * 2 * m + e] = sAcc[e];
-                } else if (warp < nsamp && lane < m) {  // warp -> sample, lane -> theta component; fp32, everything in smem
+                } else if (warp < nsamp) {  // warp -> sample, lane -> theta component; fp32, everything in smem
                     const int si = warp, r = lane;
+                    const bool act = lane < m;
                     const int combine = (int)sSched[D4S_S_COMBINE];
                     const float* acc = sAcc + si * 2 * m;
-                    float out;
-                    if (combine == D4S_COMBINE_SUM) {
-                        out = sG[si * MMAX + r] + acc[r];  // (1-n) s0 + sum_j s_ij   (nse.py:642)
-                    } else {
-                        const float aos2 = sSched[D4S_S_A_OVER_S2];
-                        const float* Minv = (combine == D4S_COMBINE_SHARED) ? sMats : sMinv + si * MMAX * MMAX;
-                        float o = 0.f;
-                        for (int c = 0; c < m; ++c) {
-                            const float w = fmaf(aos2, acc[c], acc[m + c]) + sG[si * MMAX + c];  // nse.py:631-636 / 647-652
-                            o = fmaf(Minv[r * m + c], w, o);
+                    float out = 0.f;
+                    if (act) {
+                        if (combine == D4S_COMBINE_SUM) {
+                            out = sG[si * MMAX + r] + sSched[D4S_S_S1_WEIGHT] * acc[r];  // (1-n) s0 + w sum_j s_ij (nse.py:642)
+                        } else {
+                            const float aos2 = sSched[D4S_S_A_OVER_S2];
+                            const float* Minv = (combine == D4S_COMBINE_SHARED) ? sMats : sMinv + si * MMAX * MMAX;
+                            for (int c = 0; c < m; ++c) {
+                                const float w = fmaf(aos2, acc[c], acc[m + c]) + sG[si * MMAX + c];  // nse.py:631-636 / 647-652
+                                out = fmaf(Minv[r * m + c], w, out);  // Lambda^-1 w   (nse.py:638 / 654)
+                            }
                         }
-                        out = o;  // Lambda^-1 w   (nse.py:638 / 654)
                     }
-                    float v = sSched[D4S_S_C_THETA] * sTheta[si * MMAX + r] + sSched[D4S_S_C_SCORE] * out +
-                              sSched[D4S_S_BRIDGE_STD] * sNoise[si * MMAX + r];  // nse.py:289-298
-                    if (p.fin.clip_lo <= p.fin.clip_hi) v = fminf(fmaxf(v, p.fin.clip_lo), p.fin.clip_hi);
-                    sTheta[si * MMAX + r] = v;
+                    float c_score = sSched[D4S_S_C_SCORE];
+                    const float tame = sSched[D4S_S_TAME];
+                    if (tame > 0.f) {  // tamed ULA (nse.py:336); the whole warp takes part, lanes >= m contribute 0
+                        float nrm = out * out;
+#pragma unroll
+                        for (int sh = 16; sh > 0; sh >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, sh);
+                        c_score = tame / (1.f + tame * sqrtf(nrm));
+                    }
+                    if (act) {
+                        float v = sSched[D4S_S_C_THETA] * sTheta[si * MMAX + r] + c_score * out +
+                                  sSched[D4S_S_BRIDGE_STD] * sNoise[si * MMAX + r];  // nse.py:289-298
+                        if (p.fin.clip_lo <= p.fin.clip_hi && sSched[D4S_S_CLIP] != 0.f)
+                            v = fminf(fmaxf(v, p.fin.clip_lo), p.fin.clip_hi);
+                        sTheta[si * MMAX + r] = v;
+                    }
                 }
                 compute_bar();
                 PROF_MARK(7);  // finalize

@@ -13,7 +13,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libd4s.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_LAYERS = 8
 MAX_THETA = 10
 MAX_WIDTH = 256
@@ -25,7 +25,7 @@ COMBINE_SUM, COMBINE_SHARED, COMBINE_PER_SAMPLE = 0, 1, 2
 
 # schedule table columns (must match D4S_S_* in include/d4s.h)
 S_T, S_ALPHA, S_SIGMA, S_INV_SIGMA, S_A_OVER_S2, S_C_THETA, S_C_SCORE, S_BRIDGE_STD, S_SQRT_ALPHA, S_COMBINE, \
-    S_ONE_MINUS_N = range(11)
+    S_ONE_MINUS_N, S_S1_WEIGHT, S_TAME, S_CLIP = range(14)
 
 EXPORTS = [
     "d4s_abi_version", "d4s_last_error", "d4s_device_count", "d4s_net_create", "d4s_net_free",

@@ -179,8 +179,9 @@ def _scalar64(fn, t64: torch.Tensor) -> torch.Tensor:
 
 
 def schedule_rows(nse, t: torch.Tensor, t_prev: Optional[torch.Tensor], eta: float, n_total: int,
-                  combine: Sequence[int]) -> torch.Tensor:
-    """[len(t), 16] fp64 schedule rows.  t_prev = t - dt (None => no DDIM update coefficients)."""
+                  combine: Sequence[int], coef: Optional[dict] = None) -> torch.Tensor:
+    """[len(t), 16] fp64 schedule rows.  t_prev = t - dt gives the DDIM update coefficients; `coef` overrides update
+    columns by name (c_theta, c_score, bstd, s1w, tame, clip) for the Langevin-family samplers."""
     t64 = t.to(torch.float64)
     a = _scalar64(nse.alpha, t64)
     sig = _scalar64(nse.sigma, t64)
@@ -193,6 +194,8 @@ def schedule_rows(nse, t: torch.Tensor, t_prev: Optional[torch.Tensor], eta: flo
     rows[:, abi.S_SQRT_ALPHA] = a.sqrt()
     rows[:, abi.S_COMBINE] = torch.as_tensor(list(combine), dtype=torch.float64)
     rows[:, abi.S_ONE_MINUS_N] = float(1 - n_total)
+    rows[:, abi.S_S1_WEIGHT] = 1.0
+    rows[:, abi.S_CLIP] = 1.0
     if t_prev is not None:
         a1 = _scalar64(nse.alpha, t_prev.to(torch.float64))
         bs = eta * (((1 - a1) / (1 - a)) * (1 - a / a1)).clamp_min(0).sqrt()  # nse.py:285-287
@@ -202,6 +205,11 @@ def schedule_rows(nse, t: torch.Tensor, t_prev: Optional[torch.Tensor], eta: flo
         rows[:, abi.S_C_THETA] = c_theta
         rows[:, abi.S_C_SCORE] = c_score
         rows[:, abi.S_BRIDGE_STD] = bs
+    if coef:
+        cols = dict(c_theta=abi.S_C_THETA, c_score=abi.S_C_SCORE, bstd=abi.S_BRIDGE_STD, s1w=abi.S_S1_WEIGHT,
+                    tame=abi.S_TAME, clip=abi.S_CLIP)
+        for name, val in coef.items():
+            rows[:, cols[name]] = torch.as_tensor(val, dtype=torch.float64).reshape(-1)
     return rows
 
 
@@ -342,7 +350,8 @@ class TallSetup:
 def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: Optional[torch.Tensor], eta: float,
                 prior: PriorSpec, cov_mode: str, dist_cov_est: Optional[torch.Tensor], paired: bool = False,
                 n_sizes: Optional[torch.Tensor] = None, clip=(None, None), seed: int = 0, sample_offset: int = 0,
-                weighted: bool = True, obs_slice: Optional[slice] = None, obs_chunk: int = 0) -> TallSetup:
+                weighted: bool = True, obs_slice: Optional[slice] = None, obs_chunk: int = 0,
+                coef: Optional[dict] = None) -> TallSetup:
     """`obs_slice` restricts the kernels to a shard of the observations (observation sharding over ranks):
     (1-n) and Lambda still use the total n, the partial sums are all-reduced by the caller."""
     lib = abi.require_cuda()
@@ -367,7 +376,8 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
     t = t.detach().to("cpu").reshape(-1)
     sa = _scalar64(nse.alpha, t.to(torch.float64)).sqrt()
     comb = [combine_mode(prior, cov_jac, n_total, float(s), weighted) for s in sa]
-    rows = schedule_rows(nse, t, None if t_prev is None else t_prev.detach().to("cpu").reshape(-1), eta, n_total, comb)
+    rows = schedule_rows(nse, t, None if t_prev is None else t_prev.detach().to("cpu").reshape(-1), eta, n_total, comb,
+                         coef)
     mats = mats_table(rows, prior, cov_jac, n_total, sum_q, m)
     tf = time_feat_table(nse, pn, t)
     of = obs_feat_table(nse, pn, x2, n_sizes)

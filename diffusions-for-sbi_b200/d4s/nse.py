@@ -216,6 +216,168 @@ class NSE(nn.Module):
         engine.score_partials(setup, th, 0)
         return engine.finalize(setup, th, 0)
 
+    # ---- Langevin / Geffner family (nse.py:301-542, 658-705): same kernels, SUM combination, other update rules ----
+    def _geffner_prior(self, prior_score_fun, m):
+        """F-NPSE uses the analytic diffused prior score only (nse.py:540): read its parameters off the d4s object."""
+        kind = getattr(prior_score_fun, "kind", None)
+        if kind not in ("uniform", "gaussian"):
+            raise abi.D4sError("the Langevin/Geffner samplers need a d4s.vp_diffused_priors score object "
+                               "(get_vpdiff_uniform_score / get_vpdiff_gaussian_score) as prior score function")
+        return prior_score_fun._spec()
+
+    def _run_rows(self, shape, x, t_rows, coef, prior, weighted, opts, clip, noise, seed, sample_offset):
+        """Runs a trajectory whose steps are arbitrary schedule rows (time + update coefficients per row)."""
+        N, m = int(shape[0]), self.zeros.shape[0]
+        if seed is None:
+            seed = self._draw_seed()
+        setup = engine.build_setup(self, x, N, t_rows, None, 0.0, prior, opts["cov_mode"] if weighted else "GAUSS",
+                                   opts["dist_cov_est"] if weighted else None, n_sizes=opts["n_sizes"], clip=clip,
+                                   seed=seed, sample_offset=sample_offset, weighted=weighted, coef=coef)
+        if noise is not None:
+            z0, z = noise
+            theta = z0.to(x.device, torch.float32).contiguous().clone()
+        else:
+            z = None
+            theta = engine.philox_normal(N, m, seed, -1, sample_offset, x.device)
+        return engine.run_trajectory(setup, theta, z, _use_graph_default())
+
+    def _gammas(self, grid: Tensor):
+        """gamma_t = alpha(t) / alpha(t - time[-2]) for all but the last step, alpha(t) for the last (nse.py:456-459)."""
+        t64 = grid[:-1].to(torch.float64)
+        a = engine._scalar64(self.alpha, t64)
+        a_prev = engine._scalar64(self.alpha, t64 - float(grid[-2]))
+        gamma = a / a_prev
+        gamma[-1] = a[-1]
+        return gamma
+
+    def factorized_score_geffner(self, theta: Tensor, x: Tensor, t: Tensor, prior_score_fun=None,
+                                 clf_free_guidance: bool = False, **kwargs) -> Tensor:
+        """F-NPSE score (1 - n) prior_score + sum_j score_j (nse.py:479-542), one fused call."""
+        self._require_cuda(theta, x)
+        if clf_free_guidance:
+            raise NotImplementedError("clf_free_guidance=True: next-scope row (SURVEY.md section 8(f) rank 3)")
+        m = self.zeros.shape[0]
+        spec = self._geffner_prior(prior_score_fun, m)
+        tt = torch.as_tensor(t).detach().to("cpu").reshape(1)
+        x2 = x if x.ndim > 1 else x[None]
+        setup = engine.build_setup(self, x2, theta.shape[0], tt, None, 0.0, spec, "GAUSS", None,
+                                   n_sizes=kwargs.get("n"), weighted=False)
+        th = theta.detach().to(torch.float32).contiguous()
+        engine.score_partials(setup, th, 0)
+        return engine.finalize(setup, th, 0)
+
+    def annealed_langevin_geffner(self, shape: Size, x: Tensor, prior_score_fn, prior_type: Optional[str] = None,
+                                  steps: int = 400, lsteps: int = 5, tau: float = 0.5,
+                                  theta_clipping_range=(None, None), verbose: bool = False, **kwargs) -> Tensor:
+        """Annealed Langevin dynamics with the F-NPSE score (nse.py:418-475): `steps` noise levels x `lsteps`
+        updates theta += delta * score + sqrt(2 delta) z, clipped once per level.  One fused launch."""
+        self._require_cuda(x)
+        opts, noise, seed, off = self._split_kwargs(kwargs)
+        m = self.zeros.shape[0]
+        grid = engine.time_grid(steps)
+        gamma = self._gammas(grid)
+        delta = tau * (1 - gamma) / gamma.sqrt()  # nse.py:461
+        single = x.ndim == 1 or x.shape[0] == 1  # nse.py:465
+        prior = engine.PriorSpec(abi.PRIOR_NONE) if single else self._geffner_prior(prior_score_fn, m)
+        rep = lambda v: v.repeat_interleave(lsteps)  # noqa: E731
+        clip = torch.zeros(steps, lsteps, dtype=torch.float64)
+        clip[:, -1] = 1.0
+        coef = dict(c_theta=torch.ones(steps * lsteps, dtype=torch.float64), c_score=rep(delta),
+                    bstd=rep((2 * delta).sqrt()), clip=clip.reshape(-1))
+        return self._run_rows(shape, x, rep(grid[:-1]), coef, prior, False, opts, theta_clipping_range, noise, seed, off)
+
+    def deterministic_gaussian_geffner(self, shape: Size, x: Tensor, prior_score_fn, steps: int = 1000,
+                                       verbose: bool = False, theta_clipping_range=(None, None), **kwargs) -> Tensor:
+        """Gaussian transition sampler of Geffner et al. (Algorithm 2) with the continuous schedule (nse.py:658-705):
+        theta' = c_theta theta + var_t [S1 / sqrt(gamma) + (1 - n) prior_score] + sqrt(var_t) z."""
+        self._require_cuda(x)
+        opts, noise, seed, off = self._split_kwargs(kwargs)
+        m = self.zeros.shape[0]
+        n = x.shape[0] if x.ndim > 1 else 1
+        grid = engine.time_grid(steps)
+        g = self._gammas(grid)
+        den = n - g * (n - 1)
+        var = (1 - g) / den  # nse.py:692
+        coef = dict(c_theta=(n / g.sqrt() - (n - 1) * g.sqrt()) / den, c_score=var, s1w=1 / g.sqrt(), bstd=var.sqrt())
+        prior = self._geffner_prior(prior_score_fn, m)
+        x2 = x if x.ndim > 1 else x[None]
+        return self._run_rows(shape, x2, grid[:-1], coef, prior, False, opts, theta_clipping_range, noise, seed, off)
+
+    def predictor_corrector(self, shape: Size, x: Tensor, steps: int = 1000, verbose: bool = False,
+                            predictor_type: str = "ddim", corrector_type: str = "langevin",
+                            theta_clipping_range=(None, None), **kwargs) -> Tensor:
+        """Predictor-corrector sampler (nse.py:340-416): DDIM or identity predictor at t, `lsteps` tamed-ULA corrector
+        steps (nse.py:301-338) or identity at t - dt.  kwargs as in the reference: `prior_score_fun` (F-NPSE score,
+        corrector 'langevin') or the `factorized_score` kwargs (corrector 'id'), `eta`, `lsteps`, `r`, `n`."""
+        self._require_cuda(x)
+        if predictor_type not in ("ddim", "id") or corrector_type not in ("langevin", "id"):
+            raise NotImplementedError("predictor_type in {'ddim','id'}, corrector_type in {'langevin','id'}")
+        kw = dict(kwargs)
+        eta = float(kw.pop("eta", 1.0))
+        lsteps, r = int(kw.pop("lsteps", 0)), float(kw.pop("r", 0.0))
+        prior_score_fun = kw.pop("prior_score_fun", None)
+        opts, noise, seed, off = self._split_kwargs(kw)
+        N, m = int(shape[0]), self.zeros.shape[0]
+        single = self._is_single_context(shape, x)
+        if corrector_type == "langevin" and lsteps < 1:
+            raise TypeError("corrector_type='langevin' needs lsteps and r")
+        grid = engine.time_grid(steps)
+        t64 = grid[:-1].to(torch.float64)
+        dt = 1.0 / steps
+        per = (1 if predictor_type == "ddim" else 0) + (lsteps if corrector_type == "langevin" else 0)
+        if per == 0:
+            raise NotImplementedError("identity predictor with identity corrector does nothing")
+        T = torch.zeros(steps, per, dtype=torch.float64)
+        cols = {k: torch.zeros(steps, per, dtype=torch.float64) for k in ("c_theta", "c_score", "bstd", "tame", "clip")}
+        j = 0
+        if predictor_type == "ddim":
+            rows = engine.schedule_rows(self, grid[:-1], t64 - dt, eta, 1, [0] * steps)
+            T[:, 0] = t64
+            cols["c_theta"][:, 0] = rows[:, abi.S_C_THETA]
+            cols["c_score"][:, 0] = rows[:, abi.S_C_SCORE]
+            cols["bstd"][:, 0] = rows[:, abi.S_BRIDGE_STD]
+            j = 1
+        if corrector_type == "langevin":
+            tc = t64 - dt  # nse.py:413: corrector at t - dt
+            eps = r * engine._scalar64(self.alpha, tc).sqrt() * engine._scalar64(self.sigma, tc) ** 2  # nse.py:335
+            T[:, j:] = tc[:, None]
+            cols["c_theta"][:, j:] = 1.0
+            cols["tame"][:, j:] = eps[:, None]
+            cols["bstd"][:, j:] = (2 * eps).sqrt()[:, None]
+        cols["clip"][:, -1] = 1.0
+        coef = {k: v.reshape(-1) for k, v in cols.items()}
+        if single:
+            prior, weighted = engine.PriorSpec(abi.PRIOR_NONE), False
+            paired = x.ndim > 1 and x.shape[0] == N and N > 1
+            if paired:
+                raise NotImplementedError("predictor_corrector with paired contexts")
+        elif corrector_type == "langevin":
+            prior, weighted = self._geffner_prior(prior_score_fun, m), False  # nse.py:381
+        else:
+            prior, weighted = engine.prior_spec(opts["prior_type"], opts["prior"], opts["prior_score_fn"], m), True
+        return self._run_rows(shape, x if x.ndim > 1 else x[None], T.reshape(-1), coef, prior, weighted, opts,
+                              theta_clipping_range, noise, seed, off)
+
+    def langevin_corrector(self, theta: Tensor, x: Tensor, t: Tensor, score_fun, lsteps: int, r: float, **kwargs) -> Tensor:
+        """`lsteps` tamed-ULA steps with a caller-supplied score function (nse.py:301-338); update in kernel 4."""
+        self._require_cuda(theta)
+        import ctypes as C
+        lib = abi.require_cuda()
+        tt = torch.as_tensor(t).detach().to("cpu", torch.float64).reshape(1)
+        eps = float(r * engine._scalar64(self.alpha, tt).sqrt() * engine._scalar64(self.sigma, tt) ** 2)
+        rows = engine.schedule_rows(self, tt, None, 0.0, 1, [abi.COMBINE_SUM],
+                                    dict(c_theta=[1.0], tame=[eps], bstd=[math.sqrt(2 * eps)], clip=[0.0]))
+        sched = rows.to(torch.float32).to(theta.device)
+        out = theta.detach().to(torch.float32).contiguous().clone()
+        seed = self._draw_seed()
+        for k in range(lsteps):
+            g = score_fun(out, x, t).detach().to(torch.float32).contiguous()
+            with torch.cuda.device(theta.device):
+                abi.check(lib.d4s_ddim_update(engine._ptr(out), engine._ptr(g), out.shape[0], out.shape[1],
+                                              engine._ptr(sched), None, C.c_uint64(seed), k, 0, 1.0, -1.0,
+                                              engine._stream(theta.device)))
+        return out
+
     # ---- stand-alone prior score (used by d4s.vp_diffused_priors objects) -------------------------------------
     def _prior_score_native(self, theta: Tensor, t: Tensor, spec: "engine.PriorSpec", want_jac: bool = False):
         self._require_cuda(theta)

@@ -88,3 +88,19 @@ class PF_NSE(NSE):
             ns = kwargs.pop("n")
         return super().ddim(shape=shape, x=xs, steps=steps, eta=eta, verbose=verbose,
                             theta_clipping_range=theta_clipping_range, n=ns, **kwargs)
+
+    def predictor_corrector(self, shape: Size, x: Tensor, steps: int = 64, verbose: bool = False,
+                            predictor_type="ddim", corrector_type="langevin", theta_clipping_range=(None, None),
+                            **kwargs) -> Tensor:
+        xs, ns = self._create_pf_data(x)  # pf_nse.py:235-262
+        return super().predictor_corrector(shape=shape, x=xs, steps=steps, verbose=verbose, predictor_type=predictor_type,
+                                           corrector_type=corrector_type, theta_clipping_range=theta_clipping_range,
+                                           n=ns, **kwargs)
+
+    def annealed_langevin_geffner(self, shape: Size, x: Tensor, prior_score_fn, prior_type=None, steps: int = 400,
+                                  lsteps: int = 5, tau: float = 0.5, theta_clipping_range=(None, None),
+                                  verbose: bool = False, **kwargs) -> Tensor:
+        xs, ns = self._create_pf_data(x)  # pf_nse.py:264-297 (PF-NPSE of Geffner et al.)
+        return super().annealed_langevin_geffner(shape=shape, x=xs, prior_score_fn=prior_score_fn, prior_type=prior_type,
+                                                 steps=steps, lsteps=lsteps, tau=tau,
+                                                 theta_clipping_range=theta_clipping_range, verbose=verbose, n=ns, **kwargs)

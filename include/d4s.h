@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D4S_ABI_VERSION 8
+#define D4S_ABI_VERSION 9
 
 #define D4S_OK 0
 #define D4S_ERR_ARG -1      /* bad argument / unsupported shape */
@@ -71,6 +71,11 @@ extern "C" {
 #define D4S_S_SQRT_ALPHA 8
 #define D4S_S_COMBINE 9    /* D4S_COMBINE_* for this step (the alpha-gate of nse.py:643 is decided on the host) */
 #define D4S_S_ONE_MINUS_N 10 /* (1 - n_obs) as float */
+/* generalised update  theta' = C_THETA theta + c_eff * score + BRIDGE_STD z  shared by DDIM and the Langevin family
+ * (annealed Langevin nse.py:418-475, tamed ULA nse.py:301-338, deterministic Geffner nse.py:658-705): */
+#define D4S_S_S1_WEIGHT 11  /* D4S_COMBINE_SUM: score = (1-n) s0 + S1_WEIGHT * sum_j s_ij  (nse.py:688-694: 1/sqrt(gamma)) */
+#define D4S_S_TAME 12       /* > 0: tamed step c_eff = TAME / (1 + TAME * ||score||)  (nse.py:336), else c_eff = C_SCORE */
+#define D4S_S_CLIP 13       /* 1: apply theta_clipping_range after this step (Langevin clips once per outer step) */
 
 typedef struct D4sNet D4sNet; /* packed, device-resident score network */
 

@@ -457,6 +457,106 @@ def ddim_single(net: OracleNet, x, z0, z, steps, eta, clip=(None, None)):
 
 
 # --------------------------------------------------------------------------------------
+# a16: Langevin / Geffner family (nse.py:301-542, 658-705)
+# --------------------------------------------------------------------------------------
+def factorized_score_geffner(net: OracleNet, theta, x, t, prior, ns=None):
+    """nse.py:479-542 (analytic prior): (1 - n) prior_score + sum_j score_j."""
+    n_obs = x.shape[0] if x.ndim > 1 else 1
+    inp, _ = pair_inputs(net, theta, x if x.ndim > 1 else x[None], t, ns)
+    scores = -net.net(inp) / net.sigma(t)
+    return (1 - n_obs) * prior_score(net, prior, theta, t) + scores.sum(axis=1)
+
+
+def _gamma(net: OracleNet, time, i, steps):
+    D = net.dtype
+    t = time[i]
+    if i < steps - 1:
+        return net.alpha(t) / net.alpha(np.asarray(t, dtype=D) - time[-2])  # nse.py:456-457
+    return net.alpha(t)
+
+
+def annealed_langevin_geffner(net: OracleNet, x, z0, z, prior, steps=400, lsteps=5, tau=0.5, clip=(None, None), ns=None):
+    """nse.py:418-475 with injected noise z[steps*lsteps, N, m]."""
+    D = net.dtype
+    time = time_grid(steps).astype(D)
+    theta = z0.astype(D)
+    k = 0
+    single = x.ndim == 1 or x.shape[0] == 1
+    for i in range(steps):
+        t = time[i]
+        gamma_t = _gamma(net, time, i, steps)
+        delta = D(tau) * (1 - gamma_t) / (gamma_t ** 0.5)
+        for _ in range(lsteps):
+            zz = z[k].astype(D)
+            k += 1
+            if single:
+                score = nse_score(net, theta, x, t)
+            else:
+                score = factorized_score_geffner(net, theta, x, t, prior, ns)
+            theta = theta + delta * score + ((2 * delta) ** 0.5) * zz
+        if clip[0] is not None:
+            theta = np.clip(theta, clip[0], clip[1])
+    return theta.astype(D)
+
+
+def deterministic_gaussian_geffner(net: OracleNet, x, z0, z, prior, steps=1000, clip=(None, None)):
+    """nse.py:658-705 with injected noise z[steps, N, m]."""
+    D = net.dtype
+    time = time_grid(steps).astype(D)
+    theta = z0.astype(D)
+    n = x.shape[0] if x.ndim > 1 else 1
+    for i in range(steps):
+        t = time[i]
+        g = _gamma(net, time, i, steps)
+        inp, _ = pair_inputs(net, theta, x, t)
+        scores = -net.net(inp) / net.sigma(t)
+        p_score = prior_score(net, prior, theta, t)
+        mu = 1 / g ** 0.5 * (n * theta + (1 - g) * scores.sum(axis=1)) - (n - 1) * g ** 0.5 * theta  # :688
+        mu = mu * (1 / (n - g * (n - 1)))
+        var = (1 - g) / (n - g * (n - 1))
+        mu = mu + var * (1 - n) * p_score
+        theta = mu + z[i].astype(D) * var ** 0.5
+        if clip[0] is not None:
+            theta = np.clip(theta, clip[0], clip[1])
+    return theta.astype(D)
+
+
+def predictor_corrector(net: OracleNet, x, z0, z, prior, steps, predictor="ddim", corrector="langevin", eta=1.0, lsteps=5,
+                        r=0.5, clip=(None, None), dist_cov_est=None, cov_mode="GAUSS", prior_type="gaussian", ns=None):
+    """nse.py:340-416 (tall branch) with injected noise, consumed in call order: predictor draw, then one per
+    corrector step.  corrector 'langevin' uses the F-NPSE score (nse.py:381), corrector 'id' the GAUSS/JAC score."""
+    D = net.dtype
+    time = time_grid(steps).astype(D)
+    dt = 1 / steps
+    theta = z0.astype(D)
+    k = 0
+
+    def score_fun(th, t):
+        if corrector == "langevin":
+            return factorized_score_geffner(net, th, x, t, prior, ns)
+        return factorized_score(net, th, x, t, prior, dist_cov_est, cov_mode, prior_type, ns)
+
+    for i in range(steps):
+        t = time[i]
+        if predictor == "ddim":
+            s = score_fun(theta, t)
+            theta = ddim_step(net, theta, s, t, dt, eta, z[k].astype(D))
+            k += 1
+        if corrector == "langevin":
+            tc = np.asarray(t, dtype=D) - D(dt)
+            for _ in range(lsteps):
+                zz = z[k].astype(D)
+                k += 1
+                g = score_fun(theta, tc)
+                eps = D(r) * (net.alpha(tc) ** 0.5) * (net.sigma(tc) ** 2)  # nse.py:335
+                tamed = (eps / (1 + eps * np.linalg.norm(g, axis=-1)))[..., None]
+                theta = theta + tamed * g + ((2 * eps) ** 0.5) * zz
+        if clip[0] is not None:
+            theta = np.clip(theta, clip[0], clip[1])
+    return theta.astype(D)
+
+
+# --------------------------------------------------------------------------------------
 # helpers used by tests / bench (not part of the reference)
 # --------------------------------------------------------------------------------------
 def random_net(rng: np.random.Generator, m, d, hidden=(256, 256, 256), freqs=3, n_max=1, pf=False,

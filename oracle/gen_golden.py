@@ -85,6 +85,62 @@ def run_ddim(net, x, z0, z, **kw):
         return net.ddim(shape=(z0.shape[0],), x=x, **kw)
 
 
+def run_sampler(net, method, x, z0, z, **kw):
+    """Any reference sampler under replayed noise: z0 replaces DiagNormal.sample, z[k] the k-th torch.randn_like."""
+    it = iter(z)
+    FakeDiagNormal.z0 = z0
+    with mock.patch.object(ref_nse, "DiagNormal", FakeDiagNormal), \
+            mock.patch("torch.randn_like", side_effect=lambda a: next(it).to(a)):
+        return getattr(net, method)(shape=(z0.shape[0],), x=x, **kw)
+
+
+def langevin_case(name, net32, x, prior_kind, prior_params, N, seed, steps, lsteps, traj_x=None, extra_kwargs=None):
+    """Trajectories of the Langevin / Geffner family + per-call F-NPSE scores, fp32 and fp64."""
+    out = {}
+    net_arrays(net32, out)
+    gen = torch.Generator().manual_seed(seed)
+    m = net32.zeros.shape[0]
+    theta = torch.randn(N, m, generator=gen)
+    z0 = torch.randn(N, m, generator=gen)
+    z = torch.randn(steps * (lsteps + 1), N, m, generator=gen)
+    t_grid = [0.9, 0.5, 0.1]
+    out.update(theta=npy(theta), x=npy(x), t_grid=np.asarray(t_grid, np.float32), prior_kind=np.str_(prior_kind),
+               traj_z0=npy(z0), traj_z=npy(z), traj_steps=np.int64(steps), lsteps=np.int64(lsteps),
+               dist_cov_est=npy(spd_covs(gen, x.shape[0], m)))
+    for k, v in prior_params.items():
+        out[f"prior.{k}"] = npy(v)
+    extra_kwargs = extra_kwargs or {}
+    for k, v in extra_kwargs.items():
+        out[f"kw.{k}"] = npy(v)
+    if traj_x is not None:
+        out["traj_x"] = npy(traj_x)
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        net = copy.deepcopy(net32).to(dt)
+        prior, fn = make_prior(prior_kind, m, dt, net, **prior_params)
+        kw = {k: v.to(dt) for k, v in extra_kwargs.items()}
+        xx = x.to(dt)
+        xt = xx if traj_x is None else traj_x.to(dt)
+        kwt = kw if traj_x is None else {}
+        out[f"{tag}.geffner_score"] = np.stack([
+            npy(net.factorized_score_geffner(theta.to(dt), xx, torch.tensor(tv, dtype=torch.float32).to(dt), fn, **kw))
+            for tv in t_grid])
+        out[f"{tag}.langevin.traj"] = npy(run_sampler(net, "annealed_langevin_geffner", xt, z0.to(dt), z.to(dt),
+                                                      prior_score_fn=fn, steps=steps, lsteps=lsteps, tau=0.5,
+                                                      theta_clipping_range=(-3, 3), **kwt))
+        out[f"{tag}.tamed.traj"] = npy(run_sampler(net, "predictor_corrector", xt, z0.to(dt), z.to(dt), steps=steps,
+                                                   prior_score_fun=fn, lsteps=lsteps, r=0.5, predictor_type="id",
+                                                   theta_clipping_range=(-3, 3), **kwt))
+        out[f"{tag}.pc.traj"] = npy(run_sampler(net, "predictor_corrector", xt, z0.to(dt), z.to(dt), steps=steps,
+                                                prior_score_fun=fn, lsteps=lsteps, r=0.3, eta=0.7, predictor_type="ddim",
+                                                **kwt))
+        if traj_x is None:
+            out[f"{tag}.detgef.traj"] = npy(run_sampler(net, "deterministic_gaussian_geffner", xx, z0.to(dt), z.to(dt),
+                                                        prior_score_fn=fn, steps=steps))
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name)
+
+
 def make_prior(kind, m, dt, net, low=None, high=None, loc=None, cov=None):
     if kind == "uniform":
         low, high = low.to(dt), high.to(dt)
@@ -255,6 +311,23 @@ def main(filt=None):
         high = (hi - st["theta_train_mean"]) / st["theta_train_std"] * 2
         per_call_case("jrnnm4d_n5", net, x, "uniform", dict(low=low, high=high), N=10, seed=16,
                       t_grid=[0.9, 0.5, 0.29, 0.1, 0.01], traj=dict(N=12, steps=30, eta=1.0, modes=("GAUSS",)))
+    if want("langevin"):
+        net, st = load_sbibm("sir")
+        x = sbibm_obs("sir", st, 5, log_space=False)
+        pp = lognormal_prior(st, torch.log(torch.tensor([0.4, 0.125])), torch.tensor([0.5, 0.2]))
+        langevin_case("langevin_sir_n5", net, x, "gaussian", pp, N=10, seed=21, steps=12, lsteps=3)
+        torch.manual_seed(4)
+        net = ref_nse.NSE(theta_dim=3, x_dim=4, hidden_features=[64, 64, 64]).eval()
+        gen = torch.Generator().manual_seed(7)
+        x = torch.randn(6, 4, generator=gen)
+        langevin_case("langevin_rand_uniform_n6", net, x, "uniform", dict(low=torch.full((3,), -2.5), high=torch.full((3,), 2.5)),
+                      N=9, seed=22, steps=10, lsteps=2)
+        net, st = load_sbibm("slcp", sub="n_train_10000_bs_256_n_epochs_5000_lr_0.0001", pf="pf_n_max_3")
+        st = dict(st, x_train_mean=st["x_train_mean"][0], x_train_std=st["x_train_std"][0])
+        x = sbibm_obs("slcp", st, 8)
+        xs, ns = net._create_pf_data(x)
+        langevin_case("langevin_pf_slcp_n8", net, xs, "uniform", slcp_prior(st), N=8, seed=23, steps=8, lsteps=2,
+                      traj_x=x, extra_kwargs=dict(n=ns))
     if want("rand"):
         torch.manual_seed(3)
         net = ref_nse.NSE(theta_dim=3, x_dim=4, hidden_features=[64, 96]).eval()

@@ -13,7 +13,7 @@ from oracle import d4s_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-CASES = gio.names()
+CASES = [c for c in gio.names() if not c.startswith("langevin")]
 REL_TOL = 1e-4
 TRAJ_TOL = 1e-3
 
@@ -314,3 +314,46 @@ def test_multi_gpu_obs_and_sample_sharding():
                        capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout
+
+
+# ---- Langevin / Geffner family on the same kernels -----------------------------------------
+LANGEVIN = [c for c in gio.names() if c.startswith("langevin")]
+
+
+@pytest.mark.parametrize("name", LANGEVIN)
+def test_langevin_family(name, dev, kernel_path):
+    """annealed Langevin (F-NPSE), tamed ULA, DDIM+Langevin predictor-corrector, deterministic Geffner: golden
+    trajectories of the reference under replayed noise; per-call F-NPSE score."""
+    g, onet, nse, prior, fn, ptype, kw = _setup(name, dev)
+    steps, lsteps = int(g["traj_steps"]), int(g["lsteps"])
+    x = _t(g["x"], dev)
+    xt = _t(g["traj_x"], dev) if "traj_x" in g else x
+    kwt = {} if "traj_x" in g else kw
+    noise = (torch.as_tensor(g["traj_z0"]), torch.as_tensor(g["traj_z"]))
+    for k, t in enumerate(g["t_grid"]):
+        out = nse.factorized_score_geffner(_t(g["theta"], dev), x, torch.tensor(t), fn, **kw)
+        ref = g["f64.geffner_score"][k]
+        floor = orc.rel_l2(g["f32.geffner_score"][k], ref)
+        assert orc.rel_l2(out.cpu().numpy(), ref) < max(REL_TOL, 3 * floor), (name, t)
+
+    def check(out, key, n_noise):
+        ref = g[f"f64.{key}.traj"]
+        ref32 = np.abs(g[f"f32.{key}.traj"] - ref).max()
+        scale = max(1.0, np.abs(ref).max())
+        err = np.abs(out.cpu().numpy() - ref).max()
+        print(f"{name} {key}: max|d theta| = {err:.2e} (reference fp32 vs fp64: {ref32:.2e})")
+        assert err < max(TRAJ_TOL * scale, 3 * ref32), (name, key, err)
+
+    z0, z = noise
+    out = nse.annealed_langevin_geffner((z0.shape[0],), xt, fn, steps=steps, lsteps=lsteps, tau=0.5,
+                                        theta_clipping_range=(-3, 3), _noise=(z0, z[:steps * lsteps]), **kwt)
+    check(out, "langevin", steps * lsteps)
+    out = nse.predictor_corrector((z0.shape[0],), xt, steps=steps, prior_score_fun=fn, lsteps=lsteps, r=0.5,
+                                  predictor_type="id", theta_clipping_range=(-3, 3), _noise=(z0, z[:steps * lsteps]), **kwt)
+    check(out, "tamed", steps * lsteps)
+    out = nse.predictor_corrector((z0.shape[0],), xt, steps=steps, prior_score_fun=fn, lsteps=lsteps, r=0.3, eta=0.7,
+                                  predictor_type="ddim", _noise=(z0, z[:steps * (lsteps + 1)]), **kwt)
+    check(out, "pc", steps * (lsteps + 1))
+    if "f64.detgef.traj" in g:
+        out = nse.deterministic_gaussian_geffner((z0.shape[0],), x, fn, steps=steps, _noise=(z0, z[:steps]))
+        check(out, "detgef", steps)

@@ -12,7 +12,7 @@ import torch
 import golden_io as gio
 from oracle import d4s_oracle as orc
 
-CASES = gio.names()
+CASES = [c for c in gio.names() if not c.startswith("langevin")]
 
 
 def _ns(g):
@@ -96,3 +96,35 @@ def test_trajectory_fp64(name):
                        g["dist_cov_est"].astype(np.float64), mode, str(g["prior_kind"]), clip, ns)
         err = np.abs(out - g[key]).max()
         assert err < (5e-6 if mode == "GAUSS" else 1e-4), (name, mode, err)
+
+
+# ---- Langevin / Geffner family ---------------------------------------------------------
+LANGEVIN = [c for c in gio.names() if c.startswith("langevin")]
+
+
+def _lv_setup(name):
+    g = gio.load(name)
+    net, prior, ns = gio.oracle_net(g), gio.oracle_prior(g), _ns(g)
+    steps, lsteps = int(g["traj_steps"]), int(g["lsteps"])
+    return g, net, prior, ns, steps, lsteps
+
+
+@pytest.mark.parametrize("name", LANGEVIN)
+def test_langevin_family_fp64(name):
+    g, net, prior, ns, steps, lsteps = _lv_setup(name)
+    x = g["x"].astype(np.float64)
+    z0, z = g["traj_z0"], g["traj_z"]
+    for k, t in enumerate(g["t_grid"]):
+        out = orc.factorized_score_geffner(net, g["theta"].astype(np.float64), x, np.float64(t), prior, ns)
+        assert orc.rel_l2(out, g["f64.geffner_score"][k]) < 5e-7
+    out = orc.annealed_langevin_geffner(net, x, z0, z, prior, steps, lsteps, 0.5, (-3, 3), ns)
+    assert np.abs(out - g["f64.langevin.traj"]).max() < 5e-6
+    out = orc.predictor_corrector(net, x, z0, z, prior, steps, "id", "langevin", lsteps=lsteps, r=0.5, clip=(-3, 3), ns=ns)
+    assert np.abs(out - g["f64.tamed.traj"]).max() < 5e-6
+    out = orc.predictor_corrector(net, x, z0, z, prior, steps, "ddim", "langevin", eta=0.7, lsteps=lsteps, r=0.3, ns=ns)
+    ref = g["f64.pc.traj"]
+    assert np.abs(out - ref).max() < 5e-6 * max(1.0, np.abs(ref).max())
+    if "f64.detgef.traj" in g:
+        out = orc.deterministic_gaussian_geffner(net, x, z0, z, prior, steps)
+        ref = g["f64.detgef.traj"]
+        assert np.abs(out - ref).max() < 5e-6 * max(1.0, np.abs(ref).max())
