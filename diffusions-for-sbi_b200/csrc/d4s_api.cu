@@ -67,7 +67,9 @@ struct Tiling {
 };
 
 static bool tc_eligible(const D4sNet* net, const D4sProblem* pb) {
-    return g_opt_path != 1 && pb->cov_mode == D4S_COV_GAUSS && !pb->paired && net->dev.L >= 3 && net->dev.emb_L == 0;
+    // plain Linear/ReLU nets only: the toy output head (tanh / analytic affine part) runs on the SIMT path
+    return g_opt_path != 1 && pb->cov_mode == D4S_COV_GAUSS && !pb->paired && net->dev.L >= 3 && net->dev.emb_L == 0 &&
+           net->dev.out_act == 0 && net->dev.out_scale == 1.f && pb->obs_raw == nullptr;
 }
 
 static int make_tiling(const D4sNet* net, const D4sProblem* pb, Tiling* t) {
@@ -137,6 +139,7 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
     if (L < 2 || L > D4S_MAX_LAYERS) return fail(D4S_ERR_ARG, "n_layers must be in [2, 8]");
     const int m = d->dims[L];
     if (m < 1 || m > D4S_MAX_THETA) return fail(D4S_ERR_ARG, "theta_dim must be in [1, 10]");
+    if (d->out_act != 0 && d->out_act != 1) return fail(D4S_ERR_ARG, "out_act must be 0 (identity) or 1 (tanh)");
     const int EL = d->emb_layers;
     if (EL < 0 || EL > D4S_MAX_LAYERS) return fail(D4S_ERR_ARG, "emb_layers must be in [0, 8]");
     if (EL == 0 && d->theta_cols != m) return fail(D4S_ERR_ARG, "theta_cols != theta_dim without a theta embedding net");
@@ -253,6 +256,8 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
     nd.Wout = net->blob + off_Wout;
     nd.bout = net->blob + off_bout;
     nd.WoutT = net->blob + off_WoutT;
+    nd.out_act = d->out_act;
+    nd.out_scale = d->out_scale == 0.f ? 1.f : d->out_scale;
     nd.emb_L = EL;
     for (int l = 0; l <= EL && EL > 0; ++l) nd.emb_dims[l] = d->emb_dims[l];
     for (int l = 0; l < EL; ++l) {
@@ -396,6 +401,10 @@ static int score_partials_impl(const D4sNet* net, const D4sProblem* pb, const D4
     p.time_feat = st->time_feat;
     p.obs_prec = pb->obs_prec;
     p.sched = st->sched;
+    p.affine = st->affine;
+    p.obs_raw = pb->obs_raw;
+    p.d = pb->x_dim;
+    if (p.affine && (!p.obs_raw || p.d < 1)) return fail(D4S_ERR_ARG, "affine term needs obs_raw and x_dim");
     p.part = t.tc ? nullptr : pb->workspace;  // a materialising call on a tcgen05-eligible problem leaves no partial sums
     p.scores_out = scores_out;
     p.prec_out = prec_out;
@@ -468,7 +477,7 @@ struct GraphKey {
     const D4sNet* net;
     D4sProblem pb;
     int steps;
-    const float *sched, *tf, *mats, *noise;
+    const float *sched, *tf, *mats, *noise, *affine;
     float* theta;
     uint64_t mode_hash;
     bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
@@ -484,12 +493,13 @@ std::vector<GraphEntry> g_graphs;
 
 static int enqueue_steps(const D4sNet* net, const D4sProblem* pb0, int steps, const float* sched, const float* tf,
                          const float* mats, const float* noise, float* theta, const int32_t* step_mode,
-                         cudaStream_t stream) {
+                         const float* affine, cudaStream_t stream) {
     D4sProblem pbv = *pb0;
     D4sProblem* pb = &pbv;
     const int H1 = net->dev.Hp[0];
     const int MF = d4s_mats_floats(net->dev.m);
     const size_t NM = (size_t)pb->n_samples * net->dev.m;
+    const int nm = net->dev.m;
     for (int k = 0; k < steps; ++k) {
         D4sStep st;
         st.sched = sched + (size_t)k * D4S_SCHED_STRIDE;
@@ -498,6 +508,7 @@ static int enqueue_steps(const D4sNet* net, const D4sProblem* pb0, int steps, co
         st.noise = noise ? noise + (size_t)k * NM : nullptr;
         st.step_index = k;
         st.update = 1;
+        st.affine = affine ? affine + (size_t)k * (nm * nm + nm * pb0->x_dim + nm) : nullptr;
         pb->cov_mode = step_mode ? step_mode[k] : pb0->cov_mode;
         int rc = score_partials_impl(net, pb, &st, theta, nullptr, nullptr, stream);
         if (rc) return rc;
@@ -536,7 +547,7 @@ static int try_traj_tc(const D4sNet* net, const D4sProblem* pb, int steps, const
 
 int d4s_ddim_run(const D4sNet* net, const D4sProblem* pb, int32_t steps, const float* sched_dev,
                  const float* time_feat_dev, const float* mats_dev, const float* noise_dev, float* theta_dev,
-                 const int32_t* step_mode, int32_t use_graph, void* stream_) {
+                 const int32_t* step_mode, const float* affine_dev, int32_t use_graph, void* stream_) {
     int rc = check_problem(net, pb);
     if (rc) return rc;
     if (steps < 1 || !sched_dev || !time_feat_dev || !mats_dev || !theta_dev) return fail(D4S_ERR_ARG, "bad ddim_run args");
@@ -553,12 +564,14 @@ int d4s_ddim_run(const D4sNet* net, const D4sProblem* pb, int32_t steps, const f
         for (int k = 0; k < steps; ++k)
             if (step_mode[k] != D4S_COV_GAUSS && step_mode[k] != D4S_COV_JAC) return fail(D4S_ERR_ARG, "bad step_cov_mode");
     }
-    {
+    if (affine_dev && (!pb->obs_raw || pb->x_dim < 1)) return fail(D4S_ERR_ARG, "affine table needs obs_raw and x_dim");
+    if (!affine_dev) {
         const int tc = try_traj_tc(net, pb, steps, sched_dev, time_feat_dev, mats_dev, noise_dev, theta_dev, step_mode, stream);
         if (tc <= 0) return tc;  // 0 = launched on the tcgen05 path, < 0 = error
     }
     if (!use_graph)
-        return enqueue_steps(net, pb, steps, sched_dev, time_feat_dev, mats_dev, noise_dev, theta_dev, step_mode, stream);
+        return enqueue_steps(net, pb, steps, sched_dev, time_feat_dev, mats_dev, noise_dev, theta_dev, step_mode, affine_dev,
+                             stream);
 
     GraphKey key;
     memset(&key, 0, sizeof(key));
@@ -570,6 +583,7 @@ int d4s_ddim_run(const D4sNet* net, const D4sProblem* pb, int32_t steps, const f
     key.mats = mats_dev;
     key.noise = noise_dev;
     key.theta = theta_dev;
+    key.affine = affine_dev;
     key.mode_hash = 1469598103934665603ull;
     if (step_mode)
         for (int k = 0; k < steps; ++k) key.mode_hash = (key.mode_hash ^ (uint64_t)(step_mode[k] + 1)) * 1099511628211ull;
@@ -592,7 +606,7 @@ int d4s_ddim_run(const D4sNet* net, const D4sProblem* pb, int32_t steps, const f
         cudaStreamDestroy(cap);
         return cuda_fail(e, "cudaStreamBeginCapture");
     }
-    rc = enqueue_steps(net, pb, steps, sched_dev, time_feat_dev, mats_dev, noise_dev, theta_dev, step_mode, cap);
+    rc = enqueue_steps(net, pb, steps, sched_dev, time_feat_dev, mats_dev, noise_dev, theta_dev, step_mode, affine_dev, cap);
     cudaGraph_t graph = nullptr;
     e = cudaStreamEndCapture(cap, &graph);
     const long long n_launch = g_launches - before;

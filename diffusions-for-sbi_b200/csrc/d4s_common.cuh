@@ -30,6 +30,8 @@ struct NetDev {
     const float* Wout;              // [Hp[L-2]][MMAX] k-major, zero padded columns
     const float* bout;              // [MMAX]
     const float* WoutT;             // [m][Hp[L-2]] output layer, torch layout (tcgen05 path epilogue)
+    int out_act;                    // output head: 0 identity, 1 tanh (EpsilonNet, embedding_nets.py:135)
+    float out_scale;                // eps = out_scale * act(.)   (FakeFNet.eps_net_max, embedding_nets.py:160)
     // optional theta-embedding MLP (nse.py:129): emb_L linear layers, k-major fp32, widths as given (<= 256)
     int emb_L;
     int emb_dims[D4S_MAX_LAYERS + 1];
@@ -54,6 +56,9 @@ struct ScoreParams {
     const float* time_feat;  // [Hp0]
     const float* obs_prec;   // GAUSS: [n][m][m]
     const float* sched;      // [16]
+    const float* affine;     // optional [m*m + m*d + m]: eps += M theta_i - G x_j - g   (analytic Gaussian posterior part)
+    const float* obs_raw;    // [n][d] raw observations (read with `affine`)
+    int d;
     float* part;             // [N][C][W]
     float* scores_out;       // optional [N][n][m]
     float* prec_out;         // optional JAC [N][n][m][m]

@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(NT, 2) score_simt_kernel(const ScoreParams p) 
     float* sQS = sS + TM * MMAX;                  // [TM][MMAX] GAUSS: inv(Sigma_j) s ; JAC: per-pair outputs
     float* sJ = sQS + TM * MMAX;                  // [P][m][m] d eps / d theta
     float* sTheta = sJ + TM * MMAX;               // [SG][MMAX]
-    unsigned* sMask = reinterpret_cast<unsigned*>(sTheta + TM * MMAX);  // [32][8]
+    float* sDact = sTheta + TM * MMAX;            // [TM][MMAX] d eps / d (output pre-activation) of primal rows
+    unsigned* sMask = reinterpret_cast<unsigned*>(sDact + TM * MMAX);  // [32][8]
     int* sKind = reinterpret_cast<int*>(sMask + 32 * 8);                // [TM] -1 invalid, 0 primal, 1+k tangent k
     int* sPair = sKind + TM;                                            // [TM] pair index within tile
     int* sSamp = sPair + TM;                                            // [TM] sample index within tile (per pair)
@@ -278,18 +279,45 @@ __global__ void __launch_bounds__(NT, 2) score_simt_kernel(const ScoreParams p) 
             const float dot = d0 + d1;
             const int kind = sKind[r];
             if (kind == 0) {
-                const float s = -(dot + __ldg(net.bout + o)) * inv_sigma;  // nse.py:145
-                sS[r * MMAX + o] = s;
+                const int pr = sPair[r];
+                float z = dot + __ldg(net.bout + o);
+                float dact = net.out_scale;
+                if (net.out_act == 1) {  // tanh head of the toy perturbation net (embedding_nets.py:135)
+                    z = tanhf(z);
+                    dact *= 1.f - z * z;
+                }
+                float eps = net.out_scale * z;
+                if (p.affine) {  // analytic Gaussian part: eps += M theta_i - G x_j - g  (gen_gaussian_gaussian.py:59-72)
+                    const float* M = p.affine + o * m;
+                    const float* G = p.affine + m * m + o * p.d;
+                    const float* xr = p.obs_raw + (size_t)sObs[pr] * p.d;
+                    float aff = -__ldg(p.affine + m * m + m * p.d + o);
+                    for (int k = 0; k < m; ++k) aff = fmaf(__ldg(M + k), sTheta[sSamp[pr] * MMAX + k], aff);
+                    for (int k = 0; k < p.d; ++k) aff = fmaf(-__ldg(G + k), __ldg(xr + k), aff);
+                    eps += aff;
+                }
+                const float sc = -eps * inv_sigma;  // nse.py:145
+                sS[r * MMAX + o] = sc;
+                sDact[r * MMAX + o] = dact;
                 if (p.scores_out) {
-                    const int pr = sPair[r];
                     const size_t gi = (size_t)(i0 + sSamp[pr]);
                     const size_t gj = p.paired ? 0 : (size_t)sObs[pr];
                     const size_t nn = p.paired ? 1 : (size_t)p.n;
-                    p.scores_out[(gi * nn + gj) * m + o] = s;
+                    p.scores_out[(gi * nn + gj) * m + o] = sc;
                 }
             } else if (kind > 0) {
-                sJ[(sPair[r] * m + o) * m + (kind - 1)] = dot;  // d eps_o / d theta_k
+                sJ[(sPair[r] * m + o) * m + (kind - 1)] = dot;  // d (output pre-activation)_o / d theta_k
             }
+        }
+    }
+    __syncthreads();
+    if (p.jac && (net.out_act != 0 || net.out_scale != 1.f || p.affine)) {
+        // chain rule through the output head: d eps_o / d theta_k = dact_o * dz_o/dtheta_k + M[o][k]
+        for (int e = tid; e < p.P * m * m; e += NT) {
+            const int pr = e / (m * m), ok = e - pr * m * m, o = ok / m;
+            float v = sDact[pr * MMAX + o] * sJ[e];
+            if (p.affine) v += __ldg(p.affine + ok);
+            sJ[e] = v;
         }
     }
     __syncthreads();
@@ -420,7 +448,7 @@ cudaError_t launch_theta_embed(const NetDev& net, const float* theta, int N, int
 }
 
 size_t score_simt_smem_bytes() {
-    return sizeof(float) * (HMAX * ASTR + NSTAGE * KC * HMAX + 4 * TM * MMAX) + sizeof(unsigned) * 32 * 8 +
+    return sizeof(float) * (HMAX * ASTR + NSTAGE * KC * HMAX + 5 * TM * MMAX) + sizeof(unsigned) * 32 * 8 +
            sizeof(int) * 4 * TM;
 }
 

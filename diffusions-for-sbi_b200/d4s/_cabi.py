@@ -13,7 +13,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libd4s.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 MAX_LAYERS = 8
 MAX_THETA = 10
 MAX_WIDTH = 256
@@ -49,6 +49,8 @@ class NetDesc(C.Structure):
         ("emb_dims", C.c_int32 * (MAX_LAYERS + 1)),
         ("emb_weight", C.c_void_p * MAX_LAYERS),
         ("emb_bias", C.c_void_p * MAX_LAYERS),
+        ("out_act", C.c_int32),
+        ("out_scale", C.c_float),
     ]
 
 
@@ -72,6 +74,9 @@ class Problem(C.Structure):
         ("sample_offset", C.c_int64),
         ("workspace", C.c_void_p),
         ("workspace_floats", C.c_int64),
+        ("obs_raw", C.c_void_p),
+        ("x_dim", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 
@@ -83,6 +88,7 @@ class Step(C.Structure):
         ("noise", C.c_void_p),
         ("step_index", C.c_int32),
         ("update", C.c_int32),
+        ("affine", C.c_void_p),
     ]
 
 
@@ -116,7 +122,7 @@ def load():
             "d4s_mats_floats": (i32, [i32]),
             "d4s_score_partials": (C.c_int, [vp, C.POINTER(Problem), C.POINTER(Step), vp, vp, vp, vp]),
             "d4s_finalize": (C.c_int, [vp, C.POINTER(Problem), C.POINTER(Step), vp, vp, vp]),
-            "d4s_ddim_run": (C.c_int, [vp, C.POINTER(Problem), i32, vp, vp, vp, vp, vp, C.POINTER(i32), i32, vp]),
+            "d4s_ddim_run": (C.c_int, [vp, C.POINTER(Problem), i32, vp, vp, vp, vp, vp, C.POINTER(i32), vp, i32, vp]),
             "d4s_graph_cache_clear": (None, []),
             "d4s_set_option": (C.c_int, [C.c_char_p, i32]),
             "d4s_get_profile": (C.c_int, [C.POINTER(i64)]),

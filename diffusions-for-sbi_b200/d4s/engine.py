@@ -99,7 +99,8 @@ class NetView:
 class PackedNet(NetView):
     """Device-resident packed copy of `nse.net` (d4s_net_create) + the host view."""
 
-    def __init__(self, linears, theta_cols: int, device: torch.device, emb_linears=()):
+    def __init__(self, linears, theta_cols: int, device: torch.device, emb_linears=(), out_act: int = 0,
+                 out_scale: float = 1.0):
         super().__init__(linears)
         lib = abi.require_cuda()
         L = len(linears)
@@ -115,6 +116,8 @@ class PackedNet(NetView):
             desc.dims[l + 1] = lin.out_features
             desc.weight[l] = w.data_ptr()
             desc.bias[l] = b.data_ptr()
+        desc.out_act = int(out_act)
+        desc.out_scale = float(out_scale)
         desc.emb_layers = len(emb_linears)
         for l, lin in enumerate(emb_linears):
             w = lin.weight.detach().to("cpu", torch.float32).contiguous()
@@ -137,29 +140,41 @@ class PackedNet(NetView):
 _net_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 
-def _linears(mlp) -> list:
+def _linears(mlp, allow_tanh_head: bool = False) -> list:
     mods = list(mlp.modules())[1:] if isinstance(mlp, torch.nn.Sequential) else list(mlp.children())
-    lin, prev_linear = [], False
-    for mod in mods:
+    lin = []
+    for i, mod in enumerate(mods):
         if isinstance(mod, torch.nn.Linear):
             lin.append(mod)
         elif isinstance(mod, (torch.nn.ReLU, torch.nn.Identity)):
+            continue
+        elif allow_tanh_head and isinstance(mod, torch.nn.Tanh) and i == len(mods) - 1:
             continue
         else:
             raise abi.D4sError(f"unsupported module in score MLP: {type(mod).__name__} (Linear/ReLU stacks only)")
     return lin
 
 
-def packed_net(nse, device: torch.device) -> PackedNet:
-    lin = _linears(nse.net)
+def net_description(nse) -> dict:
+    """What the kernels need to know about `nse.net`.  Modules may override it with `_d4s_net_description()`
+    (the toy `nse_toy.NSE` + `FakeFNet` does: tanh head, analytic affine part, raw-t time feature)."""
+    if hasattr(nse, "_d4s_net_description"):
+        return nse._d4s_net_description()
     emb = nse.embedding_nn_theta
-    emb_lin = [] if isinstance(emb, torch.nn.Identity) else _linears(emb)
-    key = tuple((p.data_ptr(), p._version) for l in lin + emb_lin for p in (l.weight, l.bias)) + (str(device),)
+    return dict(mlp=nse.net, emb_theta=None if isinstance(emb, torch.nn.Identity) else emb, out_act=0, out_scale=1.0,
+                theta_cols=int(getattr(nse, "theta_emb_dim", nse.zeros.shape[0])), time_features=None, affine=None)
+
+
+def packed_net(nse, device: torch.device) -> PackedNet:
+    d = net_description(nse)
+    lin = _linears(d["mlp"], allow_tanh_head=d["out_act"] == 1)
+    emb_lin = [] if d["emb_theta"] is None else _linears(d["emb_theta"])
+    key = tuple((p.data_ptr(), p._version) for l in lin + emb_lin for p in (l.weight, l.bias)) + (
+        str(device), d["out_act"], float(d["out_scale"]))
     hit = _net_cache.get(nse)
     if hit is not None and hit[0] == key:
         return hit[1]
-    theta_cols = int(getattr(nse, "theta_emb_dim", nse.zeros.shape[0]))
-    pn = PackedNet(lin, theta_cols, device, emb_lin)
+    pn = PackedNet(lin, d["theta_cols"], device, emb_lin, d["out_act"], d["out_scale"])
     _net_cache[nse] = (key, pn)
     return pn
 
@@ -214,6 +229,9 @@ def schedule_rows(nse, t: torch.Tensor, t_prev: Optional[torch.Tensor], eta: flo
 
 
 def time_embedding64(nse, t64: torch.Tensor) -> torch.Tensor:
+    fn = net_description(nse)["time_features"]
+    if fn is not None:  # e.g. the toy net feeds the raw time (embedding_nets.py:138)
+        return fn(t64)
     ang = nse.freqs.detach().to("cpu", torch.float64) * t64[..., None]  # nse.py:125
     return torch.cat((ang.cos(), ang.sin()), dim=-1)  # nse.py:126
 
@@ -222,7 +240,7 @@ def layer1_blocks(nse, pn: NetView):
     """Column blocks of the first Linear: [theta | x | temb | (one-hot n, PF_NSE only)]."""
     e_t = int(getattr(nse, "theta_emb_dim", pn.m))
     e_x = int(getattr(nse, "x_emb_dim"))
-    f2 = 2 * nse.freqs.numel()
+    f2 = int(net_description(nse).get("time_width", 2 * nse.freqs.numel()))
     cols = pn.w1.shape[1]
     n_hot = cols - e_t - e_x - f2
     if n_hot < 0:
@@ -345,6 +363,7 @@ class TallSetup:
     step_modes: Optional[np.ndarray]
     keep: tuple  # tensors referenced by raw pointers in `prob`
     n_steps: int
+    affine: Optional[torch.Tensor] = None  # [steps, m*m + m*d + m] analytic part of eps (toy nets)
 
 
 def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: Optional[torch.Tensor], eta: float,
@@ -423,8 +442,17 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
     ws = torch.empty(ws_floats, dtype=torch.float32, device=device)
     prob.workspace = ws.data_ptr()
     prob.workspace_floats = ws_floats
+    affine_fn = net_description(nse)["affine"]
+    affine_dev = x_raw = None
+    if affine_fn is not None:  # closed-form part of eps: per-row [M_t | G_t | g_t] (gen_gaussian_gaussian.py:59-72)
+        affine_dev = _dev32(affine_fn(t.to(torch.float64)), device)
+        x_raw = x2.detach().to(torch.float32).contiguous()
+        if obs_slice is not None:
+            x_raw = x_raw[obs_slice].contiguous()
+        prob.obs_raw = x_raw.data_ptr()
+        prob.x_dim = x_raw.shape[-1]
     return TallSetup(pn, prob, _dev32(rows, device), _dev32(tf, device), _dev32(mats, device), step_modes,
-                     (of_dev, q_dev, low_dev, high_dev, ws), t.numel())
+                     (of_dev, q_dev, low_dev, high_dev, ws, x_raw), t.numel(), affine_dev)
 
 
 def _stream(device) -> C.c_void_p:
@@ -454,7 +482,7 @@ def run_trajectory(setup: TallSetup, theta: torch.Tensor, noise: Optional[torch.
     with torch.cuda.device(theta.device):
         abi.check(lib.d4s_ddim_run(setup.pn.handle, C.byref(setup.prob), setup.n_steps, _ptr(setup.sched),
                                    _ptr(setup.time_feat), _ptr(setup.mats), _ptr(noise), _ptr(theta), modes,
-                                   1 if use_graph else 0, _stream(theta.device)))
+                                   _ptr(setup.affine), 1 if use_graph else 0, _stream(theta.device)))
     return theta
 
 
@@ -466,6 +494,7 @@ def step_struct(setup: TallSetup, k: int, noise_k: Optional[torch.Tensor], updat
     st.noise = 0 if noise_k is None else noise_k.data_ptr()
     st.step_index = k
     st.update = 1 if update else 0
+    st.affine = 0 if setup.affine is None else setup.affine[k].data_ptr()
     return st
 
 
@@ -507,6 +536,29 @@ def batched_inverse(a: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(a.device):
         abi.check(lib.d4s_batched_inverse(_ptr(a), _ptr(out), a.numel() // (m * m), m, _stream(a.device)))
     return out
+
+
+def prior_score_native(nse, theta: torch.Tensor, t, spec: PriorSpec, want_jac: bool = False):
+    """Diffused prior score (and, for the uniform prior, its derivative) through d4s_prior_score."""
+    if not theta.is_cuda:
+        raise abi.D4sError("d4s prior scores need CUDA tensors (no CPU fallback)")
+    lib = abi.require_cuda()
+    m = theta.shape[-1]
+    tt = torch.as_tensor(t).detach().to("cpu").reshape(1)
+    rows = schedule_rows(nse, tt, None, 0.0, 0, [abi.COMBINE_SUM])  # n = 0 => (1 - n) = 1
+    mats = mats_table(rows, spec, False, 0, None, m)
+    dev = theta.device
+    th = theta.detach().to(torch.float32).contiguous()
+    sched, mats = rows.to(torch.float32).to(dev), mats.to(torch.float32).to(dev)
+    low = high = None
+    if spec.kind == abi.PRIOR_UNIFORM:
+        low, high = spec.low.to(torch.float32).to(dev), spec.high.to(torch.float32).to(dev)
+    out = torch.empty_like(th)
+    jac = torch.empty_like(th) if (want_jac and spec.kind == abi.PRIOR_UNIFORM) else None
+    with torch.cuda.device(dev):
+        abi.check(lib.d4s_prior_score(spec.kind, _ptr(th), th.shape[0], m, _ptr(sched), _ptr(mats), _ptr(low), _ptr(high),
+                                      _ptr(out), _ptr(jac), _stream(dev)))
+    return (out, jac) if want_jac else out
 
 
 def launch_count() -> int:

@@ -380,23 +380,4 @@ class NSE(nn.Module):
 
     # ---- stand-alone prior score (used by d4s.vp_diffused_priors objects) -------------------------------------
     def _prior_score_native(self, theta: Tensor, t: Tensor, spec: "engine.PriorSpec", want_jac: bool = False):
-        self._require_cuda(theta)
-        import ctypes as C
-        lib = abi.require_cuda()
-        m = theta.shape[-1]
-        tt = torch.as_tensor(t).detach().to("cpu").reshape(1)
-        rows = engine.schedule_rows(self, tt, None, 0.0, 0, [abi.COMBINE_SUM])  # n = 0 => (1 - n) = 1
-        mats = engine.mats_table(rows, spec, False, 0, None, m)
-        dev = theta.device
-        th = theta.detach().to(torch.float32).contiguous()
-        sched, mats = rows.to(torch.float32).to(dev), mats.to(torch.float32).to(dev)
-        low = high = None
-        if spec.kind == abi.PRIOR_UNIFORM:
-            low, high = spec.low.to(torch.float32).to(dev), spec.high.to(torch.float32).to(dev)
-        out = torch.empty_like(th)
-        jac = torch.empty_like(th) if (want_jac and spec.kind == abi.PRIOR_UNIFORM) else None
-        with torch.cuda.device(dev):
-            abi.check(lib.d4s_prior_score(spec.kind, engine._ptr(th), th.shape[0], m, engine._ptr(sched),
-                                          engine._ptr(mats), engine._ptr(low), engine._ptr(high), engine._ptr(out),
-                                          engine._ptr(jac), engine._stream(dev)))
-        return (out, jac) if want_jac else out
+        return engine.prior_score_native(self, theta, t, spec, want_jac)

@@ -1,0 +1,167 @@
+"""Toy-experiment variant of the score estimator (the class of the reference's `nse_toy.py:198-625`, used by
+`gen_gaussian_gaussian.py` / `gen_mixt_gauss_gaussian.py`).  Differences to `d4s.nse.NSE` that callers rely on:
+
+* schedule `alpha(t) = exp(-0.5 (0.5 beta_d t^2 + beta_min t))`, beta in [0.1, 40] (nse_toy.py:305-339);
+* `ddim(shape, x, steps=64, verbose=False, eta=1., **kwargs)`; only `x.shape[0] == shape[0]` selects the paired
+  plain score (nse_toy.py:375);
+* `factorized_score(theta, x_obs, t, prior_score_fn, dist_cov_est=None, cov_mode='JAC')` is always the
+  precision-weighted solve and `prior_score_fn(theta, t)` returns the TRIPLE (score, mean, precision)
+  (nse_toy.py:599-625, gen_gaussian_gaussian.py:86-96) -- build it with `gaussian_prior_triple(...)`;
+* the network is `FakeFNet(AnalyticGaussianEps(...), EpsilonNet(DIM), eps_max)`: analytic eps + eps_max * tanh-MLP on
+  [theta, x, t] with the RAW time as feature (embedding_nets.py:127-160).
+
+The fused path handles exactly that network family: the MLP with its tanh head and the per-step affine form of the
+analytic part run in the fp32 SIMT kernels (theta_dim <= 10).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+from torch import Size, Tensor
+
+from . import _cabi as abi
+from . import engine
+from .embedding_nets import AnalyticGaussianEps, EpsilonNet, FakeFNet  # noqa: F401
+from .nse import NSE as _FullNSE
+from .nse import _use_graph_default
+from .vp_diffused_priors import GaussianDiffusedScore
+
+
+class GaussianPriorTriple:
+    """`prior_score(theta, t) -> (score, mean_backward, precision_backward)` for a Gaussian prior, the closure of
+    gen_gaussian_gaussian.py:86-96 as an object that exposes the prior parameters to the fused kernels."""
+    kind = "gaussian"
+
+    def __init__(self, mean, cov, nse):
+        self.mean, self.cov = torch.as_tensor(mean), torch.as_tensor(cov)
+        self.nse = nse
+        self._score = GaussianDiffusedScore(mean, cov, nse)
+
+    def _spec(self):
+        return self._score._spec()
+
+    def __call__(self, theta: Tensor, t: Tensor):
+        from .tall_posterior_sampler import prec_matrix_backward
+        score = self._score(theta, t)
+        tt = torch.as_tensor(t).detach().to("cpu", torch.float64).reshape(1)
+        a, sig = float(engine._scalar64(self.nse.alpha, tt)), float(engine._scalar64(self.nse.sigma, tt))
+        mean = (theta + sig ** 2 * score) / math.sqrt(a)  # mean_backward, tall_posterior_sampler.py:10-18
+        prec = prec_matrix_backward(t, self.cov.to(theta.device), self.nse).repeat(theta.shape[0], 1, 1)
+        return score, mean, prec
+
+
+def gaussian_prior_triple(mean, cov, nse) -> GaussianPriorTriple:
+    return GaussianPriorTriple(mean, cov, nse)
+
+
+class NSE(nn.Module):
+    def __init__(self, theta_dim: int, x_dim: int, beta_min: float = 0.1, beta_max: float = 40, M: int = 1000,
+                 eps_t: float = 1e-10, sampling_dist: str = "Uniform", **kwargs):
+        super().__init__()
+        self.eps_t = eps_t
+        self.beta_min = beta_min
+        self.beta_d = beta_max - beta_min
+        self.M = M
+        self.theta_dim, self.x_dim = theta_dim, x_dim
+        self.net = None  # callers assign `score_net.net = FakeFNet(...)` (gen_gaussian_gaussian.py:75-77)
+        self.embedding_nn_theta = nn.Identity()
+        self.embedding_nn_x = nn.Identity()
+        self.theta_emb_dim, self.x_emb_dim = theta_dim, x_dim
+        self.register_buffer("zeros", torch.zeros(theta_dim))
+        self.register_buffer("ones", torch.ones(theta_dim))
+        self.register_buffer("freqs", torch.zeros(0))
+
+    # ---- model / schedule (torch) -----------------------------------------------------------------------------
+    def forward(self, theta: Tensor, x: Tensor, t: Tensor) -> Tensor:
+        return self.net(theta, x, t)
+
+    def score(self, theta, x, t):
+        return -self(theta, x, t) / self.sigma(t)
+
+    def beta(self, t: Tensor) -> Tensor:
+        return self.beta_d * t + self.beta_min
+
+    def f(self, t: Tensor) -> Tensor:
+        return -0.5 * self.beta(t)
+
+    def g(self, t: Tensor) -> Tensor:
+        return torch.sqrt(self.beta(t))
+
+    def alpha(self, t: Tensor) -> Tensor:
+        return torch.exp(-0.5 * (0.5 * self.beta_d * (t ** 2) + self.beta_min * t))  # nse_toy.py:323-328
+
+    def sigma(self, t: Tensor) -> Tensor:
+        return torch.sqrt(1 - self.alpha(t) + math.exp(-16))  # nse_toy.py:334-339
+
+    def mean_pred(self, theta: Tensor, score: Tensor, alpha_t: Tensor, **kwargs) -> Tensor:
+        return (alpha_t ** (-0.5)) * (theta + (1 - alpha_t) * score)
+
+    def bridge_mean(self, alpha_t, alpha_t_1, theta_t, theta_0, bridge_std):
+        eps_hat = (theta_t - (alpha_t ** 0.5) * theta_0) / ((1 - alpha_t) ** 0.5)
+        return (alpha_t_1 ** 0.5) * theta_0 + ((1 - alpha_t_1 - bridge_std ** 2) ** 0.5) * eps_hat
+
+    # ---- what the kernels need to know about `net` ---------------------------------------------------------------
+    def _d4s_net_description(self) -> dict:
+        net = self.net
+        if not (isinstance(net, FakeFNet) and isinstance(net.real_eps_fun, AnalyticGaussianEps)
+                and isinstance(net.eps_net, EpsilonNet)):
+            raise abi.D4sError("d4s.nse_toy.NSE fuses FakeFNet(AnalyticGaussianEps(...), EpsilonNet(DIM), eps_max) only; "
+                               "an arbitrary Python closure as `real_eps_fun` cannot run inside a CUDA kernel")
+        return dict(mlp=net.eps_net.net, emb_theta=None, out_act=1, out_scale=float(net.eps_net_max),
+                    theta_cols=self.theta_dim, time_features=lambda t64: t64[..., None], time_width=1,
+                    affine=net.real_eps_fun.tables)
+
+    _require_cuda = staticmethod(_FullNSE._require_cuda)
+
+    def _draw_seed(self) -> int:
+        return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+    # ---- samplers ---------------------------------------------------------------------------------------------------
+    def ddim(self, shape: Size, x: Tensor, steps: int = 64, verbose: bool = False, eta: float = 1.0, **kwargs) -> Tensor:
+        """nse_toy.py:372-387: paired plain score when `x.shape[0] == shape[0]` (the covariance pre-pass), else the
+        precision-weighted tall score."""
+        self._require_cuda(x)
+        kw = dict(kwargs)
+        noise, seed, off = kw.pop("_noise", None), kw.pop("_seed", None), kw.pop("_sample_offset", 0)
+        N, m = int(shape[0]), self.theta_dim
+        grid = engine.time_grid(steps)
+        t, t_prev = grid[:-1], grid[:-1].to(torch.float64) - 1.0 / steps
+        paired = x.shape[0] == N
+        if paired:
+            prior, cov_mode, cov_est = engine.PriorSpec(abi.PRIOR_NONE), "GAUSS", None
+        else:
+            prior_fn = kw.pop("prior_score_fn")
+            cov_mode, cov_est = kw.pop("cov_mode", "JAC"), kw.pop("dist_cov_est", None)
+            prior = self._prior_spec(prior_fn)
+        if kw:
+            raise TypeError(f"unexpected keyword arguments: {sorted(kw)}")
+        if seed is None:
+            seed = self._draw_seed()
+        setup = engine.build_setup(self, x, N, t, t_prev, float(eta), prior, cov_mode, cov_est, paired=paired, seed=seed,
+                                   sample_offset=off, weighted=not paired)
+        if noise is not None:
+            z0, z = noise
+            theta = z0.to(x.device, torch.float32).contiguous().clone()
+        else:
+            z = None
+            theta = engine.philox_normal(N, m, seed, -1, off, x.device)
+        return engine.run_trajectory(setup, theta, z, _use_graph_default())
+
+    def _prior_spec(self, prior_score_fn) -> "engine.PriorSpec":
+        if getattr(prior_score_fn, "kind", None) != "gaussian" or not hasattr(prior_score_fn, "_spec"):
+            raise abi.D4sError("nse_toy.NSE needs `prior_score_fn = d4s.nse_toy.gaussian_prior_triple(mean, cov, nse)` "
+                               "(the reference's triple-returning closure cannot be introspected)")
+        return prior_score_fn._spec()
+
+    def factorized_score(self, theta, x_obs, t, prior_score_fn, dist_cov_est=None, cov_mode="JAC") -> Tensor:
+        """nse_toy.py:599-625: always the precision-weighted combination (no alpha-gate; Gaussian prior triple)."""
+        self._require_cuda(theta, x_obs)
+        spec = self._prior_spec(prior_score_fn)
+        tt = torch.as_tensor(t).detach().to("cpu").reshape(1)
+        setup = engine.build_setup(self, x_obs, theta.shape[0], tt, None, 0.0, spec, cov_mode, dist_cov_est)
+        th = theta.detach().to(torch.float32).contiguous()
+        engine.score_partials(setup, th, 0)
+        return engine.finalize(setup, th, 0)

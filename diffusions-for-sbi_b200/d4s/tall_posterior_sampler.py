@@ -72,11 +72,11 @@ def tweedies_approximation_prior(theta, t, score_fn, nse, mode="vmap"):
     alpha_t = float(engine._scalar64(nse.alpha, tt))
     sigma_t = float(engine._scalar64(nse.sigma, tt))
     if kind == "uniform":
-        score, jd = nse._prior_score_native(theta, t, spec, want_jac=True)
+        score, jd = engine.prior_score_native(nse, theta, t, spec, want_jac=True)
         prec_diag = (alpha_t / sigma_t ** 2) / (1.0 + sigma_t ** 2 * jd)
         prec = torch.diag_embed(prec_diag)
     else:
-        score = nse._prior_score_native(theta, t, spec)
+        score = engine.prior_score_native(nse, theta, t, spec)
         eye = torch.eye(m, dtype=torch.float64)
         c_t = sigma_t ** 2 * eye + alpha_t * spec.cov
         jac = -torch.linalg.inv(c_t).T

@@ -23,7 +23,7 @@ class _DiffusedPriorScore:
     def __call__(self, theta: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
         lead = theta.shape[:-1]
         th = theta.reshape(-1, theta.shape[-1])
-        out = self.nse._prior_score_native(th, t, self._spec())
+        out = engine.prior_score_native(self.nse, th, t, self._spec())
         return out.reshape(*lead, theta.shape[-1])
 
 

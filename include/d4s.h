@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D4S_ABI_VERSION 9
+#define D4S_ABI_VERSION 10
 
 #define D4S_OK 0
 #define D4S_ERR_ARG -1      /* bad argument / unsupported shape */
@@ -96,6 +96,11 @@ typedef struct {
     int32_t emb_dims[D4S_MAX_LAYERS + 1];
     const float* emb_weight[D4S_MAX_LAYERS];
     const float* emb_bias[D4S_MAX_LAYERS];
+    /* output head of the toy nets (embedding_nets.py:127-160, FakeFNet/EpsilonNet):
+     * eps = out_scale * act(W_L h + b_L) [+ analytic affine term, see D4sStep.affine]; out_act 0 = identity, 1 = tanh.
+     * out_scale == 0 is read as 1 (plain MLP). */
+    int32_t out_act;
+    float out_scale;
 } D4sNetDesc;
 
 /* Everything that is constant along one trajectory / one factorized_score call. */
@@ -117,6 +122,9 @@ typedef struct {
     int64_t sample_offset;   /* global index of local sample 0 (sample sharding keeps the noise G-invariant) */
     float* workspace;        /* partial sums, >= d4s_workspace_floats() floats */
     int64_t workspace_floats;
+    const float* obs_raw;    /* [n_obs, x_dim] raw observations, only read when D4sStep.affine != NULL */
+    int32_t x_dim;
+    int32_t reserved0;
 } D4sProblem;
 
 /* Per-step inputs. */
@@ -127,6 +135,8 @@ typedef struct {
     const float* noise;     /* [N, m] injected z for this step, or NULL => Philox(seed, step, sample, dim) */
     int32_t step_index;     /* Philox counter word; also selects nothing else */
     int32_t update;         /* 1: theta <- DDIM update (nse.py:289-298); 0: only write the score */
+    const float* affine;    /* NULL, or [m*m + m*x_dim + m]: analytic part of eps, eps += M_t theta_i - G_t x_j - g_t
+                               (the closed-form Gaussian posterior score of gen_gaussian_gaussian.py:59-72) */
 } D4sStep;
 
 /* ---- library ---------------------------------------------------------------------------------- */
@@ -163,13 +173,14 @@ D4S_API int d4s_finalize(const D4sNet* net, const D4sProblem* prob, const D4sSte
 
 /* ---- whole trajectory: replaces the loop of NSE.ddim (nse.py:263-266).  sched_dev[steps, 16],
  * time_feat_dev[steps, H1p], mats_dev[steps, d4s_mats_floats(m)], noise_dev NULL or [steps, N, m].
+ * affine_dev: NULL or [steps, m*m + m*x_dim + m] (see D4sStep.affine).
  * theta_dev holds the initial draw on entry and the samples on return (stream-ordered).
  * step_cov_mode_host: NULL, or a HOST array [steps] of D4S_COV_* overriding prob->cov_mode per step (a JAC
  * run needs no Jacobian on the steps whose combine mode is D4S_COMBINE_SUM: nse.py:642-643 discards it).
  * use_graph != 0 captures the steps into a CUDA graph (cached by argument identity). */
 D4S_API int d4s_ddim_run(const D4sNet* net, const D4sProblem* prob, int32_t steps, const float* sched_dev,
                  const float* time_feat_dev, const float* mats_dev, const float* noise_dev, float* theta_dev,
-                 const int32_t* step_cov_mode_host, int32_t use_graph, void* stream);
+                 const int32_t* step_cov_mode_host, const float* affine_dev, int32_t use_graph, void* stream);
 D4S_API void d4s_graph_cache_clear(void);
 /* Library options: "path" = 0 auto | 1 per-step fp32 SIMT kernels only | 2 require the fused tcgen05 trajectory
  * kernel (bf16x3 split on the tensor cores; GAUSS, tall grid); "tc_steps_per_launch" = DDIM steps per tcgen05

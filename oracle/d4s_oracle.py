@@ -120,12 +120,17 @@ class OracleNet:
     beta_min: float = 0.1
     beta_d: float = 39.9
     dtype: type = np.float64
+    # toy FakeFNet (embedding_nets.py:141-160): eps = real_eps + eps_max * tanh(MLP([theta, x, t])) with the analytic
+    # Gaussian-posterior eps of gen_gaussian_gaussian.py:59-72; keys post_cov, inv_lik, inv_prior_mu, eps_max
+    toy: Optional[dict] = None
 
     def astype(self, dtype) -> "OracleNet":
         return OracleNet(self.theta_dim, self.x_dim, self.freqs.astype(dtype), self.net.astype(dtype),
                          None if self.emb_theta is None else self.emb_theta.astype(dtype),
                          None if self.emb_x is None else self.emb_x.astype(dtype),
-                         self.n_max, self.pf, self.schedule, self.beta_min, self.beta_d, dtype)
+                         self.n_max, self.pf, self.schedule, self.beta_min, self.beta_d, dtype,
+                         None if self.toy is None else {k: (np.asarray(v, dtype) if k != "eps_max" else v)
+                                                        for k, v in self.toy.items()})
 
     # ---- schedule: nse.py:163-170 / nse_toy.py:323-339 --------------------------------
     def alpha(self, t):
@@ -166,6 +171,13 @@ def nse_forward(net: OracleNet, theta: np.ndarray, x: np.ndarray, t) -> np.ndarr
 
 
 def nse_score(net: OracleNet, theta, x, t) -> np.ndarray:
+    if net.toy is not None:  # paired rows: FakeFNet on (theta_i, x_i)
+        D = net.dtype
+        xx = np.broadcast_to(x, theta.shape[:-1] + x.shape[-1:])
+        inp = np.concatenate((theta, xx, np.full(theta.shape[:-1] + (1,), t, dtype=D)), -1)
+        M, G, g = toy_affine(net, t)
+        eps = theta @ M.T - (xx @ G.T + g) + D(net.toy["eps_max"]) * np.tanh(net.net(inp))
+        return -eps / net.sigma(t)
     return -nse_forward(net, theta, x, t) / net.sigma(t)  # nse.py:144-145
 
 
@@ -238,6 +250,48 @@ def pair_inputs(net: OracleNet, theta: np.ndarray, x: np.ndarray, t, ns=None):
     return np.concatenate(parts, axis=-1), th.shape[-1]
 
 
+def toy_affine(net: OracleNet, t):
+    """Analytic eps of the Gaussian toy task (gen_gaussian_gaussian.py:59-72) in affine form:
+    eps = sigma inv(alpha S_post + (1-alpha) I) (theta - sqrt(alpha) S_post (S_pr^-1 mu + S_lik^-1 x)) = M theta - G x - g."""
+    D = net.dtype
+    a, sig = net.alpha(t), net.sigma(t)
+    pc, il, ipm = (net.toy[k].astype(D) for k in ("post_cov", "inv_lik", "inv_prior_mu"))
+    m = pc.shape[0]
+    M = sig * np.linalg.inv(a * pc + (1 - a) * np.eye(m, dtype=D))
+    G = (a ** 0.5) * (M @ pc @ il)
+    g = (a ** 0.5) * (M @ pc @ ipm)
+    return M, G, g
+
+
+def pair_eps(net: OracleNet, theta, x, t, ns=None, want_jac=False):
+    """eps[N, n, m] on the (sample, observation) grid (and d eps / d theta [N, n, m, m] when asked)."""
+    if net.toy is None:
+        inp, e_theta = pair_inputs(net, theta, x, t, ns)
+        if not want_jac:
+            return net.net(inp)
+        eps, masks = net.net.forward_with_masks(inp)
+        jac = net.net.vjp_rows(masks, slice(0, e_theta))  # [N,n,m,e_theta]
+        emb_jac = _theta_jacobian_of_embedding(net, theta)
+        if emb_jac is not None:
+            jac = jac @ emb_jac[:, None]  # chain through the theta embedding
+        return eps, jac
+    # toy: FakeFNet.forward (embedding_nets.py:155-160) with the raw time as third input block
+    D = net.dtype
+    N, n, m = theta.shape[0], x.shape[0], theta.shape[1]
+    tt = np.full((N, n, 1), t, dtype=D)
+    inp = np.concatenate((np.broadcast_to(theta[:, None], (N, n, m)), np.broadcast_to(x[None], (N, n, x.shape[1])), tt), -1)
+    M, G, g = toy_affine(net, t)
+    real = (theta @ M.T)[:, None, :] - (x @ G.T + g)[None]
+    z, masks = net.net.forward_with_masks(inp)
+    th = np.tanh(z)
+    eps = real + D(net.toy["eps_max"]) * th
+    if not want_jac:
+        return eps
+    jz = net.net.vjp_rows(masks, slice(0, m))  # d z / d theta
+    jac = D(net.toy["eps_max"]) * (1 - th ** 2)[..., None] * jz + M
+    return eps, jac
+
+
 # --------------------------------------------------------------------------------------
 # a7: prec_matrix_backward (tall_posterior_sampler.py:35-43)
 # --------------------------------------------------------------------------------------
@@ -268,19 +322,14 @@ def tweedies_approximation(net: OracleNet, x, theta, t, dist_cov_est=None, mode=
     """
     alpha_t, sigma_t = net.alpha(t), net.sigma(t)
     N, m = theta.shape
-    inp, e_theta = pair_inputs(net, theta, x, t, ns)
     if mode == "GAUSS":
-        eps = net.net(inp)
+        eps = pair_eps(net, theta, x, t, ns)
         score = -eps / sigma_t
         prec = prec_matrix_backward(net, t, dist_cov_est)  # [n,m,m]
         prec = np.tile(prec[None], (N, 1, 1, 1))  # tall_posterior_sampler.py:128 (materialised)
     elif mode == "JAC":
-        eps, masks = net.net.forward_with_masks(inp)
+        eps, jac_eps = pair_eps(net, theta, x, t, ns, want_jac=True)
         score = -eps / sigma_t
-        jac_eps = net.net.vjp_rows(masks, slice(0, e_theta))  # [N,n,m,e_theta]
-        emb_jac = _theta_jacobian_of_embedding(net, theta)
-        if emb_jac is not None:
-            jac_eps = jac_eps @ emb_jac[:, None]  # chain through the theta embedding
         jac_score = -jac_eps / sigma_t
         cov = (sigma_t ** 2 / alpha_t) * (np.eye(m, dtype=net.dtype) + (sigma_t ** 2) * jac_score)  # :91-93
         prec = np.linalg.inv(cov)  # :94
@@ -462,8 +511,7 @@ def ddim_single(net: OracleNet, x, z0, z, steps, eta, clip=(None, None)):
 def factorized_score_geffner(net: OracleNet, theta, x, t, prior, ns=None):
     """nse.py:479-542 (analytic prior): (1 - n) prior_score + sum_j score_j."""
     n_obs = x.shape[0] if x.ndim > 1 else 1
-    inp, _ = pair_inputs(net, theta, x if x.ndim > 1 else x[None], t, ns)
-    scores = -net.net(inp) / net.sigma(t)
+    scores = -pair_eps(net, theta, x if x.ndim > 1 else x[None], t, ns) / net.sigma(t)
     return (1 - n_obs) * prior_score(net, prior, theta, t) + scores.sum(axis=1)
 
 
@@ -508,8 +556,7 @@ def deterministic_gaussian_geffner(net: OracleNet, x, z0, z, prior, steps=1000, 
     for i in range(steps):
         t = time[i]
         g = _gamma(net, time, i, steps)
-        inp, _ = pair_inputs(net, theta, x, t)
-        scores = -net.net(inp) / net.sigma(t)
+        scores = -pair_eps(net, theta, x, t) / net.sigma(t)
         p_score = prior_score(net, prior, theta, t)
         mu = 1 / g ** 0.5 * (n * theta + (1 - g) * scores.sum(axis=1)) - (n - 1) * g ** 0.5 * theta  # :688
         mu = mu * (1 / (n - g * (n - 1)))

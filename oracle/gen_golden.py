@@ -141,6 +141,96 @@ def langevin_case(name, net32, x, prior_kind, prior_params, N, seed, steps, lste
     print("wrote", name)
 
 
+def toy_case(name, DIM, n_obs, eps_max, N, seed, steps, eta):
+    """Config 1: the Gaussian-Gaussian toy of gen_gaussian_gaussian.py:27-96 driven on CPU -- reference `nse_toy.NSE`,
+    `FakeFNet(real_eps, EpsilonNet(DIM), eps)`, triple-returning prior score; GAUSS + JAC per-call and trajectories,
+    plus the paired covariance pre-pass (gen_gaussian_gaussian.py:143-160)."""
+    import embedding_nets as ref_emb
+    import nse_toy as ref_toy
+    from tasks.toy_examples.data_generators import Gaussian_Gaussian_mD
+    out = {}
+    torch.manual_seed(seed)
+    means = torch.rand(DIM) * 20 - 10
+    stds = torch.rand(DIM) * 25 + 0.1
+    task = Gaussian_Gaussian_mD(dim=DIM, means=means, stds=stds)
+    prior = task.prior
+    theta_true = prior.sample(sample_shape=(1,))
+    x_obs = torch.cat([task.simulator(theta_true).reshape(1, -1) for _ in range(n_obs)], dim=0)
+    eps_net32 = ref_emb.EpsilonNet(DIM)
+    gen = torch.Generator().manual_seed(seed + 100)
+    theta = prior.loc + prior.covariance_matrix.diag().sqrt() * torch.randn(N, DIM, generator=gen) * 0.3
+    cov_est = spd_covs(gen, n_obs, DIM) * 4
+    z0 = torch.randn(N, DIM, generator=gen)
+    z = torch.randn(steps, N, DIM, generator=gen)
+    Np = 3
+    z0p = torch.randn(Np * n_obs, DIM, generator=gen)
+    zp = torch.randn(steps, Np * n_obs, DIM, generator=gen)
+    t_grid = [0.9, 0.5, 0.2, 0.05]
+    mlp_arrays("net", eps_net32.net, out)
+    out.update(theta=npy(theta), x=npy(x_obs), dist_cov_est=npy(cov_est), t_grid=np.asarray(t_grid, np.float32),
+               prior_kind=np.str_("gaussian"), theta_dim=np.int64(DIM), eps_max=np.float64(eps_max),
+               traj_z0=npy(z0), traj_z=npy(z), traj_steps=np.int64(steps), traj_eta=np.float64(eta),
+               pair_z0=npy(z0p), pair_z=npy(zp), pair_reps=np.int64(Np))
+    out["prior.loc"], out["prior.cov"] = npy(prior.loc), npy(prior.covariance_matrix)
+    out["lik_cov"] = npy(task.simulator_cov)
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        score_net = ref_toy.NSE(theta_dim=DIM, x_dim=DIM)
+        idm = torch.eye(DIM, dtype=dt)
+        inv_lik = torch.linalg.inv(task.simulator_cov.to(dt))
+        inv_prior = torch.linalg.inv(prior.covariance_matrix.to(dt))
+        posterior_cov = torch.linalg.inv(inv_lik + inv_prior)
+        inv_prior_prior = inv_prior @ prior.loc.to(dt)
+
+        def real_eps(theta, x, t):  # gen_gaussian_gaussian.py:59-72
+            posterior_cov_diff = (posterior_cov[None] * score_net.alpha(t)[..., None]
+                                  + (1 - score_net.alpha(t))[..., None] * idm[None])
+            posterior_mean_0 = (posterior_cov @ (inv_prior_prior[:, None] + inv_lik @ x.mT)).mT
+            posterior_mean_diff = (score_net.alpha(t) ** 0.5) * posterior_mean_0
+            score = -(torch.linalg.inv(posterior_cov_diff) @ (theta - posterior_mean_diff)[..., None])[..., 0]
+            return -score_net.sigma(t) * score
+
+        score_net.net = ref_emb.FakeFNet(real_eps_fun=real_eps, eps_net=copy.deepcopy(eps_net32).to(dt), eps_net_max=eps_max)
+        score_net.to(dt)
+        prior_score_fn = ref_vp.get_vpdiff_gaussian_score(prior.loc.to(dt), prior.covariance_matrix.to(dt), score_net)
+
+        def prior_score(theta, t):  # gen_gaussian_gaussian.py:86-96
+            mean_prior_0_t = ref_tps.mean_backward(theta, t, prior_score_fn, score_net)
+            prec_prior_0_t = ref_tps.prec_matrix_backward(t, prior.covariance_matrix.to(dt), score_net).repeat(
+                theta.shape[0], 1, 1)
+            return prior_score_fn(theta, t), mean_prior_0_t, prec_prior_0_t
+
+        th, xx, ce = theta.to(dt), x_obs.to(dt), cov_est.to(dt)
+        for mode in ("GAUSS", "JAC"):
+            fs, sc = [], []
+            for tv in t_grid:
+                t = torch.tensor(tv, dtype=torch.float32).to(dt)
+                fs.append(npy(score_net.factorized_score(th, xx, t, prior_score, dist_cov_est=ce, cov_mode=mode)))
+                if mode == "GAUSS":
+                    sc.append(npy(ref_toy.tweedies_approximation(x=xx, theta=th, t=t, score_fn=score_net.score, nse=score_net,
+                                                                 dist_cov_est=ce, mode="GAUSS")[2]))
+            out[f"{tag}.{mode}.factorized_score"] = np.stack(fs)
+            if mode == "GAUSS":
+                out[f"{tag}.scores"] = np.stack(sc)
+            it = iter(z.to(dt))
+            FakeDiagNormal.z0 = z0.to(dt)
+            with mock.patch.object(ref_toy, "DiagNormal", FakeDiagNormal), \
+                    mock.patch("torch.randn_like", side_effect=lambda a: next(it).to(a)):
+                res = score_net.ddim(shape=(N,), x=xx, eta=eta, steps=steps, prior_score_fn=prior_score,
+                                     dist_cov_est=ce, cov_mode=mode)
+            out[f"{tag}.{mode}.traj"] = npy(res)
+        # paired covariance pre-pass: every sample carries its own observation (gen_gaussian_gaussian.py:143-156)
+        xp = xx[None, :].repeat(Np, 1, 1).reshape(Np * n_obs, -1)
+        it = iter(zp.to(dt))
+        FakeDiagNormal.z0 = z0p.to(dt)
+        with mock.patch.object(ref_toy, "DiagNormal", FakeDiagNormal), \
+                mock.patch("torch.randn_like", side_effect=lambda a: next(it).to(a)):
+            res = score_net.ddim(shape=(Np * n_obs,), x=xp, steps=steps, eta=0.5)
+        out[f"{tag}.pair.traj"] = npy(res)
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name)
+
+
 def make_prior(kind, m, dt, net, low=None, high=None, loc=None, cov=None):
     if kind == "uniform":
         low, high = low.to(dt), high.to(dt)
@@ -311,6 +401,9 @@ def main(filt=None):
         high = (hi - st["theta_train_mean"]) / st["theta_train_std"] * 2
         per_call_case("jrnnm4d_n5", net, x, "uniform", dict(low=low, high=high), N=10, seed=16,
                       t_grid=[0.9, 0.5, 0.29, 0.1, 0.01], traj=dict(N=12, steps=30, eta=1.0, modes=("GAUSS",)))
+    if want("toy"):
+        toy_case("toy_gauss_d4_n5", DIM=4, n_obs=5, eps_max=1e-1, N=12, seed=31, steps=20, eta=0.5)
+        toy_case("toy_gauss_d10_n30", DIM=10, n_obs=30, eps_max=1e-2, N=8, seed=32, steps=64, eta=0.2)  # dt = 2^-6: the fp64 run of the reference is NaN when fp32(t) - dt < 0 (toy alpha has a linear term)
     if want("langevin"):
         net, st = load_sbibm("sir")
         x = sbibm_obs("sir", st, 5, log_space=False)

@@ -52,3 +52,18 @@ def prior_objects(g, nse, device):
     loc = torch.as_tensor(g["prior.loc"], device=device)
     cov = torch.as_tensor(g["prior.cov"], device=device)
     return (torch.distributions.MultivariateNormal(loc, cov), d4s.get_vpdiff_gaussian_score(loc, cov, nse), "gaussian")
+
+
+def toy_from_golden(g, device="cpu"):
+    """(d4s.nse_toy.NSE with FakeFNet(AnalyticGaussianEps, EpsilonNet, eps_max), prior triple) of a toy fixture."""
+    from d4s import nse_toy
+    m = int(g["theta_dim"])
+    nse = nse_toy.NSE(theta_dim=m, x_dim=g["x"].shape[-1])
+    eps_net = nse_toy.EpsilonNet(m)
+    _load_mlp(eps_net.net, [g["net.W0"], g["net.W1"]], [g["net.b0"], g["net.b1"]])
+    real = nse_toy.AnalyticGaussianEps(g["prior.loc"], g["prior.cov"], g["lik_cov"], nse)
+    nse.net = nse_toy.FakeFNet(real_eps_fun=real, eps_net=eps_net, eps_net_max=float(g["eps_max"]))
+    nse = nse.to(device).eval()
+    prior_fn = nse_toy.gaussian_prior_triple(torch.as_tensor(g["prior.loc"], device=device),
+                                             torch.as_tensor(g["prior.cov"], device=device), nse)
+    return nse, prior_fn

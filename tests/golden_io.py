@@ -27,6 +27,13 @@ def _mlp(g, prefix, dtype):
 
 def oracle_net(g, dtype=np.float64):
     x_dim = g["x"].shape[-1]
+    if "eps_max" in g:  # toy FakeFNet fixture (gen_golden.toy_case)
+        pc, lc, mu = (g[k].astype(np.float64) for k in ("prior.cov", "lik_cov", "prior.loc"))
+        inv_lik, inv_prior = np.linalg.inv(lc), np.linalg.inv(pc)
+        toy = dict(post_cov=np.linalg.inv(inv_lik + inv_prior).astype(dtype), inv_lik=inv_lik.astype(dtype),
+                   inv_prior_mu=(inv_prior @ mu).astype(dtype), eps_max=float(g["eps_max"]))
+        return orc.OracleNet(int(g["theta_dim"]), x_dim, np.zeros(0, dtype), _mlp(g, "net", dtype), schedule="toy",
+                             dtype=dtype, toy=toy)
     return orc.OracleNet(int(g["theta_dim"]), x_dim, g["freqs"].astype(dtype), _mlp(g, "net", dtype),
                          _mlp(g, "embt", dtype), _mlp(g, "embx", dtype), n_max=int(g["n_max"]),
                          pf=bool(int(g["pf"])), dtype=dtype)

@@ -13,7 +13,7 @@ from oracle import d4s_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-CASES = [c for c in gio.names() if not c.startswith("langevin")]
+CASES = [c for c in gio.names() if not c.startswith(("langevin", "toy"))]
 REL_TOL = 1e-4
 TRAJ_TOL = 1e-3
 
@@ -357,3 +357,45 @@ def test_langevin_family(name, dev, kernel_path):
     if "f64.detgef.traj" in g:
         out = nse.deterministic_gaussian_geffner((z0.shape[0],), x, fn, steps=steps, _noise=(z0, z[:steps]))
         check(out, "detgef", steps)
+
+
+# ---- toy config 1: nse_toy.NSE + FakeFNet(AnalyticGaussianEps, EpsilonNet) --------------------------------------------
+TOY = [c for c in gio.names() if c.startswith("toy")]
+
+
+@pytest.mark.parametrize("name", TOY)
+def test_toy_gaussian_config(name, dev):
+    """Per-call scores / factorized_score (GAUSS, JAC), tall trajectories and the paired covariance pre-pass of the
+    Gaussian toy task against golden outputs of the reference's nse_toy.NSE (gen_gaussian_gaussian.py flow)."""
+    from d4s import nse_toy
+    from d4s_helpers import toy_from_golden
+    g = gio.load(name)
+    nse, prior_fn = toy_from_golden(g, dev)
+    theta, x, cov = _t(g["theta"], dev), _t(g["x"], dev), _t(g["dist_cov_est"], dev)
+    for k, t in enumerate(g["t_grid"]):
+        for mode in ("GAUSS", "JAC"):
+            out = nse.factorized_score(theta, x, torch.tensor(t), prior_fn, dist_cov_est=cov, cov_mode=mode)
+            ref = g[f"f64.{mode}.factorized_score"][k]
+            floor = orc.rel_l2(g[f"f32.{mode}.factorized_score"][k], ref)
+            err = orc.rel_l2(out.cpu().numpy(), ref)
+            assert err < max(REL_TOL, 3 * floor), (name, mode, float(t), err, floor)
+    steps, eta = int(g["traj_steps"]), float(g["traj_eta"])
+    noise = (torch.as_tensor(g["traj_z0"]), torch.as_tensor(g["traj_z"]))
+    for mode in ("GAUSS", "JAC"):
+        out = nse.ddim((noise[0].shape[0],), x, steps=steps, eta=eta, prior_score_fn=prior_fn, dist_cov_est=cov,
+                       cov_mode=mode, _noise=noise)
+        ref = g[f"f64.{mode}.traj"]
+        ref32 = np.abs(g[f"f32.{mode}.traj"] - ref).max()
+        err = np.abs(out.cpu().numpy() - ref).max()
+        print(f"{name} {mode}: max|d theta| = {err:.2e} (reference fp32 vs fp64: {ref32:.2e})")
+        assert err < max(TRAJ_TOL * max(1.0, np.abs(ref).max()), 3 * ref32), (name, mode, err)
+    reps = int(g["pair_reps"])
+    xp = x[None].repeat(reps, 1, 1).reshape(reps * x.shape[0], -1)
+    out = nse.ddim((xp.shape[0],), xp, steps=steps, eta=0.5, _noise=(torch.as_tensor(g["pair_z0"]), torch.as_tensor(g["pair_z"])))
+    ref = g["f64.pair.traj"]
+    assert np.abs(out.cpu().numpy() - ref).max() < TRAJ_TOL * max(1.0, np.abs(ref).max())
+    # the torch definition of the module (used outside the fused path) agrees with the kernels' affine form
+    tt = torch.tensor(0.3, device=dev)
+    e_torch = nse(theta, x[:1].expand(theta.shape[0], -1), tt)
+    prec, _, sc = __import__("d4s").tweedies_approximation(x=x[:1], theta=theta, t=tt, nse=nse, dist_cov_est=cov[:1], mode="GAUSS")
+    assert orc.rel_l2((-sc[:, 0] * nse.sigma(tt)).cpu().numpy(), e_torch.detach().cpu().numpy()) < 1e-5

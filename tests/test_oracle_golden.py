@@ -12,7 +12,7 @@ import torch
 import golden_io as gio
 from oracle import d4s_oracle as orc
 
-CASES = [c for c in gio.names() if not c.startswith("langevin")]
+CASES = [c for c in gio.names() if not c.startswith(("langevin", "toy"))]
 
 
 def _ns(g):
@@ -128,3 +128,33 @@ def test_langevin_family_fp64(name):
         out = orc.deterministic_gaussian_geffner(net, x, z0, z, prior, steps)
         ref = g["f64.detgef.traj"]
         assert np.abs(out - ref).max() < 5e-6 * max(1.0, np.abs(ref).max())
+
+
+# ---- toy Gaussian-Gaussian task, nse_toy.NSE + FakeFNet (BASELINE config 1) ---------------
+TOY = [c for c in gio.names() if c.startswith("toy")]
+
+
+@pytest.mark.parametrize("name", TOY)
+def test_toy_config_fp64(name):
+    g = gio.load(name)
+    net, prior = gio.oracle_net(g), gio.oracle_prior(g)
+    theta, x, cov = (g[k].astype(np.float64) for k in ("theta", "x", "dist_cov_est"))
+    for k, t in enumerate(g["t_grid"]):
+        t = np.float64(t)
+        _, _, sc = orc.tweedies_approximation(net, x, theta, t, cov, "GAUSS")
+        assert orc.rel_l2(sc, g["f64.scores"][k]) < 5e-7
+        for mode in ("GAUSS", "JAC"):
+            out = orc.factorized_score(net, theta, x, t, prior, cov, mode, "gaussian")  # nse_toy.py:599-625
+            ref = g[f"f64.{mode}.factorized_score"][k]
+            floor = orc.rel_l2(g[f"f32.{mode}.factorized_score"][k], ref)
+            assert orc.rel_l2(out, ref) < max(5e-7, (1e-3 if mode == "GAUSS" else 3.0) * floor), (name, mode, t)
+    steps, eta = int(g["traj_steps"]), float(g["traj_eta"])
+    for mode in ("GAUSS", "JAC"):
+        out = orc.ddim(net, x, g["traj_z0"], g["traj_z"], steps, eta, prior, cov, mode, "gaussian")
+        ref = g[f"f64.{mode}.traj"]
+        assert np.abs(out - ref).max() < 1e-5 * max(1.0, np.abs(ref).max()), (name, mode)
+    reps = int(g["pair_reps"])
+    xp = np.tile(x[None], (reps, 1, 1)).reshape(reps * x.shape[0], -1)
+    out = orc.ddim_single(net, xp, g["pair_z0"], g["pair_z"], steps, 0.5)
+    ref = g["f64.pair.traj"]
+    assert np.abs(out - ref).max() < 1e-5 * max(1.0, np.abs(ref).max())
