@@ -323,6 +323,7 @@ static int fill_traj_params(const D4sNet* net, const D4sProblem* pb, const float
     p.swap_lbo_sbo = g_opt_swap;
     p.obs_feat = pb->obs_feat;
     p.obs_prec = pb->obs_prec;
+    p.obs_weight = pb->obs_weight;
     p.sched = sched;
     p.time_feat = tf;
     p.mats = mats;
@@ -401,6 +402,7 @@ static int score_partials_impl(const D4sNet* net, const D4sProblem* pb, const D4
     p.time_feat = st->time_feat;
     p.obs_prec = pb->obs_prec;
     p.sched = st->sched;
+    p.obs_weight = pb->obs_weight;
     p.affine = st->affine;
     p.obs_raw = pb->obs_raw;
     p.d = pb->x_dim;

@@ -59,6 +59,7 @@ struct ScoreParams {
     const float* affine;     // optional [m*m + m*d + m]: eps += M theta_i - G x_j - g   (analytic Gaussian posterior part)
     const float* obs_raw;    // [n][d] raw observations (read with `affine`)
     int d;
+    const float* obs_weight; // optional [n] weights of the observations in the sums (classifier-free guidance)
     float* part;             // [N][C][W]
     float* scores_out;       // optional [N][n][m]
     float* prec_out;         // optional JAC [N][n][m][m]
@@ -89,6 +90,7 @@ struct TrajParams {
     int swap_lbo_sbo;        // debug: exchange the two descriptor strides
     const float* obs_feat;   // [n][Hp0]
     const float* obs_prec;   // [n][m][m] or NULL
+    const float* obs_weight; // [n] or NULL
     const float* sched;      // [steps][16]
     const float* time_feat;  // [steps][Hp0]
     const float* mats;       // [steps][2 m^2 + m]

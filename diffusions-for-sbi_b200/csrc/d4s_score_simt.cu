@@ -374,6 +374,7 @@ __global__ void __launch_bounds__(NT, 2) score_simt_kernel(const ScoreParams p) 
             float v;
             if (!p.jac) v = (c < m) ? sS[r * MMAX + c] : sQS[r * MMAX + (c - m)];
             else v = sQS[r * W + c];
+            if (p.obs_weight) v *= __ldg(p.obs_weight + sObs[r]);
             acc += v;
         }
         if (p.part) p.part[((size_t)(i0 + si) * p.C + chunk) * W + c] = acc;

@@ -611,13 +611,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                         float acc = 0.f;
                         for (int oj = lane; oj < nobs; oj += 32) {
                             const float* srow = sS + (si * p.OC + oj) * MMAX;
+                            const float wj = p.obs_weight ? __ldg(p.obs_weight + j0 + oj) : 1.f;
                             if (c < m) {
-                                acc += srow[c];
+                                acc = fmaf(wj, srow[c], acc);
                             } else if (p.obs_prec) {
                                 const float* Q = p.obs_prec + ((size_t)(j0 + oj) * m + (c - m)) * m;
+                                float qs = 0.f;
 #pragma unroll
                                 for (int k = 0; k < MMAX; ++k)
-                                    if (k < m) acc = fmaf(__ldg(Q + k), srow[k], acc);
+                                    if (k < m) qs = fmaf(__ldg(Q + k), srow[k], qs);
+                                acc = fmaf(wj, qs, acc);
                             }
                         }
 #pragma unroll

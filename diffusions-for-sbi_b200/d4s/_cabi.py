@@ -13,7 +13,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libd4s.so")
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 MAX_LAYERS = 8
 MAX_THETA = 10
 MAX_WIDTH = 256
@@ -77,6 +77,7 @@ class Problem(C.Structure):
         ("obs_raw", C.c_void_p),
         ("x_dim", C.c_int32),
         ("reserved0", C.c_int32),
+        ("obs_weight", C.c_void_p),
     ]
 
 

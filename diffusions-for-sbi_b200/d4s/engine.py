@@ -303,7 +303,7 @@ def combine_mode(prior: PriorSpec, cov_jac: bool, n_total: int, sqrt_alpha: floa
 
 
 def mats_table(rows: torch.Tensor, prior: PriorSpec, cov_jac: bool, n_total: int, sum_q: Optional[torch.Tensor],
-               m: int) -> torch.Tensor:
+               m: int, w_sum: Optional[float] = None) -> torch.Tensor:
     """[steps, 2 m^2 + m] fp64: Lmat | G | mu_t  (layout of D4sStep.mats)."""
     S = rows.shape[0]
     eye = torch.eye(m, dtype=torch.float64)
@@ -317,7 +317,8 @@ def mats_table(rows: torch.Tensor, prior: PriorSpec, cov_jac: bool, n_total: int
     mu = torch.zeros(S, m, dtype=torch.float64)
     base = torch.zeros(S, m, m, dtype=torch.float64)
     if not cov_jac and sum_q is not None:
-        base = sum_q[None] + (n_total * aos2)[:, None, None] * eye  # sum_j [inv(Sigma_j) + alpha/sigma^2 I]
+        # sum_j w_j [inv(Sigma_j) + alpha/sigma^2 I]; w_j = 1 except for the classifier-free-guidance pseudo-observation
+        base = sum_q[None] + ((n_total if w_sum is None else w_sum) * aos2)[:, None, None] * eye
     if prior.kind == abi.PRIOR_GAUSSIAN:
         cov0, mean0 = prior.cov, prior.mean
         c_t = sig2[:, None, None] * eye + a[:, None, None] * cov0  # vp_diffused_priors.py:65-68
@@ -338,6 +339,10 @@ def mats_table(rows: torch.Tensor, prior: PriorSpec, cov_jac: bool, n_total: int
             lmat = torch.where(shared[:, None, None], torch.linalg.inv(safe), lam)
     else:
         lmat = base  # uniform / none: per-sample prior precision is added on the device
+        shared = comb == abi.COMBINE_SHARED  # no analytic prior (classifier-free guidance): Lambda is the base itself
+        if bool(shared.any()):
+            safe = torch.where(shared[:, None, None], base, eye.expand(S, m, m))
+            lmat = torch.where(shared[:, None, None], torch.linalg.inv(safe), base)
     return torch.cat((lmat.reshape(S, -1), g.reshape(S, -1), mu), dim=1)
 
 
@@ -370,7 +375,7 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
                 prior: PriorSpec, cov_mode: str, dist_cov_est: Optional[torch.Tensor], paired: bool = False,
                 n_sizes: Optional[torch.Tensor] = None, clip=(None, None), seed: int = 0, sample_offset: int = 0,
                 weighted: bool = True, obs_slice: Optional[slice] = None, obs_chunk: int = 0,
-                coef: Optional[dict] = None) -> TallSetup:
+                coef: Optional[dict] = None, cfg: Optional[dict] = None) -> TallSetup:
     """`obs_slice` restricts the kernels to a shard of the observations (observation sharding over ranks):
     (1-n) and Lambda still use the total n, the partial sums are all-reduced by the caller."""
     lib = abi.require_cuda()
@@ -387,19 +392,42 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
     if paired:
         weighted = False
     sum_q = q_dev = None
+    # classifier-free guidance (nse.py:598-625, 532-538): the prior score/precision come from the net itself at x = 0
+    # (PF_NSE: empty set, n = 0).  That is the tall score with one more pseudo-observation of weight (1 - n).
+    w64 = None
+    if cfg is not None:
+        if paired or obs_slice is not None:
+            raise NotImplementedError("classifier-free guidance with paired contexts / observation sharding")
+        w64 = torch.cat((torch.ones(n_total, dtype=torch.float64), torch.tensor([1.0 - n_total], dtype=torch.float64)))
+        prior = PriorSpec(abi.PRIOR_NONE)
     if not cov_jac and weighted and not paired:
         if dist_cov_est is None:
             raise ValueError("cov_mode='GAUSS' needs dist_cov_est (tall_posterior_sampler.py:125)")
         q64 = torch.linalg.inv(dist_cov_est.detach().to("cpu", torch.float64))  # [n, m, m]
-        sum_q = q64.sum(dim=0)
+        if cfg is not None:
+            if cfg.get("prior_cov") is None:
+                raise ValueError("clf_free_guidance with cov_mode='GAUSS' needs dist_cov_est_prior (nse.py:613)")
+            qp = torch.linalg.inv(cfg["prior_cov"].detach().to("cpu", torch.float64).reshape(1, m, m))
+            q64 = torch.cat((q64, qp))
+            sum_q = (w64[:, None, None] * q64).sum(dim=0)
+        else:
+            sum_q = q64.sum(dim=0)
     t = t.detach().to("cpu").reshape(-1)
     sa = _scalar64(nse.alpha, t.to(torch.float64)).sqrt()
     comb = [combine_mode(prior, cov_jac, n_total, float(s), weighted) for s in sa]
+    if cfg is not None and weighted:  # nse.py:622-625: always the weighted solve
+        comb = [abi.COMBINE_PER_SAMPLE if cov_jac else abi.COMBINE_SHARED] * len(comb)
     rows = schedule_rows(nse, t, None if t_prev is None else t_prev.detach().to("cpu").reshape(-1), eta, n_total, comb,
                          coef)
-    mats = mats_table(rows, prior, cov_jac, n_total, sum_q, m)
+    mats = mats_table(rows, prior, cov_jac, n_total, sum_q, m, None if w64 is None else float(w64.sum()))
     tf = time_feat_table(nse, pn, t)
     of = obs_feat_table(nse, pn, x2, n_sizes)
+    if cfg is not None:  # layer-0 partial of the pseudo-observation: x = 0 (PF_NSE: masked empty set, no one-hot)
+        if n_sizes is None:
+            x0 = torch.zeros((1,) + tuple(x2.shape[1:]), dtype=x2.dtype, device=x2.device)
+            of = torch.cat((of, obs_feat_table(nse, pn, x0, None)))
+        else:
+            of = torch.cat((of, torch.zeros(1, of.shape[1], dtype=of.dtype)))
     if obs_slice is not None:
         of = of[obs_slice]
         if sum_q is not None:
@@ -422,6 +450,8 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
     prob.n_obs_total = n_total
     prob.obs_feat = of_dev.data_ptr()
     prob.obs_prec = 0 if q_dev is None else q_dev.data_ptr()
+    w_dev = None if w64 is None else _dev32(w64, device)
+    prob.obs_weight = 0 if w_dev is None else w_dev.data_ptr()
     prob.prior_low = 0 if low_dev is None else low_dev.data_ptr()
     prob.prior_high = 0 if high_dev is None else high_dev.data_ptr()
     lo, hi = clip
@@ -452,7 +482,7 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
         prob.obs_raw = x_raw.data_ptr()
         prob.x_dim = x_raw.shape[-1]
     return TallSetup(pn, prob, _dev32(rows, device), _dev32(tf, device), _dev32(mats, device), step_modes,
-                     (of_dev, q_dev, low_dev, high_dev, ws, x_raw), t.numel(), affine_dev)
+                     (of_dev, q_dev, low_dev, high_dev, ws, x_raw, w_dev), t.numel(), affine_dev)
 
 
 def _stream(device) -> C.c_void_p:

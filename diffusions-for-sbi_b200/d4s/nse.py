@@ -133,9 +133,12 @@ class NSE(nn.Module):
         sample_offset = kw.pop("_sample_offset", 0)
         if kw:
             raise TypeError(f"unexpected keyword arguments: {sorted(kw)}")
-        if opts["clf_free_guidance"]:
-            raise NotImplementedError("clf_free_guidance=True: next-scope row (SURVEY.md section 8(f) rank 3)")
         return opts, noise, seed, sample_offset
+
+    @staticmethod
+    def _cfg(opts):
+        """Classifier-free guidance (nse.py:598-625): prior score and precision from the net itself at x = 0."""
+        return dict(prior_cov=opts["dist_cov_est_prior"]) if opts["clf_free_guidance"] else None
 
     def _draw_seed(self) -> int:
         # one draw from torch's global CPU generator, so torch.manual_seed(...) makes runs reproducible
@@ -161,13 +164,17 @@ class NSE(nn.Module):
             weighted = False
         else:
             paired = False
-            prior = engine.prior_spec(opts["prior_type"], opts["prior"], opts["prior_score_fn"], m)
+            prior = (engine.PriorSpec(abi.PRIOR_NONE) if opts["clf_free_guidance"]
+                     else engine.prior_spec(opts["prior_type"], opts["prior"], opts["prior_score_fn"], m))
             weighted = True
         if seed is None:
             seed = self._draw_seed()
+        cfg = None if single else self._cfg(opts)
+        if cfg is not None:
+            prior = engine.PriorSpec(abi.PRIOR_NONE)
         setup = engine.build_setup(self, x, N, t, t_prev, float(eta), prior, opts["cov_mode"], opts["dist_cov_est"],
                                    paired=paired, n_sizes=opts["n_sizes"], clip=theta_clipping_range, seed=seed,
-                                   sample_offset=sample_offset, weighted=weighted)
+                                   sample_offset=sample_offset, weighted=weighted, cfg=cfg)
         if noise is not None:
             z0, z = noise
             theta = z0.to(x.device, torch.float32).contiguous().clone()
@@ -200,16 +207,15 @@ class NSE(nn.Module):
                          cov_mode="GAUSS", prior_type="gaussian", clf_free_guidance=False, **kwargs) -> Tensor:
         """Precision-weighted tall-data score ("GAUSS"/"JAC", nse.py:544-656), one fused call: kernel 1(+2) then 3."""
         self._require_cuda(theta, x_obs)
-        if clf_free_guidance:
-            raise NotImplementedError("clf_free_guidance=True: next-scope row (SURVEY.md section 8(f) rank 3)")
         n_sizes = kwargs.pop("n", None)
         if kwargs:
             raise TypeError(f"unexpected keyword arguments: {sorted(kwargs)}")
         m = self.zeros.shape[0]
-        spec = engine.prior_spec(prior_type, prior, prior_score_fn, m)
+        cfg = dict(prior_cov=dist_cov_est_prior) if clf_free_guidance else None
+        spec = engine.PriorSpec(abi.PRIOR_NONE) if clf_free_guidance else engine.prior_spec(prior_type, prior, prior_score_fn, m)
         tt = torch.as_tensor(t).detach().to("cpu").reshape(1)
         setup = engine.build_setup(self, x_obs, theta.shape[0], tt, None, 0.0, spec, cov_mode, dist_cov_est,
-                                   n_sizes=n_sizes)
+                                   n_sizes=n_sizes, cfg=cfg)
         th = theta.detach().to(torch.float32).contiguous()
         if setup.step_modes is not None:
             setup.prob.cov_mode = int(setup.step_modes[0])
@@ -225,14 +231,14 @@ class NSE(nn.Module):
                                "(get_vpdiff_uniform_score / get_vpdiff_gaussian_score) as prior score function")
         return prior_score_fun._spec()
 
-    def _run_rows(self, shape, x, t_rows, coef, prior, weighted, opts, clip, noise, seed, sample_offset):
+    def _run_rows(self, shape, x, t_rows, coef, prior, weighted, opts, clip, noise, seed, sample_offset, cfg=None):
         """Runs a trajectory whose steps are arbitrary schedule rows (time + update coefficients per row)."""
         N, m = int(shape[0]), self.zeros.shape[0]
         if seed is None:
             seed = self._draw_seed()
         setup = engine.build_setup(self, x, N, t_rows, None, 0.0, prior, opts["cov_mode"] if weighted else "GAUSS",
                                    opts["dist_cov_est"] if weighted else None, n_sizes=opts["n_sizes"], clip=clip,
-                                   seed=seed, sample_offset=sample_offset, weighted=weighted, coef=coef)
+                                   seed=seed, sample_offset=sample_offset, weighted=weighted, coef=coef, cfg=cfg)
         if noise is not None:
             z0, z = noise
             theta = z0.to(x.device, torch.float32).contiguous().clone()
@@ -254,14 +260,12 @@ class NSE(nn.Module):
                                  clf_free_guidance: bool = False, **kwargs) -> Tensor:
         """F-NPSE score (1 - n) prior_score + sum_j score_j (nse.py:479-542), one fused call."""
         self._require_cuda(theta, x)
-        if clf_free_guidance:
-            raise NotImplementedError("clf_free_guidance=True: next-scope row (SURVEY.md section 8(f) rank 3)")
         m = self.zeros.shape[0]
-        spec = self._geffner_prior(prior_score_fun, m)
+        spec = engine.PriorSpec(abi.PRIOR_NONE) if clf_free_guidance else self._geffner_prior(prior_score_fun, m)
         tt = torch.as_tensor(t).detach().to("cpu").reshape(1)
         x2 = x if x.ndim > 1 else x[None]
         setup = engine.build_setup(self, x2, theta.shape[0], tt, None, 0.0, spec, "GAUSS", None,
-                                   n_sizes=kwargs.get("n"), weighted=False)
+                                   n_sizes=kwargs.get("n"), weighted=False, cfg={} if clf_free_guidance else None)
         th = theta.detach().to(torch.float32).contiguous()
         engine.score_partials(setup, th, 0)
         return engine.finalize(setup, th, 0)
@@ -278,13 +282,14 @@ class NSE(nn.Module):
         gamma = self._gammas(grid)
         delta = tau * (1 - gamma) / gamma.sqrt()  # nse.py:461
         single = x.ndim == 1 or x.shape[0] == 1  # nse.py:465
-        prior = engine.PriorSpec(abi.PRIOR_NONE) if single else self._geffner_prior(prior_score_fn, m)
+        cfg = {} if (opts["clf_free_guidance"] and not single) else None
+        prior = engine.PriorSpec(abi.PRIOR_NONE) if (single or cfg is not None) else self._geffner_prior(prior_score_fn, m)
         rep = lambda v: v.repeat_interleave(lsteps)  # noqa: E731
         clip = torch.zeros(steps, lsteps, dtype=torch.float64)
         clip[:, -1] = 1.0
         coef = dict(c_theta=torch.ones(steps * lsteps, dtype=torch.float64), c_score=rep(delta),
                     bstd=rep((2 * delta).sqrt()), clip=clip.reshape(-1))
-        return self._run_rows(shape, x, rep(grid[:-1]), coef, prior, False, opts, theta_clipping_range, noise, seed, off)
+        return self._run_rows(shape, x, rep(grid[:-1]), coef, prior, False, opts, theta_clipping_range, noise, seed, off, cfg)
 
     def deterministic_gaussian_geffner(self, shape: Size, x: Tensor, prior_score_fn, steps: int = 1000,
                                        verbose: bool = False, theta_clipping_range=(None, None), **kwargs) -> Tensor:

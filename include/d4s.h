@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D4S_ABI_VERSION 10
+#define D4S_ABI_VERSION 11
 
 #define D4S_OK 0
 #define D4S_ERR_ARG -1      /* bad argument / unsupported shape */
@@ -125,6 +125,9 @@ typedef struct {
     const float* obs_raw;    /* [n_obs, x_dim] raw observations, only read when D4sStep.affine != NULL */
     int32_t x_dim;
     int32_t reserved0;
+    const float* obs_weight; /* NULL (all 1), or [n_obs] weights of the observations in every sum over j.  Classifier-free
+                                guidance (nse.py:598-625, 532-538) is the tall score with one extra pseudo-observation
+                                x = 0 (the net's own prior score) of weight (1 - n). */
 } D4sProblem;
 
 /* Per-step inputs. */

@@ -445,6 +445,49 @@ def factorized_score(net: OracleNet, theta, x_obs, t, prior, dist_cov_est=None, 
 
 
 # --------------------------------------------------------------------------------------
+# a15: classifier-free guidance branches (nse.py:598-625, 532-538)
+# --------------------------------------------------------------------------------------
+def _cfg_context(net: OracleNet, x_obs, ns):
+    """x_ = zeros_like(x_obs[0][None]) and, for PF_NSE, n = zeros_like(n[0][None]) (nse.py:599-606).  For a plain NSE the
+    reference leaves `kwargs_score_prior` unassigned (UnboundLocalError); the intended value {} is used here."""
+    x0 = np.zeros_like(x_obs[:1])
+    ns0 = None if ns is None else np.zeros((1, 1), dtype=ns.dtype)
+    return x0, ns0
+
+
+def factorized_score_cfg(net: OracleNet, theta, x_obs, t, dist_cov_est=None, dist_cov_est_prior=None, cov_mode="GAUSS",
+                         ns=None):
+    n_obs = x_obs.shape[0]
+    prec, _, scores = tweedies_approximation(net, x_obs, theta, t, dist_cov_est, cov_mode, ns)
+    x0, ns0 = _cfg_context(net, x_obs, ns)
+    prec_p, _, s_p = tweedies_approximation(net, x0, theta, t, dist_cov_est_prior, cov_mode, ns0)  # nse.py:607-615
+    ps_prior = (prec_p @ s_p[..., None])[..., 0][:, 0, :]
+    ps_post = (prec @ scores[..., None])[..., 0]
+    lda = prec_p[:, 0] * (1 - n_obs) + prec.sum(axis=1)
+    weighted = ps_prior + (ps_post - ps_prior[:, None]).sum(axis=1)
+    return np.linalg.solve(lda, weighted[..., None])[..., 0]  # nse.py:625
+
+
+def factorized_score_geffner_cfg(net: OracleNet, theta, x, t, ns=None):
+    """nse.py:532-541 with clf_free_guidance=True."""
+    n_obs = x.shape[0]
+    scores = -pair_eps(net, theta, x, t, ns) / net.sigma(t)
+    x0, ns0 = _cfg_context(net, x, ns)
+    s_p = -pair_eps(net, theta, x0, t, ns0) / net.sigma(t)
+    return (1 - n_obs) * s_p[:, 0] + scores.sum(axis=1)
+
+
+def ddim_cfg(net: OracleNet, x, z0, z, steps, eta, dist_cov_est, dist_cov_est_prior, cov_mode="GAUSS", ns=None):
+    D = net.dtype
+    time = time_grid(steps).astype(D)
+    theta = z0.astype(D)
+    for k in range(steps):
+        score = factorized_score_cfg(net, theta, x, time[k], dist_cov_est, dist_cov_est_prior, cov_mode, ns)
+        theta = ddim_step(net, theta, score, time[k], 1 / steps, eta, z[k].astype(D))
+    return theta
+
+
+# --------------------------------------------------------------------------------------
 # a3/a4: NSE.ddim, ddim_step, mean_pred, bridge_mean (nse.py:199-299)
 # --------------------------------------------------------------------------------------
 def time_grid(steps: int) -> np.ndarray:

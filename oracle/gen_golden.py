@@ -141,6 +141,46 @@ def langevin_case(name, net32, x, prior_kind, prior_params, N, seed, steps, lste
     print("wrote", name)
 
 
+def cfg_case(name, net32, x_raw, N, seed, steps):
+    """Classifier-free-guidance branches for PF_NSE (the only class for which they run in the reference):
+    factorized_score(GAUSS, clf_free_guidance=True), factorized_score_geffner(clf_free_guidance=True), ddim."""
+    out = {}
+    net_arrays(net32, out)
+    gen = torch.Generator().manual_seed(seed)
+    m = net32.zeros.shape[0]
+    xs, ns = net32._create_pf_data(x_raw)
+    K = xs.shape[0]
+    theta = torch.randn(N, m, generator=gen)
+    cov_est = spd_covs(gen, K, m)
+    cov_prior = spd_covs(gen, 1, m) * 3
+    z0 = torch.randn(N, m, generator=gen)
+    z = torch.randn(steps, N, m, generator=gen)
+    t_grid = [0.9, 0.5, 0.1]
+    out.update(theta=npy(theta), x=npy(xs), traj_x=npy(x_raw), dist_cov_est=npy(cov_est), dist_cov_est_prior=npy(cov_prior),
+               t_grid=np.asarray(t_grid, np.float32), traj_z0=npy(z0), traj_z=npy(z), traj_steps=np.int64(steps),
+               prior_kind=np.str_("cfg"))
+    out["kw.n"] = npy(ns)
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        net = copy.deepcopy(net32).to(dt)
+        fs, gs = [], []
+        for tv in t_grid:
+            t = torch.tensor(tv, dtype=torch.float32).to(dt)
+            fs.append(npy(net.factorized_score(theta.to(dt), xs.to(dt), t, None, None, dist_cov_est=cov_est.to(dt),
+                                               dist_cov_est_prior=cov_prior.to(dt), cov_mode="GAUSS",
+                                               clf_free_guidance=True, n=ns.to(dt))))
+            gs.append(npy(net.factorized_score_geffner(theta.to(dt), xs.to(dt), t, None, clf_free_guidance=True,
+                                                       n=ns.to(dt))))
+        out[f"{tag}.cfg.factorized_score"] = np.stack(fs)
+        out[f"{tag}.cfg.geffner_score"] = np.stack(gs)
+        out[f"{tag}.cfg.traj"] = npy(run_ddim(net, x_raw.to(dt), z0.to(dt), z.to(dt), steps=steps, eta=0.8,
+                                               prior=None, prior_score_fn=None, dist_cov_est=cov_est.to(dt),
+                                               dist_cov_est_prior=cov_prior.to(dt), cov_mode="GAUSS",
+                                               clf_free_guidance=True))
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name)
+
+
 def toy_case(name, DIM, n_obs, eps_max, N, seed, steps, eta):
     """Config 1: the Gaussian-Gaussian toy of gen_gaussian_gaussian.py:27-96 driven on CPU -- reference `nse_toy.NSE`,
     `FakeFNet(real_eps, EpsilonNet(DIM), eps)`, triple-returning prior score; GAUSS + JAC per-call and trajectories,
@@ -401,6 +441,10 @@ def main(filt=None):
         high = (hi - st["theta_train_mean"]) / st["theta_train_std"] * 2
         per_call_case("jrnnm4d_n5", net, x, "uniform", dict(low=low, high=high), N=10, seed=16,
                       t_grid=[0.9, 0.5, 0.29, 0.1, 0.01], traj=dict(N=12, steps=30, eta=1.0, modes=("GAUSS",)))
+    if want("cfg"):
+        net, st = load_sbibm("slcp", sub="n_train_10000_bs_256_n_epochs_5000_lr_0.0001", pf="pf_n_max_3")
+        st = dict(st, x_train_mean=st["x_train_mean"][0], x_train_std=st["x_train_std"][0])
+        cfg_case("cfg_pf_slcp_n8", net, sbibm_obs("slcp", st, 8), N=10, seed=41, steps=16)
     if want("toy"):
         toy_case("toy_gauss_d4_n5", DIM=4, n_obs=5, eps_max=1e-1, N=12, seed=31, steps=20, eta=0.5)
         toy_case("toy_gauss_d10_n30", DIM=10, n_obs=30, eps_max=1e-2, N=8, seed=32, steps=64, eta=0.2)  # dt = 2^-6: the fp64 run of the reference is NaN when fp32(t) - dt < 0 (toy alpha has a linear term)

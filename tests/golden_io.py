@@ -40,6 +40,8 @@ def oracle_net(g, dtype=np.float64):
 
 
 def oracle_prior(g):
+    if str(g["prior_kind"]) == "cfg":
+        return None
     if str(g["prior_kind"]) == "uniform":
         return orc.UniformPrior(g["prior.low"].astype(np.float64), g["prior.high"].astype(np.float64))
     return orc.GaussianPrior(g["prior.loc"].astype(np.float64), g["prior.cov"].astype(np.float64))

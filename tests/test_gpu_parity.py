@@ -13,7 +13,7 @@ from oracle import d4s_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-CASES = [c for c in gio.names() if not c.startswith(("langevin", "toy"))]
+CASES = [c for c in gio.names() if not c.startswith(("langevin", "toy", "cfg"))]
 REL_TOL = 1e-4
 TRAJ_TOL = 1e-3
 
@@ -399,3 +399,54 @@ def test_toy_gaussian_config(name, dev):
     e_torch = nse(theta, x[:1].expand(theta.shape[0], -1), tt)
     prec, _, sc = __import__("d4s").tweedies_approximation(x=x[:1], theta=theta, t=tt, nse=nse, dist_cov_est=cov[:1], mode="GAUSS")
     assert orc.rel_l2((-sc[:, 0] * nse.sigma(tt)).cpu().numpy(), e_torch.detach().cpu().numpy()) < 1e-5
+
+
+# ---- classifier-free guidance: prior score / precision from the net itself at x = 0 (nse.py:598-625, 532-538) ----------
+@pytest.mark.parametrize("name", [c for c in gio.names() if c.startswith("cfg")])
+def test_cfg_pf_nse_golden(name, dev, kernel_path):
+    from d4s_helpers import nse_from_oracle
+    g = gio.load(name)
+    nse = nse_from_oracle(gio.oracle_net(g), dev)
+    theta, xs, ns = _t(g["theta"], dev), _t(g["x"], dev), _t(g["kw.n"], dev)
+    cov, covp = _t(g["dist_cov_est"], dev), _t(g["dist_cov_est_prior"], dev)
+    for k, t in enumerate(g["t_grid"]):
+        out = nse.factorized_score(theta, xs, torch.tensor(t), None, None, dist_cov_est=cov, dist_cov_est_prior=covp,
+                                   cov_mode="GAUSS", clf_free_guidance=True, n=ns)
+        ref = g["f64.cfg.factorized_score"][k]
+        floor = orc.rel_l2(g["f32.cfg.factorized_score"][k], ref)
+        assert orc.rel_l2(out.cpu().numpy(), ref) < max(REL_TOL, 3 * floor), (name, float(t))
+        out = nse.factorized_score_geffner(theta, xs, torch.tensor(t), None, clf_free_guidance=True, n=ns)
+        ref = g["f64.cfg.geffner_score"][k]
+        floor = orc.rel_l2(g["f32.cfg.geffner_score"][k], ref)
+        assert orc.rel_l2(out.cpu().numpy(), ref) < max(REL_TOL, 3 * floor), (name, float(t))
+    noise = (torch.as_tensor(g["traj_z0"]), torch.as_tensor(g["traj_z"]))
+    out = nse.ddim((noise[0].shape[0],), _t(g["traj_x"], dev), steps=int(g["traj_steps"]), eta=0.8, prior=None,
+                   prior_score_fn=None, dist_cov_est=cov, dist_cov_est_prior=covp, cov_mode="GAUSS",
+                   clf_free_guidance=True, _noise=noise)
+    ref = g["f64.cfg.traj"]
+    ref32 = np.abs(g["f32.cfg.traj"] - ref).max()
+    err = np.abs(out.cpu().numpy() - ref).max()
+    assert err < max(TRAJ_TOL * max(1.0, np.abs(ref).max()), 3 * ref32), err
+
+
+@pytest.mark.parametrize("mode", ["GAUSS", "JAC"])
+def test_cfg_plain_nse_vs_oracle(mode, dev, kernel_path):
+    """Plain NSE + CFG raises UnboundLocalError in the reference; the intended semantics
+    (kwargs_score_prior = {}) are checked against the oracle."""
+    from d4s_helpers import nse_from_oracle
+    rng = np.random.default_rng(5)
+    m, d, n, N = 4, 6, 9, 33
+    onet = orc.random_net(rng, m, d, hidden=(128, 128, 64))
+    nse = nse_from_oracle(onet, dev)
+    x, theta = rng.standard_normal((n, d)), rng.standard_normal((N, m))
+    a = 0.2 * rng.standard_normal((n + 1, m, m))
+    covs = a @ a.transpose(0, 2, 1) + 0.05 * np.eye(m)
+    for t in (0.7, 0.2):
+        t32 = np.float32(t)
+        ref = orc.factorized_score_cfg(onet, theta, x, np.float64(t32), covs[:n], covs[n:], mode)
+        ref32 = orc.factorized_score_cfg(onet.astype(np.float32), theta.astype(np.float32), x.astype(np.float32), t32,
+                                         covs[:n].astype(np.float32), covs[n:].astype(np.float32), mode)
+        out = nse.factorized_score(_t(theta, dev), _t(x, dev), torch.tensor(t32), None, None, dist_cov_est=_t(covs[:n], dev),
+                                   dist_cov_est_prior=_t(covs[n:], dev), cov_mode=mode, clf_free_guidance=True)
+        err, floor = orc.rel_l2(out.cpu().numpy(), ref), orc.rel_l2(ref32, ref)
+        assert err < max(REL_TOL, 3 * floor), (mode, t, err, floor)

@@ -12,7 +12,7 @@ import torch
 import golden_io as gio
 from oracle import d4s_oracle as orc
 
-CASES = [c for c in gio.names() if not c.startswith(("langevin", "toy"))]
+CASES = [c for c in gio.names() if not c.startswith(("langevin", "toy", "cfg"))]
 
 
 def _ns(g):
@@ -158,3 +158,19 @@ def test_toy_config_fp64(name):
     out = orc.ddim_single(net, xp, g["pair_z0"], g["pair_z"], steps, 0.5)
     ref = g["f64.pair.traj"]
     assert np.abs(out - ref).max() < 1e-5 * max(1.0, np.abs(ref).max())
+
+
+# ---- classifier-free guidance (runs in the reference for PF_NSE only) ----------------------------
+@pytest.mark.parametrize("name", [c for c in gio.names() if c.startswith("cfg")])
+def test_cfg_branches_fp64(name):
+    g = gio.load(name)
+    net, ns = gio.oracle_net(g), _ns(g)
+    theta, x = g["theta"].astype(np.float64), g["x"].astype(np.float64)
+    cov, covp = g["dist_cov_est"].astype(np.float64), g["dist_cov_est_prior"].astype(np.float64)
+    for k, t in enumerate(g["t_grid"]):
+        out = orc.factorized_score_cfg(net, theta, x, np.float64(t), cov, covp, "GAUSS", ns)
+        assert orc.rel_l2(out, g["f64.cfg.factorized_score"][k]) < 5e-7
+        out = orc.factorized_score_geffner_cfg(net, theta, x, np.float64(t), ns)
+        assert orc.rel_l2(out, g["f64.cfg.geffner_score"][k]) < 5e-7
+    out = orc.ddim_cfg(net, x, g["traj_z0"], g["traj_z"], int(g["traj_steps"]), 0.8, cov, covp, "GAUSS", ns)
+    assert np.abs(out - g["f64.cfg.traj"]).max() < 5e-6
