@@ -6,9 +6,10 @@ Host-side mirror of the reference's sampling API (`NSE.ddim`, `NSE.factorized_sc
 from . import _cabi  # noqa: F401
 from .nse import NSE  # noqa: F401
 from .pf_nse import PF_NSE  # noqa: F401
-from .tall_posterior_sampler import (prec_matrix_backward, tweedies_approximation,  # noqa: F401
-                                     tweedies_approximation_prior)
+from .tall_posterior_sampler import (diffused_tall_posterior_score, euler_sde_sampler,  # noqa: F401
+                                     prec_matrix_backward, tweedies_approximation, tweedies_approximation_prior)
 from .vp_diffused_priors import get_vpdiff_gaussian_score, get_vpdiff_uniform_score  # noqa: F401
 
 __all__ = ["NSE", "PF_NSE", "tweedies_approximation", "tweedies_approximation_prior", "prec_matrix_backward",
+           "diffused_tall_posterior_score", "euler_sde_sampler",
            "get_vpdiff_gaussian_score", "get_vpdiff_uniform_score"]

@@ -86,4 +86,57 @@ def tweedies_approximation_prior(theta, t, score_fn, nse, mode="vmap"):
     return prec, mean, score
 
 
+def diffused_tall_posterior_score(theta, t, prior, prior_score_fn, x_obs, nse, score_fn=None, dist_cov_est=None,
+                                  cov_mode="JAC", prior_type="gaussian"):
+    """Functional form of the tall score (tall_posterior_sampler.py:158-214) == `nse.factorized_score(...)`; the fused
+    kernels run it in one call.  `score_fn` is accepted for signature compatibility (the scores are `nse`'s own)."""
+    return nse.factorized_score(theta, x_obs, t, prior_score_fn, prior, dist_cov_est=dist_cov_est, cov_mode=cov_mode,
+                                prior_type=prior_type)
+
+
+def euler_sde_sampler(score_fn, nsamples, dim_theta, beta, device="cuda", debug=False, theta_clipping_range=(None, None),
+                      _noise=None):
+    """Euler-Maruyama integration of the backward SDE on linspace(1, 0, 1000) (tall_posterior_sampler.py:217-281):
+    theta <- theta + (f - g^2 score) dt + g sqrt(|dt|) z with f = -0.5 beta(t) theta, g^2 = beta(t), dt < 0.
+    `score_fn(theta, t)` is any callable (e.g. `partial(diffused_tall_posterior_score, ...)`, which itself runs on the
+    fused kernels); the update runs in kernel 4.  Returns (theta, [theta_0, theta_1, ...] on the host) like the reference."""
+    import ctypes as C
+    if debug:
+        raise NotImplementedError("debug=True returns the reference's internal tensors; not provided")
+    lib = abi.require_cuda()
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise abi.D4sError("d4s.euler_sde_sampler: CUDA device required (no CPU fallback)")
+    time_pts = torch.linspace(1, 0, 1000)
+    if _noise is not None:
+        z0, z = _noise
+        theta = z0.to(dev, torch.float32).contiguous().clone()
+    else:
+        seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+        theta = engine.philox_normal(nsamples, dim_theta, seed, -1, 0, dev)
+        z = None
+    t64 = time_pts.to(torch.float64)
+    dt = t64[1:] - t64[:-1]
+    b = torch.as_tensor(beta(t64[:-1]), dtype=torch.float64)
+    rows = torch.zeros(999, abi.SCHED_STRIDE, dtype=torch.float64)
+    rows[:, abi.S_T] = t64[:-1]
+    rows[:, abi.S_C_THETA] = 1.0 - 0.5 * b * dt     # theta + f dt
+    rows[:, abi.S_C_SCORE] = -b * dt                # - g^2 score dt
+    rows[:, abi.S_BRIDGE_STD] = (b * dt.abs()).sqrt()  # g sqrt(|dt|)
+    rows[:, abi.S_CLIP] = 1.0
+    sched = rows.to(torch.float32).to(dev)
+    lo, hi = theta_clipping_range
+    clip = (1.0, -1.0) if lo is None else (float(lo), float(hi))
+    theta_list = [theta.detach().cpu()]
+    for i in range(999):
+        score = score_fn(theta, time_pts[i].to(dev)).detach().to(torch.float32).contiguous()
+        nz = None if z is None else z[i].to(dev, torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            abi.check(lib.d4s_ddim_update(engine._ptr(theta), engine._ptr(score), theta.shape[0], theta.shape[1],
+                                          engine._ptr(sched[i]), engine._ptr(nz), C.c_uint64(0 if z is not None else seed),
+                                          i, 0, clip[0], clip[1], engine._stream(dev)))
+        theta_list.append(theta.detach().cpu())
+    return theta, theta_list
+
+
 import math  # noqa: E402  (kept at the bottom: only the helpers above use it)

@@ -646,6 +646,24 @@ def predictor_corrector(net: OracleNet, x, z0, z, prior, steps, predictor="ddim"
     return theta.astype(D)
 
 
+def euler_sde_sampler(net: OracleNet, x, z0, z, prior, dist_cov_est=None, cov_mode="GAUSS", prior_type="gaussian",
+                      clip=(None, None)):
+    """tall_posterior_sampler.py:217-281 driven by diffused_tall_posterior_score (:158-214), injected noise z[999,N,m]."""
+    D = net.dtype
+    time_pts = np.linspace(np.float32(1), np.float32(0), 1000, dtype=np.float32).astype(D)
+    theta = z0.astype(D)
+    for i in range(999):
+        t = time_pts[i]
+        dt = time_pts[i + 1] - t
+        beta = 32 * t if net.schedule == "vp16" else D(net.beta_d) * t + D(net.beta_min)  # nse.py:147-149
+        score = factorized_score(net, theta, x, t, prior, dist_cov_est, cov_mode, prior_type)
+        drift = -0.5 * beta * theta - beta * score
+        theta = theta + drift * dt + beta ** 0.5 * z[i].astype(D) * abs(dt) ** 0.5
+        if clip[0] is not None:
+            theta = np.clip(theta, clip[0], clip[1])
+    return theta.astype(D)
+
+
 # --------------------------------------------------------------------------------------
 # helpers used by tests / bench (not part of the reference)
 # --------------------------------------------------------------------------------------

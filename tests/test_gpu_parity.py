@@ -450,3 +450,23 @@ def test_cfg_plain_nse_vs_oracle(mode, dev, kernel_path):
                                    dist_cov_est_prior=_t(covs[n:], dev), cov_mode=mode, clf_free_guidance=True)
         err, floor = orc.rel_l2(out.cpu().numpy(), ref), orc.rel_l2(ref32, ref)
         assert err < max(REL_TOL, 3 * floor), (mode, t, err, floor)
+
+
+def test_euler_sde_sampler_vs_oracle(dev):
+    """Euler-Maruyama sampler (tall_posterior_sampler.py:217-281) driven by diffused_tall_posterior_score."""
+    from functools import partial
+    import d4s
+    from d4s_helpers import nse_from_oracle
+    onet, x, cov, theta, oprior = _problem(3, 4, (64, 64, 64), 5, 8, "gaussian", seed=7)
+    nse = nse_from_oracle(onet, dev)
+    prior, fn = _d4s_prior(oprior, nse, dev)
+    rng = np.random.default_rng(9)
+    z0, z = rng.standard_normal((8, 3)), rng.standard_normal((999, 8, 3))
+    ref = orc.euler_sde_sampler(onet, x, z0, z, oprior, cov, "GAUSS", "gaussian", clip=(-4.0, 4.0))
+    score_fn = partial(d4s.diffused_tall_posterior_score, prior=prior, prior_type="gaussian", prior_score_fn=fn,
+                       x_obs=_t(x, dev), nse=nse, dist_cov_est=_t(cov, dev), cov_mode="GAUSS")
+    out, path = d4s.euler_sde_sampler(score_fn, 8, 3, nse.beta, device=dev, theta_clipping_range=(-4.0, 4.0),
+                                      _noise=(torch.as_tensor(z0, dtype=torch.float32), torch.as_tensor(z, dtype=torch.float32)))
+    assert len(path) == 1000
+    err = np.abs(out.cpu().numpy() - ref).max()
+    assert err < 5e-3 * max(1.0, np.abs(ref).max()), err
