@@ -13,7 +13,6 @@ namespace d4s {
 static thread_local std::string g_err;
 static long long g_launches = 0;
 static int g_opt_path = 0;      // 0 auto, 1 SIMT per-step kernels only, 2 require the tcgen05 trajectory kernel
-static int g_opt_swap = 0;      // debug: swap LBO/SBO in the UMMA descriptors
 static int g_opt_tc_steps = 0;  // > 0: DDIM steps per tcgen05 launch (0 = whole trajectory in one launch)
 static int* g_err_flag = nullptr;
 static int g_opt_profile = 0;
@@ -320,7 +319,6 @@ static int fill_traj_params(const D4sNet* net, const D4sProblem* pb, const float
     if (p.SG > 8) p.SG = 8;
     if (p.SG < 1) p.SG = 1;
     p.P = p.SG * p.OC;
-    p.swap_lbo_sbo = g_opt_swap;
     p.obs_feat = pb->obs_feat;
     p.obs_prec = pb->obs_prec;
     p.obs_weight = pb->obs_weight;
@@ -673,7 +671,6 @@ int d4s_set_option(const char* key, int32_t value) {
     if (!key) return fail(D4S_ERR_ARG, "null option key");
     const std::string k(key);
     if (k == "path") g_opt_path = value;
-    else if (k == "swap_lbo_sbo") g_opt_swap = value;
     else if (k == "tc_steps_per_launch") g_opt_tc_steps = value;
     else if (k == "profile") g_opt_profile = value;
     else return fail(D4S_ERR_ARG, "unknown option: " + k);

@@ -87,7 +87,6 @@ struct TrajParams {
     NetDev net;
     int N, n, C, SG, OC, P;
     int step_begin, step_end;
-    int swap_lbo_sbo;        // debug: exchange the two descriptor strides
     const float* obs_feat;   // [n][Hp0]
     const float* obs_prec;   // [n][m][m] or NULL
     const float* obs_weight; // [n] or NULL

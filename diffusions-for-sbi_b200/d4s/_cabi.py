@@ -144,7 +144,7 @@ def load():
 
 
 def set_option(key: str, value: int):
-    """Library switches (see d4s_set_option in include/d4s.h): path, tc_steps_per_launch, swap_lbo_sbo."""
+    """Library switches (see d4s_set_option in include/d4s.h): path, tc_steps_per_launch, profile."""
     check(load().d4s_set_option(key.encode(), int(value)))
 
 

@@ -249,8 +249,26 @@ def layer1_blocks(nse, pn: NetView):
             slice(e_t + e_x + f2, cols), n_hot)
 
 
+_tf_cache: dict = {}
+
+
 def time_feat_table(nse, pn: NetView, t: torch.Tensor) -> torch.Tensor:
-    """[len(t), H1p] fp64: W1[:, t-block] temb(t) + b1, zero padded."""
+    """[len(t), H1p] fp64: W1[:, t-block] temb(t) + b1, zero padded.  Cached per (first-layer weights, time rows): it
+    does not depend on the observations, so repeated trajectories on the same grid reuse it."""
+    lin0 = pn.linears[0]
+    key = (lin0.weight.data_ptr(), lin0.weight._version, lin0.bias._version, t.numel(), float(t.sum()), float(t[0]),
+           float(t[-1]), id(net_description(nse)["time_features"]) if net_description(nse)["time_features"] else 0)
+    hit = _tf_cache.get(key)
+    if hit is not None:
+        return hit
+    out = _time_feat_table(nse, pn, t)
+    if len(_tf_cache) > 16:
+        _tf_cache.clear()
+    _tf_cache[key] = out
+    return out
+
+
+def _time_feat_table(nse, pn: NetView, t: torch.Tensor) -> torch.Tensor:
     _, _, tcol, _, _ = layer1_blocks(nse, pn)
     temb = time_embedding64(nse, t.to(torch.float64))
     out = torch.zeros(t.numel(), pn.h1p, dtype=torch.float64)
@@ -414,7 +432,9 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
             sum_q = q64.sum(dim=0)
     t = t.detach().to("cpu").reshape(-1)
     sa = _scalar64(nse.alpha, t.to(torch.float64)).sqrt()
-    comb = [combine_mode(prior, cov_jac, n_total, float(s), weighted) for s in sa]
+    # branch of nse.py:627-654 per step; it only depends on sqrt(alpha) > 0.5, so two evaluations cover every step
+    c_hi, c_lo = (combine_mode(prior, cov_jac, n_total, v, weighted) for v in (1.0, 0.0))
+    comb = torch.where(sa > 0.5, c_hi, c_lo).tolist()
     if cfg is not None and weighted:  # nse.py:622-625: always the weighted solve
         comb = [abi.COMBINE_PER_SAMPLE if cov_jac else abi.COMBINE_SHARED] * len(comb)
     rows = schedule_rows(nse, t, None if t_prev is None else t_prev.detach().to("cpu").reshape(-1), eta, n_total, comb,

@@ -39,7 +39,6 @@ abi.set_option("path", 1)
 ref = nse.ddim((N,), xt, **kw)
 torch.cuda.synchronize()
 abi.set_option("path", 2)
-abi.set_option("swap_lbo_sbo", swap)
 out = nse.ddim((N,), xt, **kw)
 torch.cuda.synchronize()
 orc_out = orc.ddim(onet, x, z0, z, steps, 1.0, orc.UniformPrior(np.full(m, -3.46), np.full(m, 3.46)), cov, "GAUSS", "uniform")
