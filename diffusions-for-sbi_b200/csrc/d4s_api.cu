@@ -16,6 +16,7 @@ static int g_opt_path = 0;      // 0 auto, 1 SIMT per-step kernels only, 2 requi
 static int g_opt_tc_steps = 0;  // > 0: DDIM steps per tcgen05 launch (0 = whole trajectory in one launch)
 static int* g_err_flag = nullptr;
 static int g_opt_profile = 0;
+static int g_opt_tc_pairing = 1;  // interleave two sample groups per CTA in the tcgen05 kernel (0 = one after the other)
 static long long* g_prof = nullptr;
 
 static int fail(int code, const std::string& msg) {
@@ -346,6 +347,7 @@ static int fill_traj_params(const D4sNet* net, const D4sProblem* pb, const float
         cudaMemset(g_err_flag, 0, sizeof(int));
     }
     p.error_flag = g_err_flag;
+    p.pairing = g_opt_tc_pairing;
     if (g_opt_profile) {
         if (!g_prof) {
             if (cudaMalloc(&g_prof, 16 * sizeof(long long)) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaMalloc(prof)");
@@ -585,6 +587,8 @@ int d4s_ddim_run(const D4sNet* net, const D4sProblem* pb, int32_t steps, const f
     key.theta = theta_dev;
     key.affine = affine_dev;
     key.mode_hash = 1469598103934665603ull;
+    for (int v : {g_opt_path, g_opt_tc_steps, g_opt_profile, g_opt_tc_pairing})  // a captured graph froze the options it was built with
+        key.mode_hash = (key.mode_hash ^ (uint64_t)(uint32_t)v) * 1099511628211ull;
     if (step_mode)
         for (int k = 0; k < steps; ++k) key.mode_hash = (key.mode_hash ^ (uint64_t)(step_mode[k] + 1)) * 1099511628211ull;
     std::lock_guard<std::mutex> lock(g_graph_mu);
@@ -673,6 +677,7 @@ int d4s_set_option(const char* key, int32_t value) {
     if (k == "path") g_opt_path = value;
     else if (k == "tc_steps_per_launch") g_opt_tc_steps = value;
     else if (k == "profile") g_opt_profile = value;
+    else if (k == "tc_pairing") g_opt_tc_pairing = value;
     else return fail(D4S_ERR_ARG, "unknown option: " + k);
     return D4S_OK;
 }

@@ -87,6 +87,7 @@ struct TrajParams {
     NetDev net;
     int N, n, C, SG, OC, P;
     int step_begin, step_end;
+    int pairing;             // 1: a CTA that owns >= 2 sample groups interleaves them step by step (software pipeline)
     const float* obs_feat;   // [n][Hp0]
     const float* obs_prec;   // [n][m][m] or NULL
     const float* obs_weight; // [n] or NULL

@@ -44,8 +44,8 @@ constexpr int OFF_QS = OFF_S + TC_M * MMAX * 4;                // float [128][MM
 constexpr int OFF_BASE = OFF_QS + TC_M * MMAX * 4;             // float [SG_MAX][256] layer-0 per-sample part
 constexpr int OFF_WOUT = OFF_BASE + TC_SG_MAX * 256 * 4;       // float [MMAX][256] output layer (torch layout)
 constexpr int OFF_ACC = OFF_WOUT + MMAX * 256 * 4;             // float [SG_MAX][2*MMAX] sums over observations
-constexpr int OFF_THETA = OFF_ACC + TC_SG_MAX * 2 * MMAX * 4;  // float [SG_MAX][MMAX]
-constexpr int OFF_NOISE = OFF_THETA + TC_SG_MAX * MMAX * 4;    // float [SG_MAX][MMAX] DDIM noise of the step
+constexpr int OFF_THETA = OFF_ACC + TC_SG_MAX * 2 * MMAX * 4;  // float [2][SG_MAX][MMAX] (two interleaved groups)
+constexpr int OFF_NOISE = OFF_THETA + 2 * TC_SG_MAX * MMAX * 4;  // float [SG_MAX][MMAX] DDIM noise of the step
 constexpr int OFF_PRIOR = OFF_NOISE + TC_SG_MAX * MMAX * 4;    // float [SG_MAX][2][MMAX] uniform-prior score, derivative
 constexpr int OFF_SCHED = OFF_PRIOR + TC_SG_MAX * 2 * MMAX * 4;  // float [16] schedule row of the step
 constexpr int OFF_MATS = OFF_SCHED + 16 * 4;                   // float [TC_MATS_MAX] Lmat | G | mu_t of the step
@@ -285,6 +285,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
     int my_groups = 0;
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x) ++my_groups;
     const long long tile_iters = (long long)my_groups * n_steps * p.C;  // tile evaluations by this CTA
+    // Two sample groups of one CTA are interleaved step by step: the sums / tail of one group and the layer-0 sample part of
+    // the other run while the tensor core works (needs the whole observation set in one tile and the in-kernel tail).
+    const bool pairing = p.pairing && p.C == 1 && p.part_out == nullptr;
 
     if (warp == TC_CW) {
         // ================= TMA producer: streams the weight images in consumption order ===========================
@@ -343,11 +346,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
         // ================= scalar helper: everything that only needs theta at the start of the step =================
         const bool uni = (p.fin.prior_kind == D4S_PRIOR_UNIFORM);
         const int nq = (m + 3) / 4;
-        for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-            const int i0 = g * p.SG;
-            const int nsamp = min(p.SG, p.N - i0);
-            for (int step = p.step_begin; step < p.step_end; ++step) {
-                bar_sync(2, NB23);  // theta of this step is final; last step's consumers are done with our buffers
+        for (int gk = 0; gk < my_groups;) {
+            const int ngr = (pairing && gk + 1 < my_groups) ? 2 : 1;  // groups interleaved step by step (see compute warps)
+            const int total = ngr * n_steps;
+            for (int it = 0; it < total; ++it) {
+                const int gi = (ngr == 2) ? (it & 1) : 0;
+                const int step = p.step_begin + ((ngr == 2) ? (it >> 1) : it);
+                const int i0 = (blockIdx.x + (gk + gi) * (int)gridDim.x) * p.SG;
+                const int nsamp = min(p.SG, p.N - i0);
+                const float* th = sTheta + gi * TC_SG_MAX * MMAX;
+                bar_sync(2, NB23);  // theta of this item is final; the previous item's consumers are done with our buffers
                 if (p.part_out) {  // export mode: the caller reduces over ranks and finalizes; nothing to prepare
                     bar_arrive(3, NB23);
                     continue;
@@ -365,7 +373,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     for (int e = lane; e < nsamp * m; e += 32) {
                         const int si = e / m, k = e - si * m;
                         double s0, jac;
-                        uniform_prior_terms((double)sTheta[si * MMAX + k], (double)__ldg(p.fin.low + k),
+                        uniform_prior_terms((double)th[si * MMAX + k], (double)__ldg(p.fin.low + k),
                                             (double)__ldg(p.fin.high + k), sa, sg, s0, jac);
                         if (per_sample) {
                             const double p0 = aos2 / (1.0 + sg * sg * jac);  // inv(sigma^2/alpha (1 + sigma^2 J0))
@@ -381,7 +389,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     for (int e = lane; e < nsamp * m; e += 32) {
                         const int si = e / m, r = e - si * m;
                         double acc = 0.0;
-                        for (int c = 0; c < m; ++c) acc = fma((double)G[r * m + c], (double)sTheta[si * MMAX + c] - (double)mu[c], acc);
+                        for (int c = 0; c < m; ++c) acc = fma((double)G[r * m + c], (double)th[si * MMAX + c] - (double)mu[c], acc);
                         sG[si * MMAX + r] = (float)acc;
                     }
                 } else {
@@ -412,6 +420,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                 __syncwarp();
                 bar_arrive(3, NB23);
             }
+            gk += ngr;
         }
     } else {
         // ================= compute warps ==================================================================================
@@ -420,38 +429,120 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
         unsigned d_cnt = 0;
         const bool prof_on = (p.prof != nullptr) && blockIdx.x == 0 && tid == 0;
         long long prof_t = prof_on ? clock64() : 0;
-        const bool uni = (p.fin.prior_kind == D4S_PRIOR_UNIFORM);
         const int nkg = H0 / 8;
         // layer-0 theta block: thread `tid` owns column tid of A for the whole kernel (registers)
         float acol[MMAX];
 #pragma unroll
         for (int k = 0; k < MMAX; ++k) acol[k] = (k < m && tid < H0) ? __ldg(net.A + (size_t)k * H0 + tid) : 0.f;
         float tf_next = (tid < H0 && n_steps > 0) ? __ldg(p.time_feat + (size_t)p.step_begin * H0 + tid) : 0.f;
-        for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
-            const int i0 = g * p.SG;
-            const int nsamp = min(p.SG, p.N - i0);
-            for (int e = tid; e < TC_SG_MAX * MMAX; e += TC_CT) {
-                const int si = e / MMAX, k = e - si * MMAX;
-                sTheta[e] = (si < nsamp && k < m) ? p.theta[(size_t)(i0 + si) * m + k] : 0.f;
+        // ---- phases shared by the two schedules (one group after the other / two groups interleaved) ----------------------
+        // layer-0 per-sample part of an item: base[si][col] = time_feat[col] + sum_k A[k][col] theta[si][k]
+        auto do_base = [&](const float* th, int next_step) {
+            if (tid < H0) {
+                const float t0 = tf_next;
+                tf_next = __ldg(p.time_feat + (size_t)next_step * H0 + tid);  // consumed one item later: latency hidden
+                for (int si = 0; si < p.SG; ++si) {
+                    float z = t0;
+#pragma unroll
+                    for (int k = 0; k < MMAX; ++k)
+                        if (k < m) z = fmaf(acol[k], th[si * MMAX + k], z);
+                    sBase[si * 256 + tid] = z;
+                }
             }
-            compute_bar();
-            for (int step = p.step_begin; step < p.step_end; ++step) {
-                bar_arrive(2, NB23);  // theta is final: the helper warp may start on this step
-                const float inv_sigma = __ldg(p.sched + (size_t)step * D4S_SCHED_STRIDE + D4S_S_INV_SIGMA);
-                // ---- layer-0 per-sample part: base[si][col] = time_feat[col] + sum_k A[k][col] theta[si][k] ----------
-                if (tid < H0) {
-                    const float t0 = tf_next;
-                    const int nstep = (step + 1 < p.step_end) ? step + 1 : p.step_begin;  // (next group restarts the grid)
-                    tf_next = __ldg(p.time_feat + (size_t)nstep * H0 + tid);  // consumed one step later: latency hidden
-                    for (int si = 0; si < p.SG; ++si) {
-                        float z = t0;
+        };
+        // per-sample sums over the chunk's observations.  item = (sample si, component c < 2m): S1[c] = sum_j s_ij[c]
+        // (c < m), S2[c-m] = sum_j (inv(Sigma_j) s_ij)[c-m]; a warp takes one item at a time, its lanes run over the
+        // observations, one butterfly per item (fixed order => deterministic).
+        auto do_sums = [&](int nsamp, int j0, int nobs, bool first_chunk) {
+            for (int item = warp; item < nsamp * 2 * m; item += TC_CW) {
+                const int si = item / (2 * m), c = item - si * 2 * m;
+                float acc = 0.f;
+                for (int oj = lane; oj < nobs; oj += 32) {
+                    const float* srow = sS + (si * p.OC + oj) * MMAX;
+                    const float wj = p.obs_weight ? __ldg(p.obs_weight + j0 + oj) : 1.f;
+                    if (c < m) {
+                        acc = fmaf(wj, srow[c], acc);
+                    } else if (p.obs_prec) {
+                        const float* Q = p.obs_prec + ((size_t)(j0 + oj) * m + (c - m)) * m;
+                        float qs = 0.f;
 #pragma unroll
                         for (int k = 0; k < MMAX; ++k)
-                            if (k < m) z = fmaf(acol[k], sTheta[si * MMAX + k], z);
-                        sBase[si * 256 + tid] = z;
+                            if (k < m) qs = fmaf(__ldg(Q + k), srow[k], qs);
+                        acc = fmaf(wj, qs, acc);
                     }
                 }
-                compute_bar();
+#pragma unroll
+                for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+                if (lane == 0) sAcc[si * 2 * m + c] = (first_chunk ? 0.f : sAcc[si * 2 * m + c]) + acc;
+            }
+        };
+        // tail of an item: prior, Lambda solve, DDIM update (theta stays in smem); warp -> sample, lane -> theta component
+        auto do_tail = [&](float* th, int nsamp) {
+            if (warp < nsamp) {
+                const int si = warp, r = lane;
+                const bool act = lane < m;
+                const int combine = (int)sSched[D4S_S_COMBINE];
+                const float* acc = sAcc + si * 2 * m;
+                float out = 0.f;
+                if (act) {
+                    if (combine == D4S_COMBINE_SUM) {
+                        out = sG[si * MMAX + r] + sSched[D4S_S_S1_WEIGHT] * acc[r];  // (1-n) s0 + w sum_j s_ij (nse.py:642)
+                    } else {
+                        const float aos2 = sSched[D4S_S_A_OVER_S2];
+                        const float* Minv = (combine == D4S_COMBINE_SHARED) ? sMats : sMinv + si * MMAX * MMAX;
+                        for (int c = 0; c < m; ++c) {
+                            const float w = fmaf(aos2, acc[c], acc[m + c]) + sG[si * MMAX + c];  // nse.py:631-636 / 647-652
+                            out = fmaf(Minv[r * m + c], w, out);  // Lambda^-1 w   (nse.py:638 / 654)
+                        }
+                    }
+                }
+                float c_score = sSched[D4S_S_C_SCORE];
+                const float tame = sSched[D4S_S_TAME];
+                if (tame > 0.f) {  // tamed ULA (nse.py:336); the whole warp takes part, lanes >= m contribute 0
+                    float nrm = out * out;
+#pragma unroll
+                    for (int sh = 16; sh > 0; sh >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, sh);
+                    c_score = tame / (1.f + tame * sqrtf(nrm));
+                }
+                if (act) {
+                    float v = sSched[D4S_S_C_THETA] * th[si * MMAX + r] + c_score * out +
+                              sSched[D4S_S_BRIDGE_STD] * sNoise[si * MMAX + r];  // nse.py:289-298
+                    if (p.fin.clip_lo <= p.fin.clip_hi && sSched[D4S_S_CLIP] != 0.f)
+                        v = fminf(fmaxf(v, p.fin.clip_lo), p.fin.clip_hi);
+                    th[si * MMAX + r] = v;
+                }
+            }
+        };
+
+        for (int gk = 0; gk < my_groups;) {
+            const int ngr = (pairing && gk + 1 < my_groups) ? 2 : 1;
+            const bool defer = (ngr == 2);  // item it's sums / tail run inside item it+1's first tensor-core wait
+            const int total = ngr * n_steps;
+            const int lwin2 = (L - 2 >= 2) ? 2 : 1;  // hidden layer whose wait hosts the next item's layer-0 sample part
+            int i0g[2], nsg[2];
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+                i0g[gi] = (blockIdx.x + (gk + min(gi, ngr - 1)) * (int)gridDim.x) * p.SG;
+                nsg[gi] = min(p.SG, p.N - i0g[gi]);
+            }
+            for (int e = tid; e < ngr * TC_SG_MAX * MMAX; e += TC_CT) {
+                const int gi = e / (TC_SG_MAX * MMAX), r = e - gi * TC_SG_MAX * MMAX;
+                const int si = r / MMAX, k = r - si * MMAX;
+                sTheta[e] = (si < nsg[gi] && k < m) ? p.theta[(size_t)(i0g[gi] + si) * m + k] : 0.f;
+            }
+            compute_bar();
+            if (total > 0) bar_arrive(2, NB23);  // theta of item 0 is final: the helper warp may start on it
+            for (int it = 0; it < total; ++it) {
+                const int gi = defer ? (it & 1) : 0;
+                const int step = p.step_begin + (defer ? (it >> 1) : it);
+                const int i0 = i0g[gi], nsamp = nsg[gi];
+                float* th = sTheta + gi * TC_SG_MAX * MMAX;
+                const float inv_sigma = __ldg(p.sched + (size_t)step * D4S_SCHED_STRIDE + D4S_S_INV_SIGMA);
+                auto step_of = [&](int item) { return (item < total) ? p.step_begin + (defer ? (item >> 1) : item) : p.step_begin; };
+                if (!defer || it == 0) {  // (interleaved: done inside the previous item's tensor-core wait)
+                    do_base(th, step_of(it + 1));
+                    compute_bar();
+                }
                 PROF_MARK(0);  // per-sample layer-0 part
                 for (int chunk = 0; chunk < p.C; ++chunk) {
                     const int j0 = chunk * p.OC;
@@ -513,6 +604,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                         float4 bcur[4], bnxt[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) bcur[e] = __ldg(reinterpret_cast<const float4*>(bias_l) + e);  // hidden behind the MMA
+                        if (defer) {  // work of the neighbouring items that needs neither the operand images nor the accumulator
+                            if (l == 1 && it > 0) {
+                                const int pg = gi ^ 1;
+                                do_sums(nsg[pg], 0, nobs, true);
+                                compute_bar();
+                                bar_sync(3, NB23);  // schedule / matrix rows, prior terms and noise of the previous item are in smem
+                                do_tail(sTheta + pg * TC_SG_MAX * MMAX, nsg[pg]);
+                                compute_bar();
+                                bar_arrive(2, NB23);  // helper warp: buffers are free, go on with this item
+                                PROF_MARK(6);
+                            }
+                            if (l == lwin2 && it + 1 < total) {
+                                do_base(sTheta + (gi ^ 1) * TC_SG_MAX * MMAX, step_of(it + 2));
+                                PROF_MARK(7);
+                            }
+                        }
                         mbar_wait(bar_d, d_cnt & 1u, p.error_flag);
                         ++d_cnt;
                         tc_fence_after();
@@ -602,84 +709,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     }
                     compute_bar();
                     PROF_MARK(5);  // scores
-                    // ---- per-sample sums over the chunk's observations --------------------------------------------------------------
-                    // item = (sample si, component c < 2m): S1[c] = sum_j s_ij[c] (c < m), S2[c-m] = sum_j (inv(Sigma_j) s_ij)[c-m];
-                    // a warp takes one item at a time, its lanes run over the observations, one butterfly per item
-                    // (fixed order => deterministic).
-                    for (int item = warp; item < nsamp * 2 * m; item += TC_CW) {
-                        const int si = item / (2 * m), c = item - si * 2 * m;
-                        float acc = 0.f;
-                        for (int oj = lane; oj < nobs; oj += 32) {
-                            const float* srow = sS + (si * p.OC + oj) * MMAX;
-                            const float wj = p.obs_weight ? __ldg(p.obs_weight + j0 + oj) : 1.f;
-                            if (c < m) {
-                                acc = fmaf(wj, srow[c], acc);
-                            } else if (p.obs_prec) {
-                                const float* Q = p.obs_prec + ((size_t)(j0 + oj) * m + (c - m)) * m;
-                                float qs = 0.f;
-#pragma unroll
-                                for (int k = 0; k < MMAX; ++k)
-                                    if (k < m) qs = fmaf(__ldg(Q + k), srow[k], qs);
-                                acc = fmaf(wj, qs, acc);
-                            }
-                        }
-#pragma unroll
-                        for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
-                        if (lane == 0) sAcc[si * 2 * m + c] = (chunk == 0 ? 0.f : sAcc[si * 2 * m + c]) + acc;
+                    if (!defer) {
+                        do_sums(nsamp, j0, nobs, chunk == 0);
+                        compute_bar();
+                        PROF_MARK(6);  // inv(Sigma) s + sums over observations
+                    }
+                }  // chunks
+                if (!defer) {
+                    bar_sync(3, NB23);  // schedule/matrix rows, prior terms and noise of this step are in smem
+                    PROF_MARK(2);       // (time spent waiting for the helper warp, normally zero)
+                    if (p.part_out) {
+                        for (int e = tid; e < nsamp * 2 * m; e += TC_CT) p.part_out[(size_t)i0 * 2 * m + e] = sAcc[e];
+                    } else {
+                        do_tail(th, nsamp);
                     }
                     compute_bar();
-                    PROF_MARK(6);  // inv(Sigma) s + sums over observations
-                }  // chunks
-                // ---- finalize: prior, Lambda solve, DDIM update (theta stays in smem) ---------------------------------------------
-                bar_sync(3, NB23);  // schedule/matrix rows, prior terms and noise of this step are in smem
-                PROF_MARK(2);       // (time spent waiting for the helper warp, normally zero)
-                if (p.part_out) {
-                    for (int e = tid; e < nsamp * 2 * m; e += TC_CT) p.part_out[(size_t)i0 * 2 * m + e] = sAcc[e];
-                } else if (warp < nsamp) {  // warp -> sample, lane -> theta component; fp32, everything in smem
-                    const int si = warp, r = lane;
-                    const bool act = lane < m;
-                    const int combine = (int)sSched[D4S_S_COMBINE];
-                    const float* acc = sAcc + si * 2 * m;
-                    float out = 0.f;
-                    if (act) {
-                        if (combine == D4S_COMBINE_SUM) {
-                            out = sG[si * MMAX + r] + sSched[D4S_S_S1_WEIGHT] * acc[r];  // (1-n) s0 + w sum_j s_ij (nse.py:642)
-                        } else {
-                            const float aos2 = sSched[D4S_S_A_OVER_S2];
-                            const float* Minv = (combine == D4S_COMBINE_SHARED) ? sMats : sMinv + si * MMAX * MMAX;
-                            for (int c = 0; c < m; ++c) {
-                                const float w = fmaf(aos2, acc[c], acc[m + c]) + sG[si * MMAX + c];  // nse.py:631-636 / 647-652
-                                out = fmaf(Minv[r * m + c], w, out);  // Lambda^-1 w   (nse.py:638 / 654)
-                            }
-                        }
-                    }
-                    float c_score = sSched[D4S_S_C_SCORE];
-                    const float tame = sSched[D4S_S_TAME];
-                    if (tame > 0.f) {  // tamed ULA (nse.py:336); the whole warp takes part, lanes >= m contribute 0
-                        float nrm = out * out;
-#pragma unroll
-                        for (int sh = 16; sh > 0; sh >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, sh);
-                        c_score = tame / (1.f + tame * sqrtf(nrm));
-                    }
-                    if (act) {
-                        float v = sSched[D4S_S_C_THETA] * sTheta[si * MMAX + r] + c_score * out +
-                                  sSched[D4S_S_BRIDGE_STD] * sNoise[si * MMAX + r];  // nse.py:289-298
-                        if (p.fin.clip_lo <= p.fin.clip_hi && sSched[D4S_S_CLIP] != 0.f)
-                            v = fminf(fmaxf(v, p.fin.clip_lo), p.fin.clip_hi);
-                        sTheta[si * MMAX + r] = v;
-                    }
+                    if (it + 1 < total) bar_arrive(2, NB23);
+                    PROF_MARK(7);  // finalize
                 }
+            }  // items
+            if (defer && total > 0) {  // drain: the last item's sums and tail
+                const int pg = (total - 1) & 1;
+                do_sums(nsg[pg], 0, min(p.OC, p.n), true);
                 compute_bar();
-                PROF_MARK(7);  // finalize
-            }  // steps
+                bar_sync(3, NB23);
+                do_tail(sTheta + pg * TC_SG_MAX * MMAX, nsg[pg]);
+                compute_bar();
+            }
             if (!p.part_out) {
-                for (int e = tid; e < nsamp * m; e += TC_CT) {
-                    const int si = e / m, k = e - si * m;
-                    p.theta[(size_t)(i0 + si) * m + k] = sTheta[si * MMAX + k];
+                for (int e = tid; e < ngr * TC_SG_MAX * MMAX; e += TC_CT) {
+                    const int gi = e / (TC_SG_MAX * MMAX), r = e - gi * TC_SG_MAX * MMAX;
+                    const int si = r / MMAX, k = r - si * MMAX;
+                    if (si < nsg[gi] && k < m) p.theta[(size_t)(i0g[gi] + si) * m + k] = sTheta[e];
                 }
             }
             compute_bar();
-        }  // groups
+            gk += ngr;
+        }  // group blocks
     }
     tc_fence_before();
     __syncthreads();

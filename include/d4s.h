@@ -187,7 +187,9 @@ D4S_API int d4s_ddim_run(const D4sNet* net, const D4sProblem* prob, int32_t step
 D4S_API void d4s_graph_cache_clear(void);
 /* Library options: "path" = 0 auto | 1 per-step fp32 SIMT kernels only | 2 require the fused tcgen05 trajectory
  * kernel (bf16x3 split on the tensor cores; GAUSS, tall grid); "tc_steps_per_launch" = DDIM steps per tcgen05
- * launch (0 = whole trajectory in one launch); "profile" = 1 enables the in-kernel phase timers. */
+ * launch (0 = whole trajectory in one launch); "profile" = 1 enables the in-kernel phase timers; "tc_pairing" = 1
+ * (default) lets a CTA that owns two sample groups interleave them step by step, 0 runs them one after the other
+ * (same arithmetic, bit-identical results). */
 D4S_API int d4s_set_option(const char* key, int32_t value);
 /* "profile" = 1 makes CTA 0 of the tcgen05 kernel accumulate clock64() cycles per phase; this call synchronises and
  * copies the 16 counters of the last launch: 0 layer-0 sample part, 1 layer 0, 2 prior+noise, 3 tensor-core wait,

@@ -47,6 +47,12 @@ print(f"swap={swap} N={N} n={n} steps={steps} hidden={hidden}: |tc-simt|max={flo
       f"|simt-oracle|={np.abs(ref.cpu().numpy() - orc_out).max() / scale:.3e} "
       f"|tc-oracle|={np.abs(out.cpu().numpy() - orc_out).max() / scale:.3e} (rel to {scale:.2f})")
 
+abi.set_option("tc_pairing", 0)  # one sample group after the other: same arithmetic, so the result must be bit-identical
+out_seq = nse.ddim((N,), xt, **kw)
+torch.cuda.synchronize()
+abi.set_option("tc_pairing", 1)
+print("interleaved vs sequential group schedule: bit-identical =", bool(torch.equal(out, out_seq)),
+      "finite =", bool(torch.isfinite(out).all()))
 
 if os.environ.get("D4S_PROFILE"):
     abi.set_option("profile", 1)
