@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
     float* sQS = reinterpret_cast<float*>(smem + OFF_QS);
     float* sBase = reinterpret_cast<float*>(smem + OFF_BASE);
     float* sWout = reinterpret_cast<float*>(smem + OFF_WOUT);
+    float* sA = sWout + (MMAX / 2) * 256;  // [m][256] layer-0 theta block, only when m <= MMAX / 2
     float* sAcc = reinterpret_cast<float*>(smem + OFF_ACC);
     float* sTheta = reinterpret_cast<float*>(smem + OFF_THETA);
     float* sNoise = reinterpret_cast<float*>(smem + OFF_NOISE);
@@ -246,6 +247,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m = net.m, L = net.L;
     const int H0 = net.Hp[0];
+    const bool a_in_smem = (m <= MMAX / 2);
     const int n_groups = (p.N + p.SG - 1) / p.SG;
     const int mats_floats = 2 * m * m + m;
     constexpr int NB23 = TC_CT + 32;  // participants of named barriers 2 and 3
@@ -259,8 +261,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
         mbar_init(bar_d, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == TC_CW + 1) {  // TMEM: 256 fp32 accumulator columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(256));
+    if (warp == TC_CW + 1) {  // TMEM: two 256-column fp32 accumulators, used alternately layer by layer
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     // constant tables: output layer, its bias, row -> (sample, observation) maps, zeroed operand images
@@ -268,6 +270,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
     {
         const int Kout = net.Hp[L - 2];
         for (int e = tid; e < m * Kout; e += TC_THREADS) sWout[(e / Kout) * 256 + (e % Kout)] = __ldg(net.WoutT + e);
+        if (a_in_smem)  // layer-0 theta block next to the output layer when both fit (theta_dim <= 5)
+            for (int e = tid; e < m * H0; e += TC_THREADS) sA[(e / H0) * 256 + (e % H0)] = __ldg(net.A + e);
         if (tid < MMAX) sBout[tid] = (tid < m) ? __ldg(net.bout + tid) : 0.f;
         if (tid < TC_M) {
             const int si = tid / p.OC, oj = tid - si * p.OC;
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
     } else if (warp == TC_CW + 1) {
         // ================= MMA issuer ===================================================================================
         if (lane == 0) {
-            unsigned it = 0, a_cnt = 0;
+            unsigned it = 0, a_cnt = 0, lc = 0;
             const uint32_t a_hi0 = smem_u32(sAhi), a_lo0 = smem_u32(sAlo);
             for (long long ti = 0; ti < tile_iters; ++ti) {
                 for (int l = 1; l <= L - 2; ++l) {
@@ -323,6 +327,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     mbar_wait(bar_a, a_cnt & 1u, p.error_flag);
                     ++a_cnt;
                     tc_fence_after();
+                    const uint32_t dacc = tmem_d + ((lc & 1u) ? 256u : 0u);  // the other accumulator may still be read by an epilogue
+                    ++lc;
                     for (int ks = 0; ks < K / 16; ++ks, ++it) {
                         const int s = it % TC_NSTG;
                         const uint32_t ph = (it / TC_NSTG) & 1u;
@@ -333,9 +339,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                         const uint64_t b_lo = umma_desc(wb + (uint32_t)Nn * 32u, b_lbo, b_sbo);
                         const uint64_t a_hi = umma_desc(a_hi0 + ks * 4096, a_lbo, a_sbo);
                         const uint64_t a_lo = umma_desc(a_lo0 + ks * 4096, a_lbo, a_sbo);
-                        tc_mma_bf16(tmem_d, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
-                        tc_mma_bf16(tmem_d, a_lo, b_hi, idesc, 1u);
-                        tc_mma_bf16(tmem_d, a_hi, b_lo, idesc, 1u);
+                        tc_mma_bf16(dacc, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
+                        tc_mma_bf16(dacc, a_lo, b_hi, idesc, 1u);
+                        tc_mma_bf16(dacc, a_hi, b_lo, idesc, 1u);
                         tc_commit(bar_empty(s));  // ring slot is free once these MMAs have read it
                     }
                     tc_commit(bar_d);  // accumulator complete
@@ -430,45 +436,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
         const bool prof_on = (p.prof != nullptr) && blockIdx.x == 0 && tid == 0;
         long long prof_t = prof_on ? clock64() : 0;
         const int nkg = H0 / 8;
-        // layer-0 theta block: thread `tid` owns column tid of A for the whole kernel (registers)
-        float acol[MMAX];
-#pragma unroll
-        for (int k = 0; k < MMAX; ++k) acol[k] = (k < m && tid < H0) ? __ldg(net.A + (size_t)k * H0 + tid) : 0.f;
         float tf_next = (tid < H0 && n_steps > 0) ? __ldg(p.time_feat + (size_t)p.step_begin * H0 + tid) : 0.f;
         // ---- phases shared by the two schedules (one group after the other / two groups interleaved) ----------------------
         // layer-0 per-sample part of an item: base[si][col] = time_feat[col] + sum_k A[k][col] theta[si][k]
-        auto do_base = [&](const float* th, int next_step) {
+        auto do_base = [&](const float* th, bool fresh, int step, int next_step) {
             if (tid < H0) {
-                const float t0 = tf_next;
-                tf_next = __ldg(p.time_feat + (size_t)next_step * H0 + tid);  // consumed one item later: latency hidden
+                float t0;
+                if (fresh) {
+                    t0 = tf_next;
+                    tf_next = __ldg(p.time_feat + (size_t)next_step * H0 + tid);  // consumed one item later: latency hidden
+                } else {
+                    t0 = __ldg(p.time_feat + (size_t)step * H0 + tid);  // (later observation chunks of the same step)
+                }
+                float ak[MMAX];  // column tid of the layer-0 theta block
+#pragma unroll
+                for (int k = 0; k < MMAX; ++k)
+                    ak[k] = (k < m) ? (a_in_smem ? sA[k * 256 + tid] : __ldg(net.A + (size_t)k * H0 + tid)) : 0.f;
                 for (int si = 0; si < p.SG; ++si) {
                     float z = t0;
 #pragma unroll
                     for (int k = 0; k < MMAX; ++k)
-                        if (k < m) z = fmaf(acol[k], th[si * MMAX + k], z);
+                        if (k < m) z = fmaf(ak[k], th[si * MMAX + k], z);
                     sBase[si * 256 + tid] = z;
                 }
             }
         };
         // per-sample sums over the chunk's observations.  item = (sample si, component c < 2m): S1[c] = sum_j s_ij[c]
-        // (c < m), S2[c-m] = sum_j (inv(Sigma_j) s_ij)[c-m]; a warp takes one item at a time, its lanes run over the
+        // (c < m), S2[c-m] = sum_j (inv(Sigma_j) s_ij)[c-m] (rows of sQS); a warp takes one item at a time, its lanes run over the
         // observations, one butterfly per item (fixed order => deterministic).
         auto do_sums = [&](int nsamp, int j0, int nobs, bool first_chunk) {
             for (int item = warp; item < nsamp * 2 * m; item += TC_CW) {
                 const int si = item / (2 * m), c = item - si * 2 * m;
+                const float* src = (c < m) ? sS + c : sQS + (c - m);
                 float acc = 0.f;
-                for (int oj = lane; oj < nobs; oj += 32) {
-                    const float* srow = sS + (si * p.OC + oj) * MMAX;
-                    const float wj = p.obs_weight ? __ldg(p.obs_weight + j0 + oj) : 1.f;
-                    if (c < m) {
-                        acc = fmaf(wj, srow[c], acc);
-                    } else if (p.obs_prec) {
-                        const float* Q = p.obs_prec + ((size_t)(j0 + oj) * m + (c - m)) * m;
-                        float qs = 0.f;
-#pragma unroll
-                        for (int k = 0; k < MMAX; ++k)
-                            if (k < m) qs = fmaf(__ldg(Q + k), srow[k], qs);
-                        acc = fmaf(wj, qs, acc);
+                if (c < m || p.obs_prec) {
+                    for (int oj = lane; oj < nobs; oj += 32) {
+                        const float wj = p.obs_weight ? __ldg(p.obs_weight + j0 + oj) : 1.f;
+                        acc = fmaf(wj, src[(si * p.OC + oj) * MMAX], acc);
                     }
                 }
 #pragma unroll
@@ -514,11 +518,145 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
             }
         };
 
+        // layer 0 of a pass: act0[r][col] = relu(base[si][col] + obs_feat[j][col]) -> bf16 hi/lo A images, then launch layer 1
+        auto do_layer0 = [&](int nsamp, int j0, int nobs) {
+            // ---- layer 0: act0[r][col] = relu(base[si][col] + obs_feat[j][col]) -> bf16 hi/lo A images -----------
+            // warp w owns k-groups w, w+16; lanes run over the observations: one 32-byte read of obs_feat
+            // serves the rows of all SG samples, and every global load is issued before its first use.
+            for (int oj = lane; oj < p.OC; oj += 32) {
+                const bool ovalid = oj < nobs;
+                const float* up = p.obs_feat + (size_t)(j0 + (ovalid ? oj : 0)) * H0;
+                float4 u[2][2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int kg = warp + 16 * j;
+                    if (ovalid && kg < nkg) {
+                        u[j][0] = __ldg(reinterpret_cast<const float4*>(up + 8 * kg));
+                        u[j][1] = __ldg(reinterpret_cast<const float4*>(up + 8 * kg + 4));
+                    } else {
+                        u[j][0] = u[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int kg = warp + 16 * j;
+                    if (kg < nkg) {
+                        for (int si = 0; si < p.SG; ++si) {
+                            float v[8];
+                            if (ovalid && si < nsamp) {
+                                const float* brow = sBase + si * 256 + 8 * kg;
+                                const float4 b0 = *reinterpret_cast<const float4*>(brow);
+                                const float4 b1 = *reinterpret_cast<const float4*>(brow + 4);
+                                v[0] = fmaxf(u[j][0].x + b0.x, 0.f); v[1] = fmaxf(u[j][0].y + b0.y, 0.f);
+                                v[2] = fmaxf(u[j][0].z + b0.z, 0.f); v[3] = fmaxf(u[j][0].w + b0.w, 0.f);
+                                v[4] = fmaxf(u[j][1].x + b1.x, 0.f); v[5] = fmaxf(u[j][1].y + b1.y, 0.f);
+                                v[6] = fmaxf(u[j][1].z + b1.z, 0.f); v[7] = fmaxf(u[j][1].w + b1.w, 0.f);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                            }
+                            store_split8(v, sAhi, sAlo, a_off(si * p.OC + oj, kg));
+                        }
+                    }
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bar_a);
+        };
+        // one 16-column block of an accumulator row: bias + ReLU
+        auto ld_act = [&](uint32_t dacc, int col0, const float4 (&bb)[4], float (&a)[16]) {
+            uint32_t d[16];
+            tc_ld16(dacc + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, d);
+            tc_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                a[4 * e] = fmaxf(__uint_as_float(d[4 * e]) + bb[e].x, 0.f);
+                a[4 * e + 1] = fmaxf(__uint_as_float(d[4 * e + 1]) + bb[e].y, 0.f);
+                a[4 * e + 2] = fmaxf(__uint_as_float(d[4 * e + 2]) + bb[e].z, 0.f);
+                a[4 * e + 3] = fmaxf(__uint_as_float(d[4 * e + 3]) + bb[e].w, 0.f);
+            }
+        };
+        // epilogue of the last hidden layer + output layer in fp32 + scores of a pass -> sS
+        auto do_last_epilogue = [&](uint32_t dacc, float inv_sigma, int j0, int nobs) {
+            const int Nn = net.Hp[L - 2];
+            const int qcols = Nn >> 2, nblk = qcols / 16;
+            const float* bias_l = net.bias[L - 2] + cq * qcols;
+            float po[MMAX];  // output-layer partial dot products of this thread's row / column quarter
+#pragma unroll
+            for (int o = 0; o < MMAX; ++o) po[o] = 0.f;
+            for (int cb = 0; cb < nblk; ++cb) {
+                const int col0 = cq * qcols + 16 * cb;
+                float4 bb[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bias_l + 16 * cb) + e);
+                float a[16];
+                ld_act(dacc, col0, bb, a);
+                // po[o] += sum_c act[c] * Wout[o][c]   (Wout in smem, broadcast reads)
+#pragma unroll
+                for (int o = 0; o < MMAX; ++o) {
+                    if (o < m) {
+                        const float* w = sWout + o * 256 + col0;
+                        float acc = po[o];
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(w + e);
+                            acc = fmaf(a[e], w4.x, acc);
+                            acc = fmaf(a[e + 1], w4.y, acc);
+                            acc = fmaf(a[e + 2], w4.z, acc);
+                            acc = fmaf(a[e + 3], w4.w, acc);
+                        }
+                        po[o] = acc;
+                    }
+                }
+            }
+            PROF_MARK(4);  // epilogues
+            // ---- scores: the column quarters 1..3 park their partial dot products in sS / sQS / sBase (free here), quarter 0
+            // adds them up as (q0 + q1) + (q2 + q3), s = -(eps + b) / sigma, and applies inv(Sigma_j) to its row's score.
+            if (cq != 0) {
+                float* dst = (cq == 1) ? sS : (cq == 2) ? sQS : sBase;
+#pragma unroll
+                for (int o = 0; o < MMAX; ++o)
+                    if (o < m) dst[row * MMAX + o] = po[o];
+            }
+            tc_fence_before();
+            compute_bar();
+            if (cq == 0) {
+                float s[MMAX];
+#pragma unroll
+                for (int o = 0; o < MMAX; ++o) {
+                    s[o] = 0.f;
+                    if (o < m) {
+                        const float v = (po[o] + sS[row * MMAX + o]) + (sQS[row * MMAX + o] + sBase[row * MMAX + o]);
+                        s[o] = -(v + sBout[o]) * inv_sigma;
+                        sS[row * MMAX + o] = s[o];
+                    }
+                }
+                const int oj = sRowOj[row];
+                if (p.obs_prec && oj < nobs) {  // (rows past the tile's pairs carry oj = 255)
+                    const float* Q = p.obs_prec + (size_t)(j0 + oj) * m * m;
+                    for (int r = 0; r < m; ++r) {
+                        float qs = 0.f;
+#pragma unroll
+                        for (int k = 0; k < MMAX; ++k)
+                            if (k < m) qs = fmaf(__ldg(Q + r * m + k), s[k], qs);
+                        sQS[row * MMAX + r] = qs;
+                    }
+                }
+            }
+            compute_bar();
+            PROF_MARK(5);  // scores
+        };
+
+        const int Lh = L - 2;  // hidden layers on the tensor core
         for (int gk = 0; gk < my_groups;) {
             const int ngr = (pairing && gk + 1 < my_groups) ? 2 : 1;
-            const bool defer = (ngr == 2);  // item it's sums / tail run inside item it+1's first tensor-core wait
+            // Two groups interleaved: the last epilogue / scores of a pass run while the tensor core is on layer 1 of the
+            // next pass (other accumulator), its sums / tail and the layer-0 sample part of the pass after next while
+            // the tensor core is on the last layer.  One group: the same loop, everything in program order.
+            const bool defer = (ngr == 2);
             const int total = ngr * n_steps;
-            const int lwin2 = (L - 2 >= 2) ? 2 : 1;  // hidden layer whose wait hosts the next item's layer-0 sample part
+            const int total_p = total * p.C;  // passes (defer => C == 1)
             int i0g[2], nsg[2];
 #pragma unroll
             for (int gi = 0; gi < 2; ++gi) {
@@ -532,210 +670,122 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
             }
             compute_bar();
             if (total > 0) bar_arrive(2, NB23);  // theta of item 0 is final: the helper warp may start on it
-            for (int it = 0; it < total; ++it) {
+            auto step_of = [&](int item) { return (item < total) ? p.step_begin + (defer ? (item >> 1) : item) : p.step_begin; };
+            if (defer && total > 0) {  // (later items: inside the previous item's last tensor-core wait)
+                do_base(sTheta, true, step_of(0), step_of(1));
+                compute_bar();
+            }
+            for (int ps = 0; ps <= total_p; ++ps) {  // one extra iteration finishes the last pass
+                const bool have = ps < total_p, prev = ps > 0;
+                const int it = ps / p.C, chunk = ps - it * p.C;
                 const int gi = defer ? (it & 1) : 0;
-                const int step = p.step_begin + (defer ? (it >> 1) : it);
-                const int i0 = i0g[gi], nsamp = nsg[gi];
+                const int j0 = chunk * p.OC, nobs = min(p.OC, p.n - j0);
+                const int pit = prev ? (ps - 1) / p.C : 0, pchunk = prev ? (ps - 1) - pit * p.C : 0;
+                const int pgi = defer ? (pit & 1) : 0;
+                const int pj0 = pchunk * p.OC, pnobs = min(p.OC, p.n - pj0);
                 float* th = sTheta + gi * TC_SG_MAX * MMAX;
-                const float inv_sigma = __ldg(p.sched + (size_t)step * D4S_SCHED_STRIDE + D4S_S_INV_SIGMA);
-                auto step_of = [&](int item) { return (item < total) ? p.step_begin + (defer ? (item >> 1) : item) : p.step_begin; };
-                if (!defer || it == 0) {  // (interleaved: done inside the previous item's tensor-core wait)
-                    do_base(th, step_of(it + 1));
-                    compute_bar();
+                float* pth = sTheta + pgi * TC_SG_MAX * MMAX;
+                float4 bcur[4];
+                float inv_sigma_prev = 0.f;
+                uint32_t dacc_prev = 0;
+                if (prev) {  // the last layer of the previous pass: once it is done the operand images are free again
+                    inv_sigma_prev = __ldg(p.sched + (size_t)step_of(pit) * D4S_SCHED_STRIDE + D4S_S_INV_SIGMA);
+                    dacc_prev = tmem_d + ((d_cnt & 1u) ? 256u : 0u);
+                    mbar_wait(bar_d, d_cnt & 1u, p.error_flag);
+                    ++d_cnt;
+                    tc_fence_after();
+                    PROF_MARK(3);  // waiting for the tensor core
                 }
-                PROF_MARK(0);  // per-sample layer-0 part
-                for (int chunk = 0; chunk < p.C; ++chunk) {
-                    const int j0 = chunk * p.OC;
-                    const int nobs = min(p.OC, p.n - j0);
-                    // ---- layer 0: act0[r][col] = relu(base[si][col] + obs_feat[j][col]) -> bf16 hi/lo A images -----------
-                    // warp w owns k-groups w, w+16; lanes run over the observations: one 32-byte read of obs_feat
-                    // serves the rows of all SG samples, and every global load is issued before its first use.
-                    for (int oj = lane; oj < p.OC; oj += 32) {
-                        const bool ovalid = oj < nobs;
-                        const float* up = p.obs_feat + (size_t)(j0 + (ovalid ? oj : 0)) * H0;
-                        float4 u[2][2];
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const int kg = warp + 16 * j;
-                            if (ovalid && kg < nkg) {
-                                u[j][0] = __ldg(reinterpret_cast<const float4*>(up + 8 * kg));
-                                u[j][1] = __ldg(reinterpret_cast<const float4*>(up + 8 * kg + 4));
+                if (defer && have) {
+                    do_layer0(nsg[gi], j0, nobs);
+                    PROF_MARK(1);  // layer 0
+                }
+                if (prev) do_last_epilogue(dacc_prev, inv_sigma_prev, pj0, pnobs);
+                if (!defer) {
+                    if (prev) {
+                        do_sums(nsg[pgi], pj0, pnobs, pchunk == 0);
+                        compute_bar();
+                        PROF_MARK(6);  // inv(Sigma) s + sums over observations
+                        if (pchunk == p.C - 1) {
+                            bar_sync(3, NB23);  // schedule/matrix rows, prior terms and noise of this step are in smem
+                            PROF_MARK(2);       // (time spent waiting for the helper warp, normally zero)
+                            if (p.part_out) {
+                                for (int e = tid; e < nsg[pgi] * 2 * m; e += TC_CT) p.part_out[(size_t)i0g[pgi] * 2 * m + e] = sAcc[e];
                             } else {
-                                u[j][0] = u[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                do_tail(pth, nsg[pgi]);
                             }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const int kg = warp + 16 * j;
-                            if (kg < nkg) {
-                                for (int si = 0; si < p.SG; ++si) {
-                                    float v[8];
-                                    if (ovalid && si < nsamp) {
-                                        const float* brow = sBase + si * 256 + 8 * kg;
-                                        const float4 b0 = *reinterpret_cast<const float4*>(brow);
-                                        const float4 b1 = *reinterpret_cast<const float4*>(brow + 4);
-                                        v[0] = fmaxf(u[j][0].x + b0.x, 0.f); v[1] = fmaxf(u[j][0].y + b0.y, 0.f);
-                                        v[2] = fmaxf(u[j][0].z + b0.z, 0.f); v[3] = fmaxf(u[j][0].w + b0.w, 0.f);
-                                        v[4] = fmaxf(u[j][1].x + b1.x, 0.f); v[5] = fmaxf(u[j][1].y + b1.y, 0.f);
-                                        v[6] = fmaxf(u[j][1].z + b1.z, 0.f); v[7] = fmaxf(u[j][1].w + b1.w, 0.f);
-                                    } else {
-#pragma unroll
-                                        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-                                    }
-                                    store_split8(v, sAhi, sAlo, a_off(si * p.OC + oj, kg));
-                                }
-                            }
+                            compute_bar();
+                            if (have) bar_arrive(2, NB23);
+                            PROF_MARK(7);  // finalize
                         }
                     }
-                    fence_proxy_async();
-                    mbar_arrive(bar_a);
-                    PROF_MARK(1);  // layer 0
-
-                    // ---- hidden layers on the tensor core; epilogues here ----------------------------------------------------
-                    float po[MMAX];  // output-layer partial dot products of this thread's row / column half
-#pragma unroll
-                    for (int o = 0; o < MMAX; ++o) po[o] = 0.f;
-                    for (int l = 1; l <= L - 2; ++l) {
+                    if (have) {
+                        if (chunk == 0 || p.C > 1) {  // (the scores of the previous chunk used sBase as scratch)
+                            do_base(th, chunk == 0, step_of(it), step_of(it + 1));
+                            compute_bar();
+                            PROF_MARK(0);  // per-sample layer-0 part
+                        }
+                        do_layer0(nsg[gi], j0, nobs);
+                        PROF_MARK(1);  // layer 0
+                    }
+                }
+                if (have) {
+                    for (int l = 1; l < Lh; ++l) {  // hidden layers that feed another tensor-core layer
                         const int Nn = net.Hp[l];
-                        const bool last = (l == L - 2);
-                        const int qcols = Nn >> 2;  // columns of this warp's quarter: 64 / 32 / 16
-                        const int nblk = qcols / 16;
+                        const int qcols = Nn >> 2, nblk = qcols / 16;
                         const float* bias_l = net.bias[l] + cq * qcols;
-                        float4 bcur[4], bnxt[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) bcur[e] = __ldg(reinterpret_cast<const float4*>(bias_l) + e);  // hidden behind the MMA
-                        if (defer) {  // work of the neighbouring items that needs neither the operand images nor the accumulator
-                            if (l == 1 && it > 0) {
-                                const int pg = gi ^ 1;
-                                do_sums(nsg[pg], 0, nobs, true);
-                                compute_bar();
-                                bar_sync(3, NB23);  // schedule / matrix rows, prior terms and noise of the previous item are in smem
-                                do_tail(sTheta + pg * TC_SG_MAX * MMAX, nsg[pg]);
-                                compute_bar();
-                                bar_arrive(2, NB23);  // helper warp: buffers are free, go on with this item
-                                PROF_MARK(6);
-                            }
-                            if (l == lwin2 && it + 1 < total) {
-                                do_base(sTheta + (gi ^ 1) * TC_SG_MAX * MMAX, step_of(it + 2));
-                                PROF_MARK(7);
-                            }
-                        }
+                        const uint32_t dacc = tmem_d + ((d_cnt & 1u) ? 256u : 0u);
                         mbar_wait(bar_d, d_cnt & 1u, p.error_flag);
                         ++d_cnt;
                         tc_fence_after();
                         PROF_MARK(3);  // waiting for the tensor core
                         for (int cb = 0; cb < nblk; ++cb) {
                             const int col0 = cq * qcols + 16 * cb;
-                            uint32_t d[16];
-                            tc_ld16(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, d);
+                            float4 bnxt[4];
                             if (cb + 1 < nblk) {
 #pragma unroll
                                 for (int e = 0; e < 4; ++e)
                                     bnxt[e] = __ldg(reinterpret_cast<const float4*>(bias_l + 16 * (cb + 1)) + e);
                             }
-                            tc_wait_ld();
                             float a[16];
+                            ld_act(dacc, col0, bcur, a);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                a[4 * e] = fmaxf(__uint_as_float(d[4 * e]) + bcur[e].x, 0.f);
-                                a[4 * e + 1] = fmaxf(__uint_as_float(d[4 * e + 1]) + bcur[e].y, 0.f);
-                                a[4 * e + 2] = fmaxf(__uint_as_float(d[4 * e + 2]) + bcur[e].z, 0.f);
-                                a[4 * e + 3] = fmaxf(__uint_as_float(d[4 * e + 3]) + bcur[e].w, 0.f);
+                            for (int k8 = 0; k8 < 2; ++k8) {
+                                float v[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] = a[8 * k8 + e];
+                                store_split8(v, sAhi, sAlo, a_off(row, (col0 >> 3) + k8));
                             }
-                            if (!last) {
+                            if (cb + 1 < nblk) {
 #pragma unroll
-                                for (int k8 = 0; k8 < 2; ++k8) {
-                                    float v[8];
-#pragma unroll
-                                    for (int e = 0; e < 8; ++e) v[e] = a[8 * k8 + e];
-                                    store_split8(v, sAhi, sAlo, a_off(row, (col0 >> 3) + k8));
-                                }
-                            } else {
-                                // output layer in fp32: po[o] += sum_c act[c] * Wout[o][c]   (Wout in smem, broadcast reads)
-#pragma unroll
-                                for (int o = 0; o < MMAX; ++o) {
-                                    if (o < m) {
-                                        const float* w = sWout + o * 256 + col0;
-                                        float acc = po[o];
-#pragma unroll
-                                        for (int e = 0; e < 16; e += 4) {
-                                            const float4 w4 = *reinterpret_cast<const float4*>(w + e);
-                                            acc = fmaf(a[e], w4.x, acc);
-                                            acc = fmaf(a[e + 1], w4.y, acc);
-                                            acc = fmaf(a[e + 2], w4.z, acc);
-                                            acc = fmaf(a[e + 3], w4.w, acc);
-                                        }
-                                        po[o] = acc;
-                                    }
-                                }
+                                for (int e = 0; e < 4; ++e) bcur[e] = bnxt[e];
                             }
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) bcur[e] = bnxt[e];
                         }
-                        if (!last) {
-                            fence_proxy_async();
-                            tc_fence_before();
-                            mbar_arrive(bar_a);
-                        }
+                        fence_proxy_async();
+                        tc_fence_before();
+                        mbar_arrive(bar_a);
                         PROF_MARK(4);  // epilogues
                     }
-
-                    // ---- scores: combine the four column quarters (tree through sS / sQS), s = -(eps + b)/sigma ---------------
-                    if (cq == 1 || cq == 3) {
-                        float* dst = (cq == 1) ? sS : sQS;
-#pragma unroll
-                        for (int o = 0; o < MMAX; ++o)
-                            if (o < m) dst[row * MMAX + o] = po[o];
-                    }
-                    tc_fence_before();
-                    compute_bar();
-                    if (cq == 0 || cq == 2) {
-                        const float* src = (cq == 0) ? sS : sQS;
-#pragma unroll
-                        for (int o = 0; o < MMAX; ++o)
-                            if (o < m) po[o] += src[row * MMAX + o];
-                    }
-                    compute_bar();
-                    if (cq == 2) {
-#pragma unroll
-                        for (int o = 0; o < MMAX; ++o)
-                            if (o < m) sS[row * MMAX + o] = po[o];
-                    }
-                    compute_bar();
-                    if (cq == 0) {
-#pragma unroll
-                        for (int o = 0; o < MMAX; ++o)
-                            if (o < m) sS[row * MMAX + o] = -(po[o] + sS[row * MMAX + o] + sBout[o]) * inv_sigma;
-                    }
-                    compute_bar();
-                    PROF_MARK(5);  // scores
-                    if (!defer) {
-                        do_sums(nsamp, j0, nobs, chunk == 0);
-                        compute_bar();
-                        PROF_MARK(6);  // inv(Sigma) s + sums over observations
-                    }
-                }  // chunks
-                if (!defer) {
-                    bar_sync(3, NB23);  // schedule/matrix rows, prior terms and noise of this step are in smem
-                    PROF_MARK(2);       // (time spent waiting for the helper warp, normally zero)
-                    if (p.part_out) {
-                        for (int e = tid; e < nsamp * 2 * m; e += TC_CT) p.part_out[(size_t)i0 * 2 * m + e] = sAcc[e];
-                    } else {
-                        do_tail(th, nsamp);
-                    }
-                    compute_bar();
-                    if (it + 1 < total) bar_arrive(2, NB23);
-                    PROF_MARK(7);  // finalize
                 }
-            }  // items
-            if (defer && total > 0) {  // drain: the last item's sums and tail
-                const int pg = (total - 1) & 1;
-                do_sums(nsg[pg], 0, min(p.OC, p.n), true);
-                compute_bar();
-                bar_sync(3, NB23);
-                do_tail(sTheta + pg * TC_SG_MAX * MMAX, nsg[pg]);
-                compute_bar();
-            }
+                if (defer) {
+                    if (prev) {
+                        do_sums(nsg[pgi], 0, pnobs, true);
+                        compute_bar();
+                        bar_sync(3, NB23);  // schedule / matrix rows, prior terms and noise of the previous item are in smem
+                        do_tail(pth, nsg[pgi]);
+                        compute_bar();
+                        if (have) bar_arrive(2, NB23);  // helper warp: buffers are free, go on with this item
+                        PROF_MARK(6);
+                    }
+                    if (ps + 1 < total_p) {
+                        do_base(sTheta + (gi ^ 1) * TC_SG_MAX * MMAX, true, step_of(it + 1), step_of(it + 2));
+                        compute_bar();
+                        PROF_MARK(0);
+                    }
+                }
+            }  // passes
             if (!p.part_out) {
                 for (int e = tid; e < ngr * TC_SG_MAX * MMAX; e += TC_CT) {
                     const int gi = e / (TC_SG_MAX * MMAX), r = e - gi * TC_SG_MAX * MMAX;
@@ -750,7 +800,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
     tc_fence_before();
     __syncthreads();
     if (warp == TC_CW + 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(256));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512));
     }
 }
 

@@ -249,22 +249,22 @@ def layer1_blocks(nse, pn: NetView):
             slice(e_t + e_x + f2, cols), n_hot)
 
 
-_tf_cache: dict = {}
-
-
 def time_feat_table(nse, pn: NetView, t: torch.Tensor) -> torch.Tensor:
-    """[len(t), H1p] fp64: W1[:, t-block] temb(t) + b1, zero padded.  Cached per (first-layer weights, time rows): it
-    does not depend on the observations, so repeated trajectories on the same grid reuse it."""
-    lin0 = pn.linears[0]
-    key = (lin0.weight.data_ptr(), lin0.weight._version, lin0.bias._version, t.numel(), float(t.sum()), float(t[0]),
-           float(t[-1]), id(net_description(nse)["time_features"]) if net_description(nse)["time_features"] else 0)
-    hit = _tf_cache.get(key)
+    """[len(t), H1p] fp64: W1[:, t-block] temb(t) + b1, zero padded.  Cached on the packed-net view (which is rebuilt
+    whenever a weight changes) per time grid: it does not depend on the observations, so repeated trajectories on the
+    same grid reuse it."""
+    tc = t.detach().to("cpu", torch.float64).contiguous()
+    freqs = getattr(nse, "freqs", None)
+    key = (tc.numel(), hash(tc.numpy().tobytes()),
+           None if freqs is None else tuple(freqs.detach().to("cpu", torch.float64).reshape(-1).tolist()))
+    cache = pn.__dict__.setdefault("_tf_cache", {})
+    hit = cache.get(key)
     if hit is not None:
         return hit
     out = _time_feat_table(nse, pn, t)
-    if len(_tf_cache) > 16:
-        _tf_cache.clear()
-    _tf_cache[key] = out
+    if len(cache) > 16:
+        cache.clear()
+    cache[key] = out
     return out
 
 

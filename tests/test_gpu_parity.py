@@ -286,6 +286,40 @@ def test_full_size_trajectory_properties(dev):
     assert frac_close > 0.9
 
 
+@pytest.mark.parametrize("shape", [(5, 8, (256, 256, 256), 30, 1300, "uniform"), (5, 8, (64, 128), 7, 2500, "uniform"),
+                                   (4, 6, (128, 256), 12, 1190, "gaussian"), (10, 10, (256, 256), 30, 700, "gaussian")],
+                         ids=lambda s: f"m{s[0]}_n{s[3]}_N{s[4]}_{s[5]}")
+def test_tc_group_schedules_agree(shape, dev):
+    """The tcgen05 trajectory kernel interleaves two sample groups per CTA when a CTA owns several (N > 148 groups):
+    the interleaved schedule must be bit-identical to running the groups one after the other, and both must follow
+    the fp64 oracle under replayed noise."""
+    from d4s import _cabi as abi
+    from d4s_helpers import nse_from_oracle
+    m, d, hidden, n, N, pkind = shape
+    onet, x, cov, theta, oprior = _problem(m, d, hidden, n, N, pkind, seed=3)
+    nse = nse_from_oracle(onet, dev)
+    prior, fn = _d4s_prior(oprior, nse, dev)
+    steps = 5
+    rng = np.random.default_rng(1)
+    z0, z = rng.standard_normal((N, m)), rng.standard_normal((steps, N, m))
+    kw = dict(steps=steps, eta=1.0, prior=prior, prior_type=pkind, prior_score_fn=fn, dist_cov_est=_t(cov, dev),
+              cov_mode="GAUSS", _noise=(torch.as_tensor(z0, dtype=torch.float32), torch.as_tensor(z, dtype=torch.float32)))
+    abi.set_option("path", 2)
+    try:
+        out = nse.ddim((N,), _t(x, dev), **kw)
+        abi.set_option("tc_pairing", 0)
+        out_seq = nse.ddim((N,), _t(x, dev), **kw)
+    finally:
+        abi.set_option("tc_pairing", 1)
+        abi.set_option("path", 0)
+    assert torch.equal(out, out_seq)
+    ref = orc.ddim(onet, x, z0, z, steps, 1.0, oprior, cov, "GAUSS", pkind)
+    scale = max(1.0, float(np.abs(ref).max()))
+    err = float(np.abs(out.cpu().numpy() - ref).max()) / scale
+    print(f"{shape}: max |theta - oracle| / scale = {err:.2e}")
+    assert err < TRAJ_TOL, err
+
+
 def test_errors_are_loud(dev):
     import d4s
     from d4s import _cabi as abi
