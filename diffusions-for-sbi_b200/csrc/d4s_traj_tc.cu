@@ -20,6 +20,8 @@
 //             (everything that depends only on theta at the start of the step, off the critical path).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "d4s_finalize_core.cuh"
 
 namespace d4s {
@@ -60,6 +62,7 @@ static_assert(TC_SMEM_BYTES <= 232448, "shared memory budget (227 KB per CTA) ex
 static_assert(OFF_BAR % 8 == 0 && OFF_SCHED % 16 == 0, "alignment");
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
+__constant__ unsigned g_wait_hint = 20000u;
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -75,10 +78,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(g_wait_hint)  // suspend-time hint (ns): a waiting warp sleeps instead of taking issue slots
         : "memory");
     return ok != 0;
 }
@@ -158,15 +161,17 @@ __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.
 // exactly, truncated to bf16 when packed (its dropped bits are < 2^-17 |v|).  Packing is one PRMT per pair.
 __device__ __forceinline__ void store_split8(const float (&v)[8], uint8_t* a_hi, uint8_t* a_lo, int byte_off) {
     uint32_t hi[4], lo[4];
+    const float2 k = make_float2(65537.0f, 65537.0f), neg1 = make_float2(-1.0f, -1.0f);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const float x0 = v[2 * e], x1 = v[2 * e + 1];
-        // __f*_rn intrinsics are never contracted into FMAs (contraction would defeat the splitting)
-        const float c0 = __fmul_rn(x0, 65537.0f), c1 = __fmul_rn(x1, 65537.0f);
-        const float h0 = __fsub_rn(c0, __fsub_rn(c0, x0)), h1 = __fsub_rn(c1, __fsub_rn(c1, x1));
-        const float l0 = __fsub_rn(x0, h0), l1 = __fsub_rn(x1, h1);
-        hi[e] = __byte_perm(__float_as_uint(h0), __float_as_uint(h1), 0x7632);
-        lo[e] = __byte_perm(__float_as_uint(l0), __float_as_uint(l1), 0x7632);
+        // packed fp32 pairs (FMUL2 / FFMA2): a - b = fma(b, -1, a) rounds once, exactly like a subtraction
+        const float2 x = make_float2(v[2 * e], v[2 * e + 1]);
+        const float2 c = __fmul2_rn(x, k);
+        const float2 d = __ffma2_rn(x, neg1, c);  // c - x
+        const float2 h = __ffma2_rn(d, neg1, c);  // hi = c - (c - x)
+        const float2 l = __ffma2_rn(h, neg1, x);  // lo = x - hi (exact)
+        hi[e] = __byte_perm(__float_as_uint(h.x), __float_as_uint(h.y), 0x7632);
+        lo[e] = __byte_perm(__float_as_uint(l.x), __float_as_uint(l.y), 0x7632);
     }
     *reinterpret_cast<uint4*>(a_hi + byte_off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(a_lo + byte_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -187,32 +192,35 @@ __device__ __forceinline__ int a_off(int r, int kg) { return (kg >> 1) * 4096 + 
 
 // Helper warp: per-sample Lambda_i = Lbase + (1-n) diag(p0_i) and its inverse, in fp64 (nse.py:647-654 builds and
 // solves this system; here the inverse is prepared off the critical path, the solve is a mat-vec in the tail).
+// One lane per (sample, column c): it solves Lambda_i x = e_c by LU with partial pivoting, everything in registers
+// for the usual theta_dim <= 5 (an in-thread inverse with local-memory arrays costs tens of thousands of cycles
+// because the L1 is almost entirely carved out as shared memory).
 template <int M>
-__device__ __noinline__ void lambda_inverse(const float* lbase, const float* p0, double one_minus_n, float* out) {
-    double a[M][M], inv[M][M];
+__device__ __noinline__ void lambda_inverse_col(const float* lbase, const float* p0, double one_minus_n, int c, float* out) {
+    double a[M][M], b[M];
 #pragma unroll
-    for (int r = 0; r < M; ++r)
+    for (int r = 0; r < M; ++r) {
 #pragma unroll
-        for (int c = 0; c < M; ++c) a[r][c] = (double)lbase[r * M + c] + ((r == c) ? one_minus_n * (double)p0[r] : 0.0);
-    gj_inverse_t<double, M>(a, inv);
+        for (int cc = 0; cc < M; ++cc) a[r][cc] = (double)lbase[r * M + cc] + ((r == cc) ? one_minus_n * (double)p0[r] : 0.0);
+        b[r] = (r == c) ? 1.0 : 0.0;
+    }
+    lu_solve_d<M>(a, b);
 #pragma unroll
-    for (int r = 0; r < M; ++r)
-#pragma unroll
-        for (int c = 0; c < M; ++c) out[r * M + c] = (float)inv[r][c];
+    for (int r = 0; r < M; ++r) out[r * M + c] = (float)b[r];
 }
 
-__device__ __forceinline__ void lambda_inverse_dispatch(int m, const float* lbase, const float* p0, double omn, float* out) {
+__device__ __forceinline__ void lambda_inverse_dispatch(int m, const float* lbase, const float* p0, double omn, int c, float* out) {
     switch (m) {
-        case 1: lambda_inverse<1>(lbase, p0, omn, out); break;
-        case 2: lambda_inverse<2>(lbase, p0, omn, out); break;
-        case 3: lambda_inverse<3>(lbase, p0, omn, out); break;
-        case 4: lambda_inverse<4>(lbase, p0, omn, out); break;
-        case 5: lambda_inverse<5>(lbase, p0, omn, out); break;
-        case 6: lambda_inverse<6>(lbase, p0, omn, out); break;
-        case 7: lambda_inverse<7>(lbase, p0, omn, out); break;
-        case 8: lambda_inverse<8>(lbase, p0, omn, out); break;
-        case 9: lambda_inverse<9>(lbase, p0, omn, out); break;
-        default: lambda_inverse<10>(lbase, p0, omn, out); break;
+        case 1: lambda_inverse_col<1>(lbase, p0, omn, c, out); break;
+        case 2: lambda_inverse_col<2>(lbase, p0, omn, c, out); break;
+        case 3: lambda_inverse_col<3>(lbase, p0, omn, c, out); break;
+        case 4: lambda_inverse_col<4>(lbase, p0, omn, c, out); break;
+        case 5: lambda_inverse_col<5>(lbase, p0, omn, c, out); break;
+        case 6: lambda_inverse_col<6>(lbase, p0, omn, c, out); break;
+        case 7: lambda_inverse_col<7>(lbase, p0, omn, c, out); break;
+        case 8: lambda_inverse_col<8>(lbase, p0, omn, c, out); break;
+        case 9: lambda_inverse_col<9>(lbase, p0, omn, c, out); break;
+        default: lambda_inverse_col<10>(lbase, p0, omn, c, out); break;
     }
 }
 
@@ -328,6 +336,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     ++a_cnt;
                     tc_fence_after();
                     const uint32_t dacc = tmem_d + ((lc & 1u) ? 256u : 0u);  // the other accumulator may still be read by an epilogue
+                    const long long mma_t0 = (p.prof && blockIdx.x == 0) ? clock64() : 0;
                     ++lc;
                     for (int ks = 0; ks < K / 16; ++ks, ++it) {
                         const int s = it % TC_NSTG;
@@ -345,6 +354,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                         tc_commit(bar_empty(s));  // ring slot is free once these MMAs have read it
                     }
                     tc_commit(bar_d);  // accumulator complete
+                    if (p.prof && blockIdx.x == 0) {  // profiling: duration of this layer's MMAs (slots 8 / 9: first / last layer)
+                        mbar_wait(bar_d, (lc - 1u) & 1u, p.error_flag);
+                        p.prof[(l == L - 2) ? 9 : 8] += clock64() - mma_t0;
+                    }
                 }
             }
         }
@@ -402,12 +415,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     for (int e = lane; e < TC_SG_MAX * MMAX; e += 32) sG[e] = 0.f;
                 }
                 __syncwarp();
-                if (per_sample && lane < nsamp) {
-                    if (uni) {
-                        lambda_inverse_dispatch(m, sMats, sPrior + lane * MMAX, omn, sMinv + lane * MMAX * MMAX);
-                    } else {  // no per-sample prior precision: invert the step's Lambda as it is
-                        for (int k = 0; k < m; ++k) sPrior[lane * MMAX + k] = 0.f;
-                        lambda_inverse_dispatch(m, sMats, sPrior + lane * MMAX, 0.0, sMinv + lane * MMAX * MMAX);
+                if (per_sample) {
+                    if (!uni)  // no per-sample prior precision: invert the step's Lambda as it is
+                        for (int e = lane; e < nsamp * MMAX; e += 32) sPrior[e] = 0.f;
+                    __syncwarp();
+                    for (int e = lane; e < nsamp * m; e += 32) {  // one lane per (sample, column of the inverse)
+                        const int si = e / m, c = e - si * m;
+                        lambda_inverse_dispatch(m, sMats, sPrior + si * MMAX, uni ? omn : 0.0, c, sMinv + si * MMAX * MMAX);
                     }
                 }
                 for (int e = lane; e < nsamp * nq; e += 32) {  // DDIM noise: one lane per (sample, 4 dims)
@@ -519,23 +533,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
         };
 
         // layer 0 of a pass: act0[r][col] = relu(base[si][col] + obs_feat[j][col]) -> bf16 hi/lo A images, then launch layer 1
-        auto do_layer0 = [&](int nsamp, int j0, int nobs) {
+        // obs_feat rows of this thread's first layer-0 iteration (lane = observation, k-groups warp and warp + 16)
+        auto l0_load = [&](float4 (&u)[2][2], int j0, int nobs, int oj) {
+            const bool ovalid = oj < nobs;
+            const float* up = p.obs_feat + (size_t)(j0 + (ovalid ? oj : 0)) * H0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int kg = warp + 16 * j;
+                if (ovalid && kg < nkg) {
+                    u[j][0] = __ldg(reinterpret_cast<const float4*>(up + 8 * kg));
+                    u[j][1] = __ldg(reinterpret_cast<const float4*>(up + 8 * kg + 4));
+                } else {
+                    u[j][0] = u[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        };
+        auto do_layer0 = [&](int nsamp, int j0, int nobs, float4 (&upre)[2][2], bool have_pre) {
             // ---- layer 0: act0[r][col] = relu(base[si][col] + obs_feat[j][col]) -> bf16 hi/lo A images -----------
             // warp w owns k-groups w, w+16; lanes run over the observations: one 32-byte read of obs_feat
             // serves the rows of all SG samples, and every global load is issued before its first use.
             for (int oj = lane; oj < p.OC; oj += 32) {
                 const bool ovalid = oj < nobs;
-                const float* up = p.obs_feat + (size_t)(j0 + (ovalid ? oj : 0)) * H0;
                 float4 u[2][2];
+                if (have_pre && oj == lane) {  // loaded before the wait for the tensor core
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int kg = warp + 16 * j;
-                    if (ovalid && kg < nkg) {
-                        u[j][0] = __ldg(reinterpret_cast<const float4*>(up + 8 * kg));
-                        u[j][1] = __ldg(reinterpret_cast<const float4*>(up + 8 * kg + 4));
-                    } else {
-                        u[j][0] = u[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                    for (int j = 0; j < 2; ++j) { u[j][0] = upre[j][0]; u[j][1] = upre[j][1]; }
+                } else {
+                    l0_load(u, j0, nobs, oj);
                 }
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -593,20 +617,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                 float a[16];
                 ld_act(dacc, col0, bb, a);
                 // po[o] += sum_c act[c] * Wout[o][c]   (Wout in smem, broadcast reads)
+                // (five outputs at a time: their weight loads are independent and issued together)
 #pragma unroll
-                for (int o = 0; o < MMAX; ++o) {
-                    if (o < m) {
-                        const float* w = sWout + o * 256 + col0;
-                        float acc = po[o];
+                for (int oh = 0; oh < MMAX; oh += 5) {
+                    if (oh < m) {
 #pragma unroll
                         for (int e = 0; e < 16; e += 4) {
-                            const float4 w4 = *reinterpret_cast<const float4*>(w + e);
-                            acc = fmaf(a[e], w4.x, acc);
-                            acc = fmaf(a[e + 1], w4.y, acc);
-                            acc = fmaf(a[e + 2], w4.z, acc);
-                            acc = fmaf(a[e + 3], w4.w, acc);
+                            float4 w4[5];
+#pragma unroll
+                            for (int o = 0; o < 5; ++o)
+                                w4[o] = *reinterpret_cast<const float4*>(sWout + (oh + o) * 256 + col0 + e);  // rows >= m: unused, in bounds
+#pragma unroll
+                            for (int o = 0; o < 5; ++o) {
+                                float acc = po[oh + o];
+                                acc = fmaf(a[e], w4[o].x, acc);
+                                acc = fmaf(a[e + 1], w4[o].y, acc);
+                                acc = fmaf(a[e + 2], w4[o].z, acc);
+                                acc = fmaf(a[e + 3], w4[o].w, acc);
+                                po[oh + o] = acc;
+                            }
                         }
-                        po[o] = acc;
                     }
                 }
             }
@@ -688,6 +718,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                 float4 bcur[4];
                 float inv_sigma_prev = 0.f;
                 uint32_t dacc_prev = 0;
+                float4 upre[2][2];
+                const bool have_pre = defer && have && lane < p.OC;
+                if (have_pre) l0_load(upre, j0, nobs, lane);  // layer 0 follows the wait directly: hide its global loads
                 if (prev) {  // the last layer of the previous pass: once it is done the operand images are free again
                     inv_sigma_prev = __ldg(p.sched + (size_t)step_of(pit) * D4S_SCHED_STRIDE + D4S_S_INV_SIGMA);
                     dacc_prev = tmem_d + ((d_cnt & 1u) ? 256u : 0u);
@@ -697,7 +730,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     PROF_MARK(3);  // waiting for the tensor core
                 }
                 if (defer && have) {
-                    do_layer0(nsg[gi], j0, nobs);
+                    do_layer0(nsg[gi], j0, nobs, upre, have_pre);
                     PROF_MARK(1);  // layer 0
                 }
                 if (prev) do_last_epilogue(dacc_prev, inv_sigma_prev, pj0, pnobs);
@@ -725,7 +758,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                             compute_bar();
                             PROF_MARK(0);  // per-sample layer-0 part
                         }
-                        do_layer0(nsg[gi], j0, nobs);
+                        do_layer0(nsg[gi], j0, nobs, upre, false);
                         PROF_MARK(1);  // layer 0
                     }
                 }
@@ -773,7 +806,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     if (prev) {
                         do_sums(nsg[pgi], 0, pnobs, true);
                         compute_bar();
+                        PROF_MARK(6);
                         bar_sync(3, NB23);  // schedule / matrix rows, prior terms and noise of the previous item are in smem
+                        PROF_MARK(2);  // (time spent waiting for the helper warp)
                         do_tail(pth, nsg[pgi]);
                         compute_bar();
                         if (have) bar_arrive(2, NB23);  // helper warp: buffers are free, go on with this item
@@ -809,6 +844,11 @@ cudaError_t launch_traj_tc(const TrajParams& p, int n_ctas, cudaStream_t stream)
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(traj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
         if (e != cudaSuccess) return e;
+        if (const char* h = getenv("D4S_TC_WAIT_HINT")) {  // tuning knob: mbarrier.try_wait suspend-time hint in ns
+            const unsigned v = (unsigned)atoi(h);
+            e = cudaMemcpyToSymbol(g_wait_hint, &v, sizeof(v));
+            if (e != cudaSuccess) return e;
+        }
         configured = true;
     }
     traj_tc_kernel<<<n_ctas, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);

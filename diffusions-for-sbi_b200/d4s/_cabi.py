@@ -149,7 +149,7 @@ def set_option(key: str, value: int):
 
 
 PROFILE_PHASES = ["layer0_sample_part", "layer0", "prior_noise", "tensor_wait", "epilogues", "scores",
-                  "prec_and_sums", "finalize"]
+                  "prec_and_sums", "finalize", "mma_inner_layers", "mma_last_layer"]  # 8, 9: MMA issue -> commit (MMA warp)
 
 
 def get_profile():

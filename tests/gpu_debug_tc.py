@@ -59,6 +59,7 @@ if os.environ.get("D4S_PROFILE"):
     out = nse.ddim((N,), xt, **kw)
     torch.cuda.synchronize()
     prof = abi.get_profile()
+    mma = {k: prof.pop(k) for k in list(prof) if k.startswith("mma_")}
     tot = sum(prof.values())
     groups = -(-N // max(1, min(8, 128 // min(n, 128)))) 
-    print("phase cycles (CTA 0):", {k: f"{v} ({100 * v / tot:.1f}%)" for k, v in prof.items()}, "total", tot)
+    print("phase cycles (CTA 0):", {k: f"{v} ({100 * v / tot:.1f}%)" for k, v in prof.items()}, "total", tot, "| MMA issue->commit cycles:", mma)
