@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--ddim-steps", type=int, default=None, help="default 1000 (GAUSS) / 400 (JAC)")
     ap.add_argument("--cpu-sample-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--jac-tc", action="store_true",
+                    help="JAC steps on the opt-in tcgen05 score + Jacobian kernel (fp16x3) instead of the fp32 SIMT kernel")
     return ap.parse_args()
 
 
@@ -116,6 +118,7 @@ def config_dict(args, w, world):
                         f"samples per GPU, DDIM {w['ddim_steps']} steps eta={w['eta']}, {args.cov_mode}, "
                         f"{w['prior_kind']} prior; one bench step = one full trajectory",
             "n_obs": w["n"], "samples_per_gpu": args.samples, "ddim_steps": w["ddim_steps"], "cov_mode": args.cov_mode,
+            "jac_kernel": ("tcgen05 fp16x3 (opt-in)" if getattr(args, "jac_tc", False) else "fp32 SIMT") if args.cov_mode == "JAC" else None,
             "parallelism": f"samples sharded over {world} GPU(s), no collective",
             "l2": "256 MiB buffer written between timed trajectories (L2 flush)"}
 
@@ -248,6 +251,8 @@ def run_ours(args):
 
     w = workload(args)
     N, m, n = args.samples, w["m"], w["n"]
+    if getattr(args, "jac_tc", False):
+        abi.set_option("jac_tc", 1)
     nse = build_nse(w, dev)
     # host (pinned) copies of the inputs for the e2e leg
     x_h = torch.as_tensor(w["x"]).pin_memory()
@@ -390,7 +395,10 @@ def run_ours(args):
             src = "measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)" if peaks else "fallback 1590"
             ach = flops_step / (k1_ms * 1e-3) / 1e12
             roofline = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                        "traffic": None, "kernel": "score_simt_kernel (fp32 SIMT; forward-mode tangents in JAC)",
+                        "traffic": None,
+                        "kernel": ("jac_tc_kernel (tcgen05 kind::f16, fp16x3 split, forward-mode tangent rows)"
+                                   if (args.cov_mode == "JAC" and getattr(args, "jac_tc", False))
+                                   else "score_simt_kernel (fp32 SIMT; forward-mode tangents in JAC)"),
                         "peak_source": src, "flops_per_launch": flops_step, "launch_ms": k1_ms,
                         "finalize_launch_ms": k3_ms, "share_of_step": k1_ms * w["ddim_steps"] / ms_step}
         value = N * world / (ms_step * 1e-3)

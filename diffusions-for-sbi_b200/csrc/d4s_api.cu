@@ -6,6 +6,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "d4s_common.cuh"
 
 namespace d4s {
@@ -16,6 +18,7 @@ static int g_opt_path = 0;      // 0 auto, 1 SIMT per-step kernels only, 2 requi
 static int g_opt_tc_steps = 0;  // > 0: DDIM steps per tcgen05 launch (0 = whole trajectory in one launch)
 static int* g_err_flag = nullptr;
 static int g_opt_profile = 0;
+static int g_opt_jac_tc = 0;      // 1: JAC steps on the tcgen05 score + Jacobian kernel (fp16x3; faster, looser parity)
 static int g_opt_tc_pairing = 1;  // interleave two sample groups per CTA in the tcgen05 kernel (0 = one after the other)
 static long long* g_prof = nullptr;
 
@@ -64,12 +67,48 @@ struct Tiling {
     int rpp, OC, C, SG, P, W, tiles;
     int Cws;  // chunks in the workspace layout [N][Cws][W]: 1 when the tcgen05 kernel reduces over chunks itself
     bool tc;  // the tcgen05 kernel evaluates this problem (GAUSS, tall grid, >= 2 hidden layers, no theta embedding)
+    bool tcj;               // JAC step on the tcgen05 score + Jacobian kernel (d4s_jac_tc.cu)
+    int jPW, jOC, jC, jUT;  // its tiling: pairs per lane quarter, observations per unit, chunks, units per tile
 };
 
 static bool tc_eligible(const D4sNet* net, const D4sProblem* pb) {
     // plain Linear/ReLU nets only: the toy output head (tanh / analytic affine part) runs on the SIMT path
     return g_opt_path != 1 && pb->cov_mode == D4S_COV_GAUSS && !pb->paired && net->dev.L >= 3 && net->dev.emb_L == 0 &&
            net->dev.out_act == 0 && net->dev.out_scale == 1.f && pb->obs_raw == nullptr;
+}
+
+static bool jac_tc_eligible(const D4sNet* net, const D4sProblem* pb) {
+    return g_opt_path != 1 && g_opt_jac_tc != 0 && pb->cov_mode == D4S_COV_JAC && !pb->paired && net->dev.L >= 3 && net->dev.emb_L == 0 &&
+           net->dev.out_act == 0 && net->dev.out_scale == 1.f && pb->obs_raw == nullptr && net->dev.m <= 5;
+}
+
+// Units (sample, chunk of OC observations) packed UT per tile of PT pairs: pick the chunking that wastes the fewest
+// pair slots (n = 30, PT = 20: three chunks of 10, two units per tile).
+static void jac_tc_tiling(const D4sNet* net, const D4sProblem* pb, Tiling* t) {
+    const int R = 1 + net->dev.m;
+    int pw = 32 / R;
+    if (pw > 8) pw = 8;
+    const int PT = 4 * pw, n = pb->n_obs;
+    int best_c = 0, best_oc = 0;
+    double best = -1.0;
+    if (pb->obs_chunk > 0) {  // the caller fixed the chunking (ranks of an observation-sharded run must agree on it)
+        best_oc = pb->obs_chunk < PT ? pb->obs_chunk : PT;
+        if (best_oc > n) best_oc = n;
+        best_c = (n + best_oc - 1) / best_oc;
+    } else {
+        for (int c = (n + PT - 1) / PT; c <= n; ++c) {
+            const int oc = (n + c - 1) / c;
+            if ((n + oc - 1) / oc != c) continue;  // this chunk count is not reachable with equal chunks
+            const int ut = PT / oc;
+            const double eff = (double)n / ((double)c * oc) * ((double)ut * oc / PT);
+            if (eff > best + 1e-9) { best = eff; best_c = c; best_oc = oc; }
+            if (c > (n + PT - 1) / PT + 16) break;
+        }
+    }
+    t->jPW = pw;
+    t->jOC = best_oc;
+    t->jC = best_c;
+    t->jUT = PT / best_oc;
 }
 
 static int make_tiling(const D4sNet* net, const D4sProblem* pb, Tiling* t) {
@@ -101,6 +140,12 @@ static int make_tiling(const D4sNet* net, const D4sProblem* pb, Tiling* t) {
     t->tiles = (int)tiles;
     t->tc = tc_eligible(net, pb);
     t->Cws = t->tc ? 1 : t->C;
+    t->tcj = jac_tc_eligible(net, pb);
+    t->jPW = t->jOC = t->jC = t->jUT = 0;
+    if (t->tcj) {
+        jac_tc_tiling(net, pb, t);
+        t->Cws = t->jC;
+    }
     return 0;
 }
 
@@ -202,12 +247,14 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
     const size_t off_WoutT = reserve((size_t)m * Hp[L - 2]);
     for (int o = 0; o < m; ++o)
         for (int k = 0; k < Kl; ++k) h[off_WoutT + (size_t)o * Hp[L - 2] + k] = d->weight[L - 1][(size_t)o * Kl + k];
-    std::vector<size_t> off_img(L, 0);
+    std::vector<size_t> off_img(L, 0), off_img16(L, 0);
     for (int l = 1; l <= L - 2; ++l) {
         const int K = d->dims[l], Ho = d->dims[l + 1], Kp = Hp[l - 1], Np = Hp[l];
         const size_t bytes = (size_t)(Kp / 16) * Np * 64;
         off_img[l] = reserve(bytes / 4);
+        off_img16[l] = reserve(bytes / 4);
         uint16_t* img = reinterpret_cast<uint16_t*>(h.data() + off_img[l]);
+        uint16_t* img16 = reinterpret_cast<uint16_t*>(h.data() + off_img16[l]);
         for (int ks = 0; ks < Kp / 16; ++ks)
             for (int hf = 0; hf < 2; ++hf)
                 for (int nn = 0; nn < Np; ++nn)
@@ -220,6 +267,9 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
                         const size_t idx = (size_t)hf * Np * 8 + (size_t)nn * 8 + e;
                         img[base + idx] = hi;
                         img[base + (size_t)Np * 16 + idx] = lo;
+                        const __half h16 = __float2half_rn(w);  // fp16 hi / lo: 22 significant bits (JAC kernel)
+                        img16[base + idx] = __half_as_ushort(h16);
+                        img16[base + (size_t)Np * 16 + idx] = __half_as_ushort(__float2half_rn(w - __half2float(h16)));
                     }
     }
 
@@ -265,6 +315,7 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
         nd.emb_bias[l] = net->blob + off_eb[l];
     }
     for (int l = 1; l <= L - 2; ++l) nd.wimg[l] = reinterpret_cast<const uint8_t*>(net->blob + off_img[l]);
+    for (int l = 1; l <= L - 2; ++l) nd.wimg16[l] = reinterpret_cast<const uint8_t*>(net->blob + off_img16[l]);
     *out = net;
     return D4S_OK;
 }
@@ -291,7 +342,7 @@ int64_t d4s_workspace_floats(const D4sNet* net, const D4sProblem* pb) {
     if (!net || !pb) return -1;
     Tiling t;
     if (make_tiling(net, pb, &t) != 0) return -1;
-    const int64_t part = (int64_t)pb->n_samples * t.C * t.W;  // room for either kernel's layout
+    const int64_t part = (int64_t)pb->n_samples * (t.C > t.Cws ? t.C : t.Cws) * t.W;  // room for either kernel's layout
     int64_t extra = 0;
     if (net->dev.emb_L > 0) {
         extra = (int64_t)pb->n_samples * net->dev.Hp[0];
@@ -385,6 +436,39 @@ static int score_partials_impl(const D4sNet* net, const D4sProblem* pb, const D4
         ++g_launches;
         return D4S_OK;
     }
+    if (t.tcj && !scores_out && !prec_out) {
+        JacTcParams jp;
+        memset(&jp, 0, sizeof(jp));
+        jp.net = net->dev;
+        jp.N = pb->n_samples;
+        jp.n = pb->n_obs;
+        jp.C = t.jC;
+        jp.OC = t.jOC;
+        jp.UT = t.jUT;
+        jp.PW = t.jPW;
+        const long long units = (long long)pb->n_samples * t.jC;
+        const long long tiles = (units + t.jUT - 1) / t.jUT;
+        if (tiles > 2147483647LL) return fail(D4S_ERR_ARG, "too many tiles");
+        jp.n_tiles = (int)tiles;
+        jp.theta = theta;
+        jp.obs_feat = pb->obs_feat;
+        jp.time_feat = st->time_feat;
+        jp.sched = st->sched;
+        jp.obs_weight = pb->obs_weight;
+        jp.part = pb->workspace;
+        if (!g_err_flag) {
+            if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaMalloc(flag)");
+            cudaMemset(g_err_flag, 0, sizeof(int));
+        }
+        jp.error_flag = g_err_flag;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = launch_jac_tc(jp, jp.n_tiles < sms ? jp.n_tiles : sms, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "tcgen05 JAC kernel launch");
+        ++g_launches;
+        return D4S_OK;
+    }
     ScoreParams p;
     memset(&p, 0, sizeof(p));
     p.net = net->dev;
@@ -407,7 +491,7 @@ static int score_partials_impl(const D4sNet* net, const D4sProblem* pb, const D4
     p.obs_raw = pb->obs_raw;
     p.d = pb->x_dim;
     if (p.affine && (!p.obs_raw || p.d < 1)) return fail(D4S_ERR_ARG, "affine term needs obs_raw and x_dim");
-    p.part = t.tc ? nullptr : pb->workspace;  // a materialising call on a tcgen05-eligible problem leaves no partial sums
+    p.part = (t.tc || t.tcj) ? nullptr : pb->workspace;  // a materialising call on a tcgen05-eligible problem leaves no partial sums
     p.scores_out = scores_out;
     p.prec_out = prec_out;
     if (net->dev.emb_L > 0) {  // kernel 0: embedded theta -> layer-0 sample part (+ JAC tangent seeds)
@@ -587,7 +671,7 @@ int d4s_ddim_run(const D4sNet* net, const D4sProblem* pb, int32_t steps, const f
     key.theta = theta_dev;
     key.affine = affine_dev;
     key.mode_hash = 1469598103934665603ull;
-    for (int v : {g_opt_path, g_opt_tc_steps, g_opt_profile, g_opt_tc_pairing})  // a captured graph froze the options it was built with
+    for (int v : {g_opt_path, g_opt_tc_steps, g_opt_profile, g_opt_tc_pairing, g_opt_jac_tc})  // a captured graph froze the options it was built with
         key.mode_hash = (key.mode_hash ^ (uint64_t)(uint32_t)v) * 1099511628211ull;
     if (step_mode)
         for (int k = 0; k < steps; ++k) key.mode_hash = (key.mode_hash ^ (uint64_t)(step_mode[k] + 1)) * 1099511628211ull;
@@ -678,6 +762,7 @@ int d4s_set_option(const char* key, int32_t value) {
     else if (k == "tc_steps_per_launch") g_opt_tc_steps = value;
     else if (k == "profile") g_opt_profile = value;
     else if (k == "tc_pairing") g_opt_tc_pairing = value;
+    else if (k == "jac_tc") g_opt_jac_tc = value;
     else return fail(D4S_ERR_ARG, "unknown option: " + k);
     return D4S_OK;
 }

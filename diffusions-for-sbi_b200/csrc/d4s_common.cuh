@@ -38,6 +38,7 @@ struct NetDev {
     const float* emb_Wt[D4S_MAX_LAYERS];    // [in][out]
     const float* emb_bias[D4S_MAX_LAYERS];  // [out]
     const uint8_t* wimg[D4S_MAX_LAYERS];  // l = 1 .. L-2: bf16 hi/lo UMMA images, [Hp[l-1]/16][hi | lo][2][Hp[l]][8]
+    const uint8_t* wimg16[D4S_MAX_LAYERS];  // same layout, fp16 hi / lo (JAC kernel: fp16x3 split, ~fp32-exact products)
 };
 
 
@@ -103,6 +104,22 @@ struct TrajParams {
 };
 cudaError_t launch_traj_tc(const TrajParams& p, int n_ctas, cudaStream_t stream);
 int traj_tc_smem_bytes();
+
+// tcgen05 score + Jacobian kernel of one JAC step (d4s_jac_tc.cu).  Units = (sample, chunk of OC observations), UT
+// units per 128-row tile; a pair takes 1 + m tile rows, PW pairs per TMEM lane quarter.
+struct JacTcParams {
+    NetDev net;
+    int N, n, C, OC, UT, PW;
+    int n_tiles;
+    const float* theta;       // [N][m]
+    const float* obs_feat;    // [n][Hp0]
+    const float* time_feat;   // [Hp0] row of this step
+    const float* sched;       // [16] row of this step
+    const float* obs_weight;  // [n] or NULL
+    float* part;              // [N][C][m + m^2] sums over the chunk's observations of P s | P
+    int* error_flag;
+};
+cudaError_t launch_jac_tc(const JacTcParams& p, int n_ctas, cudaStream_t stream);
 
 cudaError_t launch_theta_embed(const NetDev& net, const float* theta, int N, int jac, float* base_pre, float* tan_pre,
                                cudaStream_t stream);

@@ -1,0 +1,516 @@
+// tcgen05 score + Jacobian kernel of one JAC step (tall_posterior_sampler.py:75-94 with mode="JAC": the score of every
+// (posterior sample, observation) pair, d score / d theta by vmap(jacrev), the Tweedie precision
+// P = inv(sigma^2/alpha (I + sigma^2 J)); nse.py:599-625 then sums P s and P over the observations).
+//
+// The Jacobian is propagated in forward mode: every pair owns 1 + m consecutive tile rows, the primal activations and
+// the m tangents d act / d theta_k.  All rows go through the same bf16x3 tensor-core GEMMs as in d4s_traj_tc.cu; the
+// epilogues apply the ReLU of the PRIMAL row to the pair's tangent rows (h = [pre > 0], exchanged through a per-warp
+// shared-memory slot: a pair never straddles a warp).  After the fp32 output layer the primal row holds eps, tangent
+// row k holds column k of d eps / d theta; one thread per (pair, column) then solves (I - sigma J_eps) x = e_c in fp64
+// (LU with partial pivoting in registers) and the per-unit sums over observations are written as partial sums
+// part[N][C][m + m^2] = [sum_j P s | sum_j P], the layout kernel 3 (d4s_finalize.cu) reduces.
+//
+// Tiles: pairs are packed by units (sample i, observation chunk c) of OC observations, UT units per tile, so a unit's
+// sums complete inside one tile (no atomics, fixed summation order).  The tile loop is software pipelined like the
+// interleaved schedule of the trajectory kernel: the last epilogue / pair algebra of tile t-1 run while the tensor
+// core works on tile t (two TMEM accumulators used alternately).
+//
+// Warp roles: 16 compute warps (TMEM lane quarter = warp % 4, column quarter = warp / 4), one TMA producer warp
+// (weight images, 3-stage ring), one MMA issuer warp.  theta_dim <= 5 (every JAC configuration of the reference:
+// SLCP 5, Lotka-Volterra 4, SIR 2); larger theta_dim runs on the fp32 SIMT kernel.
+#include "d4s_finalize_core.cuh"
+#include "d4s_tc_common.cuh"
+
+namespace d4s {
+
+constexpr int JT_THREADS = (TC_CW + 2) * 32;  // 576
+constexpr int JT_NSTG = 3;                    // weight ring stages
+constexpr int JT_MMAX = 5;                    // largest theta_dim of this kernel
+constexpr int JT_PMAX = 32;                   // pairs per tile <= 4 * 8
+constexpr int JT_WMAX = JT_MMAX + JT_MMAX * JT_MMAX;
+
+constexpr int JOFF_AHI = 0;
+constexpr int JOFF_ALO = JOFF_AHI + TC_A_BYTES;
+constexpr int JOFF_RING = JOFF_ALO + TC_A_BYTES;
+constexpr int JOFF_A = JOFF_RING + JT_NSTG * TC_STAGE_BYTES;  // float [m][256] layer-0 theta block
+constexpr int JOFF_AIMG = JOFF_A + JT_MMAX * 256 * 4;         // uint4 [m][32][2] its fp16 hi / lo K-groups
+constexpr int JOFF_WOUT = JOFF_AIMG + JT_MMAX * 32 * 2 * 16;  // float [m][256] output layer
+constexpr int JOFF_TF = JOFF_WOUT + JT_MMAX * 256 * 4;        // float [256] time feature row (+ layer-0 bias)
+constexpr int JOFF_RED = JOFF_TF + 256 * 4;                   // float [3][128][m] output partials of column quarters 1..3
+constexpr int JOFF_OUT = JOFF_RED + 3 * TC_M * JT_MMAX * 4;   // float [128][m] row outputs: score (primal) / J column
+constexpr int JOFF_H = JOFF_OUT + TC_M * JT_MMAX * 4;         // float [16 warps][8 pairs][16] ReLU indicators
+constexpr int JOFF_PAIR = JOFF_H + TC_CW * 8 * 16 * 4;        // float [32][m + m^2] per-pair P s | P
+constexpr int JOFF_TH = JOFF_PAIR + JT_PMAX * JT_WMAX * 4;    // float [2][32][m] theta of the pair's sample
+constexpr int JOFF_PI = JOFF_TH + 2 * JT_PMAX * JT_MMAX * 4;  // int [2][32] sample of the pair (-1: empty slot)
+constexpr int JOFF_PJ = JOFF_PI + 2 * JT_PMAX * 4;            // int [2][32] observation of the pair
+constexpr int JOFF_BOUT = JOFF_PJ + 2 * JT_PMAX * 4;          // float [8]
+constexpr int JOFF_BAR = JOFF_BOUT + 32;                      // mbarriers
+constexpr int JOFF_TMEM = JOFF_BAR + (2 * JT_NSTG + 2) * 8;
+constexpr int JT_SMEM_BYTES = JOFF_TMEM + 16;
+static_assert(JT_SMEM_BYTES <= 232448, "shared memory budget (227 KB per CTA) exceeded");
+static_assert(JOFF_BAR % 8 == 0 && JOFF_AIMG % 16 == 0 && JOFF_H % 16 == 0, "alignment");
+
+// One thread per (pair, column c): column c of P = (alpha/sigma^2) inv(I - sigma J_eps)  (fp64, registers).
+template <int M>
+__device__ __noinline__ void jac_pair_col(const float* out_rows, int row0, float sigma, float a_over_s2, int c, float* pair_out) {
+    double a[M][M], b[M];
+#pragma unroll
+    for (int o = 0; o < M; ++o) {
+#pragma unroll
+        for (int k = 0; k < M; ++k)  // tangent row 1 + k holds d eps_o / d theta_k
+            a[o][k] = ((o == k) ? 1.0 : 0.0) - (double)sigma * (double)out_rows[(row0 + 1 + k) * M + o];
+        b[o] = (o == c) ? 1.0 : 0.0;
+    }
+    lu_solve_d<M>(a, b);
+#pragma unroll
+    for (int r = 0; r < M; ++r) pair_out[M + r * M + c] = (float)((double)a_over_s2 * b[r]);
+}
+
+__device__ __forceinline__ void jac_pair_col_dispatch(int m, const float* out_rows, int row0, float sigma, float aos2, int c,
+                                                      float* pair_out) {
+    switch (m) {
+        case 1: jac_pair_col<1>(out_rows, row0, sigma, aos2, c, pair_out); break;
+        case 2: jac_pair_col<2>(out_rows, row0, sigma, aos2, c, pair_out); break;
+        case 3: jac_pair_col<3>(out_rows, row0, sigma, aos2, c, pair_out); break;
+        case 4: jac_pair_col<4>(out_rows, row0, sigma, aos2, c, pair_out); break;
+        default: jac_pair_col<5>(out_rows, row0, sigma, aos2, c, pair_out); break;
+    }
+}
+
+__global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sAhi = smem + JOFF_AHI;
+    uint8_t* sAlo = smem + JOFF_ALO;
+    float* sA = reinterpret_cast<float*>(smem + JOFF_A);
+    uint4* sAimg = reinterpret_cast<uint4*>(smem + JOFF_AIMG);
+    float* sWout = reinterpret_cast<float*>(smem + JOFF_WOUT);
+    float* sTf = reinterpret_cast<float*>(smem + JOFF_TF);
+    float* sRed = reinterpret_cast<float*>(smem + JOFF_RED);
+    float* sOut = reinterpret_cast<float*>(smem + JOFF_OUT);
+    float* sH = reinterpret_cast<float*>(smem + JOFF_H);
+    float* sPair = reinterpret_cast<float*>(smem + JOFF_PAIR);
+    float* sTh = reinterpret_cast<float*>(smem + JOFF_TH);
+    int* sPI = reinterpret_cast<int*>(smem + JOFF_PI);
+    int* sPJ = reinterpret_cast<int*>(smem + JOFF_PJ);
+    float* sBout = reinterpret_cast<float*>(smem + JOFF_BOUT);
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem + JOFF_TMEM);
+    const uint32_t bar0 = smem_u32(smem + JOFF_BAR);
+    auto bar_full = [&](int s) { return bar0 + 8u * s; };
+    auto bar_empty = [&](int s) { return bar0 + 8u * (JT_NSTG + s); };
+    const uint32_t bar_a = bar0 + 8u * (2 * JT_NSTG);      // A operand ready for the MMA warp
+    const uint32_t bar_d = bar0 + 8u * (2 * JT_NSTG + 1);  // accumulator ready for the epilogue
+
+    const NetDev& net = p.net;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m = net.m, L = net.L, Lh = L - 2;
+    const int H0 = net.Hp[0];
+    const int R = 1 + m;        // tile rows per pair
+    const int PW = p.PW;        // pairs per TMEM lane quarter (32 / R, at most 8)
+    const int PT = 4 * PW;      // pairs per tile
+    const int W = m + m * m;
+
+    if (tid == 0) {
+        for (int s = 0; s < JT_NSTG; ++s) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_empty(s), 1);
+        }
+        mbar_init(bar_a, TC_CW * 32);
+        mbar_init(bar_d, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == TC_CW + 1) {  // TMEM: two 256-column fp32 accumulators, used alternately layer by layer
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    // constant tables; operand images zeroed once (rows that belong to no pair are never written again)
+    for (int e = tid; e < 2 * TC_A_BYTES / 16; e += JT_THREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
+    {
+        const int Kout = net.Hp[L - 2];
+        for (int e = tid; e < m * Kout; e += JT_THREADS) sWout[(e / Kout) * 256 + (e % Kout)] = __ldg(net.WoutT + e);
+        for (int e = tid; e < m * H0; e += JT_THREADS) sA[(e / H0) * 256 + (e % H0)] = __ldg(net.A + e);
+        for (int e = tid; e < H0; e += JT_THREADS) sTf[e] = __ldg(p.time_feat + e);
+        if (tid < 8) sBout[tid] = (tid < m) ? __ldg(net.bout + tid) : 0.f;
+        // fp16 hi / lo K-groups of the theta block (the layer-0 tangents are masked copies of them)
+        for (int e = tid; e < m * (H0 / 8); e += JT_THREADS) {
+            const int k = e / (H0 / 8), kg = e - k * (H0 / 8);
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int q2 = 0; q2 < 4; ++q2) {
+                const float x0 = __ldg(net.A + (size_t)k * H0 + 8 * kg + 2 * q2), x1 = __ldg(net.A + (size_t)k * H0 + 8 * kg + 2 * q2 + 1);
+                const __half2 h16 = __floats2half2_rn(x0, x1);
+                const float2 hf = __half22float2(h16);
+                const __half2 l16 = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                hi[q2] = *reinterpret_cast<const uint32_t*>(&h16);
+                lo[q2] = *reinterpret_cast<const uint32_t*>(&l16);
+            }
+            sAimg[(k * 32 + kg) * 2] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            sAimg[(k * 32 + kg) * 2 + 1] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *sTmem;
+
+    int my_tiles = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) ++my_tiles;
+
+    if (warp == TC_CW) {
+        // ================= TMA producer: streams the weight images in consumption order ===========================
+        if (lane == 0) {
+            unsigned it = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                for (int l = 1; l <= Lh; ++l) {
+                    const int K = net.Hp[l - 1], Nn = net.Hp[l];
+                    const uint32_t bytes = (uint32_t)Nn * 64u;
+                    const uint8_t* src = net.wimg16[l];  // fp16 hi | lo
+                    for (int ks = 0; ks < K / 16; ++ks, ++it) {
+                        const int s = it % JT_NSTG;
+                        const uint32_t ph = (it / JT_NSTG) & 1u;
+                        mbar_wait(bar_empty(s), ph ^ 1u, p.error_flag);
+                        mbar_expect_tx(bar_full(s), bytes);
+                        tma_bulk_g2s(smem_u32(smem + JOFF_RING + s * TC_STAGE_BYTES), src + (size_t)ks * bytes, bytes, bar_full(s));
+                    }
+                }
+            }
+        }
+    } else if (warp == TC_CW + 1) {
+        // ================= MMA issuer ===================================================================================
+        if (lane == 0) {
+            unsigned it = 0, a_cnt = 0, lc = 0;
+            const uint32_t a_hi0 = smem_u32(sAhi), a_lo0 = smem_u32(sAlo);
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                for (int l = 1; l <= Lh; ++l) {
+                    const int K = net.Hp[l - 1], Nn = net.Hp[l];
+                    // fp16x3: a w ~= a_lo w_hi + a_hi w_lo + a_hi w_hi with fp16 hi / lo parts (~2^-22 per product; the bf16x3
+                    // split of the GAUSS kernel is not enough here: the Jacobian goes through inv(I - sigma J), which
+                    // amplifies the GEMM error by its condition number)
+                    const uint32_t idesc = umma_idesc_fmt(Nn, false, false);
+                    const uint32_t b_lbo = (uint32_t)Nn * 16u, b_sbo = 128u;
+                    const uint32_t a_lbo = 2048u, a_sbo = 128u;
+                    mbar_wait(bar_a, a_cnt & 1u, p.error_flag);
+                    ++a_cnt;
+                    tc_fence_after();
+                    const uint32_t dacc = tmem_d + ((lc & 1u) ? 256u : 0u);
+                    ++lc;
+                    for (int ks = 0; ks < K / 16; ++ks, ++it) {
+                        const int s = it % JT_NSTG;
+                        const uint32_t ph = (it / JT_NSTG) & 1u;
+                        mbar_wait(bar_full(s), ph, p.error_flag);
+                        tc_fence_after();
+                        const uint32_t wb = smem_u32(smem + JOFF_RING + s * TC_STAGE_BYTES);
+                        const uint64_t b_hi = umma_desc(wb, b_lbo, b_sbo);
+                        const uint64_t b_lo = umma_desc(wb + (uint32_t)Nn * 32u, b_lbo, b_sbo);
+                        const uint64_t a_hi = umma_desc(a_hi0 + ks * 4096, a_lbo, a_sbo);
+                        const uint64_t a_lo = umma_desc(a_lo0 + ks * 4096, a_lbo, a_sbo);
+                        tc_mma_bf16(dacc, a_lo, b_hi, idesc, ks > 0 ? 1u : 0u);  // small terms first
+                        tc_mma_bf16(dacc, a_hi, b_lo, idesc, 1u);
+                        tc_mma_bf16(dacc, a_hi, b_hi, idesc, 1u);
+                        tc_commit(bar_empty(s));
+                    }
+                    tc_commit(bar_d);
+                }
+            }
+        }
+    } else {
+        // ================= compute warps ==================================================================================
+        const int q = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column quarter
+        const int row = 32 * q + lane;           // the TMEM lane / tile row this thread owns in the epilogues
+        const int pl = lane / R;                 // pair slot inside the lane quarter
+        const int rc = lane - pl * R;            // 0 = primal row, 1 + k = tangent k
+        const bool rvalid = pl < PW;             // (lanes past PW * R own no row)
+        const float bsel = (rvalid && rc == 0) ? 1.f : 0.f;
+        float* hslot = sH + (warp * 8 + (rvalid ? pl : 0)) * 16;
+        const int nkg = H0 / 8;
+        unsigned d_cnt = 0;
+        const float sigma = __ldg(p.sched + D4S_S_SIGMA), inv_sigma = __ldg(p.sched + D4S_S_INV_SIGMA);
+        const float aos2 = __ldg(p.sched + D4S_S_A_OVER_S2);
+
+        // pair slot -> (sample, observation) of a tile, and the sample's theta (double buffered: tile t-1 is still
+        // being finished while tile t starts)
+        auto prepare_meta = [&](int tile, int buf) {
+            if (tid < PT) {
+                const int u = tid / p.OC, o = tid - u * p.OC;
+                const long long gu = (long long)tile * p.UT + u;
+                int i = -1, j = 0;
+                if (u < p.UT && gu < (long long)p.N * p.C) {
+                    const int ii = (int)(gu / p.C), ch = (int)(gu - (long long)ii * p.C);
+                    j = ch * p.OC + o;
+                    if (j < p.n) i = ii;
+                }
+                sPI[buf * JT_PMAX + tid] = i;
+                sPJ[buf * JT_PMAX + tid] = j;
+            }
+            for (int e = tid; e < PT * m; e += TC_CT) {
+                const int pp = e / m, k = e - pp * m;
+                const int u = pp / p.OC;
+                const long long gu = (long long)tile * p.UT + u;
+                float v = 0.f;
+                if (u < p.UT && gu < (long long)p.N * p.C) v = __ldg(p.theta + (size_t)(gu / p.C) * m + k);
+                sTh[(buf * JT_PMAX + pp) * JT_MMAX + k] = v;
+            }
+        };
+        // layer 0: lane = pair, warp = k-groups warp, warp + 16.  z = time_feat + A theta_i + obs_feat_j; the primal row
+        // stores relu(z), tangent row k the theta-block column masked by [z > 0].
+        auto do_layer0 = [&](int buf) {
+            const int pp = lane;
+            const int i = (pp < PT) ? sPI[buf * JT_PMAX + pp] : -1;
+            if (i >= 0) {
+                const int j = sPJ[buf * JT_PMAX + pp];
+                const int prow = 32 * (pp / PW) + (pp % PW) * R;  // tile row of the pair's primal
+                const float* up = p.obs_feat + (size_t)j * H0;
+                float th[JT_MMAX];
+#pragma unroll
+                for (int k = 0; k < JT_MMAX; ++k) th[k] = sTh[(buf * JT_PMAX + pp) * JT_MMAX + k];
+                float4 u[2][2];
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int kg = warp + 16 * jj;
+                    if (kg < nkg) {
+                        u[jj][0] = __ldg(reinterpret_cast<const float4*>(up + 8 * kg));
+                        u[jj][1] = __ldg(reinterpret_cast<const float4*>(up + 8 * kg + 4));
+                    }
+                }
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int kg = warp + 16 * jj;
+                    if (kg < nkg) {
+                        float z[8];
+                        const float4 t0 = *reinterpret_cast<const float4*>(sTf + 8 * kg);
+                        const float4 t1 = *reinterpret_cast<const float4*>(sTf + 8 * kg + 4);
+                        z[0] = u[jj][0].x + t0.x; z[1] = u[jj][0].y + t0.y; z[2] = u[jj][0].z + t0.z; z[3] = u[jj][0].w + t0.w;
+                        z[4] = u[jj][1].x + t1.x; z[5] = u[jj][1].y + t1.y; z[6] = u[jj][1].z + t1.z; z[7] = u[jj][1].w + t1.w;
+#pragma unroll
+                        for (int k = 0; k < JT_MMAX; ++k) {
+                            if (k < m) {
+                                const float4 a0 = *reinterpret_cast<const float4*>(sA + k * 256 + 8 * kg);
+                                const float4 a1 = *reinterpret_cast<const float4*>(sA + k * 256 + 8 * kg + 4);
+                                z[0] = fmaf(a0.x, th[k], z[0]); z[1] = fmaf(a0.y, th[k], z[1]);
+                                z[2] = fmaf(a0.z, th[k], z[2]); z[3] = fmaf(a0.w, th[k], z[3]);
+                                z[4] = fmaf(a1.x, th[k], z[4]); z[5] = fmaf(a1.y, th[k], z[5]);
+                                z[6] = fmaf(a1.z, th[k], z[6]); z[7] = fmaf(a1.w, th[k], z[7]);
+                            }
+                        }
+                        uint32_t mw[4];  // 16-bit lane masks of the bf16 pairs
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            mw[e] = (z[2 * e] > 0.f ? 0x0000FFFFu : 0u) | (z[2 * e + 1] > 0.f ? 0xFFFF0000u : 0u);
+                        float v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = fmaxf(z[e], 0.f);
+                        store_split8_f16(v, sAhi, sAlo, a_off(prow, kg));
+#pragma unroll
+                        for (int k = 0; k < JT_MMAX; ++k) {
+                            if (k < m) {
+                                const uint4 hi = sAimg[(k * 32 + kg) * 2], lo = sAimg[(k * 32 + kg) * 2 + 1];
+                                const int off = a_off(prow + 1 + k, kg);
+                                *reinterpret_cast<uint4*>(sAhi + off) = make_uint4(hi.x & mw[0], hi.y & mw[1], hi.z & mw[2], hi.w & mw[3]);
+                                *reinterpret_cast<uint4*>(sAlo + off) = make_uint4(lo.x & mw[0], lo.y & mw[1], lo.z & mw[2], lo.w & mw[3]);
+                            }
+                        }
+                    }
+                }
+            } else if (pp < PT) {  // empty pair slot: its rows must not carry the previous tile's values
+                const int prow = 32 * (pp / PW) + (pp % PW) * R;
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int kg = warp + 16 * jj;
+                    if (kg < nkg)
+                        for (int r = 0; r < R; ++r) {
+                            const int off = a_off(prow + r, kg);
+                            *reinterpret_cast<uint4*>(sAhi + off) = make_uint4(0, 0, 0, 0);
+                            *reinterpret_cast<uint4*>(sAlo + off) = make_uint4(0, 0, 0, 0);
+                        }
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bar_a);
+        };
+        // one 16-column block of an accumulator row.  Primal: x = d + bias, a = relu(x).  Tangent: a = d * [x_primal > 0].
+        auto ld_act = [&](uint32_t dacc, int col0, const float* bias16, float (&a)[16]) {
+            uint32_t d[16];
+            tc_ld16(dacc + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, d);
+            float4 bb[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bias16) + e);
+            tc_wait_ld();
+            float x[16];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                x[4 * e] = fmaf(bb[e].x, bsel, __uint_as_float(d[4 * e]));
+                x[4 * e + 1] = fmaf(bb[e].y, bsel, __uint_as_float(d[4 * e + 1]));
+                x[4 * e + 2] = fmaf(bb[e].z, bsel, __uint_as_float(d[4 * e + 2]));
+                x[4 * e + 3] = fmaf(bb[e].w, bsel, __uint_as_float(d[4 * e + 3]));
+            }
+            __syncwarp();  // the previous block's indicators have been read by every lane
+            if (bsel != 0.f) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    *reinterpret_cast<float4*>(hslot + 4 * e) =
+                        make_float4(x[4 * e] > 0.f ? 1.f : 0.f, x[4 * e + 1] > 0.f ? 1.f : 0.f, x[4 * e + 2] > 0.f ? 1.f : 0.f,
+                                    x[4 * e + 3] > 0.f ? 1.f : 0.f);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float4 h = *reinterpret_cast<const float4*>(hslot + 4 * e);
+                a[4 * e] = rvalid ? x[4 * e] * h.x : 0.f;
+                a[4 * e + 1] = rvalid ? x[4 * e + 1] * h.y : 0.f;
+                a[4 * e + 2] = rvalid ? x[4 * e + 2] * h.z : 0.f;
+                a[4 * e + 3] = rvalid ? x[4 * e + 3] * h.w : 0.f;
+            }
+        };
+        // epilogue of the last hidden layer + output layer (fp32) -> sOut[row][o]: score of the primal row, column k of
+        // d eps / d theta for tangent row k
+        auto do_last_epilogue = [&](uint32_t dacc) {
+            const int Nn = net.Hp[L - 2];
+            const int qcols = Nn >> 2, nblk = qcols / 16;
+            const float* bias_l = net.bias[L - 2] + cq * qcols;
+            float po[JT_MMAX];
+#pragma unroll
+            for (int o = 0; o < JT_MMAX; ++o) po[o] = 0.f;
+            for (int cb = 0; cb < nblk; ++cb) {
+                const int col0 = cq * qcols + 16 * cb;
+                float a[16];
+                ld_act(dacc, col0, bias_l + 16 * cb, a);
+#pragma unroll
+                for (int e = 0; e < 16; e += 4) {
+                    float4 w4[JT_MMAX];
+#pragma unroll
+                    for (int o = 0; o < JT_MMAX; ++o) w4[o] = *reinterpret_cast<const float4*>(sWout + o * 256 + col0 + e);
+#pragma unroll
+                    for (int o = 0; o < JT_MMAX; ++o) {
+                        float acc = po[o];
+                        acc = fmaf(a[e], w4[o].x, acc);
+                        acc = fmaf(a[e + 1], w4[o].y, acc);
+                        acc = fmaf(a[e + 2], w4[o].z, acc);
+                        acc = fmaf(a[e + 3], w4[o].w, acc);
+                        po[o] = acc;
+                    }
+                }
+            }
+            if (cq != 0) {
+#pragma unroll
+                for (int o = 0; o < JT_MMAX; ++o)
+                    if (o < m) sRed[((cq - 1) * TC_M + row) * JT_MMAX + o] = po[o];
+            }
+            tc_fence_before();
+            compute_bar();
+            if (cq == 0) {
+#pragma unroll
+                for (int o = 0; o < JT_MMAX; ++o) {
+                    if (o < m) {
+                        const float v = (po[o] + sRed[row * JT_MMAX + o]) +
+                                        (sRed[(TC_M + row) * JT_MMAX + o] + sRed[(2 * TC_M + row) * JT_MMAX + o]);
+                        // primal: score = -(eps + b) / sigma (nse.py:166); tangent k: d eps_o / d theta_k
+                        sOut[row * m + o] = (rc == 0) ? -(v + sBout[o]) * inv_sigma : v;
+                    }
+                }
+            }
+            compute_bar();
+        };
+        // per-pair Tweedie precision and P s, then the per-unit sums over observations -> part[N][C][W]
+        auto do_pairs = [&](int tile, int buf) {
+            if (tid < PT * m) {
+                const int pp = tid / m, c = tid - pp * m;
+                if (sPI[buf * JT_PMAX + pp] >= 0) {
+                    const int prow = 32 * (pp / PW) + (pp % PW) * R;
+                    jac_pair_col_dispatch(m, sOut, prow, sigma, aos2, c, sPair + pp * W);
+                }
+            }
+            compute_bar();
+            if (tid < PT * m) {
+                const int pp = tid / m, r = tid - pp * m;
+                if (sPI[buf * JT_PMAX + pp] >= 0) {
+                    const int prow = 32 * (pp / PW) + (pp % PW) * R;
+                    double v = 0.0;
+                    for (int k = 0; k < m; ++k) v = fma((double)sPair[pp * W + m + r * m + k], (double)sOut[prow * m + k], v);
+                    sPair[pp * W + r] = (float)v;
+                }
+            }
+            compute_bar();
+            for (int e = tid; e < p.UT * W; e += TC_CT) {
+                const int u = e / W, w = e - u * W;
+                const long long gu = (long long)tile * p.UT + u;
+                if (gu < (long long)p.N * p.C) {
+                    float acc = 0.f;
+                    for (int o = 0; o < p.OC; ++o) {
+                        const int pp = u * p.OC + o;
+                        if (sPI[buf * JT_PMAX + pp] >= 0) {
+                            const float wj = p.obs_weight ? __ldg(p.obs_weight + sPJ[buf * JT_PMAX + pp]) : 1.f;
+                            acc = fmaf(wj, sPair[pp * W + w], acc);
+                        }
+                    }
+                    p.part[(size_t)gu * W + w] = acc;  // gu = i * C + chunk
+                }
+            }
+            compute_bar();  // the pair tables of this buffer are rewritten next
+        };
+
+        if (my_tiles > 0) prepare_meta(blockIdx.x, 0);
+        compute_bar();
+        for (int ps = 0; ps <= my_tiles; ++ps) {  // one extra iteration finishes the last tile
+            const bool have = ps < my_tiles, prev = ps > 0;
+            const int tile = blockIdx.x + ps * (int)gridDim.x;
+            const int buf = ps & 1;
+            uint32_t dacc_prev = 0;
+            if (prev) {  // the last layer of the previous tile: once it is done the operand images are free again
+                dacc_prev = tmem_d + ((d_cnt & 1u) ? 256u : 0u);
+                mbar_wait(bar_d, d_cnt & 1u, p.error_flag);
+                ++d_cnt;
+                tc_fence_after();
+            }
+            if (have) do_layer0(buf);
+            if (prev) do_last_epilogue(dacc_prev);
+            if (have) {
+                for (int l = 1; l < Lh; ++l) {  // hidden layers that feed another tensor-core layer
+                    const int Nn = net.Hp[l];
+                    const int qcols = Nn >> 2, nblk = qcols / 16;
+                    const float* bias_l = net.bias[l] + cq * qcols;
+                    const uint32_t dacc = tmem_d + ((d_cnt & 1u) ? 256u : 0u);
+                    mbar_wait(bar_d, d_cnt & 1u, p.error_flag);
+                    ++d_cnt;
+                    tc_fence_after();
+                    for (int cb = 0; cb < nblk; ++cb) {
+                        const int col0 = cq * qcols + 16 * cb;
+                        float a[16];
+                        ld_act(dacc, col0, bias_l + 16 * cb, a);
+#pragma unroll
+                        for (int k8 = 0; k8 < 2; ++k8) {
+                            float v[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = a[8 * k8 + e];
+                            store_split8_f16(v, sAhi, sAlo, a_off(row, (col0 >> 3) + k8));
+                        }
+                    }
+                    fence_proxy_async();
+                    tc_fence_before();
+                    mbar_arrive(bar_a);
+                }
+            }
+            if (prev) do_pairs(tile - (int)gridDim.x, buf ^ 1);
+            if (ps + 1 < my_tiles) prepare_meta(tile + (int)gridDim.x, buf ^ 1);
+            compute_bar();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_CW + 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512));
+    }
+}
+
+cudaError_t launch_jac_tc(const JacTcParams& p, int n_ctas, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(jac_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JT_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    jac_tc_kernel<<<n_ctas, JT_THREADS, JT_SMEM_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace d4s

@@ -18,24 +18,15 @@
 //             warp 8 = TMA producer (one lane), warp 9 = TMEM allocator + MMA issuer (one lane),
 //             warp 10 = scalar helper: per-step schedule/matrix rows -> smem, fp64 diffused-prior terms, Philox noise
 //             (everything that depends only on theta at the start of the step, off the critical path).
-#include <cuda_bf16.h>
-
-#include <cstdlib>
-
 #include "d4s_finalize_core.cuh"
+#include "d4s_tc_common.cuh"
 
 namespace d4s {
 
-constexpr int TC_M = 128;                      // tile rows = TMEM lanes
-constexpr int TC_CW = 16;                      // compute warps
 constexpr int TC_THREADS = (TC_CW + 3) * 32;   // 608: + TMA producer, MMA issuer, scalar helper
-constexpr int TC_CT = TC_CW * 32;              // compute threads
 constexpr int TC_NSTG = 4;                     // weight ring stages
-constexpr int TC_STAGE_BYTES = 256 * 64;       // one K=16 step of W_hi | W_lo for N <= 256
-constexpr int TC_A_BYTES = (256 / 16) * 4096;  // 64 KB: act[128 x 256] bf16 in K16-step images
 constexpr int TC_SG_MAX = 8;                   // samples per tile (warp w < SG sums sample w)
 constexpr int TC_MATS_MAX = 2 * MMAX * MMAX + MMAX + 2;
-constexpr long long SPIN_LIMIT_CYCLES = 4000000000LL;  // ~2 s: bounded mbarrier waits trap instead of hanging
 
 // ---- shared memory carve-up (bytes) ---------------------------------------------------------------------------
 constexpr int OFF_AHI = 0;
@@ -60,125 +51,6 @@ constexpr int OFF_TMEM = OFF_BAR + (2 * TC_NSTG + 2) * 8;
 constexpr int TC_SMEM_BYTES = OFF_TMEM + 16;
 static_assert(TC_SMEM_BYTES <= 232448, "shared memory budget (227 KB per CTA) exceeded");
 static_assert(OFF_BAR % 8 == 0 && OFF_SCHED % 16 == 0, "alignment");
-
-// ---- PTX wrappers ------------------------------------------------------------------------------------------------
-__constant__ unsigned g_wait_hint = 20000u;
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(g_wait_hint)  // suspend-time hint (ns): a waiting warp sleeps instead of taking issue slots
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    unsigned polls = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++polls & 255u) == 0u && clock64() - t0 > SPIN_LIMIT_CYCLES) {
-            if (err) atomicExch(err, 1);  // a protocol bug must not hang the GPU: fail loudly instead
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-
-// UMMA shared-memory descriptor, K-major, no swizzle ("interleave"): 8x16B core matrices, 128 B each.
-//   lbo = byte distance between the two K halves of a K=16 step, sbo = byte distance between 8-row groups.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-// instruction descriptor: D fp32, A/B bf16, both K-major, dense, M = 128, N = n
-__device__ __forceinline__ uint32_t umma_idesc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-}
-
-// named barriers: 1 = compute warps only; 2 = theta of the step is final (compute arrive, helper sync);
-//                 3 = helper results ready (helper arrive, compute sync)
-__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-
-// Splits 8 fp32 activations into bf16 hi / lo and stores the two 16-byte K-groups.  hi = RN_bf16(v) by Veltkamp
-// splitting (c = v * (2^16 + 1); hi = c - (c - v): three FMA-pipe ops, no conversion-unit instruction), lo = v - hi
-// exactly, truncated to bf16 when packed (its dropped bits are < 2^-17 |v|).  Packing is one PRMT per pair.
-__device__ __forceinline__ void store_split8(const float (&v)[8], uint8_t* a_hi, uint8_t* a_lo, int byte_off) {
-    uint32_t hi[4], lo[4];
-    const float2 k = make_float2(65537.0f, 65537.0f), neg1 = make_float2(-1.0f, -1.0f);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        // packed fp32 pairs (FMUL2 / FFMA2): a - b = fma(b, -1, a) rounds once, exactly like a subtraction
-        const float2 x = make_float2(v[2 * e], v[2 * e + 1]);
-        const float2 c = __fmul2_rn(x, k);
-        const float2 d = __ffma2_rn(x, neg1, c);  // c - x
-        const float2 h = __ffma2_rn(d, neg1, c);  // hi = c - (c - x)
-        const float2 l = __ffma2_rn(h, neg1, x);  // lo = x - hi (exact)
-        hi[e] = __byte_perm(__float_as_uint(h.x), __float_as_uint(h.y), 0x7632);
-        lo[e] = __byte_perm(__float_as_uint(l.x), __float_as_uint(l.y), 0x7632);
-    }
-    *reinterpret_cast<uint4*>(a_hi + byte_off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(a_lo + byte_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-}
-
-// byte offset of (row r, k-group kg of 8 columns) inside an A image: K16 step = kg/2, half = kg%2
-__device__ __forceinline__ int a_off(int r, int kg) { return (kg >> 1) * 4096 + (kg & 1) * 2048 + r * 16; }
 
 // Optional phase timing (d4s_set_option("profile", 1)): thread 0 of CTA 0 accumulates clock64() deltas per phase.
 #define PROF_MARK(slot)                                                     \
@@ -844,11 +716,6 @@ cudaError_t launch_traj_tc(const TrajParams& p, int n_ctas, cudaStream_t stream)
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(traj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        if (const char* h = getenv("D4S_TC_WAIT_HINT")) {  // tuning knob: mbarrier.try_wait suspend-time hint in ns
-            const unsigned v = (unsigned)atoi(h);
-            e = cudaMemcpyToSymbol(g_wait_hint, &v, sizeof(v));
-            if (e != cudaSuccess) return e;
-        }
         configured = true;
     }
     traj_tc_kernel<<<n_ctas, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);

@@ -139,12 +139,14 @@ def load():
             fn.argtypes = args
         if lib.d4s_abi_version() != ABI_VERSION:
             raise D4sError(f"libd4s ABI {lib.d4s_abi_version()} != binding {ABI_VERSION}: rebuild the library")
+        if os.environ.get("D4S_JAC_TC", "0") == "1":  # opt in to the tensor-core JAC kernel for the whole process
+            lib.d4s_set_option(b"jac_tc", 1)
         _lib = lib
     return _lib
 
 
 def set_option(key: str, value: int):
-    """Library switches (see d4s_set_option in include/d4s.h): path, tc_steps_per_launch, profile."""
+    """Library switches (see d4s_set_option in include/d4s.h): path, tc_steps_per_launch, profile, tc_pairing, jac_tc."""
     check(load().d4s_set_option(key.encode(), int(value)))
 
 

@@ -189,7 +189,9 @@ D4S_API void d4s_graph_cache_clear(void);
  * kernel (bf16x3 split on the tensor cores; GAUSS, tall grid); "tc_steps_per_launch" = DDIM steps per tcgen05
  * launch (0 = whole trajectory in one launch); "profile" = 1 enables the in-kernel phase timers; "tc_pairing" = 1
  * (default) lets a CTA that owns two sample groups interleave them step by step, 0 runs them one after the other
- * (same arithmetic, bit-identical results). */
+ * (same arithmetic, bit-identical results); "jac_tc" = 1 runs JAC steps (theta_dim <= 5) on the tcgen05 score +
+ * Jacobian kernel (fp16x3 products, ~5x faster than the fp32 SIMT kernel; the tensor core's truncating accumulation
+ * costs about one decimal digit where inv(I - sigma J) is ill-conditioned, so it is off by default). */
 D4S_API int d4s_set_option(const char* key, int32_t value);
 /* "profile" = 1 makes CTA 0 of the tcgen05 kernel accumulate clock64() cycles per phase; this call synchronises and
  * copies the 16 counters of the last launch: 0 layer-0 sample part, 1 layer 0, 2 prior+noise, 3 tensor-core wait,
