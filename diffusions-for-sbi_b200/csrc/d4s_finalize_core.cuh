@@ -5,29 +5,30 @@
 
 namespace d4s {
 
-template <int M>
-__device__ __forceinline__ void lu_solve_d(double (&a)[M][M], double (&b)[M]) {
+// LU with partial pivoting, fully unrolled (row swaps as predicated moves: everything stays in registers).
+template <typename T, int M>
+__device__ __forceinline__ void lu_solve_t(T (&a)[M][M], T (&b)[M]) {
 #pragma unroll
     for (int k = 0; k < M; ++k) {
         int p = k;
-        double best = fabs(a[k][k]);
+        T best = fabs(a[k][k]);
 #pragma unroll
         for (int r = k + 1; r < M; ++r) {
-            double v = fabs(a[r][k]);
+            T v = fabs(a[r][k]);
             if (v > best) { best = v; p = r; }
         }
 #pragma unroll
         for (int r = k + 1; r < M; ++r) {
             if (r == p) {
 #pragma unroll
-                for (int c = 0; c < M; ++c) { double t = a[k][c]; a[k][c] = a[r][c]; a[r][c] = t; }
-                double t = b[k]; b[k] = b[r]; b[r] = t;
+                for (int c = 0; c < M; ++c) { T t = a[k][c]; a[k][c] = a[r][c]; a[r][c] = t; }
+                T t = b[k]; b[k] = b[r]; b[r] = t;
             }
         }
-        const double inv = 1.0 / a[k][k];
+        const T inv = T(1) / a[k][k];
 #pragma unroll
         for (int r = k + 1; r < M; ++r) {
-            const double f = a[r][k] * inv;
+            const T f = a[r][k] * inv;
 #pragma unroll
             for (int c = k + 1; c < M; ++c) a[r][c] = fma(-f, a[k][c], a[r][c]);
             b[r] = fma(-f, b[k], b[r]);
@@ -35,12 +36,14 @@ __device__ __forceinline__ void lu_solve_d(double (&a)[M][M], double (&b)[M]) {
     }
 #pragma unroll
     for (int k = M - 1; k >= 0; --k) {
-        double s = b[k];
+        T s = b[k];
 #pragma unroll
         for (int c = k + 1; c < M; ++c) s = fma(-a[k][c], b[c], s);
         b[k] = s / a[k][k];
     }
 }
+template <int M>
+__device__ __forceinline__ void lu_solve_d(double (&a)[M][M], double (&b)[M]) { lu_solve_t<double, M>(a, b); }
 
 // Phi(ub) - Phi(ua) evaluated on the tail that avoids cancellation.
 __device__ __forceinline__ double cdf_diff(double ua, double ub) {

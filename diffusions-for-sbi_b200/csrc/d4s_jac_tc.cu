@@ -6,7 +6,7 @@
 // the m tangents d act / d theta_k.  All rows go through the same bf16x3 tensor-core GEMMs as in d4s_traj_tc.cu; the
 // epilogues apply the ReLU of the PRIMAL row to the pair's tangent rows (h = [pre > 0], exchanged through a per-warp
 // shared-memory slot: a pair never straddles a warp).  After the fp32 output layer the primal row holds eps, tangent
-// row k holds column k of d eps / d theta; one thread per (pair, column) then solves (I - sigma J_eps) x = e_c in fp64
+// row k holds column k of d eps / d theta; one thread per (pair, column) then solves (I - sigma J_eps) x = e_c
 // (LU with partial pivoting in registers) and the per-unit sums over observations are written as partial sums
 // part[N][C][m + m^2] = [sum_j P s | sum_j P], the layout kernel 3 (d4s_finalize.cu) reduces.
 //
@@ -50,20 +50,22 @@ constexpr int JT_SMEM_BYTES = JOFF_TMEM + 16;
 static_assert(JT_SMEM_BYTES <= 232448, "shared memory budget (227 KB per CTA) exceeded");
 static_assert(JOFF_BAR % 8 == 0 && JOFF_AIMG % 16 == 0 && JOFF_H % 16 == 0, "alignment");
 
-// One thread per (pair, column c): column c of P = (alpha/sigma^2) inv(I - sigma J_eps)  (fp64, registers).
+// One thread per (pair, column c): column c of P = (alpha/sigma^2) inv(I - sigma J_eps), LU with partial pivoting in
+// registers.  fp32: the entries of J_eps carry the tensor core's ~1e-6 error already, so fp64 (as in the SIMT kernel's
+// jac_pair) would only add a few thousand cycles of latency per tile.
 template <int M>
 __device__ __noinline__ void jac_pair_col(const float* out_rows, int row0, float sigma, float a_over_s2, int c, float* pair_out) {
-    double a[M][M], b[M];
+    float a[M][M], b[M];
 #pragma unroll
     for (int o = 0; o < M; ++o) {
 #pragma unroll
         for (int k = 0; k < M; ++k)  // tangent row 1 + k holds d eps_o / d theta_k
-            a[o][k] = ((o == k) ? 1.0 : 0.0) - (double)sigma * (double)out_rows[(row0 + 1 + k) * M + o];
-        b[o] = (o == c) ? 1.0 : 0.0;
+            a[o][k] = ((o == k) ? 1.f : 0.f) - sigma * out_rows[(row0 + 1 + k) * M + o];
+        b[o] = (o == c) ? 1.f : 0.f;
     }
-    lu_solve_d<M>(a, b);
+    lu_solve_t<float, M>(a, b);
 #pragma unroll
-    for (int r = 0; r < M; ++r) pair_out[M + r * M + c] = (float)((double)a_over_s2 * b[r]);
+    for (int r = 0; r < M; ++r) pair_out[M + r * M + c] = a_over_s2 * b[r];
 }
 
 __device__ __forceinline__ void jac_pair_col_dispatch(int m, const float* out_rows, int row0, float sigma, float aos2, int c,
@@ -425,9 +427,9 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                 const int pp = tid / m, r = tid - pp * m;
                 if (sPI[buf * JT_PMAX + pp] >= 0) {
                     const int prow = 32 * (pp / PW) + (pp % PW) * R;
-                    double v = 0.0;
-                    for (int k = 0; k < m; ++k) v = fma((double)sPair[pp * W + m + r * m + k], (double)sOut[prow * m + k], v);
-                    sPair[pp * W + r] = (float)v;
+                    float v = 0.f;
+                    for (int k = 0; k < m; ++k) v = fmaf(sPair[pp * W + m + r * m + k], sOut[prow * m + k], v);
+                    sPair[pp * W + r] = v;
                 }
             }
             compute_bar();

@@ -195,7 +195,8 @@ D4S_API void d4s_graph_cache_clear(void);
 D4S_API int d4s_set_option(const char* key, int32_t value);
 /* "profile" = 1 makes CTA 0 of the tcgen05 kernel accumulate clock64() cycles per phase; this call synchronises and
  * copies the 16 counters of the last launch: 0 layer-0 sample part, 1 layer 0, 2 prior+noise, 3 tensor-core wait,
- * 4 epilogues, 5 scores, 6 inv(Sigma) s + sums, 7 finalize. */
+ * 4 epilogues, 5 scores, 6 inv(Sigma) s + sums, 7 finalize; 8 / 9: MMA issue -> commit of the inner / last hidden layer
+ * (measured by the MMA warp). */
 D4S_API int d4s_get_profile(int64_t* out16);
 
 /* ---- stand-alone pieces of kernel 3/4 (API parity with the reference's public helpers) ---------------- */
