@@ -325,15 +325,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
         float tf_next = (tid < H0 && n_steps > 0) ? __ldg(p.time_feat + (size_t)p.step_begin * H0 + tid) : 0.f;
         // ---- phases shared by the two schedules (one group after the other / two groups interleaved) ----------------------
         // layer-0 per-sample part of an item: base[si][col] = time_feat[col] + sum_k A[k][col] theta[si][k]
-        auto do_base = [&](const float* th, bool fresh, int step, int next_step) {
+        float tf_cur = 0.f;
+        auto do_base = [&](const float* th, bool fresh, int next_step) {
             if (tid < H0) {
-                float t0;
-                if (fresh) {
-                    t0 = tf_next;
+                if (fresh) {  // (not fresh: a later observation chunk of the same step)
+                    tf_cur = tf_next;
                     tf_next = __ldg(p.time_feat + (size_t)next_step * H0 + tid);  // consumed one item later: latency hidden
-                } else {
-                    t0 = __ldg(p.time_feat + (size_t)step * H0 + tid);  // (later observation chunks of the same step)
                 }
+                const float t0 = tf_cur;
                 float ak[MMAX];  // column tid of the layer-0 theta block
 #pragma unroll
                 for (int k = 0; k < MMAX; ++k)
@@ -574,7 +573,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
             if (total > 0) bar_arrive(2, NB23);  // theta of item 0 is final: the helper warp may start on it
             auto step_of = [&](int item) { return (item < total) ? p.step_begin + (defer ? (item >> 1) : item) : p.step_begin; };
             if (defer && total > 0) {  // (later items: inside the previous item's last tensor-core wait)
-                do_base(sTheta, true, step_of(0), step_of(1));
+                do_base(sTheta, true, step_of(1));
                 compute_bar();
             }
             for (int ps = 0; ps <= total_p; ++ps) {  // one extra iteration finishes the last pass
@@ -591,7 +590,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                 float inv_sigma_prev = 0.f;
                 uint32_t dacc_prev = 0;
                 float4 upre[2][2];
-                const bool have_pre = defer && have && lane < p.OC;
+                // layer 0 of this pass goes first when it does not depend on the previous pass: interleaved groups, or a
+                // later observation chunk of the same item (its sample part was recomputed at the end of the last pass)
+                const bool early = have && (defer || chunk > 0);
+                const bool have_pre = early && lane < p.OC;
                 if (have_pre) l0_load(upre, j0, nobs, lane);  // layer 0 follows the wait directly: hide its global loads
                 if (prev) {  // the last layer of the previous pass: once it is done the operand images are free again
                     inv_sigma_prev = __ldg(p.sched + (size_t)step_of(pit) * D4S_SCHED_STRIDE + D4S_S_INV_SIGMA);
@@ -601,7 +603,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     tc_fence_after();
                     PROF_MARK(3);  // waiting for the tensor core
                 }
-                if (defer && have) {
+                if (early) {
                     do_layer0(nsg[gi], j0, nobs, upre, have_pre);
                     PROF_MARK(1);  // layer 0
                 }
@@ -624,12 +626,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                             PROF_MARK(7);  // finalize
                         }
                     }
-                    if (have) {
-                        if (chunk == 0 || p.C > 1) {  // (the scores of the previous chunk used sBase as scratch)
-                            do_base(th, chunk == 0, step_of(it), step_of(it + 1));
-                            compute_bar();
-                            PROF_MARK(0);  // per-sample layer-0 part
-                        }
+                    if (have && !early) {  // first chunk of an item: theta comes from the tail above
+                        do_base(th, true, step_of(it + 1));
+                        compute_bar();
+                        PROF_MARK(0);  // per-sample layer-0 part
                         do_layer0(nsg[gi], j0, nobs, upre, false);
                         PROF_MARK(1);  // layer 0
                     }
@@ -674,6 +674,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                         PROF_MARK(4);  // epilogues
                     }
                 }
+                if (!defer && have && chunk + 1 < p.C) {  // next pass = next chunk of this item: the scores used sBase as scratch
+                    do_base(th, false, 0);
+                    compute_bar();
+                    PROF_MARK(0);
+                }
                 if (defer) {
                     if (prev) {
                         do_sums(nsg[pgi], 0, pnobs, true);
@@ -687,7 +692,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                         PROF_MARK(6);
                     }
                     if (ps + 1 < total_p) {
-                        do_base(sTheta + (gi ^ 1) * TC_SG_MAX * MMAX, true, step_of(it + 1), step_of(it + 2));
+                        do_base(sTheta + (gi ^ 1) * TC_SG_MAX * MMAX, true, step_of(it + 2));
                         compute_bar();
                         PROF_MARK(0);
                     }
