@@ -74,12 +74,13 @@ struct Tiling {
 static bool tc_eligible(const D4sNet* net, const D4sProblem* pb) {
     // plain Linear/ReLU nets only: the toy output head (tanh / analytic affine part) runs on the SIMT path
     return g_opt_path != 1 && pb->cov_mode == D4S_COV_GAUSS && !pb->paired && net->dev.L >= 3 && net->dev.emb_L == 0 &&
-           net->dev.out_act == 0 && net->dev.out_scale == 1.f && pb->obs_raw == nullptr;
+           net->dev.out_act == 0 && net->dev.out_scale == 1.f && pb->obs_raw == nullptr && pb->ctx_samples == 0;
 }
 
 static bool jac_tc_eligible(const D4sNet* net, const D4sProblem* pb) {
     return g_opt_path != 1 && g_opt_jac_tc != 0 && pb->cov_mode == D4S_COV_JAC && !pb->paired && net->dev.L >= 3 && net->dev.emb_L == 0 &&
-           net->dev.out_act == 0 && net->dev.out_scale == 1.f && pb->obs_raw == nullptr && net->dev.m <= 5;
+           net->dev.out_act == 0 && net->dev.out_scale == 1.f && pb->obs_raw == nullptr && net->dev.m <= 5 &&
+           pb->ctx_samples == 0;
 }
 
 // Units (sample, chunk of OC observations) packed UT per tile of PT pairs: pick the chunking that wastes the fewest
@@ -159,6 +160,9 @@ static int check_problem(const D4sNet* net, const D4sProblem* pb) {
     if (pb->prior_kind == D4S_PRIOR_UNIFORM && (!pb->prior_low || !pb->prior_high))
         return fail(D4S_ERR_ARG, "uniform prior needs prior_low/prior_high");
     if (!pb->workspace) return fail(D4S_ERR_ARG, "workspace is null");
+    if (pb->ctx_samples < 0 || (pb->ctx_samples > 0 && (pb->n_samples % pb->ctx_samples != 0 || pb->paired)))
+        return fail(D4S_ERR_ARG, "batched contexts: n_samples must be a multiple of ctx_samples (and not paired)");
+    if (pb->ctx_qsum && pb->ctx_samples <= 0) return fail(D4S_ERR_ARG, "ctx_qsum needs ctx_samples > 0");
     return D4S_OK;
 }
 
@@ -487,6 +491,7 @@ static int score_partials_impl(const D4sNet* net, const D4sProblem* pb, const D4
     p.obs_prec = pb->obs_prec;
     p.sched = st->sched;
     p.obs_weight = pb->obs_weight;
+    p.ctx_samples = pb->ctx_samples;
     p.affine = st->affine;
     p.obs_raw = pb->obs_raw;
     p.d = pb->x_dim;
@@ -535,6 +540,8 @@ static int finalize_impl(const D4sNet* net, const D4sProblem* pb, const D4sStep*
     p.clip_hi = pb->clip_hi;
     p.theta = theta;
     p.score_out = score_out;
+    p.ctx_samples = pb->ctx_samples;
+    p.ctx_qsum = pb->ctx_qsum;
     cudaError_t e = launch_finalize(p, stream);
     if (e != cudaSuccess) return cuda_fail(e, "finalize kernel launch");
     ++g_launches;

@@ -61,6 +61,7 @@ struct ScoreParams {
     const float* obs_raw;    // [n][d] raw observations (read with `affine`)
     int d;
     const float* obs_weight; // optional [n] weights of the observations in the sums (classifier-free guidance)
+    int ctx_samples;         // batched contexts: samples [c S, (c+1) S) see observations [c n, (c+1) n); 0 = one context
     float* part;             // [N][C][W]
     float* scores_out;       // optional [N][n][m]
     float* prec_out;         // optional JAC [N][n][m][m]
@@ -81,6 +82,8 @@ struct FinalizeParams {
     float clip_lo, clip_hi;
     float* theta;      // [N][m] in/out
     float* score_out;  // optional [N][m]
+    int ctx_samples;          // batched contexts (see ScoreParams)
+    const float* ctx_qsum;    // [N / ctx_samples][m][m] sum_j inv(Sigma_cj), added to the Lambda base of the step; or NULL
 };
 
 // fused tcgen05 trajectory kernel (d4s_traj_tc.cu)

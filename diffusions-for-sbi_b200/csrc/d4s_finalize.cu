@@ -21,7 +21,8 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalizeParams p) {
     if (i >= p.N) return;
     finalize_sample<M>(p, p.part + (size_t)i * p.C * p.W, p.theta + (size_t)i * M,
                        p.score_out ? p.score_out + (size_t)i * M : nullptr,
-                       p.noise ? p.noise + (size_t)i * M : nullptr, p.sample_offset + i);
+                       p.noise ? p.noise + (size_t)i * M : nullptr, p.sample_offset + i, nullptr,
+                       (p.ctx_qsum && p.ctx_samples > 0) ? p.ctx_qsum + (size_t)(i / p.ctx_samples) * M * M : nullptr);
 }
 
 cudaError_t launch_finalize(const FinalizeParams& p, cudaStream_t stream) {

@@ -75,10 +75,11 @@ __device__ __forceinline__ void uniform_prior_terms(double th, double lo, double
 //   score_out : optional [M]
 //   noise     : optional injected z[M]
 //   pre_prior : optional [2][M] doubles {s0[k]}, {jac[k]} of the uniform prior, evaluated by other threads
+//   ctx_qsum  : optional [M][M] observation part of Lambda of this sample's context (batched contexts)
 template <int M>
 __device__ __forceinline__ void finalize_sample(const FinalizeParams& p, const float* part, float* theta_io,
                                                 float* score_out, const float* noise, long long global_sample,
-                                                const double* pre_prior = nullptr) {
+                                                const double* pre_prior = nullptr, const float* ctx_qsum = nullptr) {
     constexpr int WG = 2 * M, WJ = M + M * M;
     const int combine = (int)p.sched[D4S_S_COMBINE];
     const double aos2 = (double)p.sched[D4S_S_A_OVER_S2];
@@ -98,7 +99,8 @@ __device__ __forceinline__ void finalize_sample(const FinalizeParams& p, const f
 #pragma unroll
         for (int r = 0; r < M; ++r)
 #pragma unroll
-            for (int c = 0; c < M; ++c) Lam[r][c] = (double)p.mats[r * M + c];
+            for (int c = 0; c < M; ++c)  // batched contexts: + sum_j inv(Sigma_cj) of the sample's context
+                Lam[r][c] = (double)p.mats[r * M + c] + (ctx_qsum ? (double)ctx_qsum[r * M + c] : 0.0);
     }
     const float* pp = part;
     if (!p.jac) {

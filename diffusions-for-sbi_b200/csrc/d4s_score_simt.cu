@@ -197,7 +197,9 @@ __global__ void __launch_bounds__(NT, 2) score_simt_kernel(const ScoreParams p) 
         sPair[r] = pair;
         if (r < p.P) {
             sSamp[r] = si;
-            sObs[r] = p.paired ? min(i0 + si, p.n - 1) : min(j0 + oj, p.n - 1);
+            // batched contexts: the sample's context owns observations [c n, (c + 1) n)
+            const int ctx0 = p.ctx_samples > 0 ? (min(i0 + si, p.N - 1) / p.ctx_samples) * p.n : 0;
+            sObs[r] = p.paired ? min(i0 + si, p.n - 1) : ctx0 + min(j0 + oj, p.n - 1);
         }
     }
     for (int e = tid; e < p.SG * m; e += NT) {
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(NT, 2) score_simt_kernel(const ScoreParams p) 
                 sDact[r * MMAX + o] = dact;
                 if (p.scores_out) {
                     const size_t gi = (size_t)(i0 + sSamp[pr]);
-                    const size_t gj = p.paired ? 0 : (size_t)sObs[pr];
+                    const size_t gj = p.paired ? 0 : (size_t)(p.ctx_samples > 0 ? sObs[pr] % p.n : sObs[pr]);
                     const size_t nn = p.paired ? 1 : (size_t)p.n;
                     p.scores_out[(gi * nn + gj) * m + o] = sc;
                 }
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(NT, 2) score_simt_kernel(const ScoreParams p) 
             float* po = nullptr;
             if (p.prec_out) {
                 const size_t gi = (size_t)(i0 + sSamp[r]);
-                const size_t gj = p.paired ? 0 : (size_t)sObs[r];
+                const size_t gj = p.paired ? 0 : (size_t)(p.ctx_samples > 0 ? sObs[r] % p.n : sObs[r]);
                 const size_t nn = p.paired ? 1 : (size_t)p.n;
                 po = p.prec_out + (gi * nn + gj) * m * m;
             }
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(NT, 2) score_simt_kernel(const ScoreParams p) 
             float v;
             if (!p.jac) v = (c < m) ? sS[r * MMAX + c] : sQS[r * MMAX + (c - m)];
             else v = sQS[r * W + c];
-            if (p.obs_weight) v *= __ldg(p.obs_weight + sObs[r]);
+            if (p.obs_weight) v *= __ldg(p.obs_weight + (p.ctx_samples > 0 ? sObs[r] % p.n : sObs[r]));
             acc += v;
         }
         if (p.part) p.part[((size_t)(i0 + si) * p.C + chunk) * W + c] = acc;

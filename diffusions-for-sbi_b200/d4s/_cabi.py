@@ -13,7 +13,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libd4s.so")
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 MAX_LAYERS = 8
 MAX_THETA = 10
 MAX_WIDTH = 256
@@ -76,8 +76,9 @@ class Problem(C.Structure):
         ("workspace_floats", C.c_int64),
         ("obs_raw", C.c_void_p),
         ("x_dim", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("ctx_samples", C.c_int32),
         ("obs_weight", C.c_void_p),
+        ("ctx_qsum", C.c_void_p),
     ]
 
 

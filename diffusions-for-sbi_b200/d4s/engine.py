@@ -393,9 +393,13 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
                 prior: PriorSpec, cov_mode: str, dist_cov_est: Optional[torch.Tensor], paired: bool = False,
                 n_sizes: Optional[torch.Tensor] = None, clip=(None, None), seed: int = 0, sample_offset: int = 0,
                 weighted: bool = True, obs_slice: Optional[slice] = None, obs_chunk: int = 0,
-                coef: Optional[dict] = None, cfg: Optional[dict] = None) -> TallSetup:
+                coef: Optional[dict] = None, cfg: Optional[dict] = None, contexts: int = 0) -> TallSetup:
     """`obs_slice` restricts the kernels to a shard of the observations (observation sharding over ranks):
-    (1-n) and Lambda still use the total n, the partial sums are all-reduced by the caller."""
+    (1-n) and Lambda still use the total n, the partial sums are all-reduced by the caller.
+
+    `contexts = B > 0`: B independent tall problems in one launch (replaces `vmap(sampler)` over calibration sets,
+    jrnnm_posterior_estimation.py:286-294).  `x` is [B * n, d] and `dist_cov_est` [B * n, m, m], context-major;
+    samples [c S, (c+1) S) with S = n_samples / B belong to context c."""
     lib = abi.require_cuda()
     if not x.is_cuda:
         raise abi.D4sError("d4s: observations must live on a CUDA device (no CPU fallback)")
@@ -407,9 +411,15 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
     cov_jac = cov_mode == "JAC"
     x2 = x if x.ndim > 1 else x[None]
     n_total = x2.shape[0]
+    if contexts:
+        if paired or cfg is not None or obs_slice is not None or n_sizes is not None:
+            raise NotImplementedError("batched contexts with paired / classifier-free guidance / sharded / PF_NSE inputs")
+        if x2.shape[0] % contexts or n_samples % contexts:
+            raise ValueError("batched contexts: x must be [B * n, d] and n_samples a multiple of B")
+        n_total = x2.shape[0] // contexts  # observations of ONE context: the n of (1 - n) and of Lambda
     if paired:
         weighted = False
-    sum_q = q_dev = None
+    sum_q = q_dev = ctx_qsum = None
     # classifier-free guidance (nse.py:598-625, 532-538): the prior score/precision come from the net itself at x = 0
     # (PF_NSE: empty set, n = 0).  That is the tall score with one more pseudo-observation of weight (1 - n).
     w64 = None
@@ -428,12 +438,17 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
             qp = torch.linalg.inv(cfg["prior_cov"].detach().to("cpu", torch.float64).reshape(1, m, m))
             q64 = torch.cat((q64, qp))
             sum_q = (w64[:, None, None] * q64).sum(dim=0)
+        elif contexts:  # per-context sum_j inv(Sigma_cj) goes to the device; the step matrices carry no observation term
+            ctx_qsum = q64.reshape(contexts, n_total, m, m).sum(dim=1)
+            sum_q = torch.zeros(m, m, dtype=torch.float64)
         else:
             sum_q = q64.sum(dim=0)
     t = t.detach().to("cpu").reshape(-1)
     sa = _scalar64(nse.alpha, t.to(torch.float64)).sqrt()
     # branch of nse.py:627-654 per step; it only depends on sqrt(alpha) > 0.5, so two evaluations cover every step
     c_hi, c_lo = (combine_mode(prior, cov_jac, n_total, v, weighted) for v in (1.0, 0.0))
+    if contexts:  # Lambda differs from context to context: no shared inverse, every weighted step solves per sample
+        c_hi, c_lo = (abi.COMBINE_PER_SAMPLE if c == abi.COMBINE_SHARED else c for c in (c_hi, c_lo))
     comb = torch.where(sa > 0.5, c_hi, c_lo).tolist()
     if cfg is not None and weighted:  # nse.py:622-625: always the weighted solve
         comb = [abi.COMBINE_PER_SAMPLE if cov_jac else abi.COMBINE_SHARED] * len(comb)
@@ -461,7 +476,10 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
 
     prob = abi.Problem()
     prob.n_samples = n_samples
-    prob.n_obs = of.shape[0]
+    prob.n_obs = of.shape[0] // contexts if contexts else of.shape[0]
+    prob.ctx_samples = n_samples // contexts if contexts else 0
+    qsum_dev = None if ctx_qsum is None else _dev32(ctx_qsum, device)
+    prob.ctx_qsum = 0 if qsum_dev is None else qsum_dev.data_ptr()
     prob.theta_dim = m
     prob.cov_mode = abi.COV_JAC if cov_jac else abi.COV_GAUSS
     prob.prior_kind = prior.kind
@@ -502,7 +520,7 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
         prob.obs_raw = x_raw.data_ptr()
         prob.x_dim = x_raw.shape[-1]
     return TallSetup(pn, prob, _dev32(rows, device), _dev32(tf, device), _dev32(mats, device), step_modes,
-                     (of_dev, q_dev, low_dev, high_dev, ws, x_raw, w_dev), t.numel(), affine_dev)
+                     (of_dev, q_dev, low_dev, high_dev, ws, x_raw, w_dev, qsum_dev), t.numel(), affine_dev)
 
 
 def _stream(device) -> C.c_void_p:

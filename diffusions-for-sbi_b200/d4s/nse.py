@@ -183,6 +183,54 @@ class NSE(nn.Module):
             theta = engine.philox_normal(N, m, seed, -1, sample_offset, x.device)  # nse.py:261
         return engine.run_trajectory(setup, theta, z, _use_graph_default())
 
+    def ddim_contexts(self, shape: Size, x: Tensor, steps: int = 1000, eta: float = 1.0, verbose: bool = False,
+                      theta_clipping_range=(None, None), **kwargs) -> Tensor:
+        """`torch.func.vmap(lambda x_c, cov_c: self.ddim(shape, x_c, ..., dist_cov_est=cov_c))(x, dist_cov_est)` as ONE
+        trajectory launch (the custom kernels have no vmap rule; jrnnm_posterior_estimation.py:286-294,
+        sbibm_posterior_estimation.py:306-314).
+
+        x: [B, n, d] (B independent contexts of n observations each) or [B, d] (one observation per context: the plain
+        single-observation posterior, i.e. the covariance pre-pass).  dist_cov_est: [B, n, m, m] for GAUSS.
+        Returns theta[B, shape[0], m].  Same keyword contract as `ddim`; `_noise` is (z0[B*S, m], z[steps, B*S, m])."""
+        self._require_cuda(x)
+        opts, noise, seed, sample_offset = self._split_kwargs(kwargs)
+        if opts["clf_free_guidance"] or opts["n_sizes"] is not None:
+            raise NotImplementedError("ddim_contexts: classifier-free guidance / PF_NSE subsets are not batched")
+        S, m = int(shape[0]), self.zeros.shape[0]
+        B = x.shape[0]
+        N = B * S
+        grid = engine.time_grid(steps)
+        t, t_prev = grid[:-1], grid[:-1].to(torch.float64) - 1.0 / steps
+        if seed is None:
+            seed = self._draw_seed()
+        if x.ndim == 2 or x.shape[1] == 1:  # one observation per context: plain score, row i pairs with context i // S
+            x_rows = x.reshape(B, -1).repeat_interleave(S, dim=0).contiguous()
+            setup = engine.build_setup(self, x_rows, N, t, t_prev, float(eta), engine.PriorSpec(abi.PRIOR_NONE),
+                                       opts["cov_mode"], None, paired=True, clip=theta_clipping_range, seed=seed,
+                                       sample_offset=sample_offset, weighted=False)
+        else:
+            n = x.shape[1]
+            prior = engine.prior_spec(opts["prior_type"], opts["prior"], opts["prior_score_fn"], m)
+            cov = opts["dist_cov_est"]
+            if cov is not None:
+                cov = cov.reshape(B * n, m, m)
+            setup = engine.build_setup(self, x.reshape(B * n, -1), N, t, t_prev, float(eta), prior, opts["cov_mode"], cov,
+                                       clip=theta_clipping_range, seed=seed, sample_offset=sample_offset, contexts=B)
+        if noise is not None:
+            z0, z = noise
+            theta = z0.to(x.device, torch.float32).contiguous().clone()
+        else:
+            z = None
+            theta = engine.philox_normal(N, m, seed, -1, sample_offset, x.device)
+        return engine.run_trajectory(setup, theta, z, _use_graph_default()).reshape(B, S, m)
+
+    def estimate_dist_cov(self, x: Tensor, nsamples: int = 1000, steps: int = 100, eta: float = 0.5, **kwargs) -> Tensor:
+        """Covariance pre-pass of the GAUSS mode (sbibm_posterior_estimation.py:306-314): `nsamples` draws from every
+        single-observation posterior p(theta | x_j) in one launch, then their covariance.  x: [n, d]; returns [n, m, m]."""
+        samples = self.ddim_contexts((nsamples,), x, steps=steps, eta=eta, **kwargs)  # [n, nsamples, m]
+        c = samples - samples.mean(dim=1, keepdim=True)
+        return c.transpose(1, 2) @ c / (nsamples - 1)  # == vmap(lambda s: torch.cov(s.mT))
+
     def ddim_step(self, theta: Tensor, x: Tensor, t: Tensor, score_fun: Callable[[Tensor, Tensor, Tensor], Tensor],
                   dt: float, eta: float, **kwargs) -> Tensor:
         """One DDIM step with a caller-supplied score function (nse.py:269-299); the update runs in kernel 4."""

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D4S_ABI_VERSION 11
+#define D4S_ABI_VERSION 12
 
 #define D4S_OK 0
 #define D4S_ERR_ARG -1      /* bad argument / unsupported shape */
@@ -124,10 +124,15 @@ typedef struct {
     int64_t workspace_floats;
     const float* obs_raw;    /* [n_obs, x_dim] raw observations, only read when D4sStep.affine != NULL */
     int32_t x_dim;
-    int32_t reserved0;
+    int32_t ctx_samples;     /* 0: every sample sees all n_obs observations.  S > 0 (batched contexts, replaces
+                                vmap(sampler) over calibration sets, jrnnm_posterior_estimation.py:286-294): samples
+                                [c S, (c+1) S) belong to context c and see observations [c n_obs, (c+1) n_obs) of
+                                obs_feat / obs_prec / obs_raw (n_samples must be a multiple of S) */
     const float* obs_weight; /* NULL (all 1), or [n_obs] weights of the observations in every sum over j.  Classifier-free
                                 guidance (nse.py:598-625, 532-538) is the tall score with one extra pseudo-observation
                                 x = 0 (the net's own prior score) of weight (1 - n). */
+    const float* ctx_qsum;   /* batched contexts, GAUSS: [n_samples / ctx_samples, m, m] sum_j inv(Sigma_cj) of every context,
+                                added to the step's Lambda base (which then carries no observation term); NULL otherwise */
 } D4sProblem;
 
 /* Per-step inputs. */

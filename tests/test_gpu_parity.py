@@ -384,6 +384,63 @@ def test_jac_tc_partial_sums(shape, dev):
     assert e_simt < 1e-5 and e_tc < 1e-4 and e_all < 1e-4
 
 
+@pytest.mark.parametrize("pkind", ["uniform", "gaussian"])
+@pytest.mark.parametrize("mode", ["GAUSS", "JAC"])
+def test_ddim_contexts_vs_oracle(pkind, mode, dev):
+    """Batched contexts: B independent tall problems in one launch == the reference's
+    vmap(sampler) over calibration sets (jrnnm_posterior_estimation.py:286-294), checked context by context against the
+    oracle under replayed noise; also equal to B separate `ddim` calls."""
+    from d4s_helpers import nse_from_oracle
+    m, d, B, n, S, steps = 3, 4, 5, 6, 7, 8
+    rng = np.random.default_rng(5)
+    onet = orc.random_net(rng, m, d, hidden=(64, 96))
+    nse = nse_from_oracle(onet, dev)
+    x = 0.5 * rng.standard_normal((B, n, d))
+    a = 0.2 * rng.standard_normal((B, n, m, m))
+    cov = a @ a.transpose(0, 1, 3, 2) + 0.05 * np.eye(m)
+    if pkind == "uniform":
+        oprior = orc.UniformPrior(np.full(m, -3.46), np.full(m, 3.46))
+    else:
+        b = 0.3 * rng.standard_normal((m, m))
+        oprior = orc.GaussianPrior(0.1 * rng.standard_normal(m), b @ b.T + np.eye(m))
+    prior, fn = _d4s_prior(oprior, nse, dev)
+    z0, z = rng.standard_normal((B * S, m)), rng.standard_normal((steps, B * S, m))
+    kw = dict(steps=steps, eta=0.8, prior=prior, prior_type=pkind, prior_score_fn=fn, cov_mode=mode)
+    out = nse.ddim_contexts((S,), _t(x, dev), dist_cov_est=_t(cov, dev),
+                            _noise=(torch.as_tensor(z0, dtype=torch.float32), torch.as_tensor(z, dtype=torch.float32)), **kw)
+    assert out.shape == (B, S, m)
+    worst = 0.0
+    for c in range(B):
+        sl = slice(c * S, (c + 1) * S)
+        ref = orc.ddim(onet, x[c], z0[sl], z[:, sl], steps, 0.8, oprior, cov[c], mode, pkind)
+        scale = max(1.0, float(np.abs(ref).max()))  # a random-init net gives no contraction: relative tolerance
+        one = nse.ddim((S,), _t(x[c], dev), dist_cov_est=_t(cov[c], dev),
+                       _noise=(torch.as_tensor(z0[sl], dtype=torch.float32), torch.as_tensor(z[:, sl], dtype=torch.float32)),
+                       **kw)
+        worst = max(worst, float(np.abs(out[c].cpu().numpy() - ref).max()) / scale)
+        assert float((out[c] - one).abs().max()) < 1e-4 * scale  # same kernels, per-sample instead of shared Lambda solve
+    print(f"ddim_contexts {pkind} {mode}: max |theta - oracle| / scale = {worst:.2e}")
+    assert worst < TRAJ_TOL
+
+
+def test_estimate_dist_cov_prepass(dev):
+    """sbibm_posterior_estimation.py:306-314: vmap(ddim) over the observations + torch.cov, as one launch."""
+    from d4s_helpers import nse_from_oracle
+    m, d, n, S, steps = 3, 4, 9, 300, 10
+    rng = np.random.default_rng(6)
+    onet = orc.random_net(rng, m, d, hidden=(64, 64))
+    nse = nse_from_oracle(onet, dev)
+    x = 0.5 * rng.standard_normal((n, d))
+    z0, z = rng.standard_normal((n * S, m)), rng.standard_normal((steps, n * S, m))
+    noise = (torch.as_tensor(z0, dtype=torch.float32), torch.as_tensor(z, dtype=torch.float32))
+    cov = nse.estimate_dist_cov(_t(x, dev), nsamples=S, steps=steps, eta=0.5, _noise=noise)
+    assert cov.shape == (n, m, m)
+    for j in (0, n - 1):
+        sl = slice(j * S, (j + 1) * S)
+        ref = orc.ddim_single(onet, x[j], z0[sl], z[:, sl], steps, 0.5)
+        assert np.abs(cov[j].cpu().numpy() - np.cov(ref.T)).max() < 1e-3 * max(1.0, np.abs(np.cov(ref.T)).max())
+
+
 def test_errors_are_loud(dev):
     import d4s
     from d4s import _cabi as abi
