@@ -8,6 +8,9 @@
 
 #include <cuda_fp16.h>
 
+#include <algorithm>
+#include <cmath>
+
 #include "d4s_common.cuh"
 
 namespace d4s {
@@ -251,9 +254,25 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
     const size_t off_WoutT = reserve((size_t)m * Hp[L - 2]);
     for (int o = 0; o < m; ++o)
         for (int k = 0; k < Kl; ++k) h[off_WoutT + (size_t)o * Hp[L - 2] + k] = d->weight[L - 1][(size_t)o * Kl + k];
-    std::vector<size_t> off_img(L, 0), off_img16(L, 0);
+    std::vector<size_t> off_img(L, 0), off_img16(L, 0), off_b16(L, 0);
+    std::vector<int> sw16(L, 0);
     for (int l = 1; l <= L - 2; ++l) {
         const int K = d->dims[l], Ho = d->dims[l + 1], Kp = Hp[l - 1], Np = Hp[l];
+        // fp16x3 image: weights scaled by a power of two so that max |w'| lies in [2^9, 2^10): the lo parts (2^-12 w')
+        // then stay fp16 normals for every weight within 2^-6 of the largest one
+        float wmax = 0.f;
+        for (size_t e = 0; e < (size_t)K * Ho; ++e) wmax = std::max(wmax, std::fabs(d->weight[l][e]));
+        int sw = 0;
+        if (wmax > 0.f) {
+            int ex;
+            std::frexp(wmax, &ex);  // wmax = f 2^ex, f in [0.5, 1)
+            sw = 10 - ex;
+        }
+        sw = std::max(0, std::min(sw, 20));
+        sw16[l] = sw;
+        const float wsc = std::ldexp(1.f, sw), bsc = std::ldexp(1.f, sw + D4S_ACT_SHIFT16);
+        off_b16[l] = reserve(Np);
+        for (int o = 0; o < Ho; ++o) h[off_b16[l] + o] = d->bias[l][o] * bsc;
         const size_t bytes = (size_t)(Kp / 16) * Np * 64;
         off_img[l] = reserve(bytes / 4);
         off_img16[l] = reserve(bytes / 4);
@@ -271,9 +290,10 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
                         const size_t idx = (size_t)hf * Np * 8 + (size_t)nn * 8 + e;
                         img[base + idx] = hi;
                         img[base + (size_t)Np * 16 + idx] = lo;
-                        const __half h16 = __float2half_rn(w);  // fp16 hi / lo: 22 significant bits (JAC kernel)
+                        const float ws = w * wsc;
+                        const __half h16 = __float2half_rn(ws);  // fp16 hi / lo: 22 significant bits (JAC kernel)
                         img16[base + idx] = __half_as_ushort(h16);
-                        img16[base + (size_t)Np * 16 + idx] = __half_as_ushort(__float2half_rn(w - __half2float(h16)));
+                        img16[base + (size_t)Np * 16 + idx] = __half_as_ushort(__float2half_rn(ws - __half2float(h16)));
                     }
     }
 
@@ -319,7 +339,11 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
         nd.emb_bias[l] = net->blob + off_eb[l];
     }
     for (int l = 1; l <= L - 2; ++l) nd.wimg[l] = reinterpret_cast<const uint8_t*>(net->blob + off_img[l]);
-    for (int l = 1; l <= L - 2; ++l) nd.wimg16[l] = reinterpret_cast<const uint8_t*>(net->blob + off_img16[l]);
+    for (int l = 1; l <= L - 2; ++l) {
+        nd.wimg16[l] = reinterpret_cast<const uint8_t*>(net->blob + off_img16[l]);
+        nd.sw16[l] = sw16[l];
+        nd.bias16[l] = net->blob + off_b16[l];
+    }
     *out = net;
     return D4S_OK;
 }

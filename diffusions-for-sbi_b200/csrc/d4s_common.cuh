@@ -16,6 +16,7 @@ constexpr int ASTR = 68;    // activation buffer row stride: act[k][ASTR] (k-maj
 constexpr int KC = 8;       // weight k-chunk staged per pipeline stage
 constexpr int HMAX = D4S_MAX_WIDTH;
 constexpr int MMAX = D4S_MAX_THETA;
+constexpr int D4S_ACT_SHIFT16 = 4;  // fp16x3 operands hold 2^4 x activation (d4s_jac_tc.cu)
 
 // Device view of the packed network.  Hidden widths are zero-padded to 64/128/256 so that padded
 // units produce relu(0) = 0 and contribute nothing downstream.
@@ -38,7 +39,9 @@ struct NetDev {
     const float* emb_Wt[D4S_MAX_LAYERS];    // [in][out]
     const float* emb_bias[D4S_MAX_LAYERS];  // [out]
     const uint8_t* wimg[D4S_MAX_LAYERS];  // l = 1 .. L-2: bf16 hi/lo UMMA images, [Hp[l-1]/16][hi | lo][2][Hp[l]][8]
-    const uint8_t* wimg16[D4S_MAX_LAYERS];  // same layout, fp16 hi / lo (JAC kernel: fp16x3 split, ~fp32-exact products)
+    const uint8_t* wimg16[D4S_MAX_LAYERS];  // same layout, fp16 hi / lo of 2^sw16[l] W_l (JAC kernel: fp16x3 split)
+    int sw16[D4S_MAX_LAYERS];               // power-of-two weight scale that keeps the fp16 lo parts out of the subnormals
+    const float* bias16[D4S_MAX_LAYERS];    // 2^(D4S_ACT_SHIFT16 + sw16[l]) bias_l: the JAC kernel's accumulators are scaled
 };
 
 

@@ -28,6 +28,11 @@ constexpr int JT_NSTG = 3;                    // weight ring stages
 constexpr int JT_MMAX = 5;                    // largest theta_dim of this kernel
 constexpr int JT_PMAX = 32;                   // pairs per tile <= 4 * 8
 constexpr int JT_WMAX = JT_MMAX + JT_MMAX * JT_MMAX;
+// fp16 hi / lo parts lose precision below 2^-14 (subnormals: absolute quantum 2^-24), and the lo part of v is ~2^-12 v.
+// So operands are kept in a scaled domain: activations x 2^4, weights x 2^sw16[l] (max |w'| in [2^9, 2^10), chosen on
+// the host), accumulators therefore x 2^(4 + sw16[l]); biases are pre-scaled, the ReLU indicator is scale invariant
+// and carries the 2^-sw16[l] that brings the next operand back to 2^4 x activation.  All factors are powers of two.
+constexpr float ACT_SC = float(1 << D4S_ACT_SHIFT16);
 
 constexpr int JOFF_AHI = 0;
 constexpr int JOFF_ALO = JOFF_AHI + TC_A_BYTES;
@@ -129,8 +134,9 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
     {
         const int Kout = net.Hp[L - 2];
         for (int e = tid; e < m * Kout; e += JT_THREADS) sWout[(e / Kout) * 256 + (e % Kout)] = __ldg(net.WoutT + e);
-        for (int e = tid; e < m * H0; e += JT_THREADS) sA[(e / H0) * 256 + (e % H0)] = __ldg(net.A + e);
-        for (int e = tid; e < H0; e += JT_THREADS) sTf[e] = __ldg(p.time_feat + e);
+        // the operands carry 2^4 x activation (ACT_SC), see the note at store_split8_f16: layer 0 is built in that scale
+        for (int e = tid; e < m * H0; e += JT_THREADS) sA[(e / H0) * 256 + (e % H0)] = ACT_SC * __ldg(net.A + e);
+        for (int e = tid; e < H0; e += JT_THREADS) sTf[e] = ACT_SC * __ldg(p.time_feat + e);
         if (tid < 8) sBout[tid] = (tid < m) ? __ldg(net.bout + tid) : 0.f;
         // fp16 hi / lo K-groups of the theta block (the layer-0 tangents are masked copies of them)
         for (int e = tid; e < m * (H0 / 8); e += JT_THREADS) {
@@ -138,7 +144,8 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int q2 = 0; q2 < 4; ++q2) {
-                const float x0 = __ldg(net.A + (size_t)k * H0 + 8 * kg + 2 * q2), x1 = __ldg(net.A + (size_t)k * H0 + 8 * kg + 2 * q2 + 1);
+                const float x0 = ACT_SC * __ldg(net.A + (size_t)k * H0 + 8 * kg + 2 * q2);
+                const float x1 = ACT_SC * __ldg(net.A + (size_t)k * H0 + 8 * kg + 2 * q2 + 1);
                 const __half2 h16 = __floats2half2_rn(x0, x1);
                 const float2 hf = __half22float2(h16);
                 const __half2 l16 = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
@@ -281,8 +288,10 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                         float z[8];
                         const float4 t0 = *reinterpret_cast<const float4*>(sTf + 8 * kg);
                         const float4 t1 = *reinterpret_cast<const float4*>(sTf + 8 * kg + 4);
-                        z[0] = u[jj][0].x + t0.x; z[1] = u[jj][0].y + t0.y; z[2] = u[jj][0].z + t0.z; z[3] = u[jj][0].w + t0.w;
-                        z[4] = u[jj][1].x + t1.x; z[5] = u[jj][1].y + t1.y; z[6] = u[jj][1].z + t1.z; z[7] = u[jj][1].w + t1.w;
+                        z[0] = fmaf(u[jj][0].x, ACT_SC, t0.x); z[1] = fmaf(u[jj][0].y, ACT_SC, t0.y);
+                        z[2] = fmaf(u[jj][0].z, ACT_SC, t0.z); z[3] = fmaf(u[jj][0].w, ACT_SC, t0.w);
+                        z[4] = fmaf(u[jj][1].x, ACT_SC, t1.x); z[5] = fmaf(u[jj][1].y, ACT_SC, t1.y);
+                        z[6] = fmaf(u[jj][1].z, ACT_SC, t1.z); z[7] = fmaf(u[jj][1].w, ACT_SC, t1.w);
 #pragma unroll
                         for (int k = 0; k < JT_MMAX; ++k) {
                             if (k < m) {
@@ -331,7 +340,8 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
             mbar_arrive(bar_a);
         };
         // one 16-column block of an accumulator row.  Primal: x = d + bias, a = relu(x).  Tangent: a = d * [x_primal > 0].
-        auto ld_act = [&](uint32_t dacc, int col0, const float* bias16, float (&a)[16]) {
+        // `hval` = what the indicator holds for an active unit: 2^-sw16[l] (operand of the next layer) or 1 (last layer).
+        auto ld_act = [&](uint32_t dacc, int col0, const float* bias16, float hval, float (&a)[16]) {
             uint32_t d[16];
             tc_ld16(dacc + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, d);
             float4 bb[4];
@@ -351,8 +361,8 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
                     *reinterpret_cast<float4*>(hslot + 4 * e) =
-                        make_float4(x[4 * e] > 0.f ? 1.f : 0.f, x[4 * e + 1] > 0.f ? 1.f : 0.f, x[4 * e + 2] > 0.f ? 1.f : 0.f,
-                                    x[4 * e + 3] > 0.f ? 1.f : 0.f);
+                        make_float4(x[4 * e] > 0.f ? hval : 0.f, x[4 * e + 1] > 0.f ? hval : 0.f, x[4 * e + 2] > 0.f ? hval : 0.f,
+                                    x[4 * e + 3] > 0.f ? hval : 0.f);
             }
             __syncwarp();
 #pragma unroll
@@ -369,14 +379,15 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
         auto do_last_epilogue = [&](uint32_t dacc) {
             const int Nn = net.Hp[L - 2];
             const int qcols = Nn >> 2, nblk = qcols / 16;
-            const float* bias_l = net.bias[L - 2] + cq * qcols;
+            const float* bias_l = net.bias16[L - 2] + cq * qcols;
+            const float uns = exp2f(-(float)(D4S_ACT_SHIFT16 + net.sw16[L - 2]));  // accumulator scale of the last hidden layer
             float po[JT_MMAX];
 #pragma unroll
             for (int o = 0; o < JT_MMAX; ++o) po[o] = 0.f;
             for (int cb = 0; cb < nblk; ++cb) {
                 const int col0 = cq * qcols + 16 * cb;
                 float a[16];
-                ld_act(dacc, col0, bias_l + 16 * cb, a);
+                ld_act(dacc, col0, bias_l + 16 * cb, 1.f, a);
 #pragma unroll
                 for (int e = 0; e < 16; e += 4) {
                     float4 w4[JT_MMAX];
@@ -404,8 +415,8 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
 #pragma unroll
                 for (int o = 0; o < JT_MMAX; ++o) {
                     if (o < m) {
-                        const float v = (po[o] + sRed[row * JT_MMAX + o]) +
-                                        (sRed[(TC_M + row) * JT_MMAX + o] + sRed[(2 * TC_M + row) * JT_MMAX + o]);
+                        const float v = uns * ((po[o] + sRed[row * JT_MMAX + o]) +
+                                               (sRed[(TC_M + row) * JT_MMAX + o] + sRed[(2 * TC_M + row) * JT_MMAX + o]));
                         // primal: score = -(eps + b) / sigma (nse.py:166); tangent k: d eps_o / d theta_k
                         sOut[row * m + o] = (rc == 0) ? -(v + sBout[o]) * inv_sigma : v;
                     }
@@ -470,7 +481,8 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                 for (int l = 1; l < Lh; ++l) {  // hidden layers that feed another tensor-core layer
                     const int Nn = net.Hp[l];
                     const int qcols = Nn >> 2, nblk = qcols / 16;
-                    const float* bias_l = net.bias[l] + cq * qcols;
+                    const float* bias_l = net.bias16[l] + cq * qcols;
+                    const float hval = exp2f(-(float)net.sw16[l]);
                     const uint32_t dacc = tmem_d + ((d_cnt & 1u) ? 256u : 0u);
                     mbar_wait(bar_d, d_cnt & 1u, p.error_flag);
                     ++d_cnt;
@@ -478,7 +490,7 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                     for (int cb = 0; cb < nblk; ++cb) {
                         const int col0 = cq * qcols + 16 * cb;
                         float a[16];
-                        ld_act(dacc, col0, bias_l + 16 * cb, a);
+                        ld_act(dacc, col0, bias_l + 16 * cb, hval, a);
 #pragma unroll
                         for (int k8 = 0; k8 < 2; ++k8) {
                             float v[8];
