@@ -517,11 +517,14 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
 }
 
 cudaError_t launch_jac_tc(const JacTcParams& p, int n_ctas, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
+    // the attribute is per device: keep one flag per device ordinal (a process may drive several GPUs)
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(jac_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JT_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     jac_tc_kernel<<<n_ctas, JT_THREADS, JT_SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();

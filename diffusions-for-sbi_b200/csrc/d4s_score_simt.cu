@@ -456,12 +456,14 @@ size_t score_simt_smem_bytes() {
 }
 
 cudaError_t launch_score_simt(const ScoreParams& p, int tiles, cudaStream_t stream) {
-    static bool configured = false;
+    static bool configured[64] = {};  // the attribute is per device
     const size_t smem = score_simt_smem_bytes();
-    if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(score_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     score_simt_kernel<<<tiles, NT, smem, stream>>>(p);
     return cudaGetLastError();

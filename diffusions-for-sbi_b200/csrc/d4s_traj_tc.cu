@@ -717,11 +717,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
 }
 
 cudaError_t launch_traj_tc(const TrajParams& p, int n_ctas, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
+    // the attribute is per device: keep one flag per device ordinal (a process may drive several GPUs)
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(traj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     traj_tc_kernel<<<n_ctas, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
