@@ -618,6 +618,26 @@ static int enqueue_steps(const D4sNet* net, const D4sProblem* pb0, int steps, co
     const size_t NM = (size_t)pb->n_samples * net->dev.m;
     const int nm = net->dev.m;
     for (int k = 0; k < steps; ++k) {
+        // A run of consecutive plain-sum steps of a JAC trajectory (outside the alpha-gate of nse.py:643 the Jacobian is
+        // never used) goes through the fused tcgen05 trajectory kernel in ONE launch, like a GAUSS trajectory.
+        if (step_mode && step_mode[k] == D4S_COV_GAUSS && !affine) {
+            int e = k;
+            while (e < steps && step_mode[e] == D4S_COV_GAUSS) ++e;
+            pb->cov_mode = D4S_COV_GAUSS;
+            if (e - k >= 2 && tc_eligible(net, pb)) {
+                TrajParams tp;
+                int ctas = 0;
+                int rc = fill_traj_params(net, pb, sched, tf, mats, noise, theta, &tp, &ctas, stream);
+                if (rc) return rc;
+                tp.step_begin = k;
+                tp.step_end = e;
+                cudaError_t ce = launch_traj_tc(tp, ctas, stream);
+                if (ce != cudaSuccess) return cuda_fail(ce, "tcgen05 trajectory kernel launch (plain-sum run)");
+                ++g_launches;
+                k = e - 1;
+                continue;
+            }
+        }
         D4sStep st;
         st.sched = sched + (size_t)k * D4S_SCHED_STRIDE;
         st.time_feat = tf + (size_t)k * H1;

@@ -441,6 +441,40 @@ def test_estimate_dist_cov_prepass(dev):
         assert np.abs(cov[j].cpu().numpy() - np.cov(ref.T)).max() < 1e-3 * max(1.0, np.abs(np.cov(ref.T)).max())
 
 
+def test_jac_trajectory_fuses_plain_sum_steps(dev):
+    """A JAC trajectory only needs the Jacobian inside the alpha-gate (nse.py:643).  The run of plain-sum steps before it
+    goes through the fused tcgen05 trajectory kernel in one launch; the result must follow the per-step fp32 SIMT
+    kernels and the fp64 oracle under replayed noise."""
+    from d4s import _cabi as abi
+    from d4s import engine
+    from d4s_helpers import nse_from_oracle
+    m, d, n, N, steps = 4, 6, 9, 200, 10
+    onet, x, cov, theta, oprior = _problem(m, d, (128, 256), n, N, "uniform", seed=9)
+    nse = nse_from_oracle(onet, dev)
+    prior, fn = _d4s_prior(oprior, nse, dev)
+    rng = np.random.default_rng(2)
+    z0, z = rng.standard_normal((N, m)), rng.standard_normal((steps, N, m))
+    kw = dict(steps=steps, eta=0.8, prior=prior, prior_type="uniform", prior_score_fn=fn, cov_mode="JAC",
+              _noise=(torch.as_tensor(z0, dtype=torch.float32), torch.as_tensor(z, dtype=torch.float32)))
+    before = engine.launch_count()
+    out = nse.ddim((N,), _t(x, dev), **kw)
+    fused_launches = engine.launch_count() - before
+    abi.set_option("path", 1)
+    try:
+        before = engine.launch_count()
+        simt = nse.ddim((N,), _t(x, dev), **kw)
+        simt_launches = engine.launch_count() - before
+    finally:
+        abi.set_option("path", 0)
+    ref = orc.ddim(onet, x, z0, z, steps, 0.8, oprior, None, "JAC", "uniform")
+    scale = max(1.0, float(np.abs(ref).max()))
+    e_f, e_s = (float(np.abs(o.cpu().numpy() - ref).max()) / scale for o in (out, simt))
+    print(f"JAC trajectory: fused plain-sum run {fused_launches} launches (SIMT only: {simt_launches}); "
+          f"max rel err vs oracle fused {e_f:.2e}, SIMT {e_s:.2e}")
+    assert simt_launches == 2 * steps and fused_launches < simt_launches - 4  # steps 0..6 are outside the gate
+    assert e_f < TRAJ_TOL and e_s < TRAJ_TOL
+
+
 def test_errors_are_loud(dev):
     import d4s
     from d4s import _cabi as abi
