@@ -325,14 +325,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
         float tf_next = (tid < H0 && n_steps > 0) ? __ldg(p.time_feat + (size_t)p.step_begin * H0 + tid) : 0.f;
         // ---- phases shared by the two schedules (one group after the other / two groups interleaved) ----------------------
         // layer-0 per-sample part of an item: base[si][col] = time_feat[col] + sum_k A[k][col] theta[si][k]
-        float tf_cur = 0.f;
-        auto do_base = [&](const float* th, bool fresh, int next_step) {
+        auto do_base = [&](const float* th, bool fresh, int step, int next_step) {
             if (tid < H0) {
-                if (fresh) {  // (not fresh: a later observation chunk of the same step)
-                    tf_cur = tf_next;
+                float t0;
+                if (fresh) {
+                    t0 = tf_next;
                     tf_next = __ldg(p.time_feat + (size_t)next_step * H0 + tid);  // consumed one item later: latency hidden
+                } else {
+                    t0 = __ldg(p.time_feat + (size_t)step * H0 + tid);  // (later observation chunks of the same step)
                 }
-                const float t0 = tf_cur;
                 float ak[MMAX];  // column tid of the layer-0 theta block
 #pragma unroll
                 for (int k = 0; k < MMAX; ++k)
@@ -573,7 +574,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
             if (total > 0) bar_arrive(2, NB23);  // theta of item 0 is final: the helper warp may start on it
             auto step_of = [&](int item) { return (item < total) ? p.step_begin + (defer ? (item >> 1) : item) : p.step_begin; };
             if (defer && total > 0) {  // (later items: inside the previous item's last tensor-core wait)
-                do_base(sTheta, true, step_of(1));
+                do_base(sTheta, true, 0, step_of(1));
                 compute_bar();
             }
             for (int ps = 0; ps <= total_p; ++ps) {  // one extra iteration finishes the last pass
@@ -627,7 +628,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                         }
                     }
                     if (have && !early) {  // first chunk of an item: theta comes from the tail above
-                        do_base(th, true, step_of(it + 1));
+                        do_base(th, true, 0, step_of(it + 1));
                         compute_bar();
                         PROF_MARK(0);  // per-sample layer-0 part
                         do_layer0(nsg[gi], j0, nobs, upre, false);
@@ -675,7 +676,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                     }
                 }
                 if (!defer && have && chunk + 1 < p.C) {  // next pass = next chunk of this item: the scores used sBase as scratch
-                    do_base(th, false, 0);
+                    do_base(th, false, step_of(it), 0);
                     compute_bar();
                     PROF_MARK(0);
                 }
@@ -692,7 +693,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
                         PROF_MARK(6);
                     }
                     if (ps + 1 < total_p) {
-                        do_base(sTheta + (gi ^ 1) * TC_SG_MAX * MMAX, true, step_of(it + 2));
+                        do_base(sTheta + (gi ^ 1) * TC_SG_MAX * MMAX, true, 0, step_of(it + 2));
                         compute_bar();
                         PROF_MARK(0);
                     }

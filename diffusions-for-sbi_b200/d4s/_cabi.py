@@ -11,7 +11,7 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libd4s.so")
+LIB_PATH = os.environ.get("D4S_LIB_PATH") or os.path.join(HERE, "libd4s.so")  # (override: A/B builds of the kernels)
 
 ABI_VERSION = 12
 MAX_LAYERS = 8
