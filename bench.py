@@ -36,6 +36,10 @@ SHAPES = {  # BASELINE.json configs
     "lotka_volterra": dict(m=4, d=20, hidden=(256, 256, 256), prior="gaussian"),
     "sir": dict(m=2, d=10, hidden=(256, 256, 256), prior="gaussian"),
     "stress": dict(m=10, d=10, hidden=(256, 256, 256), prior="gaussian"),
+    # config 4: Jansen-Rit nets (theta / x embedding MLPs 64-64-64 -> 32, 32 time frequencies; probed from the shipped
+    # weights) and the PF_NSE partial factorisation (n_max = 3) on the SLCP shape
+    "jrnnm": dict(m=4, d=33, hidden=(128, 256, 128), prior="uniform", freqs=32, emb=(64, 64, 64, 32)),
+    "pf_slcp": dict(m=5, d=8, hidden=(256, 256, 256), prior="uniform", n_max=3),
 }
 
 
@@ -62,14 +66,23 @@ def workload(args):
     sh = SHAPES[args.task]
     m, d, n = sh["m"], sh["d"], args.n_obs
     rng = np.random.default_rng(0)
-    widths = [m + d + 6, *sh["hidden"], m]  # freqs = 3 (nse.py:27)
-    weights, biases = [], []
-    for a_, b_ in zip(widths[:-1], widths[1:]):  # nn.Linear default init: U(-1/sqrt(in), 1/sqrt(in))
-        k_ = 1.0 / np.sqrt(a_)
-        weights.append(rng.uniform(-k_, k_, size=(b_, a_)).astype(np.float32))
-        biases.append(rng.uniform(-k_, k_, size=(b_,)).astype(np.float32))
+    F, emb, n_max = sh.get("freqs", 3), sh.get("emb"), sh.get("n_max", 1)  # freqs = 3 by default (nse.py:27)
+
+    def init_mlp(widths):  # nn.Linear default init: U(-1/sqrt(in), 1/sqrt(in))
+        ws, bs = [], []
+        for a_, b_ in zip(widths[:-1], widths[1:]):
+            k_ = 1.0 / np.sqrt(a_)
+            ws.append(rng.uniform(-k_, k_, size=(b_, a_)).astype(np.float32))
+            bs.append(rng.uniform(-k_, k_, size=(b_,)).astype(np.float32))
+        return ws, bs
+
+    n_in = (emb[-1] if emb else m) + (emb[-1] if emb else d) + 2 * F + (n_max if n_max > 1 else 0)
+    weights, biases = init_mlp([n_in, *sh["hidden"], m])
+    emb_theta = init_mlp([m, *emb]) if emb else None
+    emb_x = init_mlp([d, *emb]) if emb else None
     x = np.random.default_rng(1).standard_normal((n, d)).astype(np.float32)
-    a = 0.2 * np.random.default_rng(2).standard_normal((n, m, m))
+    n_units = -(-n // n_max)  # observations, or PF_NSE subsets of n_max observations (pf_nse.py:41-60)
+    a = 0.2 * np.random.default_rng(2).standard_normal((n_units, m, m))
     cov = (a @ a.transpose(0, 2, 1) + 0.05 * np.eye(m)).astype(np.float32)
     if sh["prior"] == "uniform":
         prior = dict(low=np.full(m, -3.46, np.float32), high=np.full(m, 3.46, np.float32))
@@ -78,28 +91,43 @@ def workload(args):
     ddim_steps = args.ddim_steps or (1000 if args.cov_mode == "GAUSS" else 400)
     eta = 1.0 if ddim_steps == 1000 else 0.8 if ddim_steps == 400 else 0.5  # sbibm_posterior_estimation.py:330-334
     return dict(weights=weights, biases=biases, x=x, cov=cov, prior=prior, m=m, d=d, n=n, ddim_steps=ddim_steps,
-                eta=eta, prior_kind=sh["prior"], hidden=sh["hidden"])
+                eta=eta, prior_kind=sh["prior"], hidden=sh["hidden"], freqs=F, emb=emb, emb_theta=emb_theta, emb_x=emb_x,
+                n_max=n_max, n_in=n_in, n_units=n_units)
 
 
 def build_nse(w, dev):
     """d4s.NSE of the task's architecture holding the synthetic weights."""
     import torch
     import d4s
-    nse = d4s.NSE(w["m"], w["d"], freqs=3, hidden_features=list(w["hidden"]))
-    lin = [mod for mod in nse.net if isinstance(mod, torch.nn.Linear)]
-    with torch.no_grad():
-        for l, wt, b in zip(lin, w["weights"], w["biases"]):
-            l.weight.copy_(torch.as_tensor(wt))
-            l.bias.copy_(torch.as_tensor(b))
+    from d4s import nn as d4nn
+
+    def load(mlp, ws, bs):
+        lin = [mod for mod in mlp if isinstance(mod, torch.nn.Linear)]
+        assert len(lin) == len(ws)
+        with torch.no_grad():
+            for l, wt, b in zip(lin, ws, bs):
+                l.weight.copy_(torch.as_tensor(wt))
+                l.bias.copy_(torch.as_tensor(b))
+
+    kw = dict(freqs=w["freqs"], hidden_features=list(w["hidden"]))
+    if w["emb"]:
+        e = w["emb"]
+        kw["embedding_nn_theta"] = d4nn.MLP(w["m"], e[-1], hidden_features=list(e[:-1]))
+        kw["embedding_nn_x"] = d4nn.MLP(w["d"], e[-1], hidden_features=list(e[:-1]))
+        load(kw["embedding_nn_theta"], *w["emb_theta"])
+        load(kw["embedding_nn_x"], *w["emb_x"])
+    nse = d4s.PF_NSE(w["m"], w["d"], w["n_max"], **kw) if w["n_max"] > 1 else d4s.NSE(w["m"], w["d"], **kw)
+    load(nse.net, w["weights"], w["biases"])
     return nse.to(dev).eval()
 
 
 def oracle_objects(w):
     """The same net / prior as oracle objects -- used ONLY by the CPU-baseline legs."""
     from oracle import d4s_oracle as orc
-    onet = orc.OracleNet(w["m"], w["d"], (np.arange(1, 4) * np.pi).astype(np.float32),
-                         orc.OracleMLP([a.copy() for a in w["weights"]], [b.copy() for b in w["biases"]]),
-                         dtype=np.float32)
+    mlp = lambda wb: None if wb is None else orc.OracleMLP([a.copy() for a in wb[0]], [b.copy() for b in wb[1]])
+    onet = orc.OracleNet(w["m"], w["d"], (np.arange(1, w["freqs"] + 1) * np.pi).astype(np.float32),
+                         mlp((w["weights"], w["biases"])), mlp(w["emb_theta"]), mlp(w["emb_x"]), n_max=w["n_max"],
+                         pf=w["n_max"] > 1, dtype=np.float32)
     if w["prior_kind"] == "uniform":
         oprior = orc.UniformPrior(w["prior"]["low"].astype(np.float64), w["prior"]["high"].astype(np.float64))
     else:
@@ -108,12 +136,13 @@ def oracle_objects(w):
 
 
 def flops_per_pair(w):
-    dims = [w["m"] + w["d"] + 6, *w["hidden"], w["m"]]
+    """Score MLP on one (sample, observation unit) pair; the embedding nets run once per sample / observation."""
+    dims = [w["n_in"], *w["hidden"], w["m"]]
     return 2 * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
 
 
 def config_dict(args, w, world):
-    return {"workload": f"sbibm {args.task} shape: theta={w['m']}, x={w['d']}, MLP {w['m'] + w['d'] + 6}->"
+    return {"workload": f"sbibm {args.task} shape: theta={w['m']}, x={w['d']}, MLP {w['n_in']}->"
                         f"{'x'.join(map(str, w['hidden']))}->{w['m']}, n_obs={w['n']}, {args.samples} posterior "
                         f"samples per GPU, DDIM {w['ddim_steps']} steps eta={w['eta']}, {args.cov_mode}, "
                         f"{w['prior_kind']} prior; one bench step = one full trajectory",
@@ -141,8 +170,10 @@ def cpu_oracle_rate(args, w, n_ddim_steps, repeats=1):
     idx = np.linspace(0, len(grid) - 1, n_ddim_steps).round().astype(int)
     z = rng.standard_normal((N, w["m"])).astype(np.float32)
 
+    x_or, ns = (orc.pf_create_data(onet, w["x"]) if w["n_max"] > 1 else (w["x"], None))
+
     def one(tv):
-        s = orc.factorized_score(onet, theta, w["x"], np.float32(tv), oprior, w["cov"], args.cov_mode, w["prior_kind"])
+        s = orc.factorized_score(onet, theta, x_or, np.float32(tv), oprior, w["cov"], args.cov_mode, w["prior_kind"], ns)
         return orc.ddim_step(onet, theta, s, np.float32(tv), 1 / w["ddim_steps"], w["eta"], z)
 
     one(grid[idx[0]])  # warm-up
@@ -292,8 +323,9 @@ def run_ours(args):
     prior, fn = make_prior()
     spec = engine.prior_spec(w["prior_kind"], prior, fn, m)
     grid = engine.time_grid(w["ddim_steps"])
-    setup = engine.build_setup(nse, x_d, N, grid[:-1], grid[:-1].double() - 1.0 / w["ddim_steps"], w["eta"], spec,
-                               args.cov_mode, cov_d, seed=seed0, sample_offset=rank * N)
+    xs_d, ns_d = nse._create_pf_data(x_d) if w["n_max"] > 1 else (x_d, None)  # PF_NSE: subsets of n_max observations
+    setup = engine.build_setup(nse, xs_d, N, grid[:-1], grid[:-1].double() - 1.0 / w["ddim_steps"], w["eta"], spec,
+                               args.cov_mode, cov_d, n_sizes=ns_d, seed=seed0, sample_offset=rank * N)
     theta0 = engine.philox_normal(N, m, seed0, -1, rank * N, dev)
     theta = theta0.clone()
     h2d = sum(t.numel() * 4 for t in (x_h, cov_h)) + sum(t.numel() * 4 for t in (setup.sched, setup.time_feat, setup.mats)) \
@@ -371,10 +403,11 @@ def run_ours(args):
         except Exception:
             pass
         rpp = (1 + m) if args.cov_mode == "JAC" else 1
-        flops_step = float(N) * n * flops_per_pair(w) * rpp  # algorithmic flops of one DDIM step
+        units = w["n_units"]  # score-net evaluations per sample and step: observations, or PF_NSE subsets
+        flops_step = float(N) * units * flops_per_pair(w) * rpp  # algorithmic flops of one DDIM step
         ms_step = tot_dev[0] / args.steps
-        dims = [m + w["d"] + 6, *w["hidden"], m]
-        hidden_flops = 2.0 * sum(a * b for a, b in zip(dims[1:-2], dims[2:-1])) * N * n  # layers on the tensor core
+        dims = [w["n_in"], *w["hidden"], m]
+        hidden_flops = 2.0 * sum(a * b for a, b in zip(dims[1:-2], dims[2:-1])) * N * units  # layers on the tensor core
         if fused:
             # dominant kernel = traj_tc_kernel: ONE launch per trajectory; its duration is the timed region itself.
             peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)

@@ -76,7 +76,9 @@ struct Tiling {
 
 static bool tc_eligible(const D4sNet* net, const D4sProblem* pb) {
     // plain Linear/ReLU nets only: the toy output head (tanh / analytic affine part) runs on the SIMT path
-    return g_opt_path != 1 && pb->cov_mode == D4S_COV_GAUSS && !pb->paired && net->dev.L >= 3 && net->dev.emb_L == 0 &&
+    bool emb_ok = true;  // a theta-embedding MLP runs inside the kernel when its layers fit the ping-pong buffers (<= 160 wide)
+    for (int l = 0; l <= net->dev.emb_L && net->dev.emb_L > 0; ++l) emb_ok = emb_ok && net->dev.emb_dims[l] <= 160;
+    return g_opt_path != 1 && pb->cov_mode == D4S_COV_GAUSS && !pb->paired && net->dev.L >= 3 && emb_ok &&
            net->dev.out_act == 0 && net->dev.out_scale == 1.f && pb->obs_raw == nullptr && pb->ctx_samples == 0;
 }
 

@@ -26,6 +26,7 @@ namespace d4s {
 constexpr int TC_THREADS = (TC_CW + 3) * 32;   // 608: + TMA producer, MMA issuer, scalar helper
 constexpr int TC_NSTG = 4;                     // weight ring stages
 constexpr int TC_SG_MAX = 8;                   // samples per tile (warp w < SG sums sample w)
+constexpr int TC_EMB_STRIDE = (TC_M * MMAX) / TC_SG_MAX;  // 160: widest theta-embedding layer (ping-pong in sS / sQS)
 constexpr int TC_MATS_MAX = 2 * MMAX * MMAX + MMAX + 2;
 
 // ---- shared memory carve-up (bytes) ---------------------------------------------------------------------------
@@ -96,7 +97,45 @@ __device__ __forceinline__ void lambda_inverse_dispatch(int m, const float* lbas
     }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams p) {
+// Layer-0 sample part for nets whose theta goes through an embedding MLP (nse.py:129, the JR-NMM nets): the MLP of the
+// group's samples (ReLU between layers, last layer linear; all compute warps, ping-pong in two free smem buffers of
+// [SG][TC_EMB_STRIDE] floats), then base[si][col] = t0[col] + sum_f A[f][col] e_f(theta_si).  Not inlined: it must not
+// weigh on the register allocation of the plain-MLP path.
+__device__ __noinline__ void theta_embed_base(const NetDev& net, const float* th, float* buf_a, float* buf_b, float* s_base,
+                                              int SG, int H0, float t0, int tid) {
+    const float* in = th;
+    int in_stride = MMAX;
+    for (int l = 0; l < net.emb_L; ++l) {
+        const int K = net.emb_dims[l], Nn = net.emb_dims[l + 1];
+        float* out = (l & 1) ? buf_b : buf_a;
+        const float* Wt = net.emb_Wt[l];
+        const bool relu = l < net.emb_L - 1;
+        for (int idx = tid; idx < SG * Nn; idx += TC_CT) {
+            const int si = idx / Nn, o = idx - si * Nn;
+            float acc = __ldg(net.emb_bias[l] + o);
+            for (int k = 0; k < K; ++k) acc = fmaf(__ldg(Wt + (size_t)k * Nn + o), in[si * in_stride + k], acc);
+            out[si * TC_EMB_STRIDE + o] = relu ? fmaxf(acc, 0.f) : acc;
+        }
+        compute_bar();
+        in = out;
+        in_stride = TC_EMB_STRIDE;
+    }
+    if (tid < H0) {
+        float z[TC_SG_MAX];
+#pragma unroll
+        for (int si = 0; si < TC_SG_MAX; ++si) z[si] = t0;
+        for (int f = 0; f < net.theta_cols; ++f) {
+            const float a = __ldg(net.A + (size_t)f * H0 + tid);
+#pragma unroll
+            for (int si = 0; si < TC_SG_MAX; ++si) z[si] = fmaf(a, in[si * TC_EMB_STRIDE + f], z[si]);
+        }
+#pragma unroll
+        for (int si = 0; si < TC_SG_MAX; ++si)
+            if (si < SG) s_base[si * 256 + tid] = z[si];
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_constant__ TrajParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sAhi = smem + OFF_AHI;
     uint8_t* sAlo = smem + OFF_ALO;
@@ -326,6 +365,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const TrajParams
         // ---- phases shared by the two schedules (one group after the other / two groups interleaved) ----------------------
         // layer-0 per-sample part of an item: base[si][col] = time_feat[col] + sum_k A[k][col] theta[si][k]
         auto do_base = [&](const float* th, bool fresh, int step, int next_step) {
+            if (net.emb_L > 0) {  // nets with a theta embedding MLP (JR-NMM): separate, non-inlined code path
+                float t0e = 0.f;
+                if (tid < H0) {
+                    if (fresh) {
+                        t0e = tf_next;
+                        tf_next = __ldg(p.time_feat + (size_t)next_step * H0 + tid);
+                    } else {
+                        t0e = __ldg(p.time_feat + (size_t)step * H0 + tid);
+                    }
+                }
+                theta_embed_base(net, th, sS, sQS, sBase, p.SG, H0, t0e, tid);
+                return;
+            }
             if (tid < H0) {
                 float t0;
                 if (fresh) {
