@@ -475,6 +475,56 @@ def test_jac_trajectory_fuses_plain_sum_steps(dev):
     assert e_f < TRAJ_TOL and e_s < TRAJ_TOL
 
 
+@pytest.mark.parametrize("N,n", [(1300, 30), (40, 300), (700, 5)], ids=["paired_groups", "obs_chunks", "many_samples_per_tile"])
+def test_tc_trajectory_with_theta_embedding(N, n, dev):
+    """Nets whose theta goes through an embedding MLP (the JR-NMM nets): the MLP runs inside the tcgen05 trajectory
+    kernel per sample group.  Interleaved / sequential group schedules must agree bit for bit, and both follow the fp32
+    SIMT path (separate theta-embedding kernel) and the fp64 oracle under replayed noise."""
+    from d4s import _cabi as abi
+    from d4s_helpers import nse_from_oracle
+    m, d, F, steps = 4, 7, 5, 5
+    rng = np.random.default_rng(21)
+
+    def mlp(widths):
+        ws, bs = [], []
+        for a, b in zip(widths[:-1], widths[1:]):
+            k = 1 / np.sqrt(a)
+            ws.append(rng.uniform(-k, k, size=(b, a)))
+            bs.append(rng.uniform(-k, k, size=(b,)))
+        return orc.OracleMLP(ws, bs)
+
+    onet = orc.OracleNet(m, d, np.arange(1, F + 1) * np.pi, mlp([24 + 16 + 2 * F, 128, 256, 64, m]), mlp([m, 48, 64, 24]),
+                         mlp([d, 32, 16]))
+    nse = nse_from_oracle(onet, dev)
+    x = 0.5 * rng.standard_normal((n, d))
+    a = 0.2 * rng.standard_normal((n, m, m))
+    cov = a @ a.transpose(0, 2, 1) + 0.05 * np.eye(m)
+    oprior = orc.UniformPrior(np.full(m, -3.46), np.full(m, 3.46))
+    prior, fn = _d4s_prior(oprior, nse, dev)
+    z0, z = rng.standard_normal((N, m)), rng.standard_normal((steps, N, m))
+    kw = dict(steps=steps, eta=1.0, prior=prior, prior_type="uniform", prior_score_fn=fn, dist_cov_est=_t(cov, dev),
+              cov_mode="GAUSS", _noise=(torch.as_tensor(z0, dtype=torch.float32), torch.as_tensor(z, dtype=torch.float32)))
+    abi.set_option("path", 2)  # the tcgen05 trajectory kernel is required: fails loudly if the net were not eligible
+    try:
+        out = nse.ddim((N,), _t(x, dev), **kw)
+        abi.set_option("tc_pairing", 0)
+        out_seq = nse.ddim((N,), _t(x, dev), **kw)
+        abi.set_option("path", 1)
+        simt = nse.ddim((N,), _t(x, dev), **kw)
+    finally:
+        abi.set_option("tc_pairing", 1)
+        abi.set_option("path", 0)
+    assert torch.equal(out, out_seq)
+    Nr = min(N, 3000 // n + 1)
+    ref = orc.ddim(onet, x, z0[:Nr], z[:, :Nr], steps, 1.0, oprior, cov, "GAUSS", "uniform")
+    scale = max(1.0, float(np.abs(ref).max()))
+    e_tc = float(np.abs(out[:Nr].cpu().numpy() - ref).max()) / scale
+    e_simt = float(np.abs(simt[:Nr].cpu().numpy() - ref).max()) / scale
+    e_all = float((out - simt).abs().max()) / max(1.0, float(simt.abs().max()))
+    print(f"theta-embedding net N={N} n={n}: tc-oracle {e_tc:.2e}, simt-oracle {e_simt:.2e}, tc-simt (all samples) {e_all:.2e}")
+    assert e_tc < TRAJ_TOL and e_simt < TRAJ_TOL and e_all < TRAJ_TOL
+
+
 def test_errors_are_loud(dev):
     import d4s
     from d4s import _cabi as abi
