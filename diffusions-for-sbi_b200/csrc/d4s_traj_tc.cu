@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     float* sQS = reinterpret_cast<float*>(smem + OFF_QS);
     float* sBase = reinterpret_cast<float*>(smem + OFF_BASE);
     float* sWout = reinterpret_cast<float*>(smem + OFF_WOUT);
+    float* sQ = sBase + 1280;
     float* sA = sWout + (MMAX / 2) * 256;  // [m][256] layer-0 theta block, only when m <= MMAX / 2
     float* sAcc = reinterpret_cast<float*>(smem + OFF_ACC);
     float* sTheta = reinterpret_cast<float*>(smem + OFF_THETA);
@@ -167,6 +168,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     const int m = net.m, L = net.L;
     const int H0 = net.Hp[0];
     const bool a_in_smem = (m <= MMAX / 2);
+    // sBase holds SG <= 8 rows of 256 floats, and its first 1280 floats double as scratch of the scores phase; with
+    // SG <= 5 the last 768 floats are free: enough for the inv(Sigma_j) of a short observation set (n = 30, m = 5: 750),
+    // which saves the scores phase its dependent global loads.
+    const bool q_in_smem = p.obs_prec != nullptr && p.C == 1 && p.SG <= 5 && p.n * m * m <= 768;
     const int n_groups = (p.N + p.SG - 1) / p.SG;
     const int mats_floats = 2 * m * m + m;
     constexpr int NB23 = TC_CT + 32;  // participants of named barriers 2 and 3
@@ -192,6 +197,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
         if (a_in_smem)  // layer-0 theta block next to the output layer when both fit (theta_dim <= 5)
             for (int e = tid; e < m * H0; e += TC_THREADS) sA[(e / H0) * 256 + (e % H0)] = __ldg(net.A + e);
         if (tid < MMAX) sBout[tid] = (tid < m) ? __ldg(net.bout + tid) : 0.f;
+        if (q_in_smem)  // inv(Sigma_j) of every observation in the tail of sBase (see q_in_smem)
+            for (int e = tid; e < p.n * m * m; e += TC_THREADS) sQ[e] = __ldg(p.obs_prec + e);
         if (tid < TC_M) {
             const int si = tid / p.OC, oj = tid - si * p.OC;
             sRowSi[tid] = (uint8_t)(tid < p.P ? si : 255);
@@ -588,13 +595,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 }
                 const int oj = sRowOj[row];
                 if (p.obs_prec && oj < nobs) {  // (rows past the tile's pairs carry oj = 255)
-                    const float* Q = p.obs_prec + (size_t)(j0 + oj) * m * m;
-                    for (int r = 0; r < m; ++r) {
-                        float qs = 0.f;
+                    if (q_in_smem) {
+                        const float* Q = sQ + oj * m * m;
+                        for (int r = 0; r < m; ++r) {
+                            float qs = 0.f;
 #pragma unroll
-                        for (int k = 0; k < MMAX; ++k)
-                            if (k < m) qs = fmaf(__ldg(Q + r * m + k), s[k], qs);
-                        sQS[row * MMAX + r] = qs;
+                            for (int k = 0; k < MMAX; ++k)
+                                if (k < m) qs = fmaf(Q[r * m + k], s[k], qs);
+                            sQS[row * MMAX + r] = qs;
+                        }
+                    } else {
+                        const float* Q = p.obs_prec + (size_t)(j0 + oj) * m * m;
+                        for (int r = 0; r < m; ++r) {
+                            float qs = 0.f;
+#pragma unroll
+                            for (int k = 0; k < MMAX; ++k)
+                                if (k < m) qs = fmaf(__ldg(Q + r * m + k), s[k], qs);
+                            sQS[row * MMAX + r] = qs;
+                        }
                     }
                 }
             }
