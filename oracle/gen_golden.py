@@ -271,6 +271,42 @@ def toy_case(name, DIM, n_obs, eps_max, N, seed, steps, eta):
     print("wrote", name)
 
 
+def contexts_case(name, net32, x_ctx, prior_kind, prior_params, S, seed, steps, eta, modes=("GAUSS", "JAC")):
+    """Batched contexts: what `vmap(sampler, randomness="different")(context, cov_est)` of
+    jrnnm_posterior_estimation.py:286-294 computes, context by context under replayed noise, and the covariance
+    pre-pass `vmap(lambda x: ddim(shape=(S,), x=x, steps, eta))` of sbibm_posterior_estimation.py:306-314 (plain
+    single-observation score).  x_ctx: [B, n, d]."""
+    m = net32.zeros.shape[0]
+    B, n, _ = x_ctx.shape
+    gen = torch.Generator().manual_seed(seed)
+    cov_est = spd_covs(gen, B * n, m).reshape(B, n, m, m)
+    z0 = torch.randn(B * S, m, generator=gen)
+    z = torch.randn(steps, B * S, m, generator=gen)
+    out = dict(x=npy(x_ctx), dist_cov_est=npy(cov_est), traj_z0=npy(z0), traj_z=npy(z), traj_steps=np.int64(steps),
+               traj_eta=np.float64(eta), prior_kind=np.array(prior_kind), samples_per_context=np.int64(S))
+    for k, v in prior_params.items():
+        out["prior." + k] = npy(v)
+    net_arrays(net32, out)
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        net = copy.deepcopy(net32).to(dt)
+        prior, fn = make_prior(prior_kind, m, dt, net, **prior_params)
+        for mode in modes:
+            res = []
+            for c in range(B):
+                sl = slice(c * S, (c + 1) * S)
+                res.append(run_ddim(net, x_ctx[c].to(dt), z0[sl].to(dt), z[:, sl].to(dt), steps=steps, eta=eta, prior=prior,
+                                    prior_type=prior_kind, prior_score_fn=fn, dist_cov_est=cov_est[c].to(dt), cov_mode=mode))
+            out[f"{tag}.{mode}.traj"] = npy(torch.stack(res))  # [B, S, m]
+        res = []
+        for c in range(B):  # one observation per context: x[c, 0]
+            sl = slice(c * S, (c + 1) * S)
+            res.append(run_ddim(net, x_ctx[c, 0].to(dt), z0[sl].to(dt), z[:, sl].to(dt), steps=steps, eta=eta))
+        out[f"{tag}.single.traj"] = npy(torch.stack(res))
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, {k: v.shape for k, v in out.items() if hasattr(v, "shape") and "traj" in k})
+
+
 def make_prior(kind, m, dt, net, low=None, high=None, loc=None, cov=None):
     if kind == "uniform":
         low, high = low.to(dt), high.to(dt)
@@ -441,6 +477,20 @@ def main(filt=None):
         high = (hi - st["theta_train_mean"]) / st["theta_train_std"] * 2
         per_call_case("jrnnm4d_n5", net, x, "uniform", dict(low=low, high=high), N=10, seed=16,
                       t_grid=[0.9, 0.5, 0.29, 0.1, 0.01], traj=dict(N=12, steps=30, eta=1.0, modes=("GAUSS",)))
+    if want("contexts"):
+        d = os.path.join(REF, "results", "jrnnm", "4d", "n_train_50000_n_epochs_5000_lr_0.001")
+        net = torch.load(os.path.join(d, "score_network.pkl"), weights_only=False, map_location="cpu").eval()
+        net.net_type = "default"
+        net.tweedies_approximator = ref_tps.tweedies_approximation
+        st = torch.load(os.path.join(d, "train_means_stds_dict.pkl"), weights_only=False)
+        x = torch.load(os.path.join(REF, "results", "jrnnm", "x_obs_100_[135.0, 220.0, 2000.0, 0.0].pkl"),
+                       weights_only=False)[:12]
+        x = ((x - st["x_train_mean"]) / st["x_train_std"]).float().reshape(3, 4, -1)  # 3 contexts of 4 observations
+        lo = torch.tensor([10.0, 50.0, 100.0, -20.0])
+        hi = torch.tensor([250.0, 500.0, 5000.0, 20.0])
+        low = (lo - st["theta_train_mean"]) / st["theta_train_std"] * 2
+        high = (hi - st["theta_train_mean"]) / st["theta_train_std"] * 2
+        contexts_case("contexts_jrnnm4d_b3_n4", net, x, "uniform", dict(low=low, high=high), S=5, seed=51, steps=12, eta=0.8)
     if want("cfg"):
         net, st = load_sbibm("slcp", sub="n_train_10000_bs_256_n_epochs_5000_lr_0.0001", pf="pf_n_max_3")
         st = dict(st, x_train_mean=st["x_train_mean"][0], x_train_std=st["x_train_std"][0])

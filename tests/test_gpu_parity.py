@@ -13,7 +13,7 @@ from oracle import d4s_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-CASES = [c for c in gio.names() if not c.startswith(("langevin", "toy", "cfg"))]
+CASES = [c for c in gio.names() if not c.startswith(("langevin", "toy", "cfg", "contexts"))]
 REL_TOL = 1e-4
 TRAJ_TOL = 1e-3
 # Opt-in tensor-core JAC path (d4s_set_option("jac_tc", 1): d4s_jac_tc.cu, fp16x3 products, fp32 accumulation in TMEM),
@@ -421,6 +421,28 @@ def test_ddim_contexts_vs_oracle(pkind, mode, dev):
         assert float((out[c] - one).abs().max()) < 1e-4 * scale  # same kernels, per-sample instead of shared Lambda solve
     print(f"ddim_contexts {pkind} {mode}: max |theta - oracle| / scale = {worst:.2e}")
     assert worst < TRAJ_TOL
+
+
+@pytest.mark.parametrize("name", [c for c in gio.names() if c.startswith("contexts")])
+def test_ddim_contexts_golden(name, dev):
+    """`NSE.ddim_contexts` against the unmodified reference run context by context (what its vmap(sampler) computes) on
+    the shipped JR-NMM net (theta / x embedding MLPs): tall GAUSS and JAC posteriors and the one-observation-per-context
+    pre-pass, fp64 reference trajectories under replayed noise."""
+    g, onet, nse, prior, fn, ptype, kw = _setup(name, dev)
+    S, steps, eta = int(g["samples_per_context"]), int(g["traj_steps"]), float(g["traj_eta"])
+    noise = (torch.as_tensor(g["traj_z0"], dtype=torch.float32), torch.as_tensor(g["traj_z"], dtype=torch.float32))
+    x = _t(g["x"], dev)
+    for mode in ("GAUSS", "JAC"):
+        out = nse.ddim_contexts((S,), x, steps=steps, eta=eta, prior=prior, prior_type=ptype, prior_score_fn=fn,
+                                dist_cov_est=_t(g["dist_cov_est"], dev), cov_mode=mode, _noise=noise)
+        ref, ref32 = g[f"f64.{mode}.traj"], g[f"f32.{mode}.traj"]
+        err, floor = float(np.abs(out.cpu().numpy() - ref).max()), float(np.abs(ref32 - ref).max())
+        print(f"{name} {mode}: max |theta - reference fp64| = {err:.2e} (reference fp32: {floor:.2e})")
+        assert err < max(TRAJ_TOL, 3 * floor), (mode, err, floor)
+    out = nse.ddim_contexts((S,), x[:, 0], steps=steps, eta=eta, _noise=noise)
+    err = float(np.abs(out.cpu().numpy() - g["f64.single.traj"]).max())
+    print(f"{name} single observation per context: max |theta - reference fp64| = {err:.2e}")
+    assert err < TRAJ_TOL
 
 
 def test_estimate_dist_cov_prepass(dev):

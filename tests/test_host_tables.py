@@ -11,7 +11,7 @@ from d4s import engine
 from d4s_helpers import nse_from_oracle
 from oracle import d4s_oracle as orc
 
-CASES = [c for c in gio.names() if not c.startswith(("langevin", "toy", "cfg"))]
+CASES = [c for c in gio.names() if not c.startswith(("langevin", "toy", "cfg", "contexts"))]
 
 
 def _spec(g):

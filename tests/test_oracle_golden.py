@@ -12,7 +12,7 @@ import torch
 import golden_io as gio
 from oracle import d4s_oracle as orc
 
-CASES = [c for c in gio.names() if not c.startswith(("langevin", "toy", "cfg"))]
+CASES = [c for c in gio.names() if not c.startswith(("langevin", "toy", "cfg", "contexts"))]
 
 
 def _ns(g):
@@ -96,6 +96,23 @@ def test_trajectory_fp64(name):
                        g["dist_cov_est"].astype(np.float64), mode, str(g["prior_kind"]), clip, ns)
         err = np.abs(out - g[key]).max()
         assert err < (5e-6 if mode == "GAUSS" else 1e-4), (name, mode, err)
+
+
+# ---- batched contexts: the reference run context by context = vmap(sampler) ----------------
+@pytest.mark.parametrize("name", [c for c in gio.names() if c.startswith("contexts")])
+def test_contexts_fp64(name):
+    g = gio.load(name)
+    net, prior = gio.oracle_net(g), gio.oracle_prior(g)
+    x, cov = g["x"].astype(np.float64), g["dist_cov_est"].astype(np.float64)
+    B, S, steps, eta = x.shape[0], int(g["samples_per_context"]), int(g["traj_steps"]), float(g["traj_eta"])
+    for c in range(B):
+        sl = slice(c * S, (c + 1) * S)
+        for mode in ("GAUSS", "JAC"):
+            out = orc.ddim(net, x[c], g["traj_z0"][sl], g["traj_z"][:, sl], steps, eta, prior, cov[c], mode, str(g["prior_kind"]))
+            err = np.abs(out - g[f"f64.{mode}.traj"][c]).max()
+            assert err < (5e-6 if mode == "GAUSS" else 1e-4), (name, c, mode, err)
+        out = orc.ddim_single(net, x[c, 0], g["traj_z0"][sl], g["traj_z"][:, sl], steps, eta)
+        assert np.abs(out - g["f64.single.traj"][c]).max() < 5e-6, (name, c)
 
 
 # ---- Langevin / Geffner family ---------------------------------------------------------
