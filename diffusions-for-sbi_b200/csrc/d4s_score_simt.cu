@@ -14,7 +14,7 @@
 // activations live in shared memory k-major and are updated in place, the weights stream from L2 through
 // a cp.async ring.  JAC rows (one primal + m tangents per pair) share the GEMM; tangents are masked by the
 // primal's ReLU pattern, published per layer as ballot words.
-#include "d4s_common.cuh"
+#include "d4s_finalize_core.cuh"
 
 namespace d4s {
 
@@ -129,31 +129,46 @@ __device__ __forceinline__ void hidden_layer(const float* __restrict__ Wt, const
     layer_epilogue<NC>(acc, bias, sAct, sMask, sKind, sPair, jac, warp, lane);
 }
 
-// JAC per-pair: Pm = (alpha/sigma^2) inv(I - sigma Jeps), v = Pm s   (tall_posterior_sampler.py:91-94)
+// JAC per-pair: Pm = (alpha/sigma^2) inv(I - sigma Jeps), v = Pm s   (tall_posterior_sampler.py:91-94).
+// One thread per (pair, column c): it solves (I - sigma Jeps) x = e_c by LU with partial pivoting and hands back column c
+// of Pm and its contribution Pm[:, c] s[c] to v.  (One thread per PAIR inverting the whole matrix left all but <= 10
+// threads of the CTA idle and, for theta_dim = 10, ran out of registers into local memory.)
+// fp64: the covariance I - sigma*Jeps of a learned (asymmetric, possibly indefinite) Jacobian is the ill-conditioned
+// step of the JAC path; m^3 flops per pair are free next to the MLP.
 template <int M>
-__device__ __noinline__ void jac_pair(const float* sJp, const float* sSp, float sigma, float a_over_s2, float* outp,
-                                      float* prec_out) {
-    // fp64: the covariance I - sigma*Jeps of a learned (asymmetric, possibly indefinite) Jacobian is the
-    // ill-conditioned step of the JAC path; m^3 flops per pair are free next to the MLP.
-    double a[M][M], inv[M][M], s[M];
+__device__ __noinline__ void jac_pair_col(const float* sJp, const float* sSp, float sigma, float a_over_s2, int c, float* outp,
+                                          float* prec_out, double* contrib) {
+    double a[M][M], b[M];
 #pragma unroll
     for (int o = 0; o < M; ++o) {
-        s[o] = (double)sSp[o];
 #pragma unroll
         for (int k = 0; k < M; ++k) a[o][k] = ((o == k) ? 1.0 : 0.0) - (double)sigma * (double)sJp[o * M + k];
+        b[o] = (o == c) ? 1.0 : 0.0;
     }
-    gj_inverse_t<double, M>(a, inv);
+    lu_solve_d<M>(a, b);
+    const double sc = (double)sSp[c];
 #pragma unroll
-    for (int o = 0; o < M; ++o) {
-        double v = 0.0;
-#pragma unroll
-        for (int k = 0; k < M; ++k) {
-            const double pr = (double)a_over_s2 * inv[o][k];
-            outp[M + o * M + k] = (float)pr;
-            if (prec_out) prec_out[o * M + k] = (float)pr;
-            v = fma(pr, s[k], v);
-        }
-        outp[o] = (float)v;
+    for (int r = 0; r < M; ++r) {
+        const double pr = (double)a_over_s2 * b[r];
+        outp[M + r * M + c] = (float)pr;
+        if (prec_out) prec_out[r * M + c] = (float)pr;
+        contrib[r] = pr * sc;
+    }
+}
+
+__device__ __forceinline__ void jac_pair_col_dispatch(int m, const float* J, const float* S, float sigma, float aos2, int c,
+                                                      float* outp, float* po, double* contrib) {
+    switch (m) {
+        case 1: jac_pair_col<1>(J, S, sigma, aos2, c, outp, po, contrib); break;
+        case 2: jac_pair_col<2>(J, S, sigma, aos2, c, outp, po, contrib); break;
+        case 3: jac_pair_col<3>(J, S, sigma, aos2, c, outp, po, contrib); break;
+        case 4: jac_pair_col<4>(J, S, sigma, aos2, c, outp, po, contrib); break;
+        case 5: jac_pair_col<5>(J, S, sigma, aos2, c, outp, po, contrib); break;
+        case 6: jac_pair_col<6>(J, S, sigma, aos2, c, outp, po, contrib); break;
+        case 7: jac_pair_col<7>(J, S, sigma, aos2, c, outp, po, contrib); break;
+        case 8: jac_pair_col<8>(J, S, sigma, aos2, c, outp, po, contrib); break;
+        case 9: jac_pair_col<9>(J, S, sigma, aos2, c, outp, po, contrib); break;
+        default: jac_pair_col<10>(J, S, sigma, aos2, c, outp, po, contrib); break;
     }
 }
 
@@ -338,29 +353,28 @@ __global__ void __launch_bounds__(NT, 2) score_simt_kernel(const ScoreParams p) 
             sQS[r * MMAX + o] = acc;
         }
     } else {
-        if (tid < p.P && sKind[tid] == 0) {
-            const int r = tid;
-            float* outp = sQS + r * (m + m * m);
-            float* po = nullptr;
-            if (p.prec_out) {
-                const size_t gi = (size_t)(i0 + sSamp[r]);
-                const size_t gj = p.paired ? 0 : (size_t)(p.ctx_samples > 0 ? sObs[r] % p.n : sObs[r]);
-                const size_t nn = p.paired ? 1 : (size_t)p.n;
-                po = p.prec_out + (gi * nn + gj) * m * m;
+        double* sC = reinterpret_cast<double*>(sAct);  // [P][m][m]: column c's contribution Pm[:, c] s[c] (activations are dead)
+        for (int e = tid; e < p.P * m; e += NT) {
+            const int r = e / m, c = e - r * m;
+            if (sKind[r] == 0) {
+                float* po = nullptr;
+                if (p.prec_out) {
+                    const size_t gi = (size_t)(i0 + sSamp[r]);
+                    const size_t gj = p.paired ? 0 : (size_t)(p.ctx_samples > 0 ? sObs[r] % p.n : sObs[r]);
+                    const size_t nn = p.paired ? 1 : (size_t)p.n;
+                    po = p.prec_out + (gi * nn + gj) * m * m;
+                }
+                jac_pair_col_dispatch(m, sJ + r * m * m, sS + r * MMAX, sigma, a_over_s2, c, sQS + r * (m + m * m), po,
+                                      sC + (size_t)(r * m + c) * m);
             }
-            const float* J = sJ + r * m * m;
-            const float* S = sS + r * MMAX;
-            switch (m) {
-                case 1: jac_pair<1>(J, S, sigma, a_over_s2, outp, po); break;
-                case 2: jac_pair<2>(J, S, sigma, a_over_s2, outp, po); break;
-                case 3: jac_pair<3>(J, S, sigma, a_over_s2, outp, po); break;
-                case 4: jac_pair<4>(J, S, sigma, a_over_s2, outp, po); break;
-                case 5: jac_pair<5>(J, S, sigma, a_over_s2, outp, po); break;
-                case 6: jac_pair<6>(J, S, sigma, a_over_s2, outp, po); break;
-                case 7: jac_pair<7>(J, S, sigma, a_over_s2, outp, po); break;
-                case 8: jac_pair<8>(J, S, sigma, a_over_s2, outp, po); break;
-                case 9: jac_pair<9>(J, S, sigma, a_over_s2, outp, po); break;
-                default: jac_pair<10>(J, S, sigma, a_over_s2, outp, po); break;
+        }
+        __syncthreads();
+        for (int e = tid; e < p.P * m; e += NT) {  // v = Pm s: the columns' contributions in a fixed order
+            const int r = e / m, o = e - r * m;
+            if (sKind[r] == 0) {
+                double v = 0.0;
+                for (int c = 0; c < m; ++c) v += sC[(size_t)(r * m + c) * m + o];
+                sQS[r * (m + m * m) + o] = (float)v;
             }
         }
     }
