@@ -547,6 +547,57 @@ def test_tc_trajectory_with_theta_embedding(N, n, dev):
     assert e_tc < TRAJ_TOL and e_simt < TRAJ_TOL and e_all < TRAJ_TOL
 
 
+def _random_tc_cases(count, seed):
+    rng = np.random.default_rng(seed)
+    cases = []
+    for _ in range(count):
+        m = int(rng.integers(1, 11))
+        d = int(rng.integers(1, 12))
+        hidden = tuple(int(rng.choice([50, 64, 96, 128, 200, 256])) for _ in range(int(rng.integers(2, 5))))
+        n = int(rng.choice([1, 2, 5, 9, 17, 30, 33, 64, 129, 300]))
+        N = int(rng.choice([1, 3, 37, 150, 601, 1500]))
+        if N * n > 60000:
+            N = max(1, 60000 // n)
+        cases.append((m, d, hidden, n, N, str(rng.choice(["uniform", "gaussian"])), int(rng.integers(0, 1 << 30))))
+    return cases
+
+
+@pytest.mark.parametrize("case", _random_tc_cases(14, 2024), ids=lambda c: f"m{c[0]}_d{c[1]}_h{'x'.join(map(str, c[2]))}_n{c[3]}_N{c[4]}_{c[5]}")
+def test_tc_trajectory_random_shapes(case, dev):
+    """Seeded random shapes (theta_dim 1..10, ragged widths, 1..300 observations, 1..1500 samples, both priors): the
+    tcgen05 trajectory kernel against the per-step fp32 SIMT kernels under replayed noise, and its two group schedules
+    against each other."""
+    from d4s import _cabi as abi
+    from d4s_helpers import nse_from_oracle
+    m, d, hidden, n, N, pkind, seed = case
+    onet, x, cov, theta, oprior = _problem(m, d, hidden, n, N, pkind, seed=seed)
+    nse = nse_from_oracle(onet, dev)
+    prior, fn = _d4s_prior(oprior, nse, dev)
+    steps = 3
+    rng = np.random.default_rng(seed + 1)
+    z0, z = rng.standard_normal((N, m)), rng.standard_normal((steps, N, m))
+    kw = dict(steps=steps, eta=1.0, prior=prior, prior_type=pkind, prior_score_fn=fn, dist_cov_est=_t(cov, dev),
+              cov_mode="GAUSS", _noise=(torch.as_tensor(z0, dtype=torch.float32), torch.as_tensor(z, dtype=torch.float32)))
+    if n == 1:
+        kw = dict(steps=steps, eta=1.0, _noise=kw["_noise"])  # one observation: the plain score (nse.py:253)
+    abi.set_option("path", 1)
+    try:
+        simt = nse.ddim((N,), _t(x, dev), **kw)
+        abi.set_option("path", 0)
+        out = nse.ddim((N,), _t(x, dev), **kw)
+        abi.set_option("tc_pairing", 0)
+        out_seq = nse.ddim((N,), _t(x, dev), **kw)
+    finally:
+        abi.set_option("tc_pairing", 1)
+        abi.set_option("path", 0)
+    assert torch.isfinite(out).all()
+    assert torch.equal(out, out_seq)
+    scale = max(1.0, float(simt.abs().max()))
+    err = float((out - simt).abs().max()) / scale
+    print(f"{case[:6]}: tc vs simt max rel diff {err:.2e}")
+    assert err < TRAJ_TOL
+
+
 def test_errors_are_loud(dev):
     import d4s
     from d4s import _cabi as abi
