@@ -23,7 +23,7 @@
 
 namespace d4s {
 
-constexpr int TC_THREADS = (TC_CW + 3) * 32;   // 608: + TMA producer, MMA issuer, scalar helper
+constexpr int TC_THREADS = (TC_CW + 4) * 32;   // 640: + TMA producer, MMA issuer, scalar helper, one idle warp (full warpgroup)
 constexpr int TC_NSTG = 4;                     // weight ring stages
 constexpr int TC_SG_MAX = 8;                   // samples per tile (warp w < SG sums sample w)
 constexpr int TC_EMB_STRIDE = (TC_M * MMAX) / TC_SG_MAX;  // 160: widest theta-embedding layer (ping-pong in sS / sQS)
@@ -219,7 +219,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     // the other run while the tensor core works (needs the whole observation set in one tile and the in-kernel tail).
     const bool pairing = p.pairing && p.C == 1 && p.part_out == nullptr;
 
-    if (warp == TC_CW) {
+    // Register reallocation between the warpgroups (setmaxnreg): the CTA is launched with 96 registers per thread; the
+    // four service warps give 32 of theirs back, the compute warps grow to 112.
+    if (warp == TC_CW + 3) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");  // idle warp: completes the service warpgroup
+    } else if (warp == TC_CW) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ================= TMA producer: streams the weight images in consumption order ===========================
         if (lane == 0) {
             unsigned it = 0;
@@ -240,6 +245,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
             }
         }
     } else if (warp == TC_CW + 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ================= MMA issuer ===================================================================================
         if (lane == 0) {
             unsigned it = 0, a_cnt = 0, lc = 0;
@@ -280,6 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
             }
         }
     } else if (warp == TC_CW + 2) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ================= scalar helper: everything that only needs theta at the start of the step =================
         const bool uni = (p.fin.prior_kind == D4S_PRIOR_UNIFORM);
         const int nq = (m + 3) / 4;
@@ -361,6 +368,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
             gk += ngr;
         }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ================= compute warps ==================================================================================
         const int q = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column quarter
         const int row = 32 * q + lane;           // the TMEM lane / tile row this thread owns in the epilogues
