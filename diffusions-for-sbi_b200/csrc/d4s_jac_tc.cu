@@ -23,7 +23,7 @@
 
 namespace d4s {
 
-constexpr int JT_THREADS = (TC_CW + 2) * 32;  // 576
+constexpr int JT_THREADS = (TC_CW + 4) * 32;  // 640: 16 compute warps + TMA producer + MMA issuer + 2 idle (full warpgroup)
 constexpr int JT_NSTG = 3;                    // weight ring stages
 constexpr int JT_MMAX = 5;                    // largest theta_dim of this kernel
 constexpr int JT_PMAX = 32;                   // pairs per tile <= 4 * 8
@@ -165,7 +165,11 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
     int my_tiles = 0;
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) ++my_tiles;
 
-    if (warp == TC_CW) {
+    // setmaxnreg: launched with 96 registers per thread; the service warpgroup keeps 32, the compute warps grow to 112
+    if (warp >= TC_CW + 2) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");  // idle warps: complete the service warpgroup
+    } else if (warp == TC_CW) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         // ================= TMA producer: streams the weight images in consumption order ===========================
         if (lane == 0) {
             unsigned it = 0;
@@ -185,6 +189,7 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
             }
         }
     } else if (warp == TC_CW + 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         // ================= MMA issuer ===================================================================================
         if (lane == 0) {
             unsigned it = 0, a_cnt = 0, lc = 0;
@@ -223,6 +228,7 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
             }
         }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         // ================= compute warps ==================================================================================
         const int q = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column quarter
         const int row = 32 * q + lane;           // the TMEM lane / tile row this thread owns in the epilogues

@@ -582,6 +582,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
             PROF_MARK(4);  // epilogues
             // ---- scores: the column quarters 1..3 park their partial dot products in sS / sQS / sBase (free here), quarter 0
             // adds them up as (q0 + q1) + (q2 + q3), s = -(eps + b) / sigma, and applies inv(Sigma_j) to its row's score.
+            // (when layer 0 of the next pass ran just before this epilogue, other warps may still be reading sBase there:
+            // nothing else orders them against the scratch writes below -- with one short tensor-core layer this raced)
+            compute_bar();
             if (cq != 0) {
                 float* dst = (cq == 1) ? sS : (cq == 2) ? sQS : sBase;
 #pragma unroll

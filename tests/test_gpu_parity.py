@@ -306,7 +306,10 @@ def test_full_size_trajectory_properties(dev):
 
 
 @pytest.mark.parametrize("shape", [(5, 8, (256, 256, 256), 30, 1300, "uniform"), (5, 8, (64, 128), 7, 2500, "uniform"),
-                                   (4, 6, (128, 256), 12, 1190, "gaussian"), (10, 10, (256, 256), 30, 700, "gaussian")],
+                                   (4, 6, (128, 256), 12, 1190, "gaussian"), (10, 10, (256, 256), 30, 700, "gaussian"),
+                                   # one short tensor-core layer, 8 samples per tile: the shape that exposed a shared-memory
+                                   # race between layer 0 of the next item and the scores scratch of the previous one
+                                   (3, 8, (64, 64), 9, 1500, "gaussian")],
                          ids=lambda s: f"m{s[0]}_n{s[3]}_N{s[4]}_{s[5]}")
 def test_tc_group_schedules_agree(shape, dev):
     """The tcgen05 trajectory kernel interleaves two sample groups per CTA when a CTA owns several (N > 148 groups):
@@ -332,6 +335,12 @@ def test_tc_group_schedules_agree(shape, dev):
         abi.set_option("tc_pairing", 1)
         abi.set_option("path", 0)
     assert torch.equal(out, out_seq)
+    abi.set_option("path", 2)
+    try:
+        for _ in range(3):  # run-to-run determinism of the interleaved schedule
+            assert torch.equal(nse.ddim((N,), _t(x, dev), **kw), out)
+    finally:
+        abi.set_option("path", 0)
     ref = orc.ddim(onet, x, z0, z, steps, 1.0, oprior, cov, "GAUSS", pkind)
     scale = max(1.0, float(np.abs(ref).max()))
     err = float(np.abs(out.cpu().numpy() - ref).max()) / scale
