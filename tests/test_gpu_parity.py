@@ -4,6 +4,8 @@ compared with (a) the golden vectors recorded from the unmodified reference and 
 Tolerances (north_star): per-call factorized_score <= 1e-4 relative L2 vs the fp64 reference, widened to
 3x the reference's OWN fp32-vs-fp64 error where that is larger (SURVEY.md Finding B); full GAUSS trajectories
 <= 1e-3 max-abs under replayed noise."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -571,7 +573,7 @@ def _random_tc_cases(count, seed):
     return cases
 
 
-@pytest.mark.parametrize("case", _random_tc_cases(14, 2024), ids=lambda c: f"m{c[0]}_d{c[1]}_h{'x'.join(map(str, c[2]))}_n{c[3]}_N{c[4]}_{c[5]}")
+@pytest.mark.parametrize("case", _random_tc_cases(int(os.environ.get("D4S_FUZZ_CASES", "14")), int(os.environ.get("D4S_FUZZ_SEED", "2024"))), ids=lambda c: f"m{c[0]}_d{c[1]}_h{'x'.join(map(str, c[2]))}_n{c[3]}_N{c[4]}_{c[5]}")
 def test_tc_trajectory_random_shapes(case, dev):
     """Seeded random shapes (theta_dim 1..10, ragged widths, 1..300 observations, 1..1500 samples, both priors): the
     tcgen05 trajectory kernel against the per-step fp32 SIMT kernels under replayed noise, and its two group schedules
@@ -605,6 +607,40 @@ def test_tc_trajectory_random_shapes(case, dev):
     err = float((out - simt).abs().max()) / scale
     print(f"{case[:6]}: tc vs simt max rel diff {err:.2e}")
     assert err < TRAJ_TOL
+
+
+@pytest.mark.parametrize("case", _random_tc_cases(int(os.environ.get("D4S_FUZZ_CASES", "12")), int(os.environ.get("D4S_FUZZ_SEED", "777"))), ids=lambda c: f"m{c[0]}_d{c[1]}_h{'x'.join(map(str, c[2]))}_n{c[3]}_N{c[4]}_{c[5]}")
+def test_tc_per_call_random_shapes(case, dev):
+    """Per-call `factorized_score` on seeded random shapes: the tcgen05 kernels in per-step mode (GAUSS: trajectory kernel
+    exporting its partial sums; JAC, theta_dim <= 5: the opt-in score + Jacobian kernel) against the fp32 SIMT kernels,
+    twice (run-to-run determinism)."""
+    from d4s import _cabi as abi
+    from d4s_helpers import nse_from_oracle
+    m, d, hidden, n, N, pkind, seed = case
+    if n == 1:
+        n = 2
+    onet, x, cov, theta, oprior = _problem(m, d, hidden, n, N, pkind, seed=seed)
+    nse = nse_from_oracle(onet, dev)
+    prior, fn = _d4s_prior(oprior, nse, dev)
+    th = _t(theta[:N], dev)
+    for mode in ("GAUSS", "JAC"):
+        for tv in (0.7, 0.2):
+            args = (th, _t(x, dev), torch.tensor(np.float32(tv)), fn, prior)
+            kw = dict(dist_cov_est=_t(cov, dev), cov_mode=mode, prior_type=pkind)
+            abi.set_option("path", 1)
+            try:
+                simt = nse.factorized_score(*args, **kw)
+                abi.set_option("path", 0)
+                abi.set_option("jac_tc", 1)
+                out = nse.factorized_score(*args, **kw)
+                out2 = nse.factorized_score(*args, **kw)
+            finally:
+                abi.set_option("path", 0)
+                abi.set_option("jac_tc", 0)
+            assert torch.equal(out, out2), (mode, tv)
+            err = float((out - simt).norm() / simt.norm())
+            tol = 1e-4 if mode == "GAUSS" else 5e-3  # JAC: both paths go through inv(I - sigma J) of a random net
+            assert err < tol, (case[:6], mode, tv, err)
 
 
 def test_errors_are_loud(dev):
