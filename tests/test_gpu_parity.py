@@ -456,6 +456,45 @@ def test_ddim_contexts_golden(name, dev):
     assert err < TRAJ_TOL
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_ddim_contexts_random_shapes(seed, dev):
+    """Seeded random (B, n, S, theta_dim, widths, prior, mode): one batched-contexts launch == B separate `ddim` calls."""
+    from d4s import _cabi as abi
+    from d4s_helpers import nse_from_oracle
+    rng = np.random.default_rng(100 + seed)
+    m, d = int(rng.integers(1, 8)), int(rng.integers(1, 9))
+    hidden = tuple(int(rng.choice([50, 64, 128, 256])) for _ in range(int(rng.integers(1, 4))))
+    B, n, S = int(rng.integers(2, 40)), int(rng.choice([2, 3, 7, 30, 70])), int(rng.choice([1, 2, 5, 33]))
+    pkind, mode, steps = str(rng.choice(["uniform", "gaussian"])), str(rng.choice(["GAUSS", "JAC"])), 4
+    onet = orc.random_net(rng, m, d, hidden=hidden)
+    nse = nse_from_oracle(onet, dev)
+    x = 0.5 * rng.standard_normal((B, n, d))
+    a = 0.2 * rng.standard_normal((B, n, m, m))
+    cov = a @ a.transpose(0, 1, 3, 2) + 0.05 * np.eye(m)
+    if pkind == "uniform":
+        oprior = orc.UniformPrior(np.full(m, -3.46), np.full(m, 3.46))
+    else:
+        b = 0.3 * rng.standard_normal((m, m))
+        oprior = orc.GaussianPrior(0.1 * rng.standard_normal(m), b @ b.T + np.eye(m))
+    prior, fn = _d4s_prior(oprior, nse, dev)
+    z0, z = rng.standard_normal((B * S, m)), rng.standard_normal((steps, B * S, m))
+    kw = dict(steps=steps, eta=0.8, prior=prior, prior_type=pkind, prior_score_fn=fn, cov_mode=mode)
+    abi.set_option("path", 1)  # same fp32 kernels on both sides: only the batching differs
+    try:
+        out = nse.ddim_contexts((S,), _t(x, dev), dist_cov_est=_t(cov, dev),
+                                _noise=(torch.as_tensor(z0, dtype=torch.float32), torch.as_tensor(z, dtype=torch.float32)), **kw)
+        for c in range(B):
+            sl = slice(c * S, (c + 1) * S)
+            one = nse.ddim((S,), _t(x[c], dev), dist_cov_est=_t(cov[c], dev),
+                           _noise=(torch.as_tensor(z0[sl], dtype=torch.float32), torch.as_tensor(z[:, sl], dtype=torch.float32)), **kw)
+            scale = max(1.0, float(one.abs().max()))
+            rel = (out[c] - one).abs().max(dim=1).values / scale
+            # (per-sample Lambda solve instead of a shared inverse; JAC: see test_tc_per_call_random_shapes)
+            assert float(rel.median()) < 1e-4 and float((rel > 1e-2).float().mean()) <= 0.05, (seed, c, mode, pkind, float(rel.max()))
+    finally:
+        abi.set_option("path", 0)
+
+
 def test_estimate_dist_cov_prepass(dev):
     """sbibm_posterior_estimation.py:306-314: vmap(ddim) over the observations + torch.cov, as one launch."""
     from d4s_helpers import nse_from_oracle
