@@ -3,7 +3,7 @@
 // A CTA owns a group of SG posterior samples for the whole trajectory (samples never interact, so there is
 // no inter-CTA dependency and no per-step launch).  Per step and per chunk of OC observations it evaluates the
 // score MLP on the 128-row tile (sample x observation pairs):
-//   layer 0   separable fp32 SIMT:  z0 = A theta_i + obs_feat_j + time_feat              (8 compute warps)
+//   layer 0   separable fp32 SIMT:  z0 = A theta_i + obs_feat_j + time_feat   (theta through its embedding MLP, if any)
 //   layer l   D[128 x N] (TMEM, fp32) = act[128 x K] (smem) x W_l^T (smem ring)  on tcgen05.mma kind::f16
 //             with the bf16x3 split  a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo   (fp32-level parity, 3 MMAs)
 //             weights: pre-packed canonical K-major bf16 images, streamed L2 -> smem by 1-D TMA bulk copies
@@ -14,10 +14,15 @@
 //
 // Replaces the same reference lines as kernels 1-4 (nse.py:263-298, 544-656; tall_posterior_sampler.py:95-128).
 //
-// Warp roles: warps 0-7 compute/epilogue (TMEM lane quarter = warp % 4, column half = warp / 4),
-//             warp 8 = TMA producer (one lane), warp 9 = TMEM allocator + MMA issuer (one lane),
-//             warp 10 = scalar helper: per-step schedule/matrix rows -> smem, fp64 diffused-prior terms, Philox noise
-//             (everything that depends only on theta at the start of the step, off the critical path).
+// Warp roles (640 threads): warps 0-15 compute / epilogue (TMEM lane quarter = warp % 4, column quarter = warp / 4),
+//             warp 16 = TMA producer (one lane), warp 17 = TMEM allocator + MMA issuer (one lane),
+//             warp 18 = scalar helper: per-step schedule / matrix rows -> smem, fp64 diffused-prior terms, per-sample
+//             Lambda inverses, Philox noise (everything that depends only on theta at the start of the step, off the
+//             critical path), warp 19 idle (completes the service warpgroup for setmaxnreg: service warps 64 registers,
+//             compute warps 104).
+// Schedule: a CTA that owns two sample groups interleaves them step by step, so that the last epilogue / scores / sums /
+// tail of one group overlap the tensor-core layers of the other (two TMEM accumulators); observation chunks of one item
+// are pipelined the same way.  DESIGN.md section 4.1, profiles/r01_tc_notes.md.
 #include "d4s_finalize_core.cuh"
 #include "d4s_tc_common.cuh"
 
