@@ -1,5 +1,6 @@
+"""GPU debug helper (not a pytest): cProfile of the host side of one end-to-end `NSE.ddim` call on the bench shape."""
 import sys, os, cProfile, pstats, io, argparse, time
-ROOT="/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "diffusions-for-sbi_b200"), os.path.join(ROOT, "tests")): sys.path.insert(0, p)
 import numpy as np, torch
 import bench, d4s
