@@ -811,6 +811,12 @@ cudaError_t launch_traj_tc(const TrajParams& p, int n_ctas, cudaStream_t stream)
     if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(traj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
         if (e != cudaSuccess) return e;
+        // setmaxnreg moves registers inside the CTA's launch allocation: with fewer than 96 registers per thread at launch
+        // the compute warps' `inc` could never be served (the kernel would hang), so refuse to launch instead
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, traj_tc_kernel);
+        if (e != cudaSuccess) return e;
+        if (fa.numRegs < 96) return cudaErrorLaunchOutOfResources;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     traj_tc_kernel<<<n_ctas, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
