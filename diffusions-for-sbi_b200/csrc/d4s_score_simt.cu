@@ -35,10 +35,13 @@ __device__ __forceinline__ void layer_gemm(float (&acc)[8][NC], const float* __r
                                            const float* sAct, float* sW, int warp, int lane, int tid) {
     constexpr int Hout = NC * 32;
     constexpr int CHUNK_F4 = KC * Hout / 4;  // float4 per stage
+    // accumulators as packed fp32 pairs over two rows: one FFMA2 does (acc[q][j], acc[q+1][j]) += (a[q], a[q+1]) * w[j],
+    // which halves the issue slots of the inner loop (the kernel is issue bound, not FMA-pipe bound)
+    float2 acc2[4][NC];
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int j = 0; j < NC; ++j) acc[q][j] = 0.f;
+        for (int j = 0; j < NC; ++j) acc2[q][j] = make_float2(0.f, 0.f);
 
     __syncthreads();  // every warp is done with the previous layer's weight ring before it is refilled
     const int nchunks = K / KC;
@@ -62,17 +65,27 @@ __device__ __forceinline__ void layer_gemm(float (&acc)[8][NC], const float* __r
         for (int kk = 0; kk < KC; ++kk) {
             float4 a0 = *reinterpret_cast<const float4*>(a + kk * ASTR);
             float4 a1 = *reinterpret_cast<const float4*>(a + kk * ASTR + 4);
-            float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            float bv[NC];
+            const float2 av[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
+            float2 bv[NC];
 #pragma unroll
-            for (int j = 0; j < NC; ++j) bv[j] = w[kk * Hout + lane + 32 * j];
+            for (int j = 0; j < NC; ++j) {
+                const float b = w[kk * Hout + lane + 32 * j];
+                bv[j] = make_float2(b, b);
+            }
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int j = 0; j < NC; ++j) acc[q][j] = fmaf(av[q], bv[j], acc[q][j]);
+                for (int j = 0; j < NC; ++j) acc2[q][j] = __ffma2_rn(av[q], bv[j], acc2[q][j]);
         }
     }
     cp_async_wait<0>();
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            acc[2 * q][j] = acc2[q][j].x;
+            acc[2 * q + 1][j] = acc2[q][j].y;
+        }
 }
 
 // bias + ReLU (+ JAC masking) and in-place write-back of one hidden layer's activations
