@@ -29,7 +29,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// One hidden layer: acc[q][j] = sum_k act[k][8*warp+q] * Wt[k][lane+32j]
+// Output columns of a lane in the hidden layers: groups of G = min(NC, 4) consecutive columns, so that a lane reads its
+// weights of one k with one vector load per group: col(lane, j) = G lane + j % G + 32 G (j / G).
+template <int NC>
+__device__ __forceinline__ int col_of(int lane, int j) {
+    constexpr int G = NC >= 4 ? 4 : NC;
+    return G * lane + (j % G) + 32 * G * (j / G);
+}
+
+// One hidden layer: acc[q][j] = sum_k act[k][8*warp+q] * Wt[k][col_of(lane, j)]
 template <int NC>
 __device__ __forceinline__ void layer_gemm(float (&acc)[8][NC], const float* __restrict__ Wt, int K,
                                            const float* sAct, float* sW, int warp, int lane, int tid) {
@@ -67,10 +75,21 @@ __device__ __forceinline__ void layer_gemm(float (&acc)[8][NC], const float* __r
             float4 a1 = *reinterpret_cast<const float4*>(a + kk * ASTR + 4);
             const float2 av[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
             float2 bv[NC];
+            constexpr int G = NC >= 4 ? 4 : NC;
 #pragma unroll
-            for (int j = 0; j < NC; ++j) {
-                const float b = w[kk * Hout + lane + 32 * j];
-                bv[j] = make_float2(b, b);
+            for (int g = 0; g < NC / G; ++g) {
+                const float* wp = w + kk * Hout + G * lane + 32 * G * g;
+                if constexpr (G == 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(wp);
+                    bv[4 * g] = make_float2(b4.x, b4.x);
+                    bv[4 * g + 1] = make_float2(b4.y, b4.y);
+                    bv[4 * g + 2] = make_float2(b4.z, b4.z);
+                    bv[4 * g + 3] = make_float2(b4.w, b4.w);
+                } else {
+                    const float2 b2 = *reinterpret_cast<const float2*>(wp);
+                    bv[2 * g] = make_float2(b2.x, b2.x);
+                    bv[2 * g + 1] = make_float2(b2.y, b2.y);
+                }
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
@@ -95,7 +114,7 @@ __device__ __forceinline__ void layer_epilogue(float (&acc)[8][NC], const float*
                                                int warp, int lane) {
     float bj[NC];
 #pragma unroll
-    for (int j = 0; j < NC; ++j) bj[j] = __ldg(bias + lane + 32 * j);
+    for (int j = 0; j < NC; ++j) bj[j] = __ldg(bias + col_of<NC>(lane, j));
     if (jac) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -126,7 +145,7 @@ __device__ __forceinline__ void layer_epilogue(float (&acc)[8][NC], const float*
                 v[q] = ((word >> lane) & 1u) ? acc[q][j] : 0.f;
             }
         }
-        float* dst = sAct + (size_t)(lane + 32 * j) * ASTR + 8 * warp;
+        float* dst = sAct + (size_t)col_of<NC>(lane, j) * ASTR + 8 * warp;
         *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
     }
