@@ -79,7 +79,7 @@ static bool tc_eligible(const D4sNet* net, const D4sProblem* pb) {
     bool emb_ok = true;  // a theta-embedding MLP runs inside the kernel when its layers fit the ping-pong buffers (<= 160 wide)
     for (int l = 0; l <= net->dev.emb_L && net->dev.emb_L > 0; ++l) emb_ok = emb_ok && net->dev.emb_dims[l] <= 160;
     return g_opt_path != 1 && pb->cov_mode == D4S_COV_GAUSS && !pb->paired && net->dev.L >= 3 && emb_ok &&
-           net->dev.out_act == 0 && net->dev.out_scale == 1.f && pb->obs_raw == nullptr && pb->ctx_samples == 0;
+           net->dev.out_act == 0 && net->dev.out_scale == 1.f && pb->obs_raw == nullptr;
 }
 
 static bool jac_tc_eligible(const D4sNet* net, const D4sProblem* pb) {
@@ -423,6 +423,8 @@ static int fill_traj_params(const D4sNet* net, const D4sProblem* pb, const float
     f.sample_offset = pb->sample_offset;
     f.clip_lo = pb->clip_lo;
     f.clip_hi = pb->clip_hi;
+    f.ctx_samples = pb->ctx_samples;
+    f.ctx_qsum = pb->ctx_qsum;
     if (!g_err_flag) {
         if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaMalloc(flag)");
         cudaMemset(g_err_flag, 0, sizeof(int));

@@ -74,12 +74,15 @@ static_assert(OFF_BAR % 8 == 0 && OFF_SCHED % 16 == 0, "alignment");
 // for the usual theta_dim <= 5 (an in-thread inverse with local-memory arrays costs tens of thousands of cycles
 // because the L1 is almost entirely carved out as shared memory).
 template <int M>
-__device__ __noinline__ void lambda_inverse_col(const float* lbase, const float* p0, double one_minus_n, int c, float* out) {
+__device__ __noinline__ void lambda_inverse_col(const float* lbase, const float* qsum, const float* p0, double one_minus_n, int c,
+                                                float* out) {
     double a[M][M], b[M];
 #pragma unroll
     for (int r = 0; r < M; ++r) {
 #pragma unroll
-        for (int cc = 0; cc < M; ++cc) a[r][cc] = (double)lbase[r * M + cc] + ((r == cc) ? one_minus_n * (double)p0[r] : 0.0);
+        for (int cc = 0; cc < M; ++cc)  // (+ the observation part of the sample's context, batched contexts only)
+            a[r][cc] = (double)lbase[r * M + cc] + (qsum ? (double)__ldg(qsum + r * M + cc) : 0.0) +
+                       ((r == cc) ? one_minus_n * (double)p0[r] : 0.0);
         b[r] = (r == c) ? 1.0 : 0.0;
     }
     lu_solve_d<M>(a, b);
@@ -87,18 +90,56 @@ __device__ __noinline__ void lambda_inverse_col(const float* lbase, const float*
     for (int r = 0; r < M; ++r) out[r * M + c] = (float)b[r];
 }
 
-__device__ __forceinline__ void lambda_inverse_dispatch(int m, const float* lbase, const float* p0, double omn, int c, float* out) {
+__device__ __forceinline__ void lambda_inverse_dispatch(int m, const float* lbase, const float* qsum, const float* p0, double omn, int c,
+                                                        float* out) {
     switch (m) {
-        case 1: lambda_inverse_col<1>(lbase, p0, omn, c, out); break;
-        case 2: lambda_inverse_col<2>(lbase, p0, omn, c, out); break;
-        case 3: lambda_inverse_col<3>(lbase, p0, omn, c, out); break;
-        case 4: lambda_inverse_col<4>(lbase, p0, omn, c, out); break;
-        case 5: lambda_inverse_col<5>(lbase, p0, omn, c, out); break;
-        case 6: lambda_inverse_col<6>(lbase, p0, omn, c, out); break;
-        case 7: lambda_inverse_col<7>(lbase, p0, omn, c, out); break;
-        case 8: lambda_inverse_col<8>(lbase, p0, omn, c, out); break;
-        case 9: lambda_inverse_col<9>(lbase, p0, omn, c, out); break;
-        default: lambda_inverse_col<10>(lbase, p0, omn, c, out); break;
+        case 1: lambda_inverse_col<1>(lbase, qsum, p0, omn, c, out); break;
+        case 2: lambda_inverse_col<2>(lbase, qsum, p0, omn, c, out); break;
+        case 3: lambda_inverse_col<3>(lbase, qsum, p0, omn, c, out); break;
+        case 4: lambda_inverse_col<4>(lbase, qsum, p0, omn, c, out); break;
+        case 5: lambda_inverse_col<5>(lbase, qsum, p0, omn, c, out); break;
+        case 6: lambda_inverse_col<6>(lbase, qsum, p0, omn, c, out); break;
+        case 7: lambda_inverse_col<7>(lbase, qsum, p0, omn, c, out); break;
+        case 8: lambda_inverse_col<8>(lbase, qsum, p0, omn, c, out); break;
+        case 9: lambda_inverse_col<9>(lbase, qsum, p0, omn, c, out); break;
+        default: lambda_inverse_col<10>(lbase, qsum, p0, omn, c, out); break;
+    }
+}
+
+// Layer 0 for batched contexts (D4sProblem.ctx_samples > 0): every sample of the tile has its own observation block, so
+// the obs_feat rows are loaded per (sample, observation) instead of once per observation.  Not inlined (see below).
+__device__ __noinline__ void layer0_contexts(const float* __restrict__ obs_feat, const float* s_base, uint8_t* a_hi, uint8_t* a_lo,
+                                             int H0, int OC, int SG, int nsamp, int n, int j0, int nobs, int ctx_samples, int i0,
+                                             int warp, int lane) {
+    const int nkg = H0 / 8;
+    for (int oj = lane; oj < OC; oj += 32) {
+        const bool ovalid = oj < nobs;
+        for (int si = 0; si < SG; ++si) {
+            const bool valid = ovalid && si < nsamp;
+            const float* up = obs_feat + ((size_t)((i0 + (valid ? si : 0)) / ctx_samples) * n + j0 + (ovalid ? oj : 0)) * H0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int kg = warp + 16 * j;
+                if (kg < nkg) {
+                    float v[8];
+                    if (valid) {
+                        const float4 u0 = __ldg(reinterpret_cast<const float4*>(up + 8 * kg));
+                        const float4 u1 = __ldg(reinterpret_cast<const float4*>(up + 8 * kg + 4));
+                        const float* brow = s_base + si * 256 + 8 * kg;
+                        const float4 b0 = *reinterpret_cast<const float4*>(brow);
+                        const float4 b1 = *reinterpret_cast<const float4*>(brow + 4);
+                        v[0] = fmaxf(u0.x + b0.x, 0.f); v[1] = fmaxf(u0.y + b0.y, 0.f);
+                        v[2] = fmaxf(u0.z + b0.z, 0.f); v[3] = fmaxf(u0.w + b0.w, 0.f);
+                        v[4] = fmaxf(u1.x + b1.x, 0.f); v[5] = fmaxf(u1.y + b1.y, 0.f);
+                        v[6] = fmaxf(u1.z + b1.z, 0.f); v[7] = fmaxf(u1.w + b1.w, 0.f);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                    }
+                    store_split8(v, a_hi, a_lo, a_off(si * OC + oj, kg));
+                }
+            }
+        }
     }
 }
 
@@ -176,7 +217,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     // sBase holds SG <= 8 rows of 256 floats, and its first 1280 floats double as scratch of the scores phase; with
     // SG <= 5 the last 768 floats are free: enough for the inv(Sigma_j) of a short observation set (n = 30, m = 5: 750),
     // which saves the scores phase its dependent global loads.
-    const bool q_in_smem = p.obs_prec != nullptr && p.C == 1 && p.SG <= 5 && p.n * m * m <= 768;
+    const bool q_in_smem = p.obs_prec != nullptr && p.C == 1 && p.SG <= 5 && p.n * m * m <= 768 && p.fin.ctx_samples == 0;
     const int n_groups = (p.N + p.SG - 1) / p.SG;
     const int mats_floats = 2 * m * m + m;
     constexpr int NB23 = TC_CT + 32;  // participants of named barriers 2 and 3
@@ -351,7 +392,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     __syncwarp();
                     for (int e = lane; e < nsamp * m; e += 32) {  // one lane per (sample, column of the inverse)
                         const int si = e / m, c = e - si * m;
-                        lambda_inverse_dispatch(m, sMats, sPrior + si * MMAX, uni ? omn : 0.0, c, sMinv + si * MMAX * MMAX);
+                        const float* qsum = (p.fin.ctx_qsum && p.fin.ctx_samples > 0)
+                                                ? p.fin.ctx_qsum + (size_t)((i0 + si) / p.fin.ctx_samples) * m * m : nullptr;
+                        lambda_inverse_dispatch(m, sMats, qsum, sPrior + si * MMAX, uni ? omn : 0.0, c, sMinv + si * MMAX * MMAX);
                     }
                 }
                 for (int e = lane; e < nsamp * nq; e += 32) {  // DDIM noise: one lane per (sample, 4 dims)
@@ -492,7 +535,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 }
             }
         };
-        auto do_layer0 = [&](int nsamp, int j0, int nobs, float4 (&upre)[2][2], bool have_pre) {
+        auto do_layer0 = [&](int i0, int nsamp, int j0, int nobs, float4 (&upre)[2][2], bool have_pre) {
+            if (p.fin.ctx_samples > 0) {
+                layer0_contexts(p.obs_feat, sBase, sAhi, sAlo, H0, p.OC, p.SG, nsamp, p.n, j0, nobs, p.fin.ctx_samples, i0, warp, lane);
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(bar_a);
+                return;
+            }
             // ---- layer 0: act0[r][col] = relu(base[si][col] + obs_feat[j][col]) -> bf16 hi/lo A images -----------
             // warp w owns k-groups w, w+16; lanes run over the observations: one 32-byte read of obs_feat
             // serves the rows of all SG samples, and every global load is issued before its first use.
@@ -546,7 +596,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
             }
         };
         // epilogue of the last hidden layer + output layer in fp32 + scores of a pass -> sS
-        auto do_last_epilogue = [&](uint32_t dacc, float inv_sigma, int j0, int nobs) {
+        auto do_last_epilogue = [&](uint32_t dacc, float inv_sigma, int j0, int nobs, int i0) {
             const int Nn = net.Hp[L - 2];
             const int qcols = Nn >> 2, nblk = qcols / 16;
             const float* bias_l = net.bias[L - 2] + cq * qcols;
@@ -621,7 +671,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                             sQS[row * MMAX + r] = qs;
                         }
                     } else {
-                        const float* Q = p.obs_prec + (size_t)(j0 + oj) * m * m;
+                        const int ctx0 = p.fin.ctx_samples > 0 ? ((i0 + sRowSi[row]) / p.fin.ctx_samples) * p.n : 0;  // batched contexts
+                        const float* Q = p.obs_prec + (size_t)(ctx0 + j0 + oj) * m * m;
                         for (int r = 0; r < m; ++r) {
                             float qs = 0.f;
 #pragma unroll
@@ -680,7 +731,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 // layer 0 of this pass goes first when it does not depend on the previous pass: interleaved groups, or a
                 // later observation chunk of the same item (its sample part was recomputed at the end of the last pass)
                 const bool early = have && (defer || chunk > 0);
-                const bool have_pre = early && lane < p.OC;
+                const bool have_pre = early && lane < p.OC && p.fin.ctx_samples == 0;
                 if (have_pre) l0_load(upre, j0, nobs, lane);  // layer 0 follows the wait directly: hide its global loads
                 if (prev) {  // the last layer of the previous pass: once it is done the operand images are free again
                     inv_sigma_prev = __ldg(p.sched + (size_t)step_of(pit) * D4S_SCHED_STRIDE + D4S_S_INV_SIGMA);
@@ -691,10 +742,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     PROF_MARK(3);  // waiting for the tensor core
                 }
                 if (early) {
-                    do_layer0(nsg[gi], j0, nobs, upre, have_pre);
+                    do_layer0(i0g[gi], nsg[gi], j0, nobs, upre, have_pre);
                     PROF_MARK(1);  // layer 0
                 }
-                if (prev) do_last_epilogue(dacc_prev, inv_sigma_prev, pj0, pnobs);
+                if (prev) do_last_epilogue(dacc_prev, inv_sigma_prev, pj0, pnobs, i0g[pgi]);
                 if (!defer) {
                     if (prev) {
                         do_sums(nsg[pgi], pj0, pnobs, pchunk == 0);
@@ -717,7 +768,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         do_base(th, true, 0, step_of(it + 1));
                         compute_bar();
                         PROF_MARK(0);  // per-sample layer-0 part
-                        do_layer0(nsg[gi], j0, nobs, upre, false);
+                        do_layer0(i0g[gi], nsg[gi], j0, nobs, upre, false);
                         PROF_MARK(1);  // layer 0
                     }
                 }
