@@ -607,6 +607,74 @@ def test_tc_trajectory_with_theta_embedding(N, n, dev):
     assert e_tc < TRAJ_TOL and e_simt < TRAJ_TOL and e_all < TRAJ_TOL
 
 
+def _random_embedding_cases(count, seed):
+    rng = np.random.default_rng(seed)
+    cases = []
+    for _ in range(count):
+        m = int(rng.integers(1, 11))
+        d = int(rng.integers(1, 10))
+        F = int(rng.integers(1, 9))
+        emb_t = tuple(int(rng.choice([16, 24, 48, 64, 100, 160])) for _ in range(int(rng.integers(1, 4))))
+        emb_x = tuple(int(rng.choice([8, 16, 32])) for _ in range(int(rng.integers(1, 3))))
+        hidden = tuple(int(rng.choice([64, 96, 128, 200, 256])) for _ in range(int(rng.integers(2, 4))))
+        n = int(rng.choice([2, 5, 17, 30, 33, 129, 300]))
+        N = int(rng.choice([1, 3, 37, 150, 601, 1500]))
+        if N * n > 40000:
+            N = max(1, 40000 // n)
+        cases.append((m, d, F, emb_t, emb_x, hidden, n, N, str(rng.choice(["uniform", "gaussian"])), int(rng.integers(0, 1 << 30))))
+    return cases
+
+
+@pytest.mark.parametrize("case", _random_embedding_cases(int(os.environ.get("D4S_FUZZ_CASES", "10")), int(os.environ.get("D4S_FUZZ_SEED", "31"))),
+                         ids=lambda c: f"m{c[0]}_d{c[1]}_F{c[2]}_et{'x'.join(map(str, c[3]))}_ex{'x'.join(map(str, c[4]))}_h{'x'.join(map(str, c[5]))}_n{c[6]}_N{c[7]}_{c[8]}")
+def test_tc_embedding_random_shapes(case, dev):
+    """Seeded random embedding nets (theta MLP 1..3 layers up to 160 wide, x MLP, 1..8 time frequencies): the in-kernel
+    theta embedding of the tcgen05 trajectory kernel against the fp32 SIMT path (separate embedding kernel) under
+    replayed noise, both group schedules bit-identical, and run-to-run determinism."""
+    from d4s import _cabi as abi
+    from d4s_helpers import nse_from_oracle
+    m, d, F, emb_t, emb_x, hidden, n, N, pkind, seed = case
+    rng = np.random.default_rng(seed)
+
+    def mlp(widths):
+        ws, bs = [], []
+        for a, b in zip(widths[:-1], widths[1:]):
+            k = 1 / np.sqrt(a)
+            ws.append(rng.uniform(-k, k, size=(b, a)))
+            bs.append(rng.uniform(-k, k, size=(b,)))
+        return orc.OracleMLP(ws, bs)
+
+    onet = orc.OracleNet(m, d, np.arange(1, F + 1) * np.pi, mlp([emb_t[-1] + emb_x[-1] + 2 * F, *hidden, m]),
+                         mlp([m, *emb_t]), mlp([d, *emb_x]))
+    nse = nse_from_oracle(onet, dev)
+    x = 0.5 * rng.standard_normal((n, d))
+    a = 0.2 * rng.standard_normal((n, m, m))
+    cov = a @ a.transpose(0, 2, 1) + 0.05 * np.eye(m)
+    oprior = (orc.UniformPrior(np.full(m, -3.46), np.full(m, 3.46)) if pkind == "uniform"
+              else orc.GaussianPrior(np.zeros(m), np.eye(m) * 4.0))
+    prior, fn = _d4s_prior(oprior, nse, dev)
+    steps = 3
+    z0, z = rng.standard_normal((N, m)), rng.standard_normal((steps, N, m))
+    kw = dict(steps=steps, eta=1.0, prior=prior, prior_type=pkind, prior_score_fn=fn, dist_cov_est=_t(cov, dev),
+              cov_mode="GAUSS", _noise=(torch.as_tensor(z0, dtype=torch.float32), torch.as_tensor(z, dtype=torch.float32)))
+    abi.set_option("path", 2)
+    try:
+        out = nse.ddim((N,), _t(x, dev), **kw)
+        out2 = nse.ddim((N,), _t(x, dev), **kw)
+        abi.set_option("tc_pairing", 0)
+        out_seq = nse.ddim((N,), _t(x, dev), **kw)
+        abi.set_option("path", 1)
+        simt = nse.ddim((N,), _t(x, dev), **kw)
+    finally:
+        abi.set_option("tc_pairing", 1)
+        abi.set_option("path", 0)
+    assert torch.isfinite(out).all()
+    assert torch.equal(out, out2) and torch.equal(out, out_seq)
+    err = float((out - simt).abs().max()) / max(1.0, float(simt.abs().max()))
+    print(f"{case[:9]}: tc vs simt max rel diff {err:.2e}")
+    assert err < TRAJ_TOL
+
+
 def _random_tc_cases(count, seed):
     rng = np.random.default_rng(seed)
     cases = []
