@@ -150,6 +150,60 @@ class NSE(nn.Module):
             theta = engine.philox_normal(N, m, seed, -1, off, x.device)
         return engine.run_trajectory(setup, theta, z, _use_graph_default())
 
+    # ---- Langevin / Geffner baselines of the toy script (gen_gaussian_gaussian.py:205-238) ---------------------------
+    _gammas = _FullNSE._gammas  # gamma_t = alpha(t) / alpha(t - time[-2]), alpha(t) on the last step (nse_toy.py:489-492)
+
+    def _run_rows(self, shape: Size, x: Tensor, t_rows: Tensor, coef: dict, prior_score_fn, kw: dict) -> Tensor:
+        """A trajectory whose steps are schedule rows (time + update coefficients) on the plain-sum score
+        (1 - n) prior_score + sum_j score_j (nse_toy.py:503, 536-545)."""
+        noise, seed, off = kw.pop("_noise", None), kw.pop("_seed", None), kw.pop("_sample_offset", 0)
+        if kw:
+            raise TypeError(f"unexpected keyword arguments: {sorted(kw)}")
+        N, m = int(shape[0]), self.theta_dim
+        if seed is None:
+            seed = self._draw_seed()
+        setup = engine.build_setup(self, x, N, t_rows, None, 0.0, self._prior_spec(prior_score_fn), "GAUSS", None,
+                                   seed=seed, sample_offset=off, weighted=False, coef=coef)
+        if noise is not None:
+            z0, z = noise
+            theta = z0.to(x.device, torch.float32).contiguous().clone()
+        else:
+            z = None
+            theta = engine.philox_normal(N, m, seed, -1, off, x.device)
+        return engine.run_trajectory(setup, theta, z, _use_graph_default())
+
+    def annealed_langevin_geffner(self, shape: Size, x: Tensor, prior_score_fn, steps: int = 64, lsteps: int = 5,
+                                  tau: float = 0.5, verbose: bool = False, **kwargs) -> Tensor:
+        """Annealed Langevin with the F-NPSE score (nse_toy.py:474-508): `steps` noise levels x `lsteps` updates
+        theta += delta score + sqrt(2 delta) z, delta = tau (1 - gamma_t) / sqrt(gamma_t); no clipping, always the
+        sum over the observations.  One fused launch."""
+        self._require_cuda(x)
+        if x.ndim != 2:
+            raise ValueError("nse_toy.annealed_langevin_geffner expects x of shape [n_obs, x_dim] (nse_toy.py:495)")
+        grid = engine.time_grid(steps)
+        gamma = self._gammas(grid)
+        delta = tau * (1 - gamma) / gamma.sqrt()
+        rep = lambda v: v.repeat_interleave(lsteps)  # noqa: E731
+        rows = steps * lsteps
+        coef = dict(c_theta=torch.ones(rows, dtype=torch.float64), c_score=rep(delta), bstd=rep((2 * delta).sqrt()),
+                    clip=torch.zeros(rows, dtype=torch.float64))
+        return self._run_rows(shape, x, rep(grid[:-1]), coef, prior_score_fn, dict(kwargs))
+
+    def deterministic_gaussian_geffner(self, shape: Size, x: Tensor, prior_score_fn, steps: int = 64,
+                                       verbose: bool = False, **kwargs) -> Tensor:
+        """Gaussian transition sampler of Geffner et al., Algorithm 2, with the continuous schedule (nse_toy.py:510-556):
+        theta' = c_theta theta + var_t [S1 / sqrt(gamma) + (1 - n) prior_score] + sqrt(var_t) z."""
+        self._require_cuda(x)
+        if x.ndim != 2:
+            raise ValueError("nse_toy.deterministic_gaussian_geffner expects x of shape [n_obs, x_dim] (nse_toy.py:531)")
+        n = x.shape[0]
+        grid = engine.time_grid(steps)
+        g = self._gammas(grid)
+        den = n - g * (n - 1)
+        var = (1 - g) / den  # nse_toy.py:548
+        coef = dict(c_theta=(n / g.sqrt() - (n - 1) * g.sqrt()) / den, c_score=var, s1w=1 / g.sqrt(), bstd=var.sqrt())
+        return self._run_rows(shape, x, grid[:-1], coef, prior_score_fn, dict(kwargs))
+
     def _prior_spec(self, prior_score_fn) -> "engine.PriorSpec":
         if getattr(prior_score_fn, "kind", None) != "gaussian" or not hasattr(prior_score_fn, "_spec"):
             raise abi.D4sError("nse_toy.NSE needs `prior_score_fn = d4s.nse_toy.gaussian_prior_triple(mean, cov, nse)` "

@@ -181,7 +181,7 @@ def cfg_case(name, net32, x_raw, N, seed, steps):
     print("wrote", name)
 
 
-def toy_case(name, DIM, n_obs, eps_max, N, seed, steps, eta):
+def toy_case(name, DIM, n_obs, eps_max, N, seed, steps, eta, lang_steps=10, lsteps_g=3):
     """Config 1: the Gaussian-Gaussian toy of gen_gaussian_gaussian.py:27-96 driven on CPU -- reference `nse_toy.NSE`,
     `FakeFNet(real_eps, EpsilonNet(DIM), eps)`, triple-returning prior score; GAUSS + JAC per-call and trajectories,
     plus the paired covariance pre-pass (gen_gaussian_gaussian.py:143-160)."""
@@ -205,8 +205,14 @@ def toy_case(name, DIM, n_obs, eps_max, N, seed, steps, eta):
     Np = 3
     z0p = torch.randn(Np * n_obs, DIM, generator=gen)
     zp = torch.randn(steps, Np * n_obs, DIM, generator=gen)
+    # Langevin / Geffner baselines of the toy script (gen_gaussian_gaussian.py:205-238); drawn after the arrays above so
+    # that the earlier fixture contents do not change
+    z_lang = torch.randn(lang_steps * lsteps_g, N, DIM, generator=gen)
+    z_det = torch.randn(steps, N, DIM, generator=gen)
     t_grid = [0.9, 0.5, 0.2, 0.05]
     mlp_arrays("net", eps_net32.net, out)
+    out.update(lang_z=npy(z_lang), lang_steps=np.int64(lang_steps), lang_lsteps=np.int64(lsteps_g), lang_tau=np.float64(0.5),
+               det_z=npy(z_det))
     out.update(theta=npy(theta), x=npy(x_obs), dist_cov_est=npy(cov_est), t_grid=np.asarray(t_grid, np.float32),
                prior_kind=np.str_("gaussian"), theta_dim=np.int64(DIM), eps_max=np.float64(eps_max),
                traj_z0=npy(z0), traj_z=npy(z), traj_steps=np.int64(steps), traj_eta=np.float64(eta),
@@ -258,6 +264,20 @@ def toy_case(name, DIM, n_obs, eps_max, N, seed, steps, eta):
                 res = score_net.ddim(shape=(N,), x=xx, eta=eta, steps=steps, prior_score_fn=prior_score,
                                      dist_cov_est=ce, cov_mode=mode)
             out[f"{tag}.{mode}.traj"] = npy(res)
+        # annealed Langevin (nse_toy.py:474-508) and the deterministic Gaussian sampler (nse_toy.py:510-556)
+        it = iter(z_lang.to(dt))
+        FakeDiagNormal.z0 = z0.to(dt)
+        with mock.patch.object(ref_toy, "DiagNormal", FakeDiagNormal), \
+                mock.patch("torch.randn_like", side_effect=lambda a: next(it).to(a)), torch.no_grad():
+            res = score_net.annealed_langevin_geffner(shape=(N,), x=xx, prior_score_fn=prior_score, lsteps=lsteps_g,
+                                                      tau=0.5, steps=lang_steps)
+        out[f"{tag}.langevin.traj"] = npy(res)
+        it = iter(z_det.to(dt))
+        FakeDiagNormal.z0 = z0.to(dt)
+        with mock.patch.object(ref_toy, "DiagNormal", FakeDiagNormal), \
+                mock.patch("torch.randn_like", side_effect=lambda a: next(it).to(a)), torch.no_grad():
+            res = score_net.deterministic_gaussian_geffner(shape=(N,), x=xx, prior_score_fn=prior_score, steps=steps)
+        out[f"{tag}.det_geffner.traj"] = npy(res)
         # paired covariance pre-pass: every sample carries its own observation (gen_gaussian_gaussian.py:143-156)
         xp = xx[None, :].repeat(Np, 1, 1).reshape(Np * n_obs, -1)
         it = iter(zp.to(dt))
@@ -497,7 +517,7 @@ def main(filt=None):
         cfg_case("cfg_pf_slcp_n8", net, sbibm_obs("slcp", st, 8), N=10, seed=41, steps=16)
     if want("toy"):
         toy_case("toy_gauss_d4_n5", DIM=4, n_obs=5, eps_max=1e-1, N=12, seed=31, steps=20, eta=0.5)
-        toy_case("toy_gauss_d10_n30", DIM=10, n_obs=30, eps_max=1e-2, N=8, seed=32, steps=64, eta=0.2)  # dt = 2^-6: the fp64 run of the reference is NaN when fp32(t) - dt < 0 (toy alpha has a linear term)
+        toy_case("toy_gauss_d10_n30", DIM=10, n_obs=30, eps_max=1e-2, N=8, seed=32, steps=64, eta=0.2, lang_steps=200, lsteps_g=2)  # dt = 2^-6: the fp64 run of the reference is NaN when fp32(t) - dt < 0 (toy alpha has a linear term)
     if want("langevin"):
         net, st = load_sbibm("sir")
         x = sbibm_obs("sir", st, 5, log_space=False)

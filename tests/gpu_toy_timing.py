@@ -71,5 +71,15 @@ for mode in ("GAUSS", "JAC"):
         rows.append({"mode": mode, "steps": steps, "sampler_s": round(t, 4), "cov_prepass_s": round(t_cov, 4) if mode == "GAUSS" else 0.0,
                      "total_s": round(total, 4), "samples_per_s": round(N / total, 1), "published_s": pub,
                      "vs_published": None if pub is None else round(pub / total, 1), "finite": bool(torch.isfinite(th).all())})
+# the Langevin (F-NPSE, 5 inner steps, tau 0.5) and deterministic Geffner baselines of the same script (:205-238)
+published_l = {1000: 16.65, 400: 6.65}
+for steps in (1000, 400):
+    for mode, f in (("Langevin", lambda: nse.annealed_langevin_geffner((N,), x_obs, prior_fn, lsteps=5, tau=0.5, steps=steps)),
+                    ("DET_GEF", lambda: nse.deterministic_gaussian_geffner((N,), x_obs, prior_fn, steps=steps))):
+        t, th = timed(f)
+        pub = published_l[steps] if (mode == "Langevin" and (DIM, n_obs) == (10, 32)) else None
+        rows.append({"mode": mode, "steps": steps, "sampler_s": round(t, 4), "cov_prepass_s": 0.0, "total_s": round(t, 4),
+                     "samples_per_s": round(N / t, 1), "published_s": pub,
+                     "vs_published": None if pub is None else round(pub / t, 1), "finite": bool(torch.isfinite(th).all())})
 print(json.dumps({"workload": f"toy Gaussian-Gaussian dim={DIM}, n_obs={n_obs}, eps={eps_max}, 1000 samples; "
                               "published = BASELINE.md section 1 (unspecified CUDA GPU, torch eager)", "rows": rows}))

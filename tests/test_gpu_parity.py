@@ -875,6 +875,21 @@ def test_toy_gaussian_config(name, dev):
     out = nse.ddim((xp.shape[0],), xp, steps=steps, eta=0.5, _noise=(torch.as_tensor(g["pair_z0"]), torch.as_tensor(g["pair_z"])))
     ref = g["f64.pair.traj"]
     assert np.abs(out.cpu().numpy() - ref).max() < TRAJ_TOL * max(1.0, np.abs(ref).max())
+    # Langevin / Geffner baselines the toy script runs next to GAUSS / JAC (nse_toy.py:474-556)
+    z0 = torch.as_tensor(g["traj_z0"])
+    out = nse.annealed_langevin_geffner((z0.shape[0],), x, prior_fn, steps=int(g["lang_steps"]), lsteps=int(g["lang_lsteps"]),
+                                        tau=float(g["lang_tau"]), _noise=(z0, torch.as_tensor(g["lang_z"])))
+    ref = g["f64.langevin.traj"]
+    ref32 = np.abs(g["f32.langevin.traj"] - ref).max()
+    err = np.abs(out.cpu().numpy() - ref).max()
+    print(f"{name} Langevin: max|d theta| = {err:.2e} (reference fp32 vs fp64: {ref32:.2e})")
+    assert err < max(TRAJ_TOL * max(1.0, np.abs(ref).max()), 3 * ref32), (name, "langevin", err)
+    out = nse.deterministic_gaussian_geffner((z0.shape[0],), x, prior_fn, steps=steps, _noise=(z0, torch.as_tensor(g["det_z"])))
+    ref = g["f64.det_geffner.traj"]
+    ref32 = np.abs(g["f32.det_geffner.traj"] - ref).max()
+    err = np.abs(out.cpu().numpy() - ref).max()
+    print(f"{name} deterministic Geffner: max|d theta| = {err:.2e} (reference fp32 vs fp64: {ref32:.2e})")
+    assert err < max(TRAJ_TOL * max(1.0, np.abs(ref).max()), 3 * ref32), (name, "det_geffner", err)
     # the torch definition of the module (used outside the fused path) agrees with the kernels' affine form
     tt = torch.tensor(0.3, device=dev)
     e_torch = nse(theta, x[:1].expand(theta.shape[0], -1), tt)

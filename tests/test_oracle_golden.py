@@ -175,6 +175,14 @@ def test_toy_config_fp64(name):
     out = orc.ddim_single(net, xp, g["pair_z0"], g["pair_z"], steps, 0.5)
     ref = g["f64.pair.traj"]
     assert np.abs(out - ref).max() < 1e-5 * max(1.0, np.abs(ref).max())
+    # Langevin / Geffner baselines of the toy script (nse_toy.py:474-556; gen_gaussian_gaussian.py:205-238)
+    out = orc.annealed_langevin_geffner(net, x, g["traj_z0"], g["lang_z"], prior, steps=int(g["lang_steps"]),
+                                        lsteps=int(g["lang_lsteps"]), tau=float(g["lang_tau"]))
+    ref = g["f64.langevin.traj"]
+    assert np.abs(out - ref).max() < 1e-5 * max(1.0, np.abs(ref).max()), name
+    out = orc.deterministic_gaussian_geffner(net, x, g["traj_z0"], g["det_z"], prior, steps=steps)
+    ref = g["f64.det_geffner.traj"]
+    assert np.abs(out - ref).max() < 1e-5 * max(1.0, np.abs(ref).max()), name
 
 
 # ---- classifier-free guidance (runs in the reference for PF_NSE only) ----------------------------
