@@ -43,6 +43,17 @@ SHAPES = {  # BASELINE.json configs
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE traj_tc_kernel launch (a whole 1000-step trajectory) of the default
+# workload, from the ncu --set full capture summarised in profiles/r01_ncu_full_traj_tc_bench.txt (3.572 MB + 0.202 MB):
+# weights, observation features and per-step tables are read once and stay in L2; the kernel is not HBM-bound.
+TRAJ_TC_DRAM_BYTES = 3572480 + 201728
+
+
+def is_default_workload(args, w) -> bool:
+    return (args.task == "slcp" and args.cov_mode == "GAUSS" and args.n_obs == 30 and w["ddim_steps"] == 1000
+            and args.samples == 1000)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -416,7 +427,10 @@ def run_ours(args):
             launch_ms = float(np.mean(ms_dev))
             ach = flops_step * w["ddim_steps"] / (launch_ms * 1e-3) / 1e12
             roofline = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                        "traffic": None, "kernel": "traj_tc_kernel (tcgen05 kind::f16, bf16x3 split, fp32 TMEM accumulators)",
+                        "traffic": TRAJ_TC_DRAM_BYTES if is_default_workload(args, w) else None,
+                        "traffic_source": "profiles/r01_ncu_full_traj_tc_bench.txt (ncu --set full of this command: "
+                                          "dram__bytes_read.sum + dram__bytes_write.sum of the one launch)",
+                        "kernel": "traj_tc_kernel (tcgen05 kind::f16, bf16x3 split, fp32 TMEM accumulators)",
                         "peak_source": src, "flops_per_launch": flops_step * w["ddim_steps"], "launch_ms": launch_ms,
                         "share_of_step": launch_ms / ms_step,
                         "note": "achieved counts ALGORITHMIC flops (2*in*out per pair and layer); the bf16x3 split issues 3 "
