@@ -273,6 +273,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ================= TMA producer: streams the weight images in consumption order ===========================
         if (lane == 0) {
+            // role-local copy of the shared-memory base: the kernel-wide one is spilled (the compute warps need every
+            // register), and a reload from local memory in each iteration of this loop costs an L1 / L2 round trip
+            uint32_t sm0 = smem_u32(smem);
+            asm volatile("" : "+r"(sm0));
             unsigned it = 0;
             for (long long ti = 0; ti < tile_iters; ++ti) {
                 for (int l = 1; l <= L - 2; ++l) {
@@ -282,10 +286,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     for (int ks = 0; ks < K / 16; ++ks, ++it) {
                         const int s = it % TC_NSTG;
                         const uint32_t ph = (it / TC_NSTG) & 1u;
-                        mbar_wait(bar_empty(s), ph ^ 1u, p.error_flag);
-                        mbar_expect_tx(bar_full(s), bytes);
-                        tma_bulk_g2s(smem_u32(smem + OFF_RING + s * TC_STAGE_BYTES), src + (size_t)ks * bytes, bytes,
-                                     bar_full(s));
+                        const uint32_t full_s = sm0 + OFF_BAR + 8u * s, empty_s = full_s + 8u * TC_NSTG;
+                        mbar_wait(empty_s, ph ^ 1u, p.error_flag);
+                        mbar_expect_tx(full_s, bytes);
+                        tma_bulk_g2s(sm0 + OFF_RING + s * TC_STAGE_BYTES, src + (size_t)ks * bytes, bytes, full_s);
                     }
                 }
             }
@@ -294,8 +298,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ================= MMA issuer ===================================================================================
         if (lane == 0) {
+            uint32_t sm0 = smem_u32(smem);  // role-local copy of the shared-memory base (see the TMA producer)
+            asm volatile("" : "+r"(sm0));
+            const uint32_t bar_a = sm0 + OFF_BAR + 8u * (2 * TC_NSTG), bar_d = bar_a + 8u;
             unsigned it = 0, a_cnt = 0, lc = 0;
-            const uint32_t a_hi0 = smem_u32(sAhi), a_lo0 = smem_u32(sAlo);
+            const uint32_t a_hi0 = sm0 + OFF_AHI, a_lo0 = sm0 + OFF_ALO;
             for (long long ti = 0; ti < tile_iters; ++ti) {
                 for (int l = 1; l <= L - 2; ++l) {
                     const int K = net.Hp[l - 1], Nn = net.Hp[l];
@@ -311,9 +318,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     for (int ks = 0; ks < K / 16; ++ks, ++it) {
                         const int s = it % TC_NSTG;
                         const uint32_t ph = (it / TC_NSTG) & 1u;
-                        mbar_wait(bar_full(s), ph, p.error_flag);
+                        const uint32_t full_s = sm0 + OFF_BAR + 8u * s;
+                        mbar_wait(full_s, ph, p.error_flag);
                         tc_fence_after();
-                        const uint32_t wb = smem_u32(smem + OFF_RING + s * TC_STAGE_BYTES);
+                        const uint32_t wb = sm0 + OFF_RING + s * TC_STAGE_BYTES;
                         const uint64_t b_hi = umma_desc(wb, b_lbo, b_sbo);
                         const uint64_t b_lo = umma_desc(wb + (uint32_t)Nn * 32u, b_lbo, b_sbo);
                         const uint64_t a_hi = umma_desc(a_hi0 + ks * 4096, a_lbo, a_sbo);
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         tc_mma_bf16(dacc, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
                         tc_mma_bf16(dacc, a_lo, b_hi, idesc, 1u);
                         tc_mma_bf16(dacc, a_hi, b_lo, idesc, 1u);
-                        tc_commit(bar_empty(s));  // ring slot is free once these MMAs have read it
+                        tc_commit(full_s + 8u * TC_NSTG);  // (= bar_empty(s)) ring slot is free once these MMAs have read it
                     }
                     tc_commit(bar_d);  // accumulator complete
                     if (p.prof && blockIdx.x == 0) {  // profiling: duration of this layer's MMAs (slots 8 / 9: first / last layer)
@@ -346,6 +354,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 const int nsamp = min(p.SG, p.N - i0);
                 const float* th = sTheta + gi * TC_SG_MAX * MMAX;
                 bar_sync(2, NB23);  // theta of this item is final; the previous item's consumers are done with our buffers
+                const long long h_t0 = (p.prof && blockIdx.x == 0 && lane == 0) ? clock64() : 0;
                 if (p.part_out) {  // export mode: the caller reduces over ranks and finalizes; nothing to prepare
                     bar_arrive(3, NB23);
                     continue;
@@ -411,6 +420,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         if (4 * qd + k < MMAX) sNoise[si * MMAX + 4 * qd + k] = z[k];
                 }
                 __syncwarp();
+                if (p.prof && blockIdx.x == 0 && lane == 0) {  // profiling: busy cycles of the helper warp (slots 10 / 11 / 12)
+                    const long long dt = clock64() - h_t0;
+                    p.prof[10] += dt;
+                    if (per_sample) { p.prof[11] += dt; p.prof[12] += 1; }
+                }
                 bar_arrive(3, NB23);
             }
             gk += ngr;
