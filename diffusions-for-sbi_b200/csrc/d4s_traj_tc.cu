@@ -73,6 +73,64 @@ static_assert(OFF_BAR % 8 == 0 && OFF_SCHED % 16 == 0, "alignment");
 // One lane per (sample, column c): it solves Lambda_i x = e_c by LU with partial pivoting, everything in registers
 // for the usual theta_dim <= 5 (an in-thread inverse with local-memory arrays costs tens of thousands of cycles
 // because the L1 is almost entirely carved out as shared memory).
+// Helper-warp variants of lu_solve_d / uniform_prior_terms (d4s_finalize_core.cuh) with the fp64 divisions replaced by
+// reciprocals that are computed once: the helper warp is bound by the SM's fp64 issue rate (ncu: 66 % of its samples on
+// the math-pipe throttle) and is on the critical path of the per-sample Lambda steps; an fp64 division is ~30 fp64-pipe
+// instructions.  Results differ from the division forms by a few fp64 ulps, far below the fp32 outputs.
+template <int M>
+__device__ __forceinline__ void lu_solve_recip(double (&a)[M][M], double (&b)[M]) {
+    double inv[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+        int p = k;
+        double best = fabs(a[k][k]);
+#pragma unroll
+        for (int r = k + 1; r < M; ++r) {
+            const double v = fabs(a[r][k]);
+            if (v > best) { best = v; p = r; }
+        }
+#pragma unroll
+        for (int r = k + 1; r < M; ++r) {
+            if (r == p) {
+#pragma unroll
+                for (int c = 0; c < M; ++c) { const double t = a[k][c]; a[k][c] = a[r][c]; a[r][c] = t; }
+                const double t = b[k]; b[k] = b[r]; b[r] = t;
+            }
+        }
+        inv[k] = 1.0 / a[k][k];
+#pragma unroll
+        for (int r = k + 1; r < M; ++r) {
+            const double f = a[r][k] * inv[k];
+#pragma unroll
+            for (int c = k + 1; c < M; ++c) a[r][c] = fma(-f, a[k][c], a[r][c]);
+            b[r] = fma(-f, b[k], b[r]);
+        }
+    }
+#pragma unroll
+    for (int k = M - 1; k >= 0; --k) {
+        double sacc = b[k];
+#pragma unroll
+        for (int c = k + 1; c < M; ++c) sacc = fma(-a[k][c], b[c], sacc);
+        b[k] = sacc * inv[k];
+    }
+}
+
+// inv_sig = 1 / sigma, inv_s = 1 / sqrt(alpha); p0 = a/s^2 / (1 + sigma^2 jac) is formed by the caller when needed
+__device__ __forceinline__ void uniform_prior_terms_recip(double th, double lo, double hi, double s, double sig, double inv_s,
+                                                          double inv_sig, double& s0, double& jac) {
+    const double inv_sqrt_2pi = 0.39894228040143267794;
+    const double ub = (hi * s - th) * inv_sig;
+    const double ua = (lo * s - th) * inv_sig;
+    const double f = cdf_diff(ua, ub) * inv_s;
+    const double pb = inv_sqrt_2pi * exp(-0.5 * ub * ub), pa = inv_sqrt_2pi * exp(-0.5 * ua * ua);
+    const double iss = inv_sig * inv_s;
+    const double fp = -(pb - pa) * iss;
+    const double inv_den = 1.0 / (f + 1e-6);  // vp_diffused_priors.py:44
+    s0 = fp * inv_den;
+    const double fpp = -(ub * pb - ua * pa) * (iss * inv_sig);
+    jac = (fpp - fp * s0) * inv_den;  // fpp / den - fp^2 / den^2
+}
+
 template <int M>
 __device__ __noinline__ void lambda_inverse_col(const float* lbase, const float* qsum, const float* p0, double one_minus_n, int c,
                                                 float* out) {
@@ -85,7 +143,7 @@ __device__ __noinline__ void lambda_inverse_col(const float* lbase, const float*
                        ((r == cc) ? one_minus_n * (double)p0[r] : 0.0);
         b[r] = (r == c) ? 1.0 : 0.0;
     }
-    lu_solve_d<M>(a, b);
+    lu_solve_recip<M>(a, b);
 #pragma unroll
     for (int r = 0; r < M; ++r) out[r * M + c] = (float)b[r];
 }
@@ -273,10 +331,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ================= TMA producer: streams the weight images in consumption order ===========================
         if (lane == 0) {
-            // role-local copy of the shared-memory base: the kernel-wide one is spilled (the compute warps need every
-            // register), and a reload from local memory in each iteration of this loop costs an L1 / L2 round trip
-            uint32_t sm0 = smem_u32(smem);
-            asm volatile("" : "+r"(sm0));
             unsigned it = 0;
             for (long long ti = 0; ti < tile_iters; ++ti) {
                 for (int l = 1; l <= L - 2; ++l) {
@@ -286,10 +340,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     for (int ks = 0; ks < K / 16; ++ks, ++it) {
                         const int s = it % TC_NSTG;
                         const uint32_t ph = (it / TC_NSTG) & 1u;
-                        const uint32_t full_s = sm0 + OFF_BAR + 8u * s, empty_s = full_s + 8u * TC_NSTG;
-                        mbar_wait(empty_s, ph ^ 1u, p.error_flag);
-                        mbar_expect_tx(full_s, bytes);
-                        tma_bulk_g2s(sm0 + OFF_RING + s * TC_STAGE_BYTES, src + (size_t)ks * bytes, bytes, full_s);
+                        mbar_wait(bar_empty(s), ph ^ 1u, p.error_flag);
+                        mbar_expect_tx(bar_full(s), bytes);
+                        tma_bulk_g2s(smem_u32(smem + OFF_RING + s * TC_STAGE_BYTES), src + (size_t)ks * bytes, bytes,
+                                     bar_full(s));
                     }
                 }
             }
@@ -298,11 +352,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ================= MMA issuer ===================================================================================
         if (lane == 0) {
-            uint32_t sm0 = smem_u32(smem);  // role-local copy of the shared-memory base (see the TMA producer)
-            asm volatile("" : "+r"(sm0));
-            const uint32_t bar_a = sm0 + OFF_BAR + 8u * (2 * TC_NSTG), bar_d = bar_a + 8u;
             unsigned it = 0, a_cnt = 0, lc = 0;
-            const uint32_t a_hi0 = sm0 + OFF_AHI, a_lo0 = sm0 + OFF_ALO;
+            const uint32_t a_hi0 = smem_u32(sAhi), a_lo0 = smem_u32(sAlo);
             for (long long ti = 0; ti < tile_iters; ++ti) {
                 for (int l = 1; l <= L - 2; ++l) {
                     const int K = net.Hp[l - 1], Nn = net.Hp[l];
@@ -318,10 +369,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     for (int ks = 0; ks < K / 16; ++ks, ++it) {
                         const int s = it % TC_NSTG;
                         const uint32_t ph = (it / TC_NSTG) & 1u;
-                        const uint32_t full_s = sm0 + OFF_BAR + 8u * s;
-                        mbar_wait(full_s, ph, p.error_flag);
+                        mbar_wait(bar_full(s), ph, p.error_flag);
                         tc_fence_after();
-                        const uint32_t wb = sm0 + OFF_RING + s * TC_STAGE_BYTES;
+                        const uint32_t wb = smem_u32(smem + OFF_RING + s * TC_STAGE_BYTES);
                         const uint64_t b_hi = umma_desc(wb, b_lbo, b_sbo);
                         const uint64_t b_lo = umma_desc(wb + (uint32_t)Nn * 32u, b_lbo, b_sbo);
                         const uint64_t a_hi = umma_desc(a_hi0 + ks * 4096, a_lbo, a_sbo);
@@ -329,7 +379,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         tc_mma_bf16(dacc, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
                         tc_mma_bf16(dacc, a_lo, b_hi, idesc, 1u);
                         tc_mma_bf16(dacc, a_hi, b_lo, idesc, 1u);
-                        tc_commit(full_s + 8u * TC_NSTG);  // (= bar_empty(s)) ring slot is free once these MMAs have read it
+                        tc_commit(bar_empty(s));  // ring slot is free once these MMAs have read it
                     }
                     tc_commit(bar_d);  // accumulator complete
                     if (p.prof && blockIdx.x == 0) {  // profiling: duration of this layer's MMAs (slots 8 / 9: first / last layer)
@@ -354,7 +404,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 const int nsamp = min(p.SG, p.N - i0);
                 const float* th = sTheta + gi * TC_SG_MAX * MMAX;
                 bar_sync(2, NB23);  // theta of this item is final; the previous item's consumers are done with our buffers
-                const long long h_t0 = (p.prof && blockIdx.x == 0 && lane == 0) ? clock64() : 0;
                 if (p.part_out) {  // export mode: the caller reduces over ranks and finalizes; nothing to prepare
                     bar_arrive(3, NB23);
                     continue;
@@ -369,11 +418,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 const bool per_sample = (combine == D4S_COMBINE_PER_SAMPLE);
                 if (uni) {  // erf/exp of the diffused-uniform score in fp64: one lane per (sample, dim)
                     const double sa = (double)sSched[D4S_S_SQRT_ALPHA], sg = (double)sSched[D4S_S_SIGMA];
+                    const double inv_sa = 1.0 / sa, inv_sg = 1.0 / sg;
                     for (int e = lane; e < nsamp * m; e += 32) {
                         const int si = e / m, k = e - si * m;
                         double s0, jac;
-                        uniform_prior_terms((double)th[si * MMAX + k], (double)__ldg(p.fin.low + k),
-                                            (double)__ldg(p.fin.high + k), sa, sg, s0, jac);
+                        uniform_prior_terms_recip((double)th[si * MMAX + k], (double)__ldg(p.fin.low + k),
+                                                  (double)__ldg(p.fin.high + k), sa, sg, inv_sa, inv_sg, s0, jac);
                         if (per_sample) {
                             const double p0 = aos2 / (1.0 + sg * sg * jac);  // inv(sigma^2/alpha (1 + sigma^2 J0))
                             sPrior[si * MMAX + k] = (float)p0;
@@ -420,11 +470,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         if (4 * qd + k < MMAX) sNoise[si * MMAX + 4 * qd + k] = z[k];
                 }
                 __syncwarp();
-                if (p.prof && blockIdx.x == 0 && lane == 0) {  // profiling: busy cycles of the helper warp (slots 10 / 11 / 12)
-                    const long long dt = clock64() - h_t0;
-                    p.prof[10] += dt;
-                    if (per_sample) { p.prof[11] += dt; p.prof[12] += 1; }
-                }
                 bar_arrive(3, NB23);
             }
             gk += ngr;

@@ -152,8 +152,7 @@ def set_option(key: str, value: int):
 
 
 PROFILE_PHASES = ["layer0_sample_part", "layer0", "prior_noise", "tensor_wait", "epilogues", "scores",
-                  "prec_and_sums", "finalize", "mma_inner_layers", "mma_last_layer",  # 8, 9: MMA issue -> commit (MMA warp)
-                  "mma_helper_busy", "mma_helper_busy_per_sample", "mma_helper_per_sample_items"]  # 10-12: scalar helper warp
+                  "prec_and_sums", "finalize", "mma_inner_layers", "mma_last_layer"]  # 8, 9: MMA issue -> commit (MMA warp)
 
 
 def get_profile():
