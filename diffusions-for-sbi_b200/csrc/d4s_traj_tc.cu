@@ -116,7 +116,7 @@ __device__ __forceinline__ void lu_solve_recip(double (&a)[M][M], double (&b)[M]
 }
 
 // inv_sig = 1 / sigma, inv_s = 1 / sqrt(alpha); p0 = a/s^2 / (1 + sigma^2 jac) is formed by the caller when needed
-__device__ __forceinline__ void uniform_prior_terms_recip(double th, double lo, double hi, double s, double sig, double inv_s,
+__device__ __noinline__ void uniform_prior_terms_recip(double th, double lo, double hi, double s, double sig, double inv_s,
                                                           double inv_sig, double& s0, double& jac) {
     const double inv_sqrt_2pi = 0.39894228040143267794;
     const double ub = (hi * s - th) * inv_sig;
