@@ -44,9 +44,9 @@ SHAPES = {  # BASELINE.json configs
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE traj_tc_kernel launch (a whole 1000-step trajectory) of the default
-# workload, from the ncu --set full capture summarised in profiles/r01_ncu_full_traj_tc_bench.txt (3.572 MB + 0.202 MB):
+# workload, from the ncu --set full capture summarised in profiles/r01_ncu_full_traj_tc_bench.txt (3.322 MB + 0.207 MB):
 # weights, observation features and per-step tables are read once and stay in L2; the kernel is not HBM-bound.
-TRAJ_TC_DRAM_BYTES = 3572480 + 201728
+TRAJ_TC_DRAM_BYTES = 3322112 + 206592
 
 
 def is_default_workload(args, w) -> bool:
