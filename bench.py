@@ -67,6 +67,10 @@ def parse():
     ap.add_argument("--ddim-steps", type=int, default=None, help="default 1000 (GAUSS) / 400 (JAC)")
     ap.add_argument("--cpu-sample-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stress-samples", type=int, default=8192, help="posterior samples of the observation-sharded record")
+    ap.add_argument("--stress-steps", type=int, default=100, help="DDIM steps of the observation-sharded record")
+    ap.add_argument("--stress-n-obs", type=int, default=10000)
+    ap.add_argument("--no-obs-sharded", action="store_true", help="skip the observation-sharded stress record")
     ap.add_argument("--jac-tc", action="store_true",
                     help="JAC steps on the opt-in tcgen05 score + Jacobian kernel (fp16x3) instead of the fp32 SIMT kernel")
     return ap.parse_args()
@@ -270,6 +274,138 @@ class Clocks:
 
 
 # ---------------------------------------------------------------------------------------------------------
+# observation-sharded stress record (BASELINE config 5): the path WITH an exchange step
+# ---------------------------------------------------------------------------------------------------------
+def obs_sharded_record(args, dev, rank, world):
+    """theta = 10, n_obs = 10^4, MLP 26->256^3->10, Gaussian prior, GAUSS: every rank evaluates its slice of the
+    observations for ALL `--stress-samples` samples; the per-step sum over ranks of the [N, 2m] partial sums happens inside
+    the fused tcgen05 trajectory kernel over mapped peer memory ("p2p").  Reported: ms per DDIM step (CUDA events, max over
+    ranks) for p2p, for the CUDA-graph-captured kernel -> ncclAllReduce -> kernel loop and for the single-GPU trajectory
+    measured in the SAME run on rank 0, the bare NCCL all-reduce latency of the exchanged buffer, and the parity of the
+    sharded result against the single-GPU one.  The reference cannot run this shape at all (it materialises
+    [N, n, m, m]: 3.3 TB at these sizes, tall_posterior_sampler.py:114-128)."""
+    import copy
+    import torch
+    import torch.distributed as dist
+    from d4s import engine, parallel
+    import d4s
+
+    a2 = copy.copy(args)
+    a2.task, a2.n_obs, a2.cov_mode, a2.ddim_steps = "stress", args.stress_n_obs, "GAUSS", args.stress_steps
+    w = workload(a2)
+    N, m, n, steps = args.stress_samples, w["m"], w["n"], args.stress_steps
+    nse = build_nse(w, dev)
+    x = torch.as_tensor(w["x"]).to(dev)
+    cov = torch.as_tensor(w["cov"]).to(dev)
+    mu, pc = torch.as_tensor(w["prior"]["mean"]).to(dev), torch.as_tensor(w["prior"]["cov"]).to(dev)
+    prior, fn = torch.distributions.MultivariateNormal(mu, pc, validate_args=False), d4s.get_vpdiff_gaussian_score(mu, pc, nse)
+    kw = dict(eta=1.0, prior=prior, prior_type="gaussian", prior_score_fn=fn, dist_cov_est=cov, cov_mode="GAUSS")
+    flops_step = float(N) * n * flops_per_pair(w)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(launch):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launch()
+        e1.record()
+        e1.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    def single_gpu_ms(n_steps):
+        grid = engine.time_grid(n_steps)
+        spec = engine.prior_spec("gaussian", prior, fn, m)
+        st = engine.build_setup(nse, x, N, grid[:-1], grid[:-1].double() - 1.0 / n_steps, 1.0, spec, "GAUSS", cov, seed=7)
+        th0 = engine.philox_normal(N, m, 7, -1, 0, dev)
+        th = th0.clone()
+        engine.run_trajectory(st, th, None, True)  # warm-up
+        torch.cuda.synchronize()
+        th.copy_(th0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        engine.run_trajectory(st, th, None, True)
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / n_steps
+
+    rec = {"workload": f"stress: theta={m}, x={w['d']}, MLP {w['n_in']}->256x256x256->{m}, n_obs={n}, {N} posterior samples "
+                       f"(all of them on every rank), DDIM {steps} steps, GAUSS, gaussian prior",
+           "n_gpus": world, "n_obs": n, "samples": N, "ddim_steps": steps}
+    if world == 1:
+        ms = single_gpu_ms(steps)
+        rec.update({"transport": "none (1 GPU: plain fused trajectory kernel)", "ms_per_ddim_step": ms,
+                    "samples_per_s": N / (ms * steps * 1e-3), "algorithmic_tflops": flops_step / (ms * 1e-3) / 1e12,
+                    "allreduce_bytes_per_step": 0})
+        return rec
+    # ---- parity: sharded vs single GPU on a small seeded problem (same Philox noise on both sides) ----------
+    Nc, sc = 64, 8
+    ref = nse.ddim((Nc,), x, steps=sc, _seed=3, **kw)
+    out = parallel.ddim_obs_sharded(nse, (Nc,), x, steps=sc, _seed=3, exchange="p2p", **kw)
+    out_n = parallel.ddim_obs_sharded(nse, (Nc,), x, steps=sc, _seed=3, exchange="nccl", **kw)
+    torch.cuda.synchronize()
+    scale = max(1.0, float(ref.abs().max()))
+    par = torch.tensor([float((out - ref).abs().max()) / scale, float((out_n - ref).abs().max()) / scale], device=dev)
+    same = out.clone()
+    dist.broadcast(same, 0)
+    ident = torch.tensor([1.0 if torch.equal(same, out) else 0.0], device=dev)
+    dist.all_reduce(par, op=dist.ReduceOp.MAX)
+    dist.all_reduce(ident, op=dist.ReduceOp.MIN)
+    # ---- p2p: one launch per rank, exchange inside the kernel ------------------------------------------------
+    traj = parallel.P2PTrajectory(nse, (N,), x, steps=steps, _seed=7, **kw)
+    warm = parallel.P2PTrajectory(nse, (N,), x, steps=3, _seed=7, **kw)
+    warm.launch()
+    ms_p2p = timed(lambda: traj.launch()) / steps
+    # ---- NCCL: kernel -> all-reduce -> kernel per step, whole loop in one CUDA graph --------------------------
+    ns = max(10, steps // 5)
+    ntraj = parallel.NcclTrajectory(nse, (N,), x, steps=ns, _seed=7, graph=True, **kw)
+    ntraj.launch()
+    ms_nccl = timed(lambda: ntraj.launch()) / ns
+    etraj = parallel.NcclTrajectory(nse, (N,), x, steps=ns, _seed=7, graph=False, **kw)
+    etraj.launch()
+    ms_eager = timed(lambda: etraj.launch()) / ns
+    # bare all-reduce of the exchanged buffer
+    buf = torch.zeros(ntraj.exchanged_bytes_per_step // 4, device=dev)
+    for _ in range(5):
+        dist.all_reduce(buf)
+    reps = 50
+
+    def ar():
+        for _ in range(reps):
+            dist.all_reduce(buf)
+    us_ar = timed(ar) / reps * 1e3
+    # single-GPU time of the same problem, measured in this run on rank 0 (the other ranks wait)
+    single = torch.zeros(1, dtype=torch.float64, device=dev)
+    if rank == 0:
+        single[0] = single_gpu_ms(max(5, steps // 10))
+    dist.all_reduce(single, op=dist.ReduceOp.MAX)
+    ms_single = float(single)
+    rec.update({"transport": "p2p: in-kernel exchange over mapped peer memory (NVLink), one launch per trajectory and rank",
+                "ms_per_ddim_step": ms_p2p, "samples_per_s": N / (ms_p2p * steps * 1e-3),
+                "algorithmic_tflops": flops_step / (ms_p2p * 1e-3) / 1e12,
+                "single_gpu_ms_per_ddim_step": ms_single, "speedup_vs_single_gpu": ms_single / ms_p2p,
+                "efficiency_vs_single_gpu": ms_single / ms_p2p / world,
+                "exchanged_bytes_per_step_per_rank": traj.exchanged_bytes_per_step * world,
+                "comm_nranks": world,
+                "nccl_graph": {"ms_per_ddim_step": ms_nccl, "steps_timed": ns, "efficiency_vs_single_gpu": ms_single / ms_nccl / world,
+                               "allreduce_bytes_per_step": ntraj.exchanged_bytes_per_step,
+                               "launches_per_step": "kernel 1 (export) + ncclAllReduce + kernel 3/4, one CUDA graph per trajectory"},
+                "nccl_eager_ms_per_ddim_step": ms_eager,
+                "nccl_allreduce_alone_us": us_ar,
+                "kernel_ms_per_step_vs_allreduce": {"kernel_ms": ms_p2p, "allreduce_ms": us_ar * 1e-3},
+                "parity_vs_single_gpu": {"samples": Nc, "steps": sc, "max_rel_diff_p2p": float(par[0]),
+                                         "max_rel_diff_nccl": float(par[1]), "identical_on_all_ranks": bool(float(ident) == 1.0)}})
+    return rec
+
+
+# ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -403,6 +539,12 @@ def run_ours(args):
     k3_ms = e0.elapsed_time(e1) / reps
     fused = launches <= 2 * args.steps  # the fused tcgen05 trajectory kernel ran (one launch per trajectory)
 
+    obs_rec = None
+    if not args.no_obs_sharded:
+        try:
+            obs_rec = obs_sharded_record(args, dev, rank, world)
+        except Exception as exc:  # reported, never silently dropped
+            obs_rec = {"error": f"{type(exc).__name__}: {exc}"}
     tot_dev = torch.tensor([sum(ms_dev), sum(ms_e2e)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot_dev, op=dist.ReduceOp.MAX)
@@ -460,6 +602,8 @@ def run_ours(args):
                 "gpu_launches": int(launches),
                 "roofline": roofline,
                 "us_per_ddim_step": ms_step * 1e3 / w["ddim_steps"]}
+        if obs_rec is not None:
+            line["obs_sharded"] = obs_rec
         if not args.no_cpu_baseline:
             rate, cores, dt = cpu_oracle_rate(args, w, args.cpu_sample_steps)
             line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",

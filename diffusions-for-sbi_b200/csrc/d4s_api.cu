@@ -383,7 +383,8 @@ int64_t d4s_workspace_floats(const D4sNet* net, const D4sProblem* pb) {
 
 // Fills the parameter block of the fused tcgen05 kernel (tile geometry, tables, finalize constants).
 static int fill_traj_params(const D4sNet* net, const D4sProblem* pb, const float* sched, const float* tf, const float* mats,
-                            const float* noise, float* theta, TrajParams* out, int* n_ctas, cudaStream_t stream) {
+                            const float* noise, float* theta, TrajParams* out, int* n_ctas, cudaStream_t stream,
+                            int sg_cap = 0) {
     const NetDev& nd = net->dev;
     TrajParams& p = *out;
     memset(&p, 0, sizeof(p));
@@ -399,6 +400,7 @@ static int fill_traj_params(const D4sNet* net, const D4sProblem* pb, const float
     p.C = (pb->n_obs + oc - 1) / oc;
     p.SG = 128 / oc;
     if (p.SG > 8) p.SG = 8;
+    if (sg_cap > 0 && p.SG > sg_cap) p.SG = sg_cap;  // observation sharding: every rank must form the same sample groups
     if (p.SG < 1) p.SG = 1;
     p.P = p.SG * p.OC;
     p.obs_feat = pb->obs_feat;
@@ -773,6 +775,101 @@ int d4s_ddim_run(const D4sNet* net, const D4sProblem* pb, int32_t steps, const f
     if (e != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
     g_launches += n_launch;
     return D4S_OK;
+}
+
+// ---- observation-sharded trajectory: in-kernel exchange over mapped peer memory ---------------------------------
+int d4s_xchg_layout(const D4sNet* net, const D4sProblem* pb, int32_t world, int64_t* data_floats, int64_t* flag_words) {
+    if (!net || !pb || !data_floats || !flag_words) return fail(D4S_ERR_ARG, "null argument");
+    if (world < 1 || world > D4S_MAX_RANKS) return fail(D4S_ERR_ARG, "world must be in [1, D4S_MAX_RANKS]");
+    // (the flags are sized for the finest grouping, one sample per group)
+    *data_floats = 2LL * world * pb->n_samples * 2 * net->dev.m;
+    *flag_words = (int64_t)world * pb->n_samples;
+    return D4S_OK;
+}
+
+int d4s_ddim_run_sharded(const D4sNet* net, const D4sProblem* pb, int32_t steps, const float* sched_dev,
+                         const float* time_feat_dev, const float* mats_dev, const float* noise_dev, float* theta_dev,
+                         const D4sExchange* xchg, void* stream_) {
+    int rc = check_problem(net, pb);
+    if (rc) return rc;
+    if (steps < 1 || !sched_dev || !time_feat_dev || !mats_dev || !theta_dev || !xchg) return fail(D4S_ERR_ARG, "bad ddim_run_sharded args");
+    if (xchg->world < 1 || xchg->world > D4S_MAX_RANKS || xchg->rank < 0 || xchg->rank >= xchg->world)
+        return fail(D4S_ERR_ARG, "bad exchange world/rank");
+    for (int r = 0; r < xchg->world; ++r)
+        if (!xchg->data[r] || !xchg->flags[r]) return fail(D4S_ERR_ARG, "exchange buffer of a rank is not mapped");
+    if (pb->ctx_samples != 0) return fail(D4S_ERR_ARG, "batched contexts cannot be observation-sharded");
+    if (!tc_eligible(net, pb)) return fail(D4S_ERR_ARG, "in-kernel exchange needs the tcgen05 trajectory kernel (GAUSS-type steps, plain MLP)");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    TrajParams p;
+    int ctas = 0;
+    // samples per group from the LARGEST observation shard (ceil(n_total / world)), so that all ranks agree on it
+    int n_loc = (pb->n_obs_total + xchg->world - 1) / xchg->world;
+    if (n_loc < pb->n_obs) n_loc = pb->n_obs;
+    int oc = pb->obs_chunk > 0 ? pb->obs_chunk : n_loc;
+    if (oc > 128) oc = 128;
+    if (oc > n_loc) oc = n_loc;
+    const int cc = (n_loc + oc - 1) / oc;
+    oc = (n_loc + cc - 1) / cc;
+    int sg = 128 / oc;
+    if (sg > 8) sg = 8;
+    if (sg < 1) sg = 1;
+    rc = fill_traj_params(net, pb, sched_dev, time_feat_dev, mats_dev, noise_dev, theta_dev, &p, &ctas, stream, sg);
+    if (rc) return rc;
+    p.xg.world = xchg->world;
+    p.xg.rank = xchg->rank;
+    p.xg.seq_base = xchg->seq_base;
+    for (int r = 0; r < xchg->world; ++r) {
+        p.xg.data[r] = xchg->data[r];
+        p.xg.flags[r] = xchg->flags[r];
+    }
+    p.step_begin = 0;
+    p.step_end = steps;
+    cudaError_t e = launch_traj_tc(p, ctas, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tcgen05 trajectory kernel launch (observation-sharded)");
+    ++g_launches;
+    return D4S_OK;
+}
+
+int d4s_xchg_alloc(int64_t bytes, void** dev_ptr_out, uint8_t* handle_out) {
+    if (bytes < 1 || !dev_ptr_out || !handle_out) return fail(D4S_ERR_ARG, "bad xchg_alloc args");
+    static_assert(sizeof(cudaIpcMemHandle_t) == D4S_IPC_HANDLE_BYTES, "IPC handle size");
+    void* ptr = nullptr;
+    cudaError_t e = cudaMalloc(&ptr, (size_t)bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(exchange buffer)");
+    e = cudaMemset(ptr, 0, (size_t)bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ptr);
+    if (e != cudaSuccess) {
+        cudaFree(ptr);
+        return cuda_fail(e, "exchange buffer setup (memset / cudaIpcGetMemHandle)");
+    }
+    memcpy(handle_out, &h, sizeof(h));
+    *dev_ptr_out = ptr;
+    return D4S_OK;
+}
+
+int d4s_xchg_free(void* dev_ptr) {
+    if (!dev_ptr) return D4S_OK;
+    cudaError_t e = cudaFree(dev_ptr);
+    return e == cudaSuccess ? D4S_OK : cuda_fail(e, "cudaFree(exchange buffer)");
+}
+
+int d4s_xchg_open(const uint8_t* handle, void** peer_ptr_out) {
+    if (!handle || !peer_ptr_out) return fail(D4S_ERR_ARG, "bad xchg_open args");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle (peer access between the GPUs of the box is required)");
+    *peer_ptr_out = ptr;
+    return D4S_OK;
+}
+
+int d4s_xchg_close(void* peer_ptr) {
+    if (!peer_ptr) return D4S_OK;
+    cudaError_t e = cudaIpcCloseMemHandle(peer_ptr);
+    return e == cudaSuccess ? D4S_OK : cuda_fail(e, "cudaIpcCloseMemHandle");
 }
 
 void d4s_graph_cache_clear(void) {

@@ -89,6 +89,19 @@ struct FinalizeParams {
     const float* ctx_qsum;    // [N / ctx_samples][m][m] sum_j inv(Sigma_cj), added to the Lambda base of the step; or NULL
 };
 
+// Observation sharding inside the trajectory kernel (D4sExchange, include/d4s.h): every rank evaluates its slice of the
+// observations for ALL samples; after the per-sample sums of a step the CTA stores them straight into every peer's
+// receive buffer (mapped peer memory, NVLink) and raises a flag there, waits for the peers' flags in its own buffer and
+// adds the contributions in rank order (identical on every rank => theta stays bit-identical without a broadcast).
+//   data [rank r]: float [2 slots][world][N][2m]   slot = (seq_base + step) & 1, second index = source rank
+//   flags[rank r]: uint32 [world][n_groups]        last sequence number published by a source rank for a sample group
+struct XchgDev {
+    int world, rank;        // world == 0: no exchange
+    unsigned seq_base;      // sequence number of step 0 of this trajectory (monotonic over the life of the buffers)
+    float* data[D4S_MAX_RANKS];
+    unsigned* flags[D4S_MAX_RANKS];
+};
+
 // fused tcgen05 trajectory kernel (d4s_traj_tc.cu)
 struct TrajParams {
     NetDev net;
@@ -105,6 +118,7 @@ struct TrajParams {
     FinalizeParams fin;      // constant part of the per-step finalize parameters
     float* theta;            // [N][m] in/out
     float* part_out;         // export mode (per-step API / observation sharding): [N][2m] sums S1 | S2, no update
+    XchgDev xg;              // in-kernel exchange of the per-sample sums between the ranks of an observation-sharded run
     int* error_flag;
     long long* prof;         // optional [16] phase cycle counters (CTA 0)
 };

@@ -94,6 +94,17 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
 }
 
+// system-scope flag accesses of the in-kernel exchange between ranks (peer memory over NVLink)
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+constexpr long long XCHG_SPIN_LIMIT_CYCLES = 40000000000LL;  // ~20 s: a missing peer makes the kernel trap, not hang
+
 // UMMA shared-memory descriptor, K-major, no swizzle ("interleave"): 8x16B core matrices, 128 B each.
 //   lbo = byte distance between the two K halves of a K=16 step, sbo = byte distance between 8-row groups.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {

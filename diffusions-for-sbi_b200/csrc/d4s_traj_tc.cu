@@ -239,6 +239,49 @@ __device__ __noinline__ void theta_embed_base(const NetDev& net, const float* th
     }
 }
 
+// Observation sharding over ranks (TrajParams.xg): the group's sums S1 | S2 over THIS rank's observations go to every
+// rank's receive buffer (plain stores to mapped peer memory over NVLink), then one flag per peer; once every rank's flag
+// for this (group, step) has arrived the contributions are added in rank order -> s_acc holds the sums over ALL
+// observations, bit-identical on every rank.  Slots alternate with the sequence number: a peer can be at most one step
+// ahead (it needs our flag of step s before it can publish step s + 1).  Called by all compute threads.  Not inlined: it
+// must not weigh on the register allocation of the single-GPU path.
+__device__ __noinline__ void xchg_group_sums(const XchgDev& xg, float* s_acc, int N, int m, int n_groups, int SG, int step,
+                                             int i0, int nsamp, int tid, int* error_flag) {
+    const int W2 = 2 * m, cnt = nsamp * W2;
+    const unsigned seq = xg.seq_base + (unsigned)step;
+    const size_t per_rank = (size_t)N * W2;
+    const size_t slot_off = (size_t)(seq & 1u) * xg.world * per_rank;
+    const int gidx = i0 / SG;
+    for (int e = tid; e < cnt * xg.world; e += TC_CT) {
+        const int r = e / cnt, k = e - r * cnt;
+        xg.data[r][slot_off + (size_t)xg.rank * per_rank + (size_t)i0 * W2 + k] = s_acc[k];
+    }
+    __threadfence_system();
+    compute_bar();
+    if (tid < xg.world) {
+        st_release_sys(xg.flags[tid] + (size_t)xg.rank * n_groups + gidx, seq + 1u);
+        const unsigned* mine = xg.flags[xg.rank] + (size_t)tid * n_groups + gidx;
+        if ((int)(ld_acquire_sys(mine) - (seq + 1u)) < 0) {
+            const long long t0 = clock64();
+            unsigned polls = 0;
+            while ((int)(ld_acquire_sys(mine) - (seq + 1u)) < 0) {
+                if ((++polls & 1023u) == 0u && clock64() - t0 > XCHG_SPIN_LIMIT_CYCLES) {
+                    if (error_flag) atomicExch(error_flag, 2);  // a missing peer must not hang the GPU
+                    __trap();
+                }
+            }
+        }
+    }
+    compute_bar();
+    if (tid < cnt) {
+        const float* src = xg.data[xg.rank] + slot_off + (size_t)i0 * W2 + tid;
+        float acc = 0.f;
+        for (int r = 0; r < xg.world; ++r) acc += __ldcg(src + (size_t)r * per_rank);
+        s_acc[tid] = acc;
+    }
+    compute_bar();
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_constant__ TrajParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sAhi = smem + OFF_AHI;
@@ -816,6 +859,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                             if (p.part_out) {
                                 for (int e = tid; e < nsg[pgi] * 2 * m; e += TC_CT) p.part_out[(size_t)i0g[pgi] * 2 * m + e] = sAcc[e];
                             } else {
+                                if (p.xg.world > 0) xchg_group_sums(p.xg, sAcc, p.N, m, n_groups, p.SG, step_of(pit), i0g[pgi], nsg[pgi], tid, p.error_flag);
                                 do_tail(pth, nsg[pgi]);
                             }
                             compute_bar();
@@ -883,6 +927,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         PROF_MARK(6);
                         bar_sync(3, NB23);  // schedule / matrix rows, prior terms and noise of the previous item are in smem
                         PROF_MARK(2);  // (time spent waiting for the helper warp)
+                        if (p.xg.world > 0) xchg_group_sums(p.xg, sAcc, p.N, m, n_groups, p.SG, step_of(pit), i0g[pgi], nsg[pgi], tid, p.error_flag);
                         do_tail(pth, nsg[pgi]);
                         compute_bar();
                         if (have) bar_arrive(2, NB23);  // helper warp: buffers are free, go on with this item

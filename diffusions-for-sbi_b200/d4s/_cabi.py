@@ -13,11 +13,13 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("D4S_LIB_PATH") or os.path.join(HERE, "libd4s.so")  # (override: A/B builds of the kernels)
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 MAX_LAYERS = 8
 MAX_THETA = 10
 MAX_WIDTH = 256
 SCHED_STRIDE = 16
+MAX_RANKS = 8
+IPC_HANDLE_BYTES = 64
 
 COV_GAUSS, COV_JAC = 0, 1
 PRIOR_NONE, PRIOR_GAUSSIAN, PRIOR_UNIFORM = 0, 1, 2
@@ -30,7 +32,8 @@ S_T, S_ALPHA, S_SIGMA, S_INV_SIGMA, S_A_OVER_S2, S_C_THETA, S_C_SCORE, S_BRIDGE_
 EXPORTS = [
     "d4s_abi_version", "d4s_last_error", "d4s_device_count", "d4s_net_create", "d4s_net_free",
     "d4s_net_h1_padded", "d4s_workspace_floats", "d4s_partials_floats", "d4s_mats_floats", "d4s_score_partials", "d4s_finalize",
-    "d4s_ddim_run", "d4s_graph_cache_clear", "d4s_set_option", "d4s_get_profile", "d4s_prior_score", "d4s_ddim_update", "d4s_batched_inverse", "d4s_philox_normal", "d4s_launch_count",
+    "d4s_ddim_run", "d4s_graph_cache_clear", "d4s_ddim_run_sharded", "d4s_xchg_layout", "d4s_xchg_alloc", "d4s_xchg_free",
+    "d4s_xchg_open", "d4s_xchg_close", "d4s_set_option", "d4s_get_profile", "d4s_prior_score", "d4s_ddim_update", "d4s_batched_inverse", "d4s_philox_normal", "d4s_launch_count",
 ]
 
 
@@ -94,6 +97,17 @@ class Step(C.Structure):
     ]
 
 
+class Exchange(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32),
+        ("rank", C.c_int32),
+        ("seq_base", C.c_uint32),
+        ("reserved", C.c_int32),
+        ("data", C.c_void_p * MAX_RANKS),
+        ("flags", C.c_void_p * MAX_RANKS),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -126,6 +140,12 @@ def load():
             "d4s_finalize": (C.c_int, [vp, C.POINTER(Problem), C.POINTER(Step), vp, vp, vp]),
             "d4s_ddim_run": (C.c_int, [vp, C.POINTER(Problem), i32, vp, vp, vp, vp, vp, C.POINTER(i32), vp, i32, vp]),
             "d4s_graph_cache_clear": (None, []),
+            "d4s_ddim_run_sharded": (C.c_int, [vp, C.POINTER(Problem), i32, vp, vp, vp, vp, vp, C.POINTER(Exchange), vp]),
+            "d4s_xchg_layout": (C.c_int, [vp, C.POINTER(Problem), i32, C.POINTER(i64), C.POINTER(i64)]),
+            "d4s_xchg_alloc": (C.c_int, [i64, C.POINTER(vp), C.c_char_p]),
+            "d4s_xchg_free": (C.c_int, [vp]),
+            "d4s_xchg_open": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+            "d4s_xchg_close": (C.c_int, [vp]),
             "d4s_set_option": (C.c_int, [C.c_char_p, i32]),
             "d4s_get_profile": (C.c_int, [C.POINTER(i64)]),
             "d4s_prior_score": (C.c_int, [i32, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]),

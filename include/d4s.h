@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D4S_ABI_VERSION 12
+#define D4S_ABI_VERSION 13
 
 #define D4S_OK 0
 #define D4S_ERR_ARG -1      /* bad argument / unsupported shape */
@@ -45,6 +45,8 @@ extern "C" {
 #define D4S_MAX_THETA 10    /* theta_dim m supported by the register-resident solvers */
 #define D4S_MAX_WIDTH 256   /* widest hidden layer */
 #define D4S_SCHED_STRIDE 16 /* floats per step in the schedule table */
+#define D4S_MAX_RANKS 8     /* ranks (GPUs of one NVSwitch box) of an observation-sharded run */
+#define D4S_IPC_HANDLE_BYTES 64 /* opaque handle of an exchange buffer (sizeof(cudaIpcMemHandle_t)) */
 
 /* covariance mode of tweedies_approximation (tall_posterior_sampler.py:46-135) */
 #define D4S_COV_GAUSS 0
@@ -147,6 +149,26 @@ typedef struct {
                                (the closed-form Gaussian posterior score of gen_gaussian_gaussian.py:59-72) */
 } D4sStep;
 
+/* Observation sharding over the GPUs of one box (the reference cannot run this shape: it
+ * materialises [N, n, m, m], tall_posterior_sampler.py:114-128).  Rank r evaluates the score network on ITS slice of
+ * the observations for all N samples.  The one exchange step of the path -- the sum over ranks of the per-sample
+ * vectors S1_i = sum_j s_ij and S2_i = sum_j inv(Sigma_j) s_ij -- happens INSIDE the trajectory kernel: a CTA stores
+ * its partial sums into every peer's receive buffer through mapped peer memory (NVLink / NVSwitch), raises a flag
+ * there, waits for the peers' flags in its own buffer and adds the contributions in rank order, so that every rank
+ * continues with bit-identical theta and no broadcast is needed.  One launch still runs every DDIM step.
+ * Buffers come from d4s_xchg_alloc (cudaMalloc + IPC handle); peers map them with d4s_xchg_open.
+ *   data [r]: float  [2][world][N][2 m]      (slot = (seq_base + step) & 1, second index = source rank)
+ *   flags[r]: uint32 [world][n_groups]       zero-initialised once; n_groups from d4s_xchg_layout()
+ * seq_base must be the same on every rank and grow by `steps` from one trajectory to the next on the same buffers. */
+typedef struct {
+    int32_t world;                 /* ranks taking part (1 .. D4S_MAX_RANKS) */
+    int32_t rank;                  /* this process */
+    uint32_t seq_base;             /* sequence number of step 0 */
+    int32_t reserved;
+    float* data[D4S_MAX_RANKS];    /* data[r]  = rank r's receive buffer as mapped in THIS process (data[rank] is local) */
+    uint32_t* flags[D4S_MAX_RANKS]; /* flags[r] = rank r's flag array as mapped in this process */
+} D4sExchange;
+
 /* ---- library ---------------------------------------------------------------------------------- */
 D4S_API int d4s_abi_version(void);
 D4S_API const char* d4s_last_error(void);
@@ -190,6 +212,23 @@ D4S_API int d4s_ddim_run(const D4sNet* net, const D4sProblem* prob, int32_t step
                  const float* time_feat_dev, const float* mats_dev, const float* noise_dev, float* theta_dev,
                  const int32_t* step_cov_mode_host, const float* affine_dev, int32_t use_graph, void* stream);
 D4S_API void d4s_graph_cache_clear(void);
+
+/* ---- observation-sharded trajectory with the in-kernel exchange (see D4sExchange) ------------------------------
+ * Same arguments as d4s_ddim_run; prob describes THIS rank's observation slice (n_obs local, n_obs_total global; the
+ * schedule / matrix tables are built from the global n).  GAUSS-type steps on the fused tcgen05 trajectory kernel only
+ * (returns D4S_ERR_ARG otherwise: callers then use d4s_score_partials + a collective + d4s_finalize per step). */
+D4S_API int d4s_ddim_run_sharded(const D4sNet* net, const D4sProblem* prob, int32_t steps, const float* sched_dev,
+                         const float* time_feat_dev, const float* mats_dev, const float* noise_dev, float* theta_dev,
+                         const D4sExchange* xchg, void* stream);
+/* floats of one rank's data buffer and uint32 words of its flag array for this problem (both ranks-symmetric) */
+D4S_API int d4s_xchg_layout(const D4sNet* net, const D4sProblem* prob, int32_t world, int64_t* data_floats,
+                    int64_t* flag_words);
+/* Exchange buffers: plain device allocations of this process that peers can map (cudaIpcGetMemHandle /
+ * cudaIpcOpenMemHandle).  alloc zero-fills; handle_out receives D4S_IPC_HANDLE_BYTES opaque bytes to send to the peers. */
+D4S_API int d4s_xchg_alloc(int64_t bytes, void** dev_ptr_out, uint8_t* handle_out);
+D4S_API int d4s_xchg_free(void* dev_ptr);
+D4S_API int d4s_xchg_open(const uint8_t* handle, void** peer_ptr_out);
+D4S_API int d4s_xchg_close(void* peer_ptr);
 /* Library options: "path" = 0 auto | 1 per-step fp32 SIMT kernels only | 2 require the fused tcgen05 trajectory
  * kernel (bf16x3 split on the tensor cores; GAUSS, tall grid); "tc_steps_per_launch" = DDIM steps per tcgen05
  * launch (0 = whole trajectory in one launch); "profile" = 1 enables the in-kernel phase timers; "tc_pairing" = 1

@@ -1,6 +1,7 @@
 """Multi-GPU check, launched with torchrun (one rank per GPU):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/gpu_multi.py
-(1) observation-sharded DDIM (NCCL all-reduce of the partial sums each step) == single-GPU DDIM under replayed noise;
+(1) observation-sharded DDIM == single-GPU DDIM under replayed noise, for every transport: the in-kernel exchange over
+    mapped peer memory ("p2p", GAUSS), the CUDA-graph-captured NCCL all-reduce loop ("nccl") and the eager loop;
 (2) sample-sharded DDIM: concatenating the ranks' blocks == the single-GPU run with the same seed."""
 import os
 import sys
@@ -42,19 +43,41 @@ for pkind in ("gaussian", "uniform"):
         prior, fn = torch.distributions.MultivariateNormal(mu, pc), d4s.get_vpdiff_gaussian_score(mu, pc, nse)
     for mode in ("GAUSS", "JAC"):
         kw = dict(steps=steps, eta=0.8, prior=prior, prior_type=pkind, prior_score_fn=fn, dist_cov_est=cov, cov_mode=mode)
-        abi.set_option("path", 1)  # same fp32 kernels on both sides: only the summation order over ranks differs
+        abi.set_option("path", 1)  # per-step fp32 kernels as the single-GPU reference
         ref = nse.ddim((N,), x, _noise=(z0, z), **kw)
         abi.set_option("path", 0)
-        out = parallel.ddim_obs_sharded(nse, (N,), x, _noise=(z0, z), **kw)
-        scale = max(1.0, float(ref.abs().max()))
-        err = float((out - ref).abs().max()) / scale
-        tol = 1e-4 if mode == "GAUSS" else 2e-2
-        if rank == 0:
-            print(f"obs-sharded {pkind} {mode}: world={world} max rel diff vs 1 GPU = {err:.2e} (tol {tol})")
-        ok &= err < tol
-        full = out.clone()
-        dist.broadcast(full, 0)
-        ok &= bool(torch.equal(full, out))  # every rank holds the same theta (identical Philox / injected noise)
+        ref_tc = nse.ddim((N,), x, _noise=(z0, z), **kw)  # (GAUSS: fused tcgen05 trajectory kernel)
+        for exch in (["p2p"] if mode == "GAUSS" else []) + ["nccl", "nccl_eager"]:
+            out = parallel.ddim_obs_sharded(nse, (N,), x, _noise=(z0, z), exchange=exch, **kw)
+            torch.cuda.synchronize()
+            scale = max(1.0, float(ref.abs().max()))
+            err = float((out - ref).abs().max()) / scale
+            err_tc = float((out - ref_tc).abs().max()) / scale
+            tol = 1e-4 if mode == "GAUSS" else 2e-2
+            if rank == 0:
+                print(f"obs-sharded {pkind} {mode} [{exch}]: world={world} max rel diff vs 1 GPU = {err:.2e} "
+                      f"(vs the tcgen05 run {err_tc:.2e}; tol {tol})")
+            ok &= err < tol
+            full = out.clone()
+            dist.broadcast(full, 0)
+            ok &= bool(torch.equal(full, out))  # every rank holds the same theta (identical Philox / injected noise)
+
+# a taller problem with observation chunks inside each rank's slice and Philox noise, p2p twice on the same buffers
+n2, N2 = 700, 333
+x2 = torch.as_tensor(rng.standard_normal((n2, d)), dtype=torch.float32, device=dev)
+a2 = 0.2 * rng.standard_normal((n2, m, m))
+cov2 = torch.as_tensor(a2 @ a2.transpose(0, 2, 1) + 0.05 * np.eye(m), dtype=torch.float32, device=dev)
+mu, pc = torch.zeros(m, device=dev), torch.eye(m, device=dev)
+kw2 = dict(steps=25, eta=1.0, prior=torch.distributions.MultivariateNormal(mu, pc), prior_type="gaussian",
+           prior_score_fn=d4s.get_vpdiff_gaussian_score(mu, pc, nse), dist_cov_est=cov2, cov_mode="GAUSS")
+ref2 = nse.ddim((N2,), x2, _seed=5, **kw2)
+for rep in range(2):
+    out2 = parallel.ddim_obs_sharded(nse, (N2,), x2, _seed=5, exchange="p2p", **kw2)
+    torch.cuda.synchronize()
+    err = float((out2 - ref2).abs().max()) / max(1.0, float(ref2.abs().max()))
+    if rank == 0:
+        print(f"obs-sharded tall (n={n2}, N={N2}) [p2p, run {rep}]: max rel diff vs 1 GPU = {err:.2e}")
+    ok &= err < 1e-4
 
 # sample sharding
 lo, hi = torch.full((m,), -3.0, device=dev), torch.full((m,), 3.0, device=dev)

@@ -782,21 +782,6 @@ def test_errors_are_loud(dev):
         wide.ddim((8,), torch.randn(1, 4, device=dev), steps=2)
 
 
-def test_multi_gpu_obs_and_sample_sharding():
-    """Runs tests/gpu_multi.py under torchrun when the box has >= 2 GPUs (NCCL all-reduce of the partial sums)."""
-    import os
-    import subprocess
-    import sys
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs")
-    here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(here, "gpu_multi.py")],
-                       capture_output=True, text=True, timeout=600)
-    print(r.stdout[-2000:], r.stderr[-2000:])
-    assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout
-
-
 # ---- Langevin / Geffner family on the same kernels (SURVEY.md 8(a) a16) -----------------------------------------
 LANGEVIN = [c for c in gio.names() if c.startswith("langevin")]
 
