@@ -67,10 +67,15 @@ def parse():
     ap.add_argument("--ddim-steps", type=int, default=None, help="default 1000 (GAUSS) / 400 (JAC)")
     ap.add_argument("--cpu-sample-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="cpu", help="--impl reference: 'cpu' (default) or 'cuda' (torch eager on the B200)")
+    ap.add_argument("--ref-ddim-steps", type=int, default=None,
+                    help="--impl reference: DDIM steps of the complete trajectory timed per bench step "
+                         "(default 50 GAUSS / 20 JAC on the CPU, the full trajectory on cuda)")
     ap.add_argument("--stress-samples", type=int, default=8192, help="posterior samples of the observation-sharded record")
     ap.add_argument("--stress-steps", type=int, default=100, help="DDIM steps of the observation-sharded record")
     ap.add_argument("--stress-n-obs", type=int, default=10000)
     ap.add_argument("--no-obs-sharded", action="store_true", help="skip the observation-sharded stress record")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the n_obs sweep and the JAC sub-record (1 GPU only)")
     ap.add_argument("--jac-tc", action="store_true",
                     help="JAC steps on the opt-in tcgen05 score + Jacobian kernel (fp16x3) instead of the fp32 SIMT kernel")
     return ap.parse_args()
@@ -203,28 +208,95 @@ def cpu_oracle_rate(args, w, n_ddim_steps, repeats=1):
     return rate, cores, best
 
 
+def reference_rate(args, w, ref_steps, device="cpu", repeats=1):
+    """posterior samples/s of the UNMODIFIED reference (oracle/_ref, staged by oracle/make_ref.sh): ONE complete
+    `NSE.ddim` call with `ref_steps` DDIM steps on linspace(1, 0, ref_steps + 1) -- the same share of steps inside the
+    alpha-gate of nse.py:643 as the full trajectory -- timed as a whole.  The rate is normalised to the workload's
+    trajectory length: samples * (ref_steps / ddim_steps) / seconds.  Returns (rate, cores, seconds of the call)."""
+    import torch
+    from oracle import ref_runner
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    key = (device, args.task, args.n_obs)
+    if key not in reference_rate.cache:
+        net, prior, fn = ref_runner.build(w, device)
+        ref_runner.ddim_seconds(net, prior, fn, w, args.samples, 2, args.cov_mode, device)  # warm-up (thread pools, vmap)
+        reference_rate.cache[key] = (net, prior, fn)
+    net, prior, fn = reference_rate.cache[key]
+    best = min(ref_runner.ddim_seconds(net, prior, fn, w, args.samples, ref_steps, args.cov_mode, device)
+               for _ in range(repeats))
+    return args.samples * (ref_steps / w["ddim_steps"]) / best, cores, best
+
+
+reference_rate.cache = {}
+
+
+def cpu_baseline_record(args, w):
+    """The reference's CPU path on the box's host cores (bounded sample, ~10-30 s): the staged unmodified reference when
+    present (kind "reference"), else the oracle port (kind "port")."""
+    from oracle import ref_runner
+    N, n = args.samples, w["n"]
+    if ref_runner.available():
+        ref_steps = 100 if args.cov_mode == "GAUSS" else 40
+        ref_steps = min(ref_steps, w["ddim_steps"])
+        rate, cores, secs = reference_rate(args, w, ref_steps, "cpu", repeats=2)
+        return {"value": rate, "unit": "samples/s", "cores": cores, "kind": "reference",
+                "sample": f"unmodified reference NSE.ddim (oracle/_ref) on the host cores: best of 2 complete {ref_steps}-step "
+                          f"trajectories at N={N}, n_obs={n}; rate normalised to the {w['ddim_steps']}-step trajectory",
+                "ms_per_ddim_step": secs / ref_steps * 1e3, "seconds_timed": secs}
+    rate, cores, dt = cpu_oracle_rate(args, w, args.cpu_sample_steps)
+    return {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{args.cpu_sample_steps} of {w['ddim_steps']} DDIM steps at N={N}, n_obs={n}, extrapolated "
+                      f"linearly; oracle port with torch-CPU GEMMs (oracle/_ref not staged)",
+            "ms_per_ddim_step": dt * 1e3}
+
+
 def run_reference(args):
+    """Reference arm: the reference's own `NSE.ddim` (torch, CPU by default; `--ref-device cuda` = torch eager on the
+    B200) on this arm's config.  One bench step = one complete reference trajectory of `--ref-ddim-steps` steps."""
     w = workload(args)
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    for _ in range(args.warmup):
-        cpu_oracle_rate(args, w, 2)
-    rates, per_step = [], []
+    from oracle import ref_runner
     t_all = time.perf_counter()
-    for _ in range(args.steps):
-        r, cores, dt = cpu_oracle_rate(args, w, max(2, args.cpu_sample_steps // 2))
-        rates.append(r)
-        per_step.append(dt)
+    if ref_runner.available():
+        dev = args.ref_device
+        ref_steps = args.ref_ddim_steps or ((50 if args.cov_mode == "GAUSS" else 20) if dev == "cpu" else w["ddim_steps"])
+        ref_steps = min(ref_steps, w["ddim_steps"])
+        for _ in range(min(args.warmup, 1)):
+            reference_rate(args, w, 2, dev)
+        rates, secs = [], []
+        for _ in range(args.steps):
+            r, cores, dt = reference_rate(args, w, ref_steps, dev)
+            rates.append(r)
+            secs.append(dt)
+        kind = "reference"
+        sample = (f"unmodified reference NSE.ddim (oracle/_ref, torch {'CPU, all host threads' if dev == 'cpu' else 'eager on ' + dev}): "
+                  f"one complete {ref_steps}-step trajectory per bench step (N={args.samples}, n_obs={w['n']}); value = samples x "
+                  f"({ref_steps}/{w['ddim_steps']}) / seconds, i.e. normalised to the {w['ddim_steps']}-step trajectory")
+        ms_per_step = float(np.median(secs)) * 1e3
+    else:  # the staged reference is missing (make_ref.sh was not run where /root/reference exists): oracle port
+        rates, secs = [], []
+        n_s = max(2, args.cpu_sample_steps // 2)
+        for _ in range(min(args.warmup, 1)):
+            cpu_oracle_rate(args, w, 2)
+        for _ in range(args.steps):
+            r, cores, dt = cpu_oracle_rate(args, w, n_s)
+            rates.append(r)
+            secs.append(dt * n_s)
+        kind = "port"
+        ref_steps = n_s
+        sample = (f"oracle port (numpy + torch-CPU GEMMs): {n_s} of {w['ddim_steps']} DDIM steps per bench step "
+                  f"(N={args.samples}, n_obs={w['n']}), rate normalised to the full trajectory")
+        ms_per_step = float(np.median(secs)) * 1e3
     value = float(np.median(rates))
-    sample = (f"{max(2, args.cpu_sample_steps // 2)} of {w['ddim_steps']} DDIM steps per bench step (N={args.samples}, "
-              f"n_obs={w['n']}), extrapolated linearly; oracle port, torch-CPU GEMM backend")
     line = {"impl": "reference", "metric": "posterior samples/sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": float(np.median(per_step)) * w["ddim_steps"] * 1e3, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args, w, 1),
-            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "ref_ddim_steps_per_bench_step": ref_steps, "ref_device": args.ref_device,
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t_all}
     print(json.dumps(line))
@@ -368,6 +440,7 @@ def obs_sharded_record(args, dev, rank, world):
     ntraj = parallel.NcclTrajectory(nse, (N,), x, steps=ns, _seed=7, graph=True, **kw)
     ntraj.launch()
     ms_nccl = timed(lambda: ntraj.launch()) / ns
+    ntraj.close()  # a graph holding NCCL kernels must not outlive the process group
     etraj = parallel.NcclTrajectory(nse, (N,), x, steps=ns, _seed=7, graph=False, **kw)
     etraj.launch()
     ms_eager = timed(lambda: etraj.launch()) / ns
@@ -402,6 +475,118 @@ def obs_sharded_record(args, dev, rank, world):
                 "kernel_ms_per_step_vs_allreduce": {"kernel_ms": ms_p2p, "allreduce_ms": us_ar * 1e-3},
                 "parity_vs_single_gpu": {"samples": Nc, "steps": sc, "max_rel_diff_p2p": float(par[0]),
                                          "max_rel_diff_nccl": float(par[1]), "identical_on_all_ranks": bool(float(ident) == 1.0)}})
+    return rec
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the metric's other axes: samples/s vs n_obs for GAUSS and JAC (sbibm_posterior_estimation.py:21 N_OBS_LIST)
+# ---------------------------------------------------------------------------------------------------------
+def trajectory_rate(args, dev, n_obs, cov_mode, reps=2, e2e=False):
+    """(device-resident samples/s, ms per trajectory, launches per trajectory, e2e samples/s or None) of one config of the
+    default task: tables resident, CUDA events around d4s_ddim_run, L2 flushed by the caller's 256 MiB buffer."""
+    import copy
+    import torch
+    import d4s
+    from d4s import engine
+    a2 = copy.copy(args)
+    a2.n_obs, a2.cov_mode, a2.ddim_steps = n_obs, cov_mode, None
+    w = workload(a2)
+    N, m = args.samples, w["m"]
+    nse = build_nse(w, dev)
+    x = torch.as_tensor(w["x"]).to(dev)
+    cov = torch.as_tensor(w["cov"]).to(dev)
+    if w["prior_kind"] == "uniform":
+        lo, hi = torch.as_tensor(w["prior"]["low"]).to(dev), torch.as_tensor(w["prior"]["high"]).to(dev)
+        prior, fn = torch.distributions.Uniform(lo, hi, validate_args=False), d4s.get_vpdiff_uniform_score(lo, hi, nse)
+    else:
+        mu, pc = torch.as_tensor(w["prior"]["mean"]).to(dev), torch.as_tensor(w["prior"]["cov"]).to(dev)
+        prior, fn = torch.distributions.MultivariateNormal(mu, pc, validate_args=False), d4s.get_vpdiff_gaussian_score(mu, pc, nse)
+    kw = dict(steps=w["ddim_steps"], eta=w["eta"], prior=prior, prior_type=w["prior_kind"], prior_score_fn=fn,
+              dist_cov_est=cov, cov_mode=cov_mode)
+    xs, kwn = x, {}
+    if w["n_max"] > 1:
+        xs, ns = nse._create_pf_data(x)
+        kwn = dict(n=ns)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    # the public call once (warm-up; also the e2e figure), then the resident-table launches
+    nse.ddim((N,), xs, _seed=1, **kw, **kwn)
+    torch.cuda.synchronize()
+    e2e_rate = None
+    if e2e:
+        flush.fill_(1.0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = nse.ddim((N,), xs, _seed=2, **kw, **kwn).cpu()
+        e2e_rate = N / (time.perf_counter() - t0)
+        assert bool(torch.isfinite(out).all())
+    single = n_obs == 1
+    spec = engine.PriorSpec(0) if single else engine.prior_spec(w["prior_kind"], prior, fn, m)
+    grid = engine.time_grid(w["ddim_steps"])
+    setup = engine.build_setup(nse, xs, N, grid[:-1], grid[:-1].double() - 1.0 / w["ddim_steps"], w["eta"], spec, cov_mode,
+                               None if single else cov, n_sizes=kwn.get("n"), seed=5, weighted=not single)
+    th0 = engine.philox_normal(N, m, 5, -1, 0, dev)
+    th = th0.clone()
+    ms = []
+    l0 = engine.launch_count()
+    for k in range(reps + 1):
+        th.copy_(th0)
+        flush.fill_(float(k))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        engine.run_trajectory(setup, th, None, True)
+        e1.record()
+        e1.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    launches = (engine.launch_count() - l0) // (reps + 1)
+    assert bool(torch.isfinite(th).all())
+    best = float(np.mean(ms[1:]))
+    return N / (best * 1e-3), best, int(launches), e2e_rate, w
+
+
+def n_obs_sweep(args, dev):
+    """samples/s of complete trajectories for n_obs in {1, 8, 14, 22, 30} x {GAUSS (1000 steps, eta 1), JAC (400 steps,
+    eta 0.8)} on the default task's shape, N = --samples (sbibm_posterior_estimation.py:21, 330-334, 617-619)."""
+    out = {"n_obs": [1, 8, 14, 22, 30], "unit": "samples/s", "samples": args.samples,
+           "note": "device-resident tables, CUDA events around d4s_ddim_run, mean of 2 trajectories after 1 warm-up; "
+                   "launches = kernel launches per trajectory (1 = fused tcgen05 trajectory kernel)"}
+    for mode in ("GAUSS", "JAC"):
+        rates, launches = {}, {}
+        for n in out["n_obs"]:
+            r, _, l, _, _ = trajectory_rate(args, dev, n, mode)
+            rates[str(n)] = r
+            launches[str(n)] = l
+        out[mode] = rates
+        out[mode + "_launches"] = launches
+    return out
+
+
+def jac_record(args, dev, peaks):
+    """The JAC half of the metric on the default task (n_obs = --n-obs, 400 steps, eta 0.8): value, e2e, roofline of the
+    Jacobian step kernel, and the reference's CPU path on the same config."""
+    import copy
+    import torch
+    from d4s import engine
+    rate, ms, launches, e2e_rate, w = trajectory_rate(args, dev, args.n_obs, "JAC", reps=2, e2e=True)
+    a2 = copy.copy(args)
+    a2.cov_mode, a2.ddim_steps = "JAC", None
+    N, m = args.samples, w["m"]
+    # steps inside the alpha-gate evaluate the Jacobian (forward-mode: 1 + m rows per pair); the others are plain-sum steps
+    t = engine.time_grid(w["ddim_steps"])[:-1].double()
+    gate = int((torch.exp(-16 * t ** 2).sqrt() > 0.5).sum()) if args.n_obs > 1 else 0
+    flops = float(N) * w["n_units"] * flops_per_pair(w) * ((1 + m) * gate + (w["ddim_steps"] - gate))
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    ach = flops / (ms * 1e-3) / 1e12
+    rec = {"value": rate, "unit": "samples/s", "ms_per_trajectory": ms, "ddim_steps": w["ddim_steps"], "eta": w["eta"],
+           "gpu_launches_per_trajectory": launches, "jacobian_steps": gate,
+           "e2e": {"value": e2e_rate, "unit": "samples/s"},
+           "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                        "flops_per_trajectory": flops,
+                        "note": "algorithmic flops of the whole JAC trajectory (forward-mode tangents counted on the "
+                                "Jacobian steps only) / trajectory time; kernels: traj_tc_kernel on the plain-sum steps, "
+                                "the JAC step kernel + finalize_kernel inside the alpha-gate"}}
+    if not args.no_cpu_baseline:
+        rec["cpu_baseline"] = cpu_baseline_record(a2, workload(a2))
     return rec
 
 
@@ -561,6 +746,7 @@ def run_ours(args):
         ms_step = tot_dev[0] / args.steps
         dims = [w["n_in"], *w["hidden"], m]
         hidden_flops = 2.0 * sum(a * b for a, b in zip(dims[1:-2], dims[2:-1])) * N * units  # layers on the tensor core
+        n_k1 = w["ddim_steps"] if setup.step_modes is None else int((setup.step_modes == 1).sum())
         if fused:
             # dominant kernel = traj_tc_kernel: ONE launch per trajectory; its duration is the timed region itself.
             peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
@@ -589,7 +775,10 @@ def run_ours(args):
                                    if (args.cov_mode == "JAC" and getattr(args, "jac_tc", False))
                                    else "score_simt_kernel (fp32 SIMT; forward-mode tangents in JAC)"),
                         "peak_source": src, "flops_per_launch": flops_step, "launch_ms": k1_ms,
-                        "finalize_launch_ms": k3_ms, "share_of_step": k1_ms * w["ddim_steps"] / ms_step}
+                        "finalize_launch_ms": k3_ms,
+                        # launches of this kernel per trajectory = steps inside the alpha-gate (the others run fused)
+                        "launches_per_trajectory": int(n_k1),
+                        "share_of_step": min(1.0, k1_ms * n_k1 / ms_step)}
         value = N * world / (ms_step * 1e-3)
         e2e_val = N * world / (tot_dev[1] / args.steps * 1e-3)
         line = {"metric": "posterior samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
@@ -604,14 +793,15 @@ def run_ours(args):
                 "us_per_ddim_step": ms_step * 1e3 / w["ddim_steps"]}
         if obs_rec is not None:
             line["obs_sharded"] = obs_rec
+        if world == 1 and not args.no_sweep and args.task == "slcp" and args.cov_mode == "GAUSS":
+            line["sweep"] = n_obs_sweep(args, dev)
+            line["jac"] = jac_record(args, dev, peaks)
         if not args.no_cpu_baseline:
-            rate, cores, dt = cpu_oracle_rate(args, w, args.cpu_sample_steps)
-            line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_sample_steps} of {w['ddim_steps']} DDIM steps at N={N}, "
-                                              f"n_obs={n}, extrapolated linearly; oracle port with torch-CPU GEMMs",
-                                    "ms_per_ddim_step": dt * 1e3}
+            line["cpu_baseline"] = cpu_baseline_record(args, w)
         print(json.dumps(line))
     if world > 1:
+        from d4s import parallel
+        parallel.shutdown()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -63,6 +63,7 @@ struct D4sNet {
     NetDev dev;
     float* blob = nullptr;  // one device allocation holding every packed array
     size_t blob_floats = 0;
+    uint64_t id = 0;        // unique over the life of the library: a host address can be reused by a later net
 };
 
 // Tiling of the (sample x observation) grid into TM-row tiles of SG samples x OC observations.
@@ -300,6 +301,12 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
     }
 
     D4sNet* net = new D4sNet();
+    {
+        static std::mutex id_mu;
+        static uint64_t next_id = 1;
+        std::lock_guard<std::mutex> lock(id_mu);
+        net->id = next_id++;
+    }
     cudaError_t e = cudaMalloc(&net->blob, h.size() * sizeof(float));
     if (e != cudaSuccess) {
         delete net;
@@ -350,8 +357,11 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
     return D4S_OK;
 }
 
+static void graph_cache_drop_net(const D4sNet* net);
+
 void d4s_net_free(D4sNet* net) {
     if (!net) return;
+    graph_cache_drop_net(net);  // cached graph execs captured this net's device pointers by value
     if (net->blob) cudaFree(net->blob);
     delete net;
 }
@@ -598,6 +608,7 @@ int d4s_finalize(const D4sNet* net, const D4sProblem* pb, const D4sStep* st, flo
 namespace {
 struct GraphKey {
     const D4sNet* net;
+    uint64_t net_id;
     D4sProblem pb;
     int steps;
     const float *sched, *tf, *mats, *noise, *affine;
@@ -613,6 +624,18 @@ struct GraphEntry {
 std::mutex g_graph_mu;
 std::vector<GraphEntry> g_graphs;
 }  // namespace
+
+static void graph_cache_drop_net(const D4sNet* net) {
+    std::lock_guard<std::mutex> lock(g_graph_mu);
+    for (size_t i = 0; i < g_graphs.size();) {
+        if (g_graphs[i].key.net == net) {
+            cudaGraphExecDestroy(g_graphs[i].exec);
+            g_graphs.erase(g_graphs.begin() + i);
+        } else {
+            ++i;
+        }
+    }
+}
 
 static int enqueue_steps(const D4sNet* net, const D4sProblem* pb0, int steps, const float* sched, const float* tf,
                          const float* mats, const float* noise, float* theta, const int32_t* step_mode,
@@ -719,6 +742,7 @@ int d4s_ddim_run(const D4sNet* net, const D4sProblem* pb, int32_t steps, const f
     GraphKey key;
     memset(&key, 0, sizeof(key));
     key.net = net;
+    key.net_id = net->id;
     memcpy(&key.pb, pb, sizeof(D4sProblem));
     key.steps = steps;
     key.sched = sched_dev;

@@ -33,7 +33,8 @@ class PriorSpec:
     low: Optional[torch.Tensor] = None  # uniform: [m] fp64 cpu
     high: Optional[torch.Tensor] = None
     mean: Optional[torch.Tensor] = None  # gaussian: [m], [m, m] fp64 cpu
-    cov: Optional[torch.Tensor] = None
+    cov: Optional[torch.Tensor] = None   # covariance of the diffused prior SCORE (prior_score_fn's own, vp_diffused_priors.py:65)
+    cov_prec: Optional[torch.Tensor] = None  # covariance behind the backward precision P0 (`prior.covariance_matrix`, nse.py:630)
 
 
 def _cpu64(v) -> torch.Tensor:
@@ -54,9 +55,10 @@ def prior_spec(prior_type: Optional[str], prior, prior_score_fn, m: int) -> Prio
             mean, cov = _cpu64(prior.loc), _cpu64(prior.covariance_matrix)
         else:
             raise ValueError("gaussian prior: pass a d4s.vp_diffused_priors score fn or a MultivariateNormal `prior`")
+        cov_prec = cov
         if prior is not None and hasattr(prior, "covariance_matrix"):
-            cov = _cpu64(prior.covariance_matrix)  # nse.py:630 reads the precision from `prior`
-        return PriorSpec(abi.PRIOR_GAUSSIAN, mean=mean.reshape(m), cov=cov.reshape(m, m))
+            cov_prec = _cpu64(prior.covariance_matrix)  # nse.py:630 reads the precision from `prior`, the score from the fn
+        return PriorSpec(abi.PRIOR_GAUSSIAN, mean=mean.reshape(m), cov=cov.reshape(m, m), cov_prec=cov_prec.reshape(m, m))
     if prior_type == "uniform":
         if fn_kind == "uniform":
             low, high = _cpu64(prior_score_fn.low), _cpu64(prior_score_fn.high)
@@ -341,7 +343,8 @@ def mats_table(rows: torch.Tensor, prior: PriorSpec, cov_jac: bool, n_total: int
         cov0, mean0 = prior.cov, prior.mean
         c_t = sig2[:, None, None] * eye + a[:, None, None] * cov0  # vp_diffused_priors.py:65-68
         c_inv = torch.linalg.inv(c_t)
-        p0 = torch.linalg.inv(cov0)[None] + aos2[:, None, None] * eye  # prec_matrix_backward(prior cov), nse.py:630
+        cov_p = prior.cov_prec if prior.cov_prec is not None else cov0
+        p0 = torch.linalg.inv(cov_p)[None] + aos2[:, None, None] * eye  # prec_matrix_backward(prior cov), nse.py:630
         mu = a.sqrt()[:, None] * mean0
         weighted = comb != abi.COMBINE_SUM
         # score_prior = -(theta - mu_t) C^-1 (row-vector form, vp_diffused_priors.py:71) = -C^-T (theta - mu_t)
@@ -362,6 +365,82 @@ def mats_table(rows: torch.Tensor, prior: PriorSpec, cov_jac: bool, n_total: int
             safe = torch.where(shared[:, None, None], base, eye.expand(S, m, m))
             lmat = torch.where(shared[:, None, None], torch.linalg.inv(safe), base)
     return torch.cat((lmat.reshape(S, -1), g.reshape(S, -1), mu), dim=1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# caches of the observation-dependent tables (per-call API: factorized_score in a user loop, euler_sde_sampler)
+# ---------------------------------------------------------------------------------------------------------
+class _LRU:
+    """Tiny LRU keyed by tensor identity.  Every entry keeps a strong reference to the tensors its key was derived from,
+    so their storage cannot be freed and handed to another tensor while the entry lives (a key is (data_ptr, _version,
+    shape, ...): an in-place update bumps `_version`, and a live reference rules out address reuse)."""
+
+    def __init__(self, cap: int):
+        self.cap, self.d = cap, {}
+
+    def get(self, key):
+        hit = self.d.get(key)
+        if hit is not None:
+            self.d[key] = self.d.pop(key)  # most recent last
+            return hit[0]
+        return None
+
+    def put(self, key, value, refs=()):
+        self.d[key] = (value, refs)
+        while len(self.d) > self.cap:
+            self.d.pop(next(iter(self.d)))
+
+    def clear(self):
+        self.d.clear()
+
+
+def tensor_key(t):
+    """Identity of a tensor's current contents (None-safe)."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        return ("py", repr(t))
+    return (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), str(t.dtype), str(t.device))
+
+
+_qinv_cache = _LRU(8)     # dist_cov_est -> inv (fp64, host)
+_obsfeat_cache = _LRU(8)  # (packed net, x, n_sizes) -> layer-0 observation partials (fp64, host)
+_dev_cache = _LRU(64)     # host fp64 table -> fp32 device copy (keyed by the host tensor's identity)
+_setup_cache = _LRU(1200)  # whole per-call setups (NSE.factorized_score with the same inputs and the same t)
+
+
+def clear_caches():
+    for c in (_qinv_cache, _obsfeat_cache, _dev_cache, _setup_cache):
+        c.clear()
+
+
+def _inv_cov64(cov: torch.Tensor) -> torch.Tensor:
+    key = tensor_key(cov)
+    hit = _qinv_cache.get(key)
+    if hit is None:
+        hit = torch.linalg.inv(cov.detach().to("cpu", torch.float64))
+        _qinv_cache.put(key, hit, (cov,))
+    return hit
+
+
+def _obs_feat_cached(nse, pn, x, n_sizes):
+    emb_key = tuple((q.data_ptr(), q._version) for q in nse.embedding_nn_x.parameters())  # not part of the packed net
+    key = (id(pn), tensor_key(x), tensor_key(n_sizes), emb_key)
+    hit = _obsfeat_cache.get(key)
+    if hit is None:
+        hit = obs_feat_table(nse, pn, x, n_sizes)
+        _obsfeat_cache.put(key, hit, (pn, x, n_sizes))
+    return hit
+
+
+def _dev32_cached(t64: torch.Tensor, device) -> torch.Tensor:
+    """fp32 device copy of a host table that is itself cached (its identity is stable across calls)."""
+    key = (tensor_key(t64), str(device))
+    hit = _dev_cache.get(key)
+    if hit is None:
+        hit = _dev32(t64, device)
+        _dev_cache.put(key, hit, (t64,))
+    return hit
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -431,7 +510,8 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
     if not cov_jac and weighted and not paired:
         if dist_cov_est is None:
             raise ValueError("cov_mode='GAUSS' needs dist_cov_est (tall_posterior_sampler.py:125)")
-        q64 = torch.linalg.inv(dist_cov_est.detach().to("cpu", torch.float64))  # [n, m, m]
+        q64 = _inv_cov64(dist_cov_est)  # [n, m, m] fp64 on the host, cached per dist_cov_est tensor
+        q_cached = cfg is None
         if cfg is not None:
             if cfg.get("prior_cov") is None:
                 raise ValueError("clf_free_guidance with cov_mode='GAUSS' needs dist_cov_est_prior (nse.py:613)")
@@ -456,7 +536,8 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
                          coef)
     mats = mats_table(rows, prior, cov_jac, n_total, sum_q, m, None if w64 is None else float(w64.sum()))
     tf = time_feat_table(nse, pn, t)
-    of = obs_feat_table(nse, pn, x2, n_sizes)
+    of = _obs_feat_cached(nse, pn, x2, n_sizes)
+    of_cached = cfg is None and obs_slice is None
     if cfg is not None:  # layer-0 partial of the pseudo-observation: x = 0 (PF_NSE: masked empty set, no one-hot)
         if n_sizes is None:
             x0 = torch.zeros((1,) + tuple(x2.shape[1:]), dtype=x2.dtype, device=x2.device)
@@ -467,9 +548,10 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
         of = of[obs_slice]
         if sum_q is not None:
             q64 = q64[obs_slice]
+            q_cached = False
     if sum_q is not None:
-        q_dev = _dev32(q64, device)
-    of_dev = _dev32(of, device)
+        q_dev = _dev32_cached(q64, device) if q_cached else _dev32(q64, device)
+    of_dev = _dev32_cached(of, device) if of_cached else _dev32(of, device)
     low_dev = high_dev = None
     if prior.kind == abi.PRIOR_UNIFORM:
         low_dev, high_dev = _dev32(prior.low, device), _dev32(prior.high, device)
@@ -555,6 +637,16 @@ def run_trajectory(setup: TallSetup, theta: torch.Tensor, noise: Optional[torch.
 
 
 def step_struct(setup: TallSetup, k: int, noise_k: Optional[torch.Tensor], update: bool) -> abi.Step:
+    if noise_k is None:  # (the struct only holds pointers into the setup's own tables: reusable)
+        cache = setup.__dict__.setdefault("_steps", {})
+        hit = cache.get((k, update))
+        if hit is None:
+            hit = cache[(k, update)] = _step_struct(setup, k, None, update)
+        return hit
+    return _step_struct(setup, k, noise_k, update)
+
+
+def _step_struct(setup: TallSetup, k: int, noise_k: Optional[torch.Tensor], update: bool) -> abi.Step:
     st = abi.Step()
     st.sched = setup.sched[k].data_ptr()
     st.time_feat = setup.time_feat[k].data_ptr()

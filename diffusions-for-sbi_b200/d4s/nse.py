@@ -149,7 +149,9 @@ class NSE(nn.Module):
              theta_clipping_range=(None, None), **kwargs) -> Tensor:
         """DDIM sampler adapted to n context observations (nse.py:223-267); returns theta[shape[0], m] on x.device.
 
-        The whole `steps`-long loop is enqueued by one C-ABI call (two kernels per step, CUDA-graph captured).
+        The whole `steps`-long loop is enqueued by one C-ABI call (`d4s_ddim_run`): ONE launch of the fused tcgen05
+        trajectory kernel for GAUSS-type runs; JAC steps inside the alpha-gate (nse.py:643) and the toy nets run two
+        kernels per step, captured in a CUDA graph.
         """
         self._require_cuda(x)
         opts, noise, seed, sample_offset = self._split_kwargs(kwargs)
@@ -237,6 +239,10 @@ class NSE(nn.Module):
         self._require_cuda(theta)
         score = score_fun(theta, x, t).detach()
         noise = kwargs.pop("_noise", None)
+        if noise is not None:  # the kernel reads raw fp32 device memory
+            noise = torch.as_tensor(noise).detach().to(theta.device, torch.float32).contiguous()
+            if tuple(noise.shape) != tuple(theta.shape):
+                raise ValueError(f"_noise must have the shape of theta {tuple(theta.shape)}, got {tuple(noise.shape)}")
         tt = torch.as_tensor(t).detach().to("cpu").reshape(1)
         rows = engine.schedule_rows(self, tt, tt.to(torch.float64) - dt, float(eta), 1, [abi.COMBINE_SUM])
         sched = rows.to(torch.float32).to(theta.device)
@@ -259,14 +265,25 @@ class NSE(nn.Module):
         if kwargs:
             raise TypeError(f"unexpected keyword arguments: {sorted(kwargs)}")
         m = self.zeros.shape[0]
-        cfg = dict(prior_cov=dist_cov_est_prior) if clf_free_guidance else None
-        spec = engine.PriorSpec(abi.PRIOR_NONE) if clf_free_guidance else engine.prior_spec(prior_type, prior, prior_score_fn, m)
+        # Every table of the call (layer-0 partials of the observations, inv(Sigma_j), schedule row, step matrices) is a
+        # function of (weights, x_obs, dist_cov_est, prior, t): a loop that calls this with the same inputs -- the
+        # reference's euler_sde_sampler, user-written samplers -- reuses them instead of rebuilding them on the host.
         tt = torch.as_tensor(t).detach().to("cpu").reshape(1)
-        setup = engine.build_setup(self, x_obs, theta.shape[0], tt, None, 0.0, spec, cov_mode, dist_cov_est,
-                                   n_sizes=n_sizes, cfg=cfg)
+        pn = engine.packed_net(self, x_obs.device)
+        key = ("fs", id(pn), engine.tensor_key(x_obs), engine.tensor_key(dist_cov_est), engine.tensor_key(dist_cov_est_prior),
+               int(theta.shape[0]), float(tt), cov_mode, prior_type, id(prior_score_fn), id(prior), bool(clf_free_guidance),
+               engine.tensor_key(n_sizes), tuple((q.data_ptr(), q._version) for q in self.embedding_nn_x.parameters()))
+        setup = engine._setup_cache.get(key)
+        if setup is None:
+            cfg = dict(prior_cov=dist_cov_est_prior) if clf_free_guidance else None
+            spec = (engine.PriorSpec(abi.PRIOR_NONE) if clf_free_guidance
+                    else engine.prior_spec(prior_type, prior, prior_score_fn, m))
+            setup = engine.build_setup(self, x_obs, theta.shape[0], tt, None, 0.0, spec, cov_mode, dist_cov_est,
+                                       n_sizes=n_sizes, cfg=cfg)
+            if setup.step_modes is not None:
+                setup.prob.cov_mode = int(setup.step_modes[0])
+            engine._setup_cache.put(key, setup, (pn, x_obs, dist_cov_est, dist_cov_est_prior, prior_score_fn, prior, n_sizes))
         th = theta.detach().to(torch.float32).contiguous()
-        if setup.step_modes is not None:
-            setup.prob.cov_mode = int(setup.step_modes[0])
         engine.score_partials(setup, th, 0)
         return engine.finalize(setup, th, 0)
 
@@ -434,3 +451,20 @@ class NSE(nn.Module):
     # ---- stand-alone prior score (used by d4s.vp_diffused_priors objects) -------------------------------------
     def _prior_score_native(self, theta: Tensor, t: Tensor, spec: "engine.PriorSpec", want_jac: bool = False):
         return engine.prior_score_native(self, theta, t, spec, want_jac)
+
+
+class NSELoss(nn.Module):
+    """Noise-parametrised denoising score matching loss (nse.py:708-751): t ~ U(0, 1), eps ~ N(0, I),
+    theta_t = sqrt(alpha(t)) theta + sigma(t) eps, loss = mean ||estimator(theta_t, x, t) - eps||^2.  Pure torch
+    (training is outside the sampling hot path); kept so that the reference drivers' `from nse import NSE, NSELoss`
+    resolves against the drop-in modules."""
+
+    def __init__(self, estimator: NSE):
+        super().__init__()
+        self.estimator = estimator
+
+    def forward(self, theta: Tensor, x: Tensor, **kwargs) -> Tensor:
+        t = torch.rand(theta.shape[0], dtype=theta.dtype, device=theta.device)
+        noise = torch.randn_like(theta)
+        theta_t = self.estimator.alpha(t).sqrt()[:, None] * theta + self.estimator.sigma(t)[:, None] * noise
+        return (self.estimator(theta_t, x, t, **kwargs) - noise).square().mean()

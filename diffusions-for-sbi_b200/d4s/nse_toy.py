@@ -27,6 +27,7 @@ from . import engine
 from .embedding_nets import AnalyticGaussianEps, EpsilonNet, FakeFNet  # noqa: F401
 from .nse import NSE as _FullNSE
 from .nse import _use_graph_default
+from .tall_posterior_sampler import mean_backward, prec_matrix_backward, sigma_backward  # noqa: F401  (nse_toy.py:20-50)
 from .vp_diffused_priors import GaussianDiffusedScore
 
 
@@ -219,3 +220,19 @@ class NSE(nn.Module):
         th = theta.detach().to(torch.float32).contiguous()
         engine.score_partials(setup, th, 0)
         return engine.finalize(setup, th, 0)
+
+
+class NSELoss(nn.Module):
+    """Denoising score matching loss of the toy module (nse_toy.py:628-660 declares it; same objective as nse.py:708-751).
+    Pure torch; present for import compatibility of the reference's toy drivers."""
+
+    def __init__(self, estimator: NSE, eps_t: float = 1e-5):
+        super().__init__()
+        self.eps_t = eps_t
+        self.estimator = estimator
+
+    def forward(self, theta: Tensor, x: Tensor, **kwargs) -> Tensor:
+        t = torch.rand(theta.shape[0], dtype=theta.dtype, device=theta.device) * (1 - self.eps_t) + self.eps_t
+        noise = torch.randn_like(theta)
+        theta_t = self.estimator.alpha(t).sqrt()[:, None] * theta + self.estimator.sigma(t)[:, None] * noise
+        return (self.estimator(theta_t, x, t[:, None], **kwargs) - noise).square().mean()

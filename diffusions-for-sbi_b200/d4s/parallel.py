@@ -122,6 +122,18 @@ class PeerExchange:
         self.seq = 0  # fresh (zeroed) flags on every rank
         dist.barrier(group=self.group)
 
+    @classmethod
+    def shutdown(cls):
+        """Collective: unmaps the peers' buffers and frees the local ones.  Call it before
+        `dist.destroy_process_group()` (a process must not exit while a peer still has its memory mapped and in use)."""
+        for px in list(cls._instances.values()):
+            if px.local[0] is not None:
+                torch.cuda.synchronize()
+                dist.barrier(group=px.group)
+                px._release()
+                px.data_bytes = px.flag_bytes = 0
+        cls._instances.clear()
+
     def struct(self, steps: int) -> "abi.Exchange":
         xg = abi.Exchange()
         xg.world, xg.rank, xg.seq_base = self.world, self.rank, self.seq & 0xFFFFFFFF
@@ -268,6 +280,14 @@ class NcclTrajectory:
             dist.all_reduce(ws[:n_floats], group=self.group)  # NCCL sum of the [N, C, W] partial sums
             engine.finalize(st, self.theta, k, noise_k=None if self.z is None else self.z[k], update=True, want_score=False)
 
+    def close(self):
+        """Destroys the captured graph.  A CUDA graph that holds NCCL kernels keeps the communicator alive:
+        `dist.destroy_process_group()` waits for it (observed: the process never exits), so release it first."""
+        if self.graph is not None:
+            torch.cuda.synchronize(self.device)
+            self.graph.reset()
+            self.graph = None
+
     def launch(self) -> torch.Tensor:
         """Runs the trajectory from theta0 (every rank must call it); returns the internal theta buffer."""
         self.theta.copy_(self.theta0)
@@ -280,6 +300,11 @@ class NcclTrajectory:
 
 def _ddim_obs_sharded_nccl(nse, shape, x, steps, eta, clip, group, _seed, _noise, kwargs, graph=True):
     traj = NcclTrajectory(nse, shape, x, steps, eta, clip, group, _seed, _noise, graph=graph, **kwargs)
-    theta = traj.launch()
-    theta._d4s_keep = traj
+    theta = traj.launch().clone()
+    traj.close()  # (synchronises; the graph must not outlive the process group)
     return theta
+
+
+def shutdown():
+    """Releases everything that must not outlive the process group (exchange buffers mapped by the peers)."""
+    PeerExchange.shutdown()

@@ -17,6 +17,21 @@ def _t_cpu(t):
     return torch.as_tensor(t).detach().to("cpu").reshape(1)
 
 
+def mean_backward(theta, t, score_fn, nse, **kwargs):
+    """Tweedie mean of p(theta_0 | theta_t): (theta + sigma^2 score) / sqrt(alpha) (tall_posterior_sampler.py:10-18).
+    `score_fn(theta=, t=, **kwargs)` is any callable, e.g. a d4s.vp_diffused_priors object."""
+    alpha_t, sigma_t = nse.alpha(t), nse.sigma(t)
+    return (theta + sigma_t ** 2 * score_fn(theta=theta, t=t, **kwargs)) / alpha_t ** 0.5
+
+
+def sigma_backward(t, dist_cov, nse):
+    """Covariance of p(theta_0 | theta_t) for a Gaussian p(theta_0) = N(., dist_cov): inv(inv(Sigma) + alpha/sigma^2 I)
+    (tall_posterior_sampler.py:21-32; the reference switches to a Woodbury form of the same matrix when
+    sqrt(alpha) >= 0.5 -- one formula serves both here, the inverses run in fp64 in batched_inverse_kernel)."""
+    return engine.batched_inverse(prec_matrix_backward(t, dist_cov, nse).reshape(-1, dist_cov.shape[-1], dist_cov.shape[-1])
+                                  ).reshape(dist_cov.shape)
+
+
 def prec_matrix_backward(t, dist_cov, nse):
     """inv(Sigma) + alpha/sigma^2 I for Sigma[*, m, m] (tall_posterior_sampler.py:35-43)."""
     if not dist_cov.is_cuda:
@@ -127,7 +142,8 @@ def euler_sde_sampler(score_fn, nsamples, dim_theta, beta, device="cuda", debug=
     sched = rows.to(torch.float32).to(dev)
     lo, hi = theta_clipping_range
     clip = (1.0, -1.0) if lo is None else (float(lo), float(hi))
-    theta_list = [theta.detach().cpu()]
+    hist = torch.empty(1000, theta.shape[0], theta.shape[1], dtype=torch.float32, device=dev)  # one D2H copy at the end
+    hist[0].copy_(theta)
     for i in range(999):
         score = score_fn(theta, time_pts[i].to(dev)).detach().to(torch.float32).contiguous()
         nz = None if z is None else z[i].to(dev, torch.float32).contiguous()
@@ -135,8 +151,8 @@ def euler_sde_sampler(score_fn, nsamples, dim_theta, beta, device="cuda", debug=
             abi.check(lib.d4s_ddim_update(engine._ptr(theta), engine._ptr(score), theta.shape[0], theta.shape[1],
                                           engine._ptr(sched[i]), engine._ptr(nz), C.c_uint64(0 if z is not None else seed),
                                           i, 0, clip[0], clip[1], engine._stream(dev)))
-        theta_list.append(theta.detach().cpu())
-    return theta, theta_list
+        hist[i + 1].copy_(theta)
+    return theta, list(hist.cpu().unbind(0))
 
 
 import math  # noqa: E402  (kept at the bottom: only the helpers above use it)

@@ -95,7 +95,9 @@ if rank == 0:
 ok &= same
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-dist.destroy_process_group()
+passed = bool(int(flag))
 if rank == 0:
-    print("MULTI_GPU_OK" if int(flag) else "MULTI_GPU_FAIL")
-sys.exit(0 if int(flag) else 1)
+    print("MULTI_GPU_OK" if passed else "MULTI_GPU_FAIL", flush=True)
+parallel.shutdown()
+dist.destroy_process_group()
+sys.exit(0 if passed else 1)

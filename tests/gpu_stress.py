@@ -90,6 +90,7 @@ if world > 1:
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     ok = bool(int(flag))
+    parallel.shutdown()
     dist.destroy_process_group()
 if rank == 0:
     print("STRESS_OK" if ok else "STRESS_FAIL")

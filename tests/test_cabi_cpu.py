@@ -92,3 +92,29 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("oracle_", ""), f"{f} mentions the oracle"
+
+
+def test_dropin_resolves_every_hot_path_import_of_the_reference_drivers():
+    """The exact hot-path import lines of the reference drivers (sbibm_posterior_estimation.py:6,13,14,
+    jrnnm_posterior_estimation.py:5,14,16,17, sbibm_pf_npse.py:5,6,13, gen_gaussian_gaussian.py:11-13,15,
+    gen_mixt_gauss_gaussian.py:7,8,12) against the drop-in directory (no reference checkout needed)."""
+    import subprocess
+    import sys
+    lines = [
+        "from nse import NSE, NSELoss",
+        "from tall_posterior_sampler import diffused_tall_posterior_score, euler_sde_sampler, tweedies_approximation",
+        "from vp_diffused_priors import get_vpdiff_gaussian_score, get_vpdiff_uniform_score",
+        "from zuko.nn import MLP",
+        "from nse import NSELoss",
+        "from pf_nse import PF_NSE",
+        "from embedding_nets import EpsilonNet, FakeFNet",
+        "from nse_toy import NSE",
+        "from tall_posterior_sampler import mean_backward, prec_matrix_backward",
+        "from nse_toy import mean_backward, prec_matrix_backward",
+        "from nse_toy import NSELoss as ToyLoss",
+        "from tall_posterior_sampler import sigma_backward",
+    ]
+    dropin = os.path.join(ROOT, "diffusions-for-sbi_b200", "dropin")
+    code = f"import sys; sys.path.insert(0, {dropin!r})\n" + "\n".join(lines) + "\nprint('IMPORTS_OK')"
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert "IMPORTS_OK" in r.stdout, r.stderr[-2000:]
