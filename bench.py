@@ -544,6 +544,46 @@ def trajectory_rate(args, dev, n_obs, cov_mode, reps=2, e2e=False):
     return N / (best * 1e-3), best, int(launches), e2e_rate, w
 
 
+def per_call_record(args, dev):
+    """`NSE.factorized_score` through the public per-call API at the bench shape (what `euler_sde_sampler` or a
+    user-written sampler calls once per step): steady-state wall time per call over a loop that revisits 20 time points
+    (tables cached per (x, dist_cov_est, prior, t)), and the first-visit cost of a new t."""
+    import torch
+    import d4s
+    w = workload(args)
+    N, m = args.samples, w["m"]
+    nse = build_nse(w, dev)
+    x, cov = torch.as_tensor(w["x"]).to(dev), torch.as_tensor(w["cov"]).to(dev)
+    if w["prior_kind"] == "uniform":
+        lo, hi = torch.as_tensor(w["prior"]["low"]).to(dev), torch.as_tensor(w["prior"]["high"]).to(dev)
+        prior, fn = torch.distributions.Uniform(lo, hi, validate_args=False), d4s.get_vpdiff_uniform_score(lo, hi, nse)
+    else:
+        mu, pc = torch.as_tensor(w["prior"]["mean"]).to(dev), torch.as_tensor(w["prior"]["cov"]).to(dev)
+        prior, fn = torch.distributions.MultivariateNormal(mu, pc, validate_args=False), d4s.get_vpdiff_gaussian_score(mu, pc, nse)
+    theta = torch.randn(N, m, device=dev)
+    ts = [torch.tensor(0.05 + 0.045 * k) for k in range(20)]
+    out = {}
+    for mode in ("GAUSS", "JAC"):
+        call = lambda t: nse.factorized_score(theta, x, t, fn, prior, dist_cov_est=cov, cov_mode=mode,  # noqa: E731
+                                              prior_type=w["prior_kind"])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in ts:
+            call(t)
+        torch.cuda.synchronize()
+        first = (time.perf_counter() - t0) / len(ts)
+        reps = 10
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for t in ts:
+                call(t)
+        torch.cuda.synchronize()
+        out[mode] = {"steady_us": (time.perf_counter() - t0) / (reps * len(ts)) * 1e6, "first_visit_us": first * 1e6}
+    out["note"] = (f"N={N}, n_obs={w['n']}; steady = tables of the (x, cov, prior, t) combination cached on the device, "
+                   "loop not synchronised per call; first_visit = new t (schedule row + step matrices built on the host)")
+    return out
+
+
 def n_obs_sweep(args, dev):
     """samples/s of complete trajectories for n_obs in {1, 8, 14, 22, 30} x {GAUSS (1000 steps, eta 1), JAC (400 steps,
     eta 0.8)} on the default task's shape, N = --samples (sbibm_posterior_estimation.py:21, 330-334, 617-619)."""
@@ -796,6 +836,7 @@ def run_ours(args):
         if world == 1 and not args.no_sweep and args.task == "slcp" and args.cov_mode == "GAUSS":
             line["sweep"] = n_obs_sweep(args, dev)
             line["jac"] = jac_record(args, dev, peaks)
+            line["per_call_us"] = per_call_record(args, dev)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_record(args, w)
         print(json.dumps(line))

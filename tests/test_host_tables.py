@@ -7,6 +7,7 @@ import torch
 
 import golden_io as gio
 from d4s import _cabi as abi
+import d4s
 from d4s import engine
 from d4s_helpers import nse_from_oracle
 from oracle import d4s_oracle as orc
@@ -159,3 +160,28 @@ def test_combine_mode_gate():
     assert engine.combine_mode(uni, False, 30, 0.5) == abi.COMBINE_SUM  # strict > (nse.py:643)
     assert engine.combine_mode(uni, True, 1, 0.9) == abi.COMBINE_SUM
     assert engine.combine_mode(engine.PriorSpec(abi.PRIOR_NONE), False, 1, 0.9) == abi.COMBINE_SUM
+
+
+def test_driver_normalisation_wrappers_cpu():
+    """d4s.io.normalize_context / normalize_prior / unnormalize_samples restate sbibm_posterior_estimation.py:179-212,
+    385-388; checked against the formulas written out by hand (and against the golden fixtures' normalised priors)."""
+    from d4s import io
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(7, 4, generator=g) + 0.5
+    mean, std = torch.tensor([0.1, 0.2, 0.3, 0.4]), torch.tensor([1.0, 2.0, 0.0, 0.5])  # a zero std -> inf/nan -> 0
+    out = io.normalize_context(x, mean, std, x_log_space=True)
+    ref = (torch.log(x) - mean) / std
+    assert torch.equal(out[:, [0, 1, 3]], ref[:, [0, 1, 3]]) and bool((out[:, 2] == 0).all())
+    tm, ts = torch.tensor([0.5, -1.0]), torch.tensor([2.0, 0.25])
+    nse = d4s.NSE(2, 4, hidden_features=[64, 64])
+    uni = torch.distributions.Independent(torch.distributions.Uniform(torch.tensor([-3.0, -3.0]), torch.tensor([3.0, 3.0])), 1)
+    pn, fn = io.normalize_prior(uni, "uniform", tm, ts, nse, "cpu")
+    assert torch.allclose(pn.low, (torch.tensor([-3.0, -3.0]) - tm) / ts * 2) and fn.kind == "uniform"
+    assert torch.allclose(torch.as_tensor(fn.high), (torch.tensor([3.0, 3.0]) - tm) / ts * 2)
+    logn = torch.distributions.LogNormal(torch.tensor([-0.125, -3.0]), torch.tensor([0.5, 0.5]))
+    pn, fn = io.normalize_prior(torch.distributions.Independent(logn, 1), "gaussian", tm, ts, nse, "cpu", theta_log_space=True)
+    assert torch.allclose(pn.loc, (torch.tensor([-0.125, -3.0]) - tm) / ts)
+    assert torch.allclose(pn.covariance_matrix, torch.diag(torch.tensor([0.25, 0.25]) / ts ** 2)) and fn.kind == "gaussian"
+    s = torch.randn(5, 2, generator=g)
+    assert torch.allclose(io.unnormalize_samples(s, tm, ts, theta_log_space=True), torch.exp(s * ts + tm))
+    assert torch.allclose(io.unnormalize_samples(s, tm, ts), s * ts + tm)
