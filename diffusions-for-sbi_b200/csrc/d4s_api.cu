@@ -401,7 +401,10 @@ static int fill_traj_params(const D4sNet* net, const D4sProblem* pb, const float
     p.net = nd;
     p.N = pb->n_samples;
     p.n = pb->n_obs;
-    int oc = pb->obs_chunk > 0 ? pb->obs_chunk : pb->n_obs;
+    // observation chunk of a tile: the whole set when it fits (<= 128 rows, one pass per item); taller sets are cut into
+    // chunks of <= 64 observations x 2 samples -- measured 10 % faster than 125 x 1 on the stress shape (n_obs = 10^4:
+    // half as many distinct obs_feat rows and inv(Sigma_j) per tile, profiles/r02_obs_chunk_probe.txt)
+    int oc = pb->obs_chunk > 0 ? pb->obs_chunk : (pb->n_obs > 128 ? 64 : pb->n_obs);
     if (oc > 128) oc = 128;
     if (oc > pb->n_obs) oc = pb->n_obs;
     const int c = (pb->n_obs + oc - 1) / oc;
@@ -829,7 +832,7 @@ int d4s_ddim_run_sharded(const D4sNet* net, const D4sProblem* pb, int32_t steps,
     // samples per group from the LARGEST observation shard (ceil(n_total / world)), so that all ranks agree on it
     int n_loc = (pb->n_obs_total + xchg->world - 1) / xchg->world;
     if (n_loc < pb->n_obs) n_loc = pb->n_obs;
-    int oc = pb->obs_chunk > 0 ? pb->obs_chunk : n_loc;
+    int oc = pb->obs_chunk > 0 ? pb->obs_chunk : (n_loc > 128 ? 64 : n_loc);  // same rule as fill_traj_params
     if (oc > 128) oc = 128;
     if (oc > n_loc) oc = n_loc;
     const int cc = (n_loc + oc - 1) / oc;

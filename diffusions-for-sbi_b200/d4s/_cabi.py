@@ -162,13 +162,23 @@ def load():
             raise D4sError(f"libd4s ABI {lib.d4s_abi_version()} != binding {ABI_VERSION}: rebuild the library")
         if os.environ.get("D4S_JAC_TC", "0") == "1":  # opt in to the tensor-core JAC kernel for the whole process
             lib.d4s_set_option(b"jac_tc", 1)
+            _options["jac_tc"] = 1
         _lib = lib
     return _lib
+
+
+_options: dict = {}
 
 
 def set_option(key: str, value: int):
     """Library switches (see d4s_set_option in include/d4s.h): path, tc_steps_per_launch, profile, tc_pairing, jac_tc."""
     check(load().d4s_set_option(key.encode(), int(value)))
+    _options[key] = int(value)
+
+
+def options_key() -> tuple:
+    """Current option state: part of every cache key whose value depends on the kernel path (workspace layouts do)."""
+    return tuple(sorted(_options.items()))
 
 
 PROFILE_PHASES = ["layer0_sample_part", "layer0", "prior_noise", "tensor_wait", "epilogues", "scores",

@@ -272,7 +272,8 @@ class NSE(nn.Module):
         pn = engine.packed_net(self, x_obs.device)
         key = ("fs", id(pn), engine.tensor_key(x_obs), engine.tensor_key(dist_cov_est), engine.tensor_key(dist_cov_est_prior),
                int(theta.shape[0]), float(tt), cov_mode, prior_type, id(prior_score_fn), id(prior), bool(clf_free_guidance),
-               engine.tensor_key(n_sizes), tuple((q.data_ptr(), q._version) for q in self.embedding_nn_x.parameters()))
+               engine.tensor_key(n_sizes), tuple((q.data_ptr(), q._version) for q in self.embedding_nn_x.parameters()),
+               abi.options_key())
         setup = engine._setup_cache.get(key)
         if setup is None:
             cfg = dict(prior_cov=dist_cov_est_prior) if clf_free_guidance else None

@@ -413,6 +413,56 @@ def per_call_case(name, net32, x, prior_kind, prior_params, N, seed, extra_kwarg
     print("wrote", name, {k: v.shape for k, v in out.items() if hasattr(v, "shape") and "traj" in k})
 
 
+def replay_noise(seed, steps, N, m):
+    """Injected noise as a pure function of a seed (numpy PCG64: stable across versions), so that fixtures of long
+    trajectories store the seed instead of [steps, N, m] floats; the tests regenerate the same arrays."""
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal((N, m)).astype(np.float32), rng.standard_normal((steps, N, m)).astype(np.float32)
+
+
+def euler_case(name, base, net32, x, prior_kind, prior_params, cov_est, N, seed):
+    """`euler_sde_sampler` on `diffused_tall_posterior_score` (tall_posterior_sampler.py:158-281; the call of
+    sbibm_posterior_estimation.py:347-372) under replayed noise, GAUSS and JAC, fp32 and fp64.  The net, observations,
+    prior and dist_cov_est are those of the fixture `base`."""
+    m = net32.zeros.shape[0]
+    z0, z = replay_noise(seed, 999, N, m)
+    out = dict(base=np.str_(base), seed=np.int64(seed), N=np.int64(N), checkpoints=np.asarray([100, 500, 900, 999]))
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        net = copy.deepcopy(net32).to(dt)
+        prior, fn = make_prior(prior_kind, m, dt, net, **prior_params)
+        for mode in ("GAUSS", "JAC"):
+            score_fn = partial(ref_tps.diffused_tall_posterior_score, prior=prior, prior_type=prior_kind, prior_score_fn=fn,
+                               x_obs=x.to(dt), nse=net, dist_cov_est=cov_est.to(dt), cov_mode=mode)
+            it = iter(torch.as_tensor(z).to(dt))
+            with mock.patch("torch.randn", side_effect=lambda *a, **k: torch.as_tensor(z0).to(dt)), \
+                    mock.patch("torch.randn_like", side_effect=lambda a: next(it).to(a)):
+                theta, hist = ref_tps.euler_sde_sampler(score_fn, N, dim_theta=m, beta=net.beta, device="cpu")
+            out[f"{tag}.{mode}.theta"] = npy(theta)
+            out[f"{tag}.{mode}.hist"] = np.stack([npy(hist[k]) for k in (100, 500, 900, 999)])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, {k: v.shape for k, v in out.items() if hasattr(v, "shape") and "theta" in k})
+
+
+def jac_dist_case(name, base, net32, x, prior_kind, prior_params, N, seed, steps=400, eta=0.8, clip=(None, None)):
+    """Reference sample SETS of a complete JAC trajectory (400 steps, eta 0.8: sbibm_posterior_estimation.py:330-334,
+    617-619) in fp32 and fp64 under the same replayed noise: the distribution-level gate of SURVEY.md section 8(c).
+    The net / observations / prior are those of the fixture `base`; only the samples and the seed are stored."""
+    m = net32.zeros.shape[0]
+    z0, z = replay_noise(seed, steps, N, m)
+    out = dict(base=np.str_(base), seed=np.int64(seed), N=np.int64(N), steps=np.int64(steps), eta=np.float64(eta),
+               clip=np.asarray([np.nan if c is None else c for c in clip], np.float64))
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        net = copy.deepcopy(net32).to(dt)
+        prior, fn = make_prior(prior_kind, m, dt, net, **prior_params)
+        res = run_ddim(net, x.to(dt), torch.as_tensor(z0).to(dt), torch.as_tensor(z).to(dt), steps=steps, eta=eta,
+                       prior=prior, prior_type=prior_kind, prior_score_fn=fn, cov_mode="JAC", theta_clipping_range=clip)
+        out[f"{tag}.samples"] = npy(res).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    a, b = out["f32.samples"], out["f64.samples"]
+    print("wrote", name, a.shape, "nan rows:", int(np.isnan(a).any(1).sum()), int(np.isnan(b).any(1).sum()),
+          "max |f32 - f64|:", float(np.nanmax(np.abs(a - b))))
+
+
 def load_sbibm(task, sub="n_train_30000_bs_256_n_epochs_5000_lr_0.0001", pf=None):
     d = os.path.join(REF, "results", "sbibm", task, sub)
     if pf:
@@ -535,6 +585,28 @@ def main(filt=None):
         xs, ns = net._create_pf_data(x)
         langevin_case("langevin_pf_slcp_n8", net, xs, "uniform", slcp_prior(st), N=8, seed=23, steps=8, lsteps=2,
                       traj_x=x, extra_kwargs=dict(n=ns))
+    if want("euler"):
+        net, st = load_sbibm("slcp")
+        x = sbibm_obs("slcp", st, 6)
+        g0 = dict(np.load(os.path.join(OUT, "slcp_n6.npz")))
+        euler_case("euler_slcp_n6", "slcp_n6", net, x, "uniform", slcp_prior(st), torch.as_tensor(g0["dist_cov_est"]), N=8, seed=61)
+        net, st = load_sbibm("sir")
+        x = sbibm_obs("sir", st, 8, log_space=False)
+        pp = lognormal_prior(st, torch.log(torch.tensor([0.4, 0.125])), torch.tensor([0.5, 0.2]))
+        g0 = dict(np.load(os.path.join(OUT, "sir_n8.npz")))
+        euler_case("euler_sir_n8", "sir_n8", net, x, "gaussian", pp, torch.as_tensor(g0["dist_cov_est"]), N=8, seed=62)
+    if want("jacdist"):
+        net, st = load_sbibm("slcp")
+        jac_dist_case("jacdist_slcp_n6", "slcp_n6", net, sbibm_obs("slcp", st, 6), "uniform", slcp_prior(st), N=256, seed=71,
+                      clip=(-3.0, 3.0))
+        net, st = load_sbibm("lotka_volterra")
+        pp = lognormal_prior(st, torch.tensor([-0.125, -3.0, -0.125, -3.0]), torch.full((4,), 0.5))
+        jac_dist_case("jacdist_lv_n6", "lv_n6", net, sbibm_obs("lotka_volterra", st, 6, log_space=True), "gaussian", pp,
+                      N=256, seed=72)
+        net, st = load_sbibm("sir")
+        pp = lognormal_prior(st, torch.log(torch.tensor([0.4, 0.125])), torch.tensor([0.5, 0.2]))
+        jac_dist_case("jacdist_sir_n8", "sir_n8", net, sbibm_obs("sir", st, 8, log_space=False), "gaussian", pp, N=256,
+                      seed=73)
     if want("rand"):
         torch.manual_seed(3)
         net = ref_nse.NSE(theta_dim=3, x_dim=4, hidden_features=[64, 96]).eval()

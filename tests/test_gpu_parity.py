@@ -15,7 +15,7 @@ from oracle import d4s_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-CASES = [c for c in gio.names() if not c.startswith(("langevin", "toy", "cfg", "contexts"))]
+CASES = [c for c in gio.names() if not c.startswith(("langevin", "toy", "cfg", "contexts", "euler", "jacdist"))]
 REL_TOL = 1e-4
 TRAJ_TOL = 1e-3
 # Opt-in tensor-core JAC path (d4s_set_option("jac_tc", 1): d4s_jac_tc.cu, fp16x3 products, fp32 accumulation in TMEM),
@@ -301,6 +301,8 @@ def test_full_size_trajectory_properties(dev):
         assert engine.launch_count() - before >= 2 * 1000 + 1
     finally:
         abi.set_option("path", 0)
+    # (random-init nets do not contract: the two precisions' trajectories drift apart on some samples; the pathwise
+    # 1000-step gate is tests/test_gpu_long_runs.py::test_long_interleaved_trajectory_vs_fp64_oracle on shipped weights)
     frac_close = float(((out3 - out).abs() < 1e-2).float().mean())
     print(f"tcgen05 vs SIMT after 1000 steps: median |d| = {float((out3 - out).abs().median()):.2e}, "
           f"within 1e-2: {frac_close:.3f}")

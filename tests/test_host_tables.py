@@ -12,7 +12,7 @@ from d4s import engine
 from d4s_helpers import nse_from_oracle
 from oracle import d4s_oracle as orc
 
-CASES = [c for c in gio.names() if not c.startswith(("langevin", "toy", "cfg", "contexts"))]
+CASES = [c for c in gio.names() if not c.startswith(("langevin", "toy", "cfg", "contexts", "euler", "jacdist"))]
 
 
 def _spec(g):
