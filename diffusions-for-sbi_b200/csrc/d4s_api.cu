@@ -954,6 +954,57 @@ int d4s_get_profile(int64_t* out16) {
     return D4S_OK;
 }
 
+int d4s_reduce_pairs(const float* scores_dev, const float* pair_prec_dev, const float* obs_prec_dev, const float* obs_weight_dev,
+                     int64_t n_samples, int32_t n_obs, int32_t theta_dim, float* part_out_dev, void* stream) {
+    if (!scores_dev || !part_out_dev || n_samples < 1 || n_obs < 1) return fail(D4S_ERR_ARG, "bad reduce_pairs args");
+    if (theta_dim < 1 || theta_dim > D4S_MAX_THETA_WIDE) return fail(D4S_ERR_ARG, "theta_dim must be in [1, 32]");
+    if (n_samples > 2147483647LL) return fail(D4S_ERR_ARG, "too many samples");
+    cudaError_t e = launch_reduce_pairs(scores_dev, pair_prec_dev, obs_prec_dev, obs_weight_dev, n_samples, n_obs, theta_dim,
+                                        part_out_dev, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "reduce_pairs launch");
+    ++g_launches;
+    return D4S_OK;
+}
+
+int d4s_finalize_wide(const float* part_dev, int64_t n_samples, int32_t theta_dim, int32_t layout_jac, const float* sched_dev,
+                      const float* mats_dev, int32_t prior_kind, const float* low_dev, const float* high_dev,
+                      const float* ext_s0_dev, const float* ext_p0_dev, const float* noise_dev, uint64_t seed,
+                      int32_t step_index, int64_t sample_offset, float clip_lo, float clip_hi, int32_t update, float* theta_dev,
+                      float* score_out_dev, void* stream) {
+    if (!part_dev || !sched_dev || !theta_dev || n_samples < 1) return fail(D4S_ERR_ARG, "bad finalize_wide args");
+    if (theta_dim < 1 || theta_dim > D4S_MAX_THETA_WIDE) return fail(D4S_ERR_ARG, "theta_dim must be in [1, 32]");
+    if (prior_kind == D4S_PRIOR_UNIFORM && (!low_dev || !high_dev)) return fail(D4S_ERR_ARG, "uniform prior needs low/high");
+    if (prior_kind == D4S_PRIOR_GAUSSIAN && !mats_dev) return fail(D4S_ERR_ARG, "gaussian prior needs the mats row");
+    if (prior_kind == D4S_PRIOR_EXTERNAL && !ext_s0_dev) return fail(D4S_ERR_ARG, "external prior needs the prior score tensor");
+    if (prior_kind < D4S_PRIOR_NONE || prior_kind > D4S_PRIOR_EXTERNAL) return fail(D4S_ERR_ARG, "bad prior kind");
+    WideParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = n_samples;
+    p.m = theta_dim;
+    p.layout_jac = layout_jac ? 1 : 0;
+    p.prior_kind = prior_kind;
+    p.update = update;
+    p.part = part_dev;
+    p.sched = sched_dev;
+    p.mats = mats_dev;
+    p.low = low_dev;
+    p.high = high_dev;
+    p.ext_s0 = ext_s0_dev;
+    p.ext_p0 = ext_p0_dev;
+    p.noise = noise_dev;
+    p.seed = seed;
+    p.step_index = step_index;
+    p.sample_offset = sample_offset;
+    p.clip_lo = clip_lo;
+    p.clip_hi = clip_hi;
+    p.theta = theta_dev;
+    p.score_out = score_out_dev;
+    cudaError_t e = launch_finalize_wide(p, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "finalize_wide launch");
+    ++g_launches;
+    return D4S_OK;
+}
+
 int d4s_batched_inverse(const float* a_dev, float* out_dev, int32_t batch, int32_t m, void* stream) {
     if (!a_dev || !out_dev || batch < 1) return fail(D4S_ERR_ARG, "bad batched_inverse args");
     if (m < 1 || m > D4S_MAX_THETA) return fail(D4S_ERR_ARG, "m must be in [1, 10]");

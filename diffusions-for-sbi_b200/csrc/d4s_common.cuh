@@ -141,6 +141,29 @@ struct JacTcParams {
 };
 cudaError_t launch_jac_tc(const JacTcParams& p, int n_ctas, cudaStream_t stream);
 
+// generic path (d4s_generic.cu): kernel 3b + 4 for theta_dim <= D4S_MAX_THETA_WIDE
+struct WideParams {
+    long long N;
+    int m, layout_jac, prior_kind, update;
+    const float* part;    // [N][2m] or [N][m + m*m]
+    const float* sched;   // [16]
+    const float* mats;    // Lmat | G | mu_t, or NULL
+    const float* low;
+    const float* high;
+    const float* ext_s0;  // [N][m] prior score from the caller's closure (D4S_PRIOR_EXTERNAL)
+    const float* ext_p0;  // [N][m][m] prior precision (weighted steps), or NULL
+    const float* noise;   // [N][m] or NULL
+    uint64_t seed;
+    int step_index;
+    long long sample_offset;
+    float clip_lo, clip_hi;
+    float* theta;
+    float* score_out;
+};
+cudaError_t launch_finalize_wide(const WideParams& p, cudaStream_t stream);
+cudaError_t launch_reduce_pairs(const float* scores, const float* pair_prec, const float* obs_prec, const float* obs_weight,
+                                long long N, int n, int m, float* part, cudaStream_t stream);
+
 cudaError_t launch_theta_embed(const NetDev& net, const float* theta, int N, int jac, float* base_pre, float* tan_pre,
                                cudaStream_t stream);
 cudaError_t launch_score_simt(const ScoreParams& p, int tiles, cudaStream_t stream);

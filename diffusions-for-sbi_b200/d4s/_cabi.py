@@ -13,16 +13,17 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("D4S_LIB_PATH") or os.path.join(HERE, "libd4s.so")  # (override: A/B builds of the kernels)
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 MAX_LAYERS = 8
 MAX_THETA = 10
+MAX_THETA_WIDE = 32
 MAX_WIDTH = 256
 SCHED_STRIDE = 16
 MAX_RANKS = 8
 IPC_HANDLE_BYTES = 64
 
 COV_GAUSS, COV_JAC = 0, 1
-PRIOR_NONE, PRIOR_GAUSSIAN, PRIOR_UNIFORM = 0, 1, 2
+PRIOR_NONE, PRIOR_GAUSSIAN, PRIOR_UNIFORM, PRIOR_EXTERNAL = 0, 1, 2, 3
 COMBINE_SUM, COMBINE_SHARED, COMBINE_PER_SAMPLE = 0, 1, 2
 
 # schedule table columns (must match D4S_S_* in include/d4s.h)
@@ -33,7 +34,7 @@ EXPORTS = [
     "d4s_abi_version", "d4s_last_error", "d4s_device_count", "d4s_net_create", "d4s_net_free",
     "d4s_net_h1_padded", "d4s_workspace_floats", "d4s_partials_floats", "d4s_mats_floats", "d4s_score_partials", "d4s_finalize",
     "d4s_ddim_run", "d4s_graph_cache_clear", "d4s_ddim_run_sharded", "d4s_xchg_layout", "d4s_xchg_alloc", "d4s_xchg_free",
-    "d4s_xchg_open", "d4s_xchg_close", "d4s_set_option", "d4s_get_profile", "d4s_prior_score", "d4s_ddim_update", "d4s_batched_inverse", "d4s_philox_normal", "d4s_launch_count",
+    "d4s_xchg_open", "d4s_xchg_close", "d4s_set_option", "d4s_get_profile", "d4s_prior_score", "d4s_ddim_update", "d4s_batched_inverse", "d4s_philox_normal", "d4s_launch_count", "d4s_reduce_pairs", "d4s_finalize_wide",
 ]
 
 
@@ -153,6 +154,9 @@ def load():
             "d4s_batched_inverse": (C.c_int, [vp, vp, i32, i32, vp]),
             "d4s_philox_normal": (C.c_int, [vp, i64, i32, u64, i32, i64, vp]),
             "d4s_launch_count": (i64, []),
+            "d4s_reduce_pairs": (C.c_int, [vp, vp, vp, vp, i64, i32, i32, vp, vp]),
+            "d4s_finalize_wide": (C.c_int, [vp, i64, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, u64, i32, i64, C.c_float,
+                                            C.c_float, i32, vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)

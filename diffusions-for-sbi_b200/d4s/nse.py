@@ -22,6 +22,7 @@ from torch import Size, Tensor
 
 from . import _cabi as abi
 from . import engine
+from . import generic
 from .nn import MLP
 
 
@@ -174,15 +175,22 @@ class NSE(nn.Module):
         cfg = None if single else self._cfg(opts)
         if cfg is not None:
             prior = engine.PriorSpec(abi.PRIOR_NONE)
-        setup = engine.build_setup(self, x, N, t, t_prev, float(eta), prior, opts["cov_mode"], opts["dist_cov_est"],
-                                   paired=paired, n_sizes=opts["n_sizes"], clip=theta_clipping_range, seed=seed,
-                                   sample_offset=sample_offset, weighted=weighted, cfg=cfg)
         if noise is not None:
             z0, z = noise
             theta = z0.to(x.device, torch.float32).contiguous().clone()
         else:
             z = None
             theta = engine.philox_normal(N, m, seed, -1, sample_offset, x.device)  # nse.py:261
+        if not generic.fusable(self):  # nets libd4s cannot pack (other modules, theta_dim > 10): torch scores + kernels 3/4
+            if cfg is not None or opts["n_sizes"] is not None:
+                raise NotImplementedError("generic path: classifier-free guidance / PF_NSE subsets need a fusable net")
+            run = generic.GenericTall(self, x, N, t, t_prev, float(eta), prior, opts["cov_mode"], opts["dist_cov_est"],
+                                      toy=False, paired=paired, weighted=weighted, clip=theta_clipping_range, seed=seed,
+                                      sample_offset=sample_offset)
+            return run.run(theta, z)
+        setup = engine.build_setup(self, x, N, t, t_prev, float(eta), prior, opts["cov_mode"], opts["dist_cov_est"],
+                                   paired=paired, n_sizes=opts["n_sizes"], clip=theta_clipping_range, seed=seed,
+                                   sample_offset=sample_offset, weighted=weighted, cfg=cfg)
         return engine.run_trajectory(setup, theta, z, _use_graph_default())
 
     def ddim_contexts(self, shape: Size, x: Tensor, steps: int = 1000, eta: float = 1.0, verbose: bool = False,
@@ -269,6 +277,12 @@ class NSE(nn.Module):
         # function of (weights, x_obs, dist_cov_est, prior, t): a loop that calls this with the same inputs -- the
         # reference's euler_sde_sampler, user-written samplers -- reuses them instead of rebuilding them on the host.
         tt = torch.as_tensor(t).detach().to("cpu").reshape(1)
+        if not generic.fusable(self):
+            if clf_free_guidance or n_sizes is not None:
+                raise NotImplementedError("generic path: classifier-free guidance / PF_NSE subsets need a fusable net")
+            run = generic.GenericTall(self, x_obs, theta.shape[0], tt, None, 0.0,
+                                      engine.prior_spec(prior_type, prior, prior_score_fn, m), cov_mode, dist_cov_est, toy=False)
+            return run.step(0, theta.detach().to(torch.float32).contiguous(), update=False, want_score=True)
         pn = engine.packed_net(self, x_obs.device)
         key = ("fs", id(pn), engine.tensor_key(x_obs), engine.tensor_key(dist_cov_est), engine.tensor_key(dist_cov_est_prior),
                int(theta.shape[0]), float(tt), cov_mode, prior_type, id(prior_score_fn), id(prior), bool(clf_free_guidance),

@@ -24,6 +24,7 @@ from torch import Size, Tensor
 
 from . import _cabi as abi
 from . import engine
+from . import generic
 from .embedding_nets import AnalyticGaussianEps, EpsilonNet, FakeFNet  # noqa: F401
 from .nse import NSE as _FullNSE
 from .nse import _use_graph_default
@@ -141,15 +142,25 @@ class NSE(nn.Module):
             raise TypeError(f"unexpected keyword arguments: {sorted(kw)}")
         if seed is None:
             seed = self._draw_seed()
-        setup = engine.build_setup(self, x, N, t, t_prev, float(eta), prior, cov_mode, cov_est, paired=paired, seed=seed,
-                                   sample_offset=off, weighted=not paired)
         if noise is not None:
             z0, z = noise
             theta = z0.to(x.device, torch.float32).contiguous().clone()
         else:
             z = None
             theta = engine.philox_normal(N, m, seed, -1, off, x.device)
+        if self._generic(prior):  # closure nets / closure priors / theta_dim > 10: torch scores + native kernels 3/4
+            run = generic.GenericTall(self, x, N, t, t_prev, float(eta), prior, cov_mode, cov_est, toy=True, paired=paired,
+                                      weighted=not paired, seed=seed, sample_offset=off)
+            return run.run(theta, z)
+        setup = engine.build_setup(self, x, N, t, t_prev, float(eta), prior, cov_mode, cov_est, paired=paired, seed=seed,
+                                   sample_offset=off, weighted=not paired)
         return engine.run_trajectory(setup, theta, z, _use_graph_default())
+
+    def _generic(self, prior) -> bool:
+        """The fused kernels take FakeFNet(AnalyticGaussianEps, EpsilonNet, eps) with theta_dim <= 10 and a prior that exposes
+        its parameters; everything else (the reference's `real_eps` closure, its triple-returning prior closure, DIM 16 / 32:
+        gen_gaussian_gaussian.py:24, 59-72, 86-96) runs on the generic path (d4s/generic.py)."""
+        return not generic.fusable(self) or not isinstance(prior, engine.PriorSpec)
 
     # ---- Langevin / Geffner baselines of the toy script (gen_gaussian_gaussian.py:205-238) ---------------------------
     _gammas = _FullNSE._gammas  # gamma_t = alpha(t) / alpha(t - time[-2]), alpha(t) on the last step (nse_toy.py:489-492)
@@ -163,14 +174,19 @@ class NSE(nn.Module):
         N, m = int(shape[0]), self.theta_dim
         if seed is None:
             seed = self._draw_seed()
-        setup = engine.build_setup(self, x, N, t_rows, None, 0.0, self._prior_spec(prior_score_fn), "GAUSS", None,
-                                   seed=seed, sample_offset=off, weighted=False, coef=coef)
+        prior = self._prior_spec(prior_score_fn)
         if noise is not None:
             z0, z = noise
             theta = z0.to(x.device, torch.float32).contiguous().clone()
         else:
             z = None
             theta = engine.philox_normal(N, m, seed, -1, off, x.device)
+        if self._generic(prior):
+            run = generic.GenericTall(self, x, N, t_rows, None, 0.0, prior, "GAUSS", None, toy=True, weighted=False,
+                                      seed=seed, sample_offset=off, coef=coef)
+            return run.run(theta, z)
+        setup = engine.build_setup(self, x, N, t_rows, None, 0.0, prior, "GAUSS", None,
+                                   seed=seed, sample_offset=off, weighted=False, coef=coef)
         return engine.run_trajectory(setup, theta, z, _use_graph_default())
 
     def annealed_langevin_geffner(self, shape: Size, x: Tensor, prior_score_fn, steps: int = 64, lsteps: int = 5,
@@ -205,17 +221,25 @@ class NSE(nn.Module):
         coef = dict(c_theta=(n / g.sqrt() - (n - 1) * g.sqrt()) / den, c_score=var, s1w=1 / g.sqrt(), bstd=var.sqrt())
         return self._run_rows(shape, x, grid[:-1], coef, prior_score_fn, dict(kwargs))
 
-    def _prior_spec(self, prior_score_fn) -> "engine.PriorSpec":
-        if getattr(prior_score_fn, "kind", None) != "gaussian" or not hasattr(prior_score_fn, "_spec"):
-            raise abi.D4sError("nse_toy.NSE needs `prior_score_fn = d4s.nse_toy.gaussian_prior_triple(mean, cov, nse)` "
-                               "(the reference's triple-returning closure cannot be introspected)")
-        return prior_score_fn._spec()
+    def _prior_spec(self, prior_score_fn):
+        """`engine.PriorSpec` of a `gaussian_prior_triple(...)` object (closed forms inside the kernels), or the callable
+        itself when it is an opaque closure like gen_gaussian_gaussian.py:86-96 (evaluated by torch, generic path)."""
+        if getattr(prior_score_fn, "kind", None) == "gaussian" and hasattr(prior_score_fn, "_spec"):
+            return prior_score_fn._spec()
+        if callable(prior_score_fn):
+            return prior_score_fn
+        raise abi.D4sError("nse_toy.NSE needs a prior score function: `d4s.nse_toy.gaussian_prior_triple(mean, cov, nse)` "
+                           "or a callable (theta, t) -> (score, mean, precision)")
 
     def factorized_score(self, theta, x_obs, t, prior_score_fn, dist_cov_est=None, cov_mode="JAC") -> Tensor:
         """nse_toy.py:599-625: always the precision-weighted combination (no alpha-gate; Gaussian prior triple)."""
         self._require_cuda(theta, x_obs)
         spec = self._prior_spec(prior_score_fn)
         tt = torch.as_tensor(t).detach().to("cpu").reshape(1)
+        if self._generic(spec):
+            run = generic.GenericTall(self, x_obs, theta.shape[0], tt, None, 0.0, spec, cov_mode, dist_cov_est, toy=True,
+                                      always_weighted=True)
+            return run.step(0, theta.detach().to(torch.float32).contiguous(), update=False, want_score=True)
         setup = engine.build_setup(self, x_obs, theta.shape[0], tt, None, 0.0, spec, cov_mode, dist_cov_est)
         th = theta.detach().to(torch.float32).contiguous()
         engine.score_partials(setup, th, 0)

@@ -39,7 +39,10 @@ def prec_matrix_backward(t, dist_cov, nse):
     m = dist_cov.shape[-1]
     tt = _t_cpu(t).to(torch.float64)
     aos2 = float(engine._scalar64(nse.alpha, tt) / engine._scalar64(nse.sigma, tt) ** 2)
-    inv = engine.batched_inverse(dist_cov.reshape(-1, m, m)).reshape(dist_cov.shape)
+    if m <= abi.MAX_THETA:
+        inv = engine.batched_inverse(dist_cov.reshape(-1, m, m)).reshape(dist_cov.shape)
+    else:  # (the register-resident inverse kernel stops at theta_dim 10; wider toy problems use cuSOLVER through torch)
+        inv = torch.linalg.inv(dist_cov.to(torch.float64)).to(torch.float32)
     return inv + aos2 * torch.eye(m, device=dist_cov.device, dtype=inv.dtype)
 
 
@@ -58,6 +61,24 @@ def tweedies_approximation(x, theta, t, score_fn=None, nse=None, dist_cov_est=No
     nse._require_cuda(theta, x)
     N, m = theta.shape
     tt = _t_cpu(t)
+    from . import generic
+    if not generic.fusable(nse):  # closure nets / theta_dim > 10: torch evaluates the grid (this API materialises anyway)
+        toy = not hasattr(nse, "net_type")
+        t_dev = torch.as_tensor(t, dtype=torch.float32, device=theta.device)
+        th = theta.detach().to(torch.float32)
+        t64 = tt.to(torch.float64)
+        alpha_t, sigma_t = float(engine._scalar64(nse.alpha, t64)), float(engine._scalar64(nse.sigma, t64))
+        if mode == "JAC":
+            jac, scores = generic.jacobians_on_grid(nse, th, x, t_dev, toy)
+            eye = torch.eye(m, device=theta.device)
+            prec = torch.linalg.inv((sigma_t ** 2 / alpha_t) * (eye + sigma_t ** 2 * jac))
+        else:
+            scores = generic.scores_on_grid(nse, th, x, t_dev, toy)
+            prec = prec_matrix_backward(t, dist_cov_est, nse)[None].expand(N, -1, -1, -1)
+        mean = (th[:, None] + sigma_t ** 2 * scores) / math.sqrt(alpha_t)
+        if clip_mean_bounds[0]:
+            mean = mean.clip(*clip_mean_bounds)
+        return prec, mean, scores
     setup = engine.build_setup(nse, x, N, tt, None, 0.0, engine.PriorSpec(abi.PRIOR_NONE), mode,
                                dist_cov_est if mode == "GAUSS" else None, n_sizes=n, weighted=False)
     th = theta.detach().to(torch.float32).contiguous()

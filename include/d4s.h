@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D4S_ABI_VERSION 13
+#define D4S_ABI_VERSION 14
 
 #define D4S_OK 0
 #define D4S_ERR_ARG -1      /* bad argument / unsupported shape */
@@ -43,6 +43,7 @@ extern "C" {
 
 #define D4S_MAX_LAYERS 8    /* linear layers of the score MLP (zuko MLP: 4) */
 #define D4S_MAX_THETA 10    /* theta_dim m supported by the register-resident solvers */
+#define D4S_MAX_THETA_WIDE 32 /* theta_dim of the generic path (torch scores + native kernels 3/4: d4s_reduce_pairs, d4s_finalize_wide) */
 #define D4S_MAX_WIDTH 256   /* widest hidden layer */
 #define D4S_SCHED_STRIDE 16 /* floats per step in the schedule table */
 #define D4S_MAX_RANKS 8     /* ranks (GPUs of one NVSwitch box) of an observation-sharded run */
@@ -55,6 +56,7 @@ extern "C" {
 #define D4S_PRIOR_NONE 0
 #define D4S_PRIOR_GAUSSIAN 1
 #define D4S_PRIOR_UNIFORM 2
+#define D4S_PRIOR_EXTERNAL 3 /* generic path only: prior score / precision tensors evaluated by the caller's closure */
 /* how the per-sample total score is assembled (nse.py:628-654) */
 #define D4S_COMBINE_SUM 0        /* (1-n) s0 + sum_j s_ij                    (nse.py:642, gate closed / geffner) */
 #define D4S_COMBINE_SHARED 1     /* Lambda^-1 w with one Lambda per step     (GAUSS + Gaussian prior, nse.py:628-638) */
@@ -255,6 +257,29 @@ D4S_API int d4s_prior_score(int32_t prior_kind, const float* theta_dev, int64_t 
 D4S_API int d4s_ddim_update(float* theta_dev, const float* score_dev, int64_t n_rows, int32_t m, const float* sched_dev,
                     const float* noise_dev, uint64_t seed, int32_t step_index, int64_t sample_offset, float clip_lo,
                     float clip_hi, void* stream);
+
+/* ---- generic path: score networks that cannot be fused (a Python closure inside FakeFNet, gen_gaussian_gaussian.py:59-72;
+ * modules other than Linear/ReLU stacks; theta_dim up to D4S_MAX_THETA_WIDE, gen_gaussian_gaussian.py:24).  torch evaluates
+ * the scores (and, in JAC mode, the per-pair precisions) on the (sample x observation) grid; kernels 3 and 4 stay native.
+ *
+ * d4s_reduce_pairs = kernel 3a, the reduction over observations (nse.py:631-636, nse_toy.py:619-622 do it with torch on
+ * materialised [N, n, m, m] tensors): scores_dev[N, n, m];
+ *   pair_prec_dev != NULL ([N, n, m, m], JAC): part_out[N, m + m*m] = sum_j w_j P_ij s_ij | sum_j w_j P_ij
+ *   else (GAUSS):                              part_out[N, 2m]      = sum_j w_j s_ij | sum_j w_j Q_j s_ij, Q = obs_prec_dev[n, m, m] or NULL
+ * obs_weight_dev NULL (all 1) or [n]. */
+D4S_API int d4s_reduce_pairs(const float* scores_dev, const float* pair_prec_dev, const float* obs_prec_dev,
+                     const float* obs_weight_dev, int64_t n_samples, int32_t n_obs, int32_t theta_dim, float* part_out_dev,
+                     void* stream);
+/* d4s_finalize_wide = kernel 3b + 4 for theta_dim <= D4S_MAX_THETA_WIDE on the buffer written by d4s_reduce_pairs (one warp
+ * per sample, LU with partial pivoting in fp64).  Same step semantics as d4s_finalize (sched / mats rows, prior kinds, combine
+ * modes, update rule, Philox keying); in addition prior_kind == D4S_PRIOR_EXTERNAL takes the prior score ext_s0_dev[N, m] and
+ * (weighted steps) the prior precision ext_p0_dev[N, m, m] that the caller's prior closure returned (nse_toy.py:618):
+ * g = (1-n) P0 s0, Lambda += (1-n) P0.  mats_dev may be NULL when no step matrix applies. */
+D4S_API int d4s_finalize_wide(const float* part_dev, int64_t n_samples, int32_t theta_dim, int32_t layout_jac,
+                      const float* sched_dev, const float* mats_dev, int32_t prior_kind, const float* low_dev,
+                      const float* high_dev, const float* ext_s0_dev, const float* ext_p0_dev, const float* noise_dev,
+                      uint64_t seed, int32_t step_index, int64_t sample_offset, float clip_lo, float clip_hi, int32_t update,
+                      float* theta_dev, float* score_out_dev, void* stream);
 
 /* ---- utilities ---------------------------------------------------------------------------------- */
 /* out[b] = inv(a[b]) for b < batch, m x m, LU with partial pivoting (torch.linalg.inv at

@@ -568,6 +568,9 @@ def main(filt=None):
     if want("toy"):
         toy_case("toy_gauss_d4_n5", DIM=4, n_obs=5, eps_max=1e-1, N=12, seed=31, steps=20, eta=0.5)
         toy_case("toy_gauss_d10_n30", DIM=10, n_obs=30, eps_max=1e-2, N=8, seed=32, steps=64, eta=0.2, lang_steps=200, lsteps_g=2)  # dt = 2^-6: the fp64 run of the reference is NaN when fp32(t) - dt < 0 (toy alpha has a linear term)
+    if want("toywide"):  # DIM 16 / 32 of gen_gaussian_gaussian.py:24 (generic path: torch scores + native kernels 3/4)
+        toy_case("toy_gauss_d16_n8", DIM=16, n_obs=8, eps_max=1e-2, N=6, seed=33, steps=16, eta=0.5, lang_steps=8, lsteps_g=2)
+        toy_case("toy_gauss_d32_n4", DIM=32, n_obs=4, eps_max=1e-2, N=6, seed=34, steps=16, eta=0.5, lang_steps=8, lsteps_g=2)
     if want("langevin"):
         net, st = load_sbibm("sir")
         x = sbibm_obs("sir", st, 5, log_space=False)

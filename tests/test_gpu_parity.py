@@ -779,9 +779,13 @@ def test_errors_are_loud(dev):
         nse.ddim((8,), torch.randn(5, 4, device=dev), steps=3, prior_type="gaussian",
                  prior=torch.distributions.MultivariateNormal(torch.zeros(3, device=dev), torch.eye(3, device=dev)),
                  cov_mode="GAUSS")  # GAUSS without dist_cov_est
+    # a net the kernels cannot pack (512-wide layer) is NOT an error any more: it runs on the generic path (torch scores +
+    # native kernels 3/4), still on the GPU only
     wide = d4s.NSE(3, 4, hidden_features=[512]).to(dev)
+    out = wide.ddim((8,), torch.randn(1, 4, device=dev), steps=2)
+    assert out.shape == (8, 3) and bool(torch.isfinite(out).all())
     with pytest.raises(abi.D4sError):
-        wide.ddim((8,), torch.randn(1, 4, device=dev), steps=2)
+        wide.ddim((8,), torch.randn(1, 4), steps=2)
 
 
 # ---- Langevin / Geffner family on the same kernels -----------------------------------------
