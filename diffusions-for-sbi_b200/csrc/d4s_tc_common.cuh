@@ -94,6 +94,28 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
 }
 
+// tcgen05.mma with the A operand in TENSOR MEMORY (D[tmem] (+)= A[tmem] x B[smem]): A row r sits in TMEM lane r, its K = 16
+// bf16 elements of one instruction in 8 consecutive 32-bit columns (two elements per column, K-contiguous).
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane <- registers
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // system-scope flag accesses of the in-kernel exchange between ranks (peer memory over NVLink)
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -145,6 +167,21 @@ __device__ __forceinline__ void store_split8(const float (&v)[8], uint8_t* a_hi,
     }
     *reinterpret_cast<uint4*>(a_hi + byte_off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(a_lo + byte_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// the same split into registers: hi[e] / lo[e] = packed bf16 pair of elements (2e, 2e + 1)
+__device__ __forceinline__ void split8_regs(const float (&v)[8], uint32_t* hi, uint32_t* lo) {
+    const float2 k = make_float2(65537.0f, 65537.0f), neg1 = make_float2(-1.0f, -1.0f);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 x = make_float2(v[2 * e], v[2 * e + 1]);
+        const float2 c = __fmul2_rn(x, k);
+        const float2 d = __ffma2_rn(x, neg1, c);
+        const float2 h = __ffma2_rn(d, neg1, c);
+        const float2 l = __ffma2_rn(h, neg1, x);
+        hi[e] = __byte_perm(__float_as_uint(h.x), __float_as_uint(h.y), 0x7632);
+        lo[e] = __byte_perm(__float_as_uint(l.x), __float_as_uint(l.y), 0x7632);
+    }
 }
 
 // two floats -> packed fp16 pair (x0 in the low half), round to nearest, saturating at +-65504 instead of overflowing to inf

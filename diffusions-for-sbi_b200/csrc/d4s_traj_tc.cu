@@ -26,6 +26,13 @@
 #include "d4s_finalize_core.cuh"
 #include "d4s_tc_common.cuh"
 
+#ifndef D4S_EXP
+#define D4S_EXP 57  // feature bit mask (A/B builds: -DD4S_EXP=..., tests/gpu_ab.py; round-2 measurements in profiles/r02_tc_notes.md): 1 base on 16 warps, 2 Wout prefetch, 4 one barrier less,
+                   // 8 A operand of the layers >= 2 in tensor memory (TS form), written in place over the accumulator,
+                   // 16 (needs 8) layer 0 of the next pass is written while the last tensor-core layer of this one runs,
+                   // 32 per-sample sums straight from the output-layer partials (no per-row scores in shared memory)
+#endif
+
 namespace d4s {
 
 constexpr int TC_THREADS = (TC_CW + 4) * 32;   // 640: + TMA producer, MMA issuer, scalar helper, one idle warp (full warpgroup)
@@ -53,7 +60,7 @@ constexpr int OFF_ROWS = OFF_BOUT + (MMAX + 2) * 4;            // uint8 [128] sa
 constexpr int OFF_MINV = OFF_ROWS + 256;                       // float [SG_MAX][MMAX*MMAX] per-sample inverse of Lambda_i
 constexpr int OFF_G = OFF_MINV + TC_SG_MAX * MMAX * MMAX * 4;  // float [SG_MAX][MMAX] prior term of the step
 constexpr int OFF_BAR = OFF_G + TC_SG_MAX * MMAX * 4;          // mbarriers
-constexpr int OFF_TMEM = OFF_BAR + (2 * TC_NSTG + 2) * 8;
+constexpr int OFF_TMEM = OFF_BAR + (2 * TC_NSTG + 3) * 8;
 constexpr int TC_SMEM_BYTES = OFF_TMEM + 16;
 static_assert(TC_SMEM_BYTES <= 232448, "shared memory budget (227 KB per CTA) exceeded");
 static_assert(OFF_BAR % 8 == 0 && OFF_SCHED % 16 == 0, "alignment");
@@ -308,7 +315,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     auto bar_full = [&](int s) { return bar0 + 8u * s; };
     auto bar_empty = [&](int s) { return bar0 + 8u * (TC_NSTG + s); };
     const uint32_t bar_a = bar0 + 8u * (2 * TC_NSTG);      // A operand (and TMEM D) ready for the MMA warp
-    const uint32_t bar_d = bar0 + 8u * (2 * TC_NSTG + 1);  // accumulator ready for the epilogue
+    // accumulator ready for the epilogue: two barriers used alternately, layer by layer (the MMA warp may complete two layers
+    // -- the last layer of an item and the first layer of the next one -- before the compute warps look at the first)
+    auto bar_dn = [&](unsigned n) { return bar0 + 8u * (2 * TC_NSTG + 1 + (n & 1u)); };
 
     const NetDev& net = p.net;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -318,7 +327,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     // sBase holds SG <= 8 rows of 256 floats, and its first 1280 floats double as scratch of the scores phase; with
     // SG <= 5 the last 768 floats are free: enough for the inv(Sigma_j) of a short observation set (n = 30, m = 5: 750),
     // which saves the scores phase its dependent global loads.
-    const bool q_in_smem = p.obs_prec != nullptr && p.C == 1 && p.SG <= 5 && p.n * m * m <= 768 && p.fin.ctx_samples == 0;
+    // (row stride odd: lanes = observations read Q_j[r][k] at the same (r, k), an even stride would be a 16-way bank conflict)
+    const int qstr = (m * m) | 1;
+    const bool q_in_smem = p.obs_prec != nullptr && p.C == 1 && p.SG <= 5 && p.n * qstr <= 768 && p.fin.ctx_samples == 0;
+#if D4S_EXP & 32
+    const bool fused_sums = m <= 5 && (p.obs_prec == nullptr || q_in_smem) && p.fin.ctx_samples == 0;
+#else
+    constexpr bool fused_sums = false;
+#endif
     const int n_groups = (p.N + p.SG - 1) / p.SG;
     const int mats_floats = 2 * m * m + m;
     constexpr int NB23 = TC_CT + 32;  // participants of named barriers 2 and 3
@@ -329,7 +345,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
             mbar_init(bar_empty(s), 1);
         }
         mbar_init(bar_a, TC_CW * 32);
-        mbar_init(bar_d, 1);
+        mbar_init(bar_dn(0), 1);
+        mbar_init(bar_dn(1), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC_CW + 1) {  // TMEM: two 256-column fp32 accumulators, used alternately layer by layer
@@ -345,7 +362,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
             for (int e = tid; e < m * H0; e += TC_THREADS) sA[(e / H0) * 256 + (e % H0)] = __ldg(net.A + e);
         if (tid < MMAX) sBout[tid] = (tid < m) ? __ldg(net.bout + tid) : 0.f;
         if (q_in_smem)  // inv(Sigma_j) of every observation in the tail of sBase (see q_in_smem)
-            for (int e = tid; e < p.n * m * m; e += TC_THREADS) sQ[e] = __ldg(p.obs_prec + e);
+            for (int e = tid; e < p.n * m * m; e += TC_THREADS) sQ[(e / (m * m)) * qstr + e % (m * m)] = __ldg(p.obs_prec + e);
         if (tid < TC_M) {
             const int si = tid / p.OC, oj = tid - si * p.OC;
             sRowSi[tid] = (uint8_t)(tid < p.P ? si : 255);
@@ -405,8 +422,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     const uint32_t a_lbo = 2048u, a_sbo = 128u;
                     mbar_wait(bar_a, a_cnt & 1u, p.error_flag);
                     ++a_cnt;
+#if D4S_EXP & 16
+                    // early layer 0: this layer's accumulator is the region the previous (TS-form) layer reads its A operand
+                    // from; wait until that layer has completed before overwriting it
+                    if (l == 1 && lc > 0 && L - 2 >= 2) mbar_wait(bar_dn(lc - 1u), ((lc - 1u) >> 1) & 1u, p.error_flag);
+#endif
                     tc_fence_after();
                     const uint32_t dacc = tmem_d + ((lc & 1u) ? 256u : 0u);  // the other accumulator may still be read by an epilogue
+                    const uint32_t dprev = tmem_d + ((lc & 1u) ? 0u : 256u);  // accumulator of the previous layer (TS form: its A operand)
+                    (void)dprev;
                     const long long mma_t0 = (p.prof && blockIdx.x == 0) ? clock64() : 0;
                     ++lc;
                     for (int ks = 0; ks < K / 16; ++ks, ++it) {
@@ -417,16 +441,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         const uint32_t wb = smem_u32(smem + OFF_RING + s * TC_STAGE_BYTES);
                         const uint64_t b_hi = umma_desc(wb, b_lbo, b_sbo);
                         const uint64_t b_lo = umma_desc(wb + (uint32_t)Nn * 32u, b_lbo, b_sbo);
-                        const uint64_t a_hi = umma_desc(a_hi0 + ks * 4096, a_lbo, a_sbo);
-                        const uint64_t a_lo = umma_desc(a_lo0 + ks * 4096, a_lbo, a_sbo);
-                        tc_mma_bf16(dacc, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
-                        tc_mma_bf16(dacc, a_lo, b_hi, idesc, 1u);
-                        tc_mma_bf16(dacc, a_hi, b_lo, idesc, 1u);
+#if D4S_EXP & 8
+                        if (l > 1) {  // A = the previous layer's accumulator region, converted in place by the epilogue
+                            const uint32_t a_t = dprev + (uint32_t)ks * 16u;  // K-step ks: hi in columns 16 ks .. +7, lo in +8 .. +15
+                            tc_mma_bf16_ts(dacc, a_t, b_hi, idesc, ks > 0 ? 1u : 0u);
+                            tc_mma_bf16_ts(dacc, a_t + 8u, b_hi, idesc, 1u);
+                            tc_mma_bf16_ts(dacc, a_t, b_lo, idesc, 1u);
+                        } else
+#endif
+                        {
+                            const uint64_t a_hi = umma_desc(a_hi0 + ks * 4096, a_lbo, a_sbo);
+                            const uint64_t a_lo = umma_desc(a_lo0 + ks * 4096, a_lbo, a_sbo);
+                            tc_mma_bf16(dacc, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
+                            tc_mma_bf16(dacc, a_lo, b_hi, idesc, 1u);
+                            tc_mma_bf16(dacc, a_hi, b_lo, idesc, 1u);
+                        }
                         tc_commit(bar_empty(s));  // ring slot is free once these MMAs have read it
                     }
-                    tc_commit(bar_d);  // accumulator complete
+                    tc_commit(bar_dn(lc - 1u));  // accumulator complete
                     if (p.prof && blockIdx.x == 0) {  // profiling: duration of this layer's MMAs (slots 8 / 9: first / last layer)
-                        mbar_wait(bar_d, (lc - 1u) & 1u, p.error_flag);
+                        mbar_wait(bar_dn(lc - 1u), ((lc - 1u) >> 1) & 1u, p.error_flag);
                         p.prof[(l == L - 2) ? 9 : 8] += clock64() - mma_t0;
                     }
                 }
@@ -526,7 +560,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
         const bool prof_on = (p.prof != nullptr) && blockIdx.x == 0 && tid == 0;
         long long prof_t = prof_on ? clock64() : 0;
         const int nkg = H0 / 8;
+#if D4S_EXP & 1
+        const int bcol = tid & 255, bhalf = tid >> 8;  // layer-0 sample part: column, and which half of the samples
+        float tf_next = (bcol < H0 && n_steps > 0) ? __ldg(p.time_feat + (size_t)p.step_begin * H0 + bcol) : 0.f;
+#else
         float tf_next = (tid < H0 && n_steps > 0) ? __ldg(p.time_feat + (size_t)p.step_begin * H0 + tid) : 0.f;
+#endif
         // ---- phases shared by the two schedules (one group after the other / two groups interleaved) ----------------------
         // layer-0 per-sample part of an item: base[si][col] = time_feat[col] + sum_k A[k][col] theta[si][k]
         auto do_base = [&](const float* th, bool fresh, int step, int next_step) {
@@ -543,6 +582,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 theta_embed_base(net, th, sS, sQS, sBase, p.SG, H0, t0e, tid);
                 return;
             }
+#if D4S_EXP & 1
+            if (bcol < H0) {  // all 16 compute warps: thread = (column, half of the group's samples)
+                float t0;
+                if (fresh) {
+                    t0 = tf_next;
+                    tf_next = __ldg(p.time_feat + (size_t)next_step * H0 + bcol);
+                } else {
+                    t0 = __ldg(p.time_feat + (size_t)step * H0 + bcol);
+                }
+                float ak[MMAX];
+#pragma unroll
+                for (int k = 0; k < MMAX; ++k)
+                    ak[k] = (k < m) ? (a_in_smem ? sA[k * 256 + bcol] : __ldg(net.A + (size_t)k * H0 + bcol)) : 0.f;
+                for (int si = bhalf; si < p.SG; si += 2) {
+                    float z = t0;
+#pragma unroll
+                    for (int k = 0; k < MMAX; ++k)
+                        if (k < m) z = fmaf(ak[k], th[si * MMAX + k], z);
+                    sBase[si * 256 + bcol] = z;
+                }
+            }
+#else
             if (tid < H0) {
                 float t0;
                 if (fresh) {
@@ -563,6 +624,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     sBase[si * 256 + tid] = z;
                 }
             }
+#endif
         };
         // per-sample sums over the chunk's observations.  item = (sample si, component c < 2m): S1[c] = sum_j s_ij[c]
         // (c < m), S2[c-m] = sum_j (inv(Sigma_j) s_ij)[c-m] (rows of sQS); a warp takes one item at a time, its lanes run over the
@@ -698,7 +760,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
             }
         };
         // epilogue of the last hidden layer + output layer in fp32 + scores of a pass -> sS
-        auto do_last_epilogue = [&](uint32_t dacc, float inv_sigma, int j0, int nobs, int i0) {
+        auto do_last_epilogue = [&](uint32_t dacc, float inv_sigma, int j0, int nobs, int i0, int nsamp, bool first_chunk) {
             const int Nn = net.Hp[L - 2];
             const int qcols = Nn >> 2, nblk = qcols / 16;
             const float* bias_l = net.bias[L - 2] + cq * qcols;
@@ -714,6 +776,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 ld_act(dacc, col0, bb, a);
                 // po[o] += sum_c act[c] * Wout[o][c]   (Wout in smem, broadcast reads)
                 // (five outputs at a time: their weight loads are independent and issued together)
+#if D4S_EXP & 2
+                // software pipeline over the 4-column groups: the weights of group e + 1 are loaded before the FMAs of group e
+#pragma unroll
+                for (int oh = 0; oh < MMAX; oh += 5) {
+                    if (oh < m) {
+                        float4 wc[5], wn[5];
+#pragma unroll
+                        for (int o = 0; o < 5; ++o) wc[o] = *reinterpret_cast<const float4*>(sWout + (oh + o) * 256 + col0);
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4) {
+                            if (e + 4 < 16) {
+#pragma unroll
+                                for (int o = 0; o < 5; ++o)
+                                    wn[o] = *reinterpret_cast<const float4*>(sWout + (oh + o) * 256 + col0 + e + 4);
+                            }
+#pragma unroll
+                            for (int o = 0; o < 5; ++o) {
+                                float acc = po[oh + o];
+                                acc = fmaf(a[e], wc[o].x, acc);
+                                acc = fmaf(a[e + 1], wc[o].y, acc);
+                                acc = fmaf(a[e + 2], wc[o].z, acc);
+                                acc = fmaf(a[e + 3], wc[o].w, acc);
+                                po[oh + o] = acc;
+                            }
+                            if (e + 4 < 16) {
+#pragma unroll
+                                for (int o = 0; o < 5; ++o) wc[o] = wn[o];
+                            }
+                        }
+                    }
+                }
+#else
 #pragma unroll
                 for (int oh = 0; oh < MMAX; oh += 5) {
                     if (oh < m) {
@@ -735,8 +829,73 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         }
                     }
                 }
+#endif
             }
             PROF_MARK(4);  // epilogues
+#if D4S_EXP & 32
+            if (fused_sums) {
+                // The sums over the observations are LINEAR in the output-layer partials: S1 = -1/sigma sum_rows sum_quarters (po + b),
+                // S2 = -1/sigma sum_rows Q_j sum_quarters (po + b).  Every thread applies inv(Sigma_j) to its own partial (bias added by
+                // quarter 0), the lanes of one sample are reduced with a segmented shuffle tree, the segment heads park 10 floats per
+                // (warp, sample) and a fixed-order sum over at most (quarters x lane quarters) slots finishes -- no per-row scores in
+                // shared memory, one barrier instead of four.
+                const int si = sRowSi[row], oj = sRowOj[row];
+                const bool in_tile = si != 255;
+                float val[10];
+#pragma unroll
+                for (int e = 0; e < 10; ++e) val[e] = 0.f;
+                if (in_tile && oj < nobs) {
+                    const float wj = p.obs_weight ? __ldg(p.obs_weight + j0 + oj) : 1.f;
+#pragma unroll
+                    for (int o = 0; o < 5; ++o)
+                        if (o < m) val[o] = (po[o] + (cq == 0 ? sBout[o] : 0.f)) * wj;
+                    if (p.obs_prec) {
+                        const float* Q = sQ + oj * qstr;
+#pragma unroll
+                        for (int r = 0; r < 5; ++r) {
+                            if (r < m) {
+                                float acc = 0.f;
+#pragma unroll
+                                for (int k = 0; k < 5; ++k)
+                                    if (k < m) acc = fmaf(Q[r * m + k], val[k], acc);
+                                val[5 + r] = acc;
+                            }
+                        }
+                    }
+                }
+                const int reach = in_tile ? min(31 - lane, p.OC - 1 - oj) : 0;  // lanes after this one that hold the same sample
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+                    for (int e = 0; e < 10; ++e) {
+                        const float t = __shfl_down_sync(0xffffffffu, val[e], off);
+                        if (off <= reach) val[e] += t;
+                    }
+                }
+                if (in_tile && (oj == 0 || lane == 0)) {  // head of a segment: sample si, lane quarter q, column quarter cq
+                    float* dst = sS + (((q * 4 + cq) * TC_SG_MAX) + (si - (32 * q) / p.OC)) * 10;
+#pragma unroll
+                    for (int e = 0; e < 10; ++e) dst[e] = val[e];
+                }
+                tc_fence_before();
+                PROF_MARK(11);  // per-thread contributions + segmented shuffle tree (the barrier wait below stays in slot 5)
+                compute_bar();
+                if (tid < nsamp * 2 * m) {
+                    const int s_i = tid / (2 * m), c = tid - s_i * 2 * m;
+                    const int e = c < m ? c : 5 + (c - m);
+                    const int r0 = s_i * p.OC, q0 = r0 >> 5, q1 = (r0 + p.OC - 1) >> 5;
+                    float acc = 0.f;
+                    for (int qq = q0; qq <= q1; ++qq) {
+                        const float* src = sS + ((qq * 4 * TC_SG_MAX) + (s_i - (32 * qq) / p.OC)) * 10 + e;
+#pragma unroll
+                        for (int c2 = 0; c2 < 4; ++c2) acc += src[c2 * TC_SG_MAX * 10];
+                    }
+                    sAcc[tid] = (first_chunk ? 0.f : sAcc[tid]) - inv_sigma * acc;
+                }
+                PROF_MARK(5);
+                return;
+            }
+#endif
             // ---- scores: the column quarters 1..3 park their partial dot products in sS / sQS / sBase (free here), quarter 0
             // adds them up as (q0 + q1) + (q2 + q3), s = -(eps + b) / sigma, and applies inv(Sigma_j) to its row's score.
             // (when layer 0 of the next pass ran just before this epilogue, other warps may still be reading sBase there:
@@ -764,7 +923,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 const int oj = sRowOj[row];
                 if (p.obs_prec && oj < nobs) {  // (rows past the tile's pairs carry oj = 255)
                     if (q_in_smem) {
-                        const float* Q = sQ + oj * m * m;
+                        const float* Q = sQ + oj * qstr;
                         for (int r = 0; r < m; ++r) {
                             float qs = 0.f;
 #pragma unroll
@@ -833,24 +992,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 // layer 0 of this pass goes first when it does not depend on the previous pass: interleaved groups, or a
                 // later observation chunk of the same item (its sample part was recomputed at the end of the last pass)
                 const bool early = have && (defer || chunk > 0);
+#if D4S_EXP & 16
+                const bool have_pre = early && (ps == 0 || Lh < 2) && lane < p.OC && p.fin.ctx_samples == 0;
+#else
                 const bool have_pre = early && lane < p.OC && p.fin.ctx_samples == 0;
+#endif
                 if (have_pre) l0_load(upre, j0, nobs, lane);  // layer 0 follows the wait directly: hide its global loads
                 if (prev) {  // the last layer of the previous pass: once it is done the operand images are free again
                     inv_sigma_prev = __ldg(p.sched + (size_t)step_of(pit) * D4S_SCHED_STRIDE + D4S_S_INV_SIGMA);
                     dacc_prev = tmem_d + ((d_cnt & 1u) ? 256u : 0u);
-                    mbar_wait(bar_d, d_cnt & 1u, p.error_flag);
+                    mbar_wait(bar_dn(d_cnt), (d_cnt >> 1) & 1u, p.error_flag);
                     ++d_cnt;
                     tc_fence_after();
                     PROF_MARK(3);  // waiting for the tensor core
                 }
+#if D4S_EXP & 16
+                const bool l0_early = Lh >= 2;  // the operand image in shared memory is free once layer 1 has completed
+                if (early && (ps == 0 || !l0_early)) {
+#else
                 if (early) {
+#endif
                     do_layer0(i0g[gi], nsg[gi], j0, nobs, upre, have_pre);
                     PROF_MARK(1);  // layer 0
                 }
-                if (prev) do_last_epilogue(dacc_prev, inv_sigma_prev, pj0, pnobs, i0g[pgi]);
+                if (prev) do_last_epilogue(dacc_prev, inv_sigma_prev, pj0, pnobs, i0g[pgi], nsg[pgi], pchunk == 0);
                 if (!defer) {
                     if (prev) {
-                        do_sums(nsg[pgi], pj0, pnobs, pchunk == 0);
+                        if (!fused_sums) do_sums(nsg[pgi], pj0, pnobs, pchunk == 0);
                         compute_bar();
                         PROF_MARK(6);  // inv(Sigma) s + sums over observations
                         if (pchunk == p.C - 1) {
@@ -883,7 +1051,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
 #pragma unroll
                         for (int e = 0; e < 4; ++e) bcur[e] = __ldg(reinterpret_cast<const float4*>(bias_l) + e);  // hidden behind the MMA
                         const uint32_t dacc = tmem_d + ((d_cnt & 1u) ? 256u : 0u);
-                        mbar_wait(bar_d, d_cnt & 1u, p.error_flag);
+                        mbar_wait(bar_dn(d_cnt), (d_cnt >> 1) & 1u, p.error_flag);
                         ++d_cnt;
                         tc_fence_after();
                         PROF_MARK(3);  // waiting for the tensor core
@@ -897,6 +1065,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                             }
                             float a[16];
                             ld_act(dacc, col0, bcur, a);
+#if D4S_EXP & 8
+                            {   // next layer's A operand goes back to TENSOR MEMORY, in place over the 16 accumulator columns just
+                                // read: columns col0 .. +7 = bf16 hi of K elements col0 .. col0 + 15, columns +8 .. +15 = lo
+                                uint32_t w[16];
+#pragma unroll
+                                for (int k8 = 0; k8 < 2; ++k8) {
+                                    float v[8];
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) v[e] = a[8 * k8 + e];
+                                    split8_regs(v, w + 4 * k8, w + 8 + 4 * k8);
+                                }
+                                tc_st16(dacc + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, w);
+                            }
+#else
 #pragma unroll
                             for (int k8 = 0; k8 < 2; ++k8) {
                                 float v[8];
@@ -904,12 +1086,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                                 for (int e = 0; e < 8; ++e) v[e] = a[8 * k8 + e];
                                 store_split8(v, sAhi, sAlo, a_off(row, (col0 >> 3) + k8));
                             }
+#endif
                             if (cb + 1 < nblk) {
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) bcur[e] = bnxt[e];
                             }
                         }
+#if D4S_EXP & 8
+                        tc_wait_st();
+#else
                         fence_proxy_async();
+#endif
                         tc_fence_before();
                         mbar_arrive(bar_a);
                         PROF_MARK(4);  // epilogues
@@ -919,16 +1106,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     do_base(th, false, step_of(it), 0);
                     compute_bar();
                     PROF_MARK(0);
+#if D4S_EXP & 16
+                    if (l0_early) {  // its layer 0 now, under the last tensor-core layer of this chunk
+                        const int nj0 = (chunk + 1) * p.OC;
+                        do_layer0(i0g[gi], nsg[gi], nj0, min(p.OC, p.n - nj0), upre, false);
+                        PROF_MARK(1);
+                    }
+#endif
                 }
                 if (defer) {
+#if D4S_EXP & 16
+                    const bool pre_next = l0_early && ps + 1 < total_p && lane < p.OC && p.fin.ctx_samples == 0;
+                    if (pre_next) l0_load(upre, 0, min(p.OC, p.n), lane);  // obs_feat rows of the next item's layer 0: latency hidden
+#endif
                     if (prev) {
-                        do_sums(nsg[pgi], 0, pnobs, true);
-                        compute_bar();
+                        if (!fused_sums) do_sums(nsg[pgi], 0, pnobs, true);
+#if !(D4S_EXP & 4)
+                        compute_bar();  // (redundant: every compute thread also takes part in barrier 3 below)
+#endif
                         PROF_MARK(6);
                         bar_sync(3, NB23);  // schedule / matrix rows, prior terms and noise of the previous item are in smem
                         PROF_MARK(2);  // (time spent waiting for the helper warp)
                         if (p.xg.world > 0) xchg_group_sums(p.xg, sAcc, p.N, m, n_groups, p.SG, step_of(pit), i0g[pgi], nsg[pgi], tid, p.error_flag);
                         do_tail(pth, nsg[pgi]);
+                        PROF_MARK(10);  // tail proper (the barrier wait below stays in slot 6)
                         compute_bar();
                         if (have) bar_arrive(2, NB23);  // helper warp: buffers are free, go on with this item
                         PROF_MARK(6);
@@ -937,6 +1138,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         do_base(sTheta + (gi ^ 1) * TC_SG_MAX * MMAX, true, 0, step_of(it + 2));
                         compute_bar();
                         PROF_MARK(0);
+#if D4S_EXP & 16
+                        if (l0_early) {  // layer 0 of the next item now, under the last tensor-core layer of this one
+                            do_layer0(i0g[gi ^ 1], nsg[gi ^ 1], 0, min(p.OC, p.n), upre, pre_next);
+                            PROF_MARK(1);
+                        }
+#endif
                     }
                 }
             }  // passes

@@ -28,14 +28,17 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compiles every CUDA source of the package into d4s/libd4s.so.  Returns the library path."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=(), out=None, obj_dir=None):
+    """Compiles every CUDA source of the package into d4s/libd4s.so.  Returns the library path.
+    `extra_flags` / `out` / `obj_dir` build an experimental variant next to it (A/B runs with D4S_LIB_PATH)."""
+    if out is None and not force and not needs_build():
         return LIB
     objs = []
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + list(extra_flags)
+    if obj_dir:
+        os.makedirs(obj_dir, exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        obj = os.path.join(obj_dir or CSRC, src.replace(".cu", ".o"))
         cmd = [_nvcc(), *flags, "-Xptxas", "-v" if verbose else "-warn-spills", "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
@@ -43,12 +46,13 @@ def build(force=False, verbose=False):
         if r.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
-    cmd = [_nvcc(), "-shared", "-cudart", "static", "-o", LIB, *objs]
+    target = out or LIB
+    cmd = [_nvcc(), "-shared", "-cudart", "static", "-o", target, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

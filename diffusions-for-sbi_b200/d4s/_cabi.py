@@ -186,7 +186,8 @@ def options_key() -> tuple:
 
 
 PROFILE_PHASES = ["layer0_sample_part", "layer0", "prior_noise", "tensor_wait", "epilogues", "scores",
-                  "prec_and_sums", "finalize", "mma_inner_layers", "mma_last_layer"]  # 8, 9: MMA issue -> commit (MMA warp)
+                  "prec_and_sums", "finalize", "mma_inner_layers", "mma_last_layer",  # 8, 9: MMA issue -> commit (MMA warp)
+                  "tail", "fused_sums_tree"]
 
 
 def get_profile():
