@@ -415,7 +415,19 @@ static int fill_traj_params(const D4sNet* net, const D4sProblem* pb, const float
     if (p.SG > 8) p.SG = 8;
     if (sg_cap > 0 && p.SG > sg_cap) p.SG = sg_cap;  // observation sharding: every rank must form the same sample groups
     if (p.SG < 1) p.SG = 1;
-    p.P = p.SG * p.OC;
+    // Row stride of a sample inside the tile.  When rounding OC up to a power of two costs no sample per tile (n = 30: 4 x 32),
+    // every sample's rows sit inside one lane quarter at a position-independent offset pattern: that is what the fused
+    // per-sample sums of the kernel need to keep the summation order of a sample independent of its slot in the tile
+    // (sample sharding stays bit-exact).  Same conditions as `fused_sums` / `q_in_smem` in d4s_traj_tc.cu.
+    p.RS = p.OC;
+    if (p.C == 1 && p.OC <= 32 && nd.m <= 5 && pb->ctx_samples == 0) {
+        int rs = 1;
+        while (rs < p.OC) rs <<= 1;
+        const int qstr = (nd.m * nd.m) | 1;
+        const bool q_fits = pb->obs_prec == nullptr || (p.SG <= 5 && pb->n_obs * qstr <= 768);
+        if (rs * p.SG <= 128 && q_fits) p.RS = rs;
+    }
+    p.P = p.SG * p.RS;
     p.obs_feat = pb->obs_feat;
     p.obs_prec = pb->obs_prec;
     p.obs_weight = pb->obs_weight;

@@ -106,6 +106,7 @@ struct XchgDev {
 struct TrajParams {
     NetDev net;
     int N, n, C, SG, OC, P;
+    int RS;                  // tile row of (sample si, observation oj) = si * RS + oj; RS == OC, or OC rounded up to a power of two
     int step_begin, step_end;
     int pairing;             // 1: a CTA that owns >= 2 sample groups interleaves them step by step (software pipeline)
     const float* obs_feat;   // [n][Hp0]

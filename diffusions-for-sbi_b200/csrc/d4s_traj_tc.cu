@@ -331,7 +331,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     const int qstr = (m * m) | 1;
     const bool q_in_smem = p.obs_prec != nullptr && p.C == 1 && p.SG <= 5 && p.n * qstr <= 768 && p.fin.ctx_samples == 0;
 #if D4S_EXP & 32
-    const bool fused_sums = m <= 5 && (p.obs_prec == nullptr || q_in_smem) && p.fin.ctx_samples == 0;
+    // needs the aligned tile layout (row stride RS of a sample = power of two <= 32, chosen by the host when it costs no rows)
+    const bool fused_sums = m <= 5 && (p.obs_prec == nullptr || q_in_smem) && p.fin.ctx_samples == 0 && p.C == 1 &&
+                            p.RS <= 32 && (p.RS & (p.RS - 1)) == 0;
 #else
     constexpr bool fused_sums = false;
 #endif
@@ -364,9 +366,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
         if (q_in_smem)  // inv(Sigma_j) of every observation in the tail of sBase (see q_in_smem)
             for (int e = tid; e < p.n * m * m; e += TC_THREADS) sQ[(e / (m * m)) * qstr + e % (m * m)] = __ldg(p.obs_prec + e);
         if (tid < TC_M) {
-            const int si = tid / p.OC, oj = tid - si * p.OC;
-            sRowSi[tid] = (uint8_t)(tid < p.P ? si : 255);
-            sRowOj[tid] = (uint8_t)(tid < p.P ? oj : 255);
+            const int si = tid / p.RS, oj = tid - si * p.RS;  // row = si * RS + oj (RS >= OC: rows oj >= OC of a sample are padding)
+            const bool used = si < p.SG && oj < p.OC;
+            sRowSi[tid] = (uint8_t)(used ? si : 255);
+            sRowOj[tid] = (uint8_t)(used ? oj : 255);
         }
     }
     fence_proxy_async();
@@ -637,7 +640,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 if (c < m || p.obs_prec) {
                     for (int oj = lane; oj < nobs; oj += 32) {
                         const float wj = p.obs_weight ? __ldg(p.obs_weight + j0 + oj) : 1.f;
-                        acc = fmaf(wj, src[(si * p.OC + oj) * MMAX], acc);
+                        acc = fmaf(wj, src[(si * p.RS + oj) * MMAX], acc);
                     }
                 }
 #pragma unroll
@@ -701,7 +704,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
         };
         auto do_layer0 = [&](int i0, int nsamp, int j0, int nobs, float4 (&upre)[2][2], bool have_pre) {
             if (p.fin.ctx_samples > 0) {
-                layer0_contexts(p.obs_feat, sBase, sAhi, sAlo, H0, p.OC, p.SG, nsamp, p.n, j0, nobs, p.fin.ctx_samples, i0, warp, lane);
+                layer0_contexts(p.obs_feat, sBase, sAhi, sAlo, H0, p.OC, p.SG, nsamp, p.n, j0, nobs, p.fin.ctx_samples, i0, warp, lane);  // (RS == OC there)
                 fence_proxy_async();
                 tc_fence_before();
                 mbar_arrive(bar_a);
@@ -737,7 +740,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) v[e] = 0.f;
                             }
-                            store_split8(v, sAhi, sAlo, a_off(si * p.OC + oj, kg));
+                            store_split8(v, sAhi, sAlo, a_off(si * p.RS + oj, kg));
                         }
                     }
                 }
@@ -873,7 +876,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     }
                 }
                 if (in_tile && (oj == 0 || lane == 0)) {  // head of a segment: sample si, lane quarter q, column quarter cq
-                    float* dst = sS + (((q * 4 + cq) * TC_SG_MAX) + (si - (32 * q) / p.OC)) * 10;
+                    float* dst = sS + (((q * 4 + cq) * TC_SG_MAX) + (si - (32 * q) / p.RS)) * 10;
 #pragma unroll
                     for (int e = 0; e < 10; ++e) dst[e] = val[e];
                 }
@@ -883,13 +886,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 if (tid < nsamp * 2 * m) {
                     const int s_i = tid / (2 * m), c = tid - s_i * 2 * m;
                     const int e = c < m ? c : 5 + (c - m);
-                    const int r0 = s_i * p.OC, q0 = r0 >> 5, q1 = (r0 + p.OC - 1) >> 5;
+                    // (RS is a power of two <= 32: the rows of a sample sit in ONE lane quarter, at a fixed offset pattern, so
+                    // the summation order of a sample does not depend on its slot in the tile => sample sharding stays bit-exact)
+                    const int qq = (s_i * p.RS) >> 5;
+                    const float* src = sS + ((qq * 4 * TC_SG_MAX) + (s_i - (32 * qq) / p.RS)) * 10 + e;
                     float acc = 0.f;
-                    for (int qq = q0; qq <= q1; ++qq) {
-                        const float* src = sS + ((qq * 4 * TC_SG_MAX) + (s_i - (32 * qq) / p.OC)) * 10 + e;
 #pragma unroll
-                        for (int c2 = 0; c2 < 4; ++c2) acc += src[c2 * TC_SG_MAX * 10];
-                    }
+                    for (int c2 = 0; c2 < 4; ++c2) acc += src[c2 * TC_SG_MAX * 10];
                     sAcc[tid] = (first_chunk ? 0.f : sAcc[tid]) - inv_sigma * acc;
                 }
                 PROF_MARK(5);

@@ -264,6 +264,20 @@ def test_ddim_seeded_runs_are_reproducible_and_shardable(dev):
     hi = nse.ddim((312,), _t(x, dev), _seed=77, _sample_offset=200, **kw)
     full = nse.ddim((512,), _t(x, dev), _seed=77, **kw)
     assert torch.equal(torch.cat((lo, hi)), full)  # posterior samples shard over ranks with no communication
+    # shards whose boundaries are NOT multiples of the samples-per-tile: a sample lands in a different slot of its tile than in
+    # the full run, and must still come out bit-identical (8 ranks, 203 samples: the split tests/gpu_multi.py makes)
+    from d4s import parallel
+    for n_obs, pk in ((30, "uniform"), (22, "uniform"), (7, "gaussian")):
+        onet2, x2, cov2, _, op2 = _problem(5, 8, (256, 256, 256), n_obs, 8, pk, seed=n_obs)
+        nse2 = nse_from_oracle(onet2, dev)
+        prior2, fn2 = _d4s_prior(op2, nse2, dev)
+        kw2 = dict(steps=12, eta=1.0, prior=prior2, prior_type=pk, prior_score_fn=fn2, dist_cov_est=_t(cov2, dev), cov_mode="GAUSS")
+        full = nse2.ddim((203,), _t(x2, dev), _seed=99, **kw2)
+        parts = []
+        for r in range(8):
+            off, cnt = parallel.sample_shard(203, r, 8)
+            parts.append(nse2.ddim((cnt,), _t(x2, dev), _seed=99, _sample_offset=off, **kw2))
+        assert torch.equal(torch.cat(parts), full), (n_obs, pk, float((torch.cat(parts) - full).abs().max()))
 
 
 def test_batched_inverse(dev):
