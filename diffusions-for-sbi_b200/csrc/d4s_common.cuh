@@ -122,6 +122,7 @@ struct TrajParams {
     XchgDev xg;              // in-kernel exchange of the per-sample sums between the ranks of an observation-sharded run
     int* error_flag;
     long long* prof;         // optional [16] phase cycle counters (CTA 0)
+    long long* trace;        // -DD4S_TRACE builds only: [20 warps][256][tag, clock] event timeline of CTA 0 (tests/gpu_trace_tc.py)
 };
 cudaError_t launch_traj_tc(const TrajParams& p, int n_ctas, cudaStream_t stream);
 int traj_tc_smem_bytes();

@@ -23,6 +23,10 @@
 // Schedule: a CTA that owns two sample groups interleaves them step by step, so that the last epilogue / scores / sums /
 // tail of one group overlap the tensor-core layers of the other (two TMEM accumulators); observation chunks of one item
 // are pipelined the same way.  DESIGN.md section 4.1, profiles/r01_tc_notes.md.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "d4s_finalize_core.cuh"
 #include "d4s_tc_common.cuh"
 
@@ -31,6 +35,11 @@
                    // 8 A operand of the layers >= 2 in tensor memory (TS form), written in place over the accumulator,
                    // 16 (needs 8) layer 0 of the next pass is written while the last tensor-core layer of this one runs,
                    // 32 per-sample sums straight from the output-layer partials (no per-row scores in shared memory)
+                   // 64 (needs 8) the mid epilogue hands its 16-column blocks to the MMA warp one by one (one mbarrier per block index,
+                   //    K-steps of the TS-form layers issued in block order): the next layer starts after the first block
+#endif
+#if (D4S_EXP & 64) && !(D4S_EXP & 8)
+#error "D4S_EXP bit 64 needs bit 8"
 #endif
 
 namespace d4s {
@@ -60,7 +69,7 @@ constexpr int OFF_ROWS = OFF_BOUT + (MMAX + 2) * 4;            // uint8 [128] sa
 constexpr int OFF_MINV = OFF_ROWS + 256;                       // float [SG_MAX][MMAX*MMAX] per-sample inverse of Lambda_i
 constexpr int OFF_G = OFF_MINV + TC_SG_MAX * MMAX * MMAX * 4;  // float [SG_MAX][MMAX] prior term of the step
 constexpr int OFF_BAR = OFF_G + TC_SG_MAX * MMAX * 4;          // mbarriers
-constexpr int OFF_TMEM = OFF_BAR + (2 * TC_NSTG + 3) * 8;
+constexpr int OFF_TMEM = OFF_BAR + (2 * TC_NSTG + 3 + 4) * 8;
 constexpr int TC_SMEM_BYTES = OFF_TMEM + 16;
 static_assert(TC_SMEM_BYTES <= 232448, "shared memory budget (227 KB per CTA) exceeded");
 static_assert(OFF_BAR % 8 == 0 && OFF_SCHED % 16 == 0, "alignment");
@@ -68,12 +77,31 @@ static_assert(OFF_BAR % 8 == 0 && OFF_SCHED % 16 == 0, "alignment");
 // Optional phase timing (d4s_set_option("profile", 1)): thread 0 of CTA 0 accumulates clock64() deltas per phase.
 #define PROF_MARK(slot)                                                     \
     do {                                                                    \
+        TRACE(slot);                                                        \
         if (prof_on) {                                                      \
             const long long now_ = clock64();                               \
             p.prof[slot] += now_ - prof_t;                                  \
             prof_t = now_;                                                  \
         }                                                                   \
     } while (0)
+
+// Event timeline of CTA 0 (-DD4S_TRACE variant builds, tests/build_variant.py + tests/gpu_trace_tc.py): lane 0 of every warp
+// appends (tag, clock64) pairs for the items [TRACE_FROM, TRACE_TO); launch_traj_tc() writes the buffer to $D4S_TRACE_FILE.
+// Tags: the PROF_MARK slots at the END of a phase; 20 item start, 21 / 22 before the wait for the last / a mid tensor-core layer;
+// MMA warp: 30 + l first MMA of layer l issued, 40 + l all MMAs of layer l issued.
+constexpr int TRACE_MAX = 256, TRACE_FROM = 40, TRACE_TO = 46;
+#ifdef D4S_TRACE
+#define TRACE(tag)                                                                          \
+    do {                                                                                    \
+        if (tr_go && lane == 0 && tr_n < TRACE_MAX) {                                       \
+            p.trace[(warp * TRACE_MAX + tr_n) * 2] = (tag);                                 \
+            p.trace[(warp * TRACE_MAX + tr_n) * 2 + 1] = clock64();                         \
+            ++tr_n;                                                                         \
+        }                                                                                   \
+    } while (0)
+#else
+#define TRACE(tag) do { } while (0)
+#endif
 
 // Helper warp: per-sample Lambda_i = Lbase + (1-n) diag(p0_i) and its inverse, in fp64 (nse.py:647-654 builds and
 // solves this system; here the inverse is prepared off the critical path, the solve is a mat-vec in the tail).
@@ -318,6 +346,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     // accumulator ready for the epilogue: two barriers used alternately, layer by layer (the MMA warp may complete two layers
     // -- the last layer of an item and the first layer of the next one -- before the compute warps look at the first)
     auto bar_dn = [&](unsigned n) { return bar0 + 8u * (2 * TC_NSTG + 1 + (n & 1u)); };
+    // block cb of a mid epilogue is in tensor memory (every compute warp has converted its cb-th 16-column block): K-steps
+    // {cq * nblk + cb, cq = 0..3} of the next layer may be issued
+    auto bar_c = [&](int cb) { return bar0 + 8u * (2 * TC_NSTG + 3 + cb); };
+    // i-th K-step of a TS-form layer in issue order (K = 64 nblk): block index first, column quarter second
+    auto ks_of = [](int i, int nblk) { return (i & 3) * nblk + (i >> 2); };
 
     const NetDev& net = p.net;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -349,6 +382,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
         mbar_init(bar_a, TC_CW * 32);
         mbar_init(bar_dn(0), 1);
         mbar_init(bar_dn(1), 1);
+        for (int cb = 0; cb < 4; ++cb) mbar_init(bar_c(cb), TC_CW * 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC_CW + 1) {  // TMEM: two 256-column fp32 accumulators, used alternately layer by layer
@@ -400,7 +434,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     const int K = net.Hp[l - 1], Nn = net.Hp[l];
                     const uint32_t bytes = (uint32_t)Nn * 64u;
                     const uint8_t* src = net.wimg[l];
-                    for (int ks = 0; ks < K / 16; ++ks, ++it) {
+                    for (int i = 0; i < K / 16; ++i, ++it) {
+#if D4S_EXP & 64
+                        const int ks = (l > 1) ? ks_of(i, K / 64) : i;  // the order the MMA warp consumes them in
+#else
+                        const int ks = i;
+#endif
                         const int s = it % TC_NSTG;
                         const uint32_t ph = (it / TC_NSTG) & 1u;
                         mbar_wait(bar_empty(s), ph ^ 1u, p.error_flag);
@@ -415,16 +454,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ================= MMA issuer ===================================================================================
         if (lane == 0) {
-            unsigned it = 0, a_cnt = 0, lc = 0;
+            int tr_n = 0;
+            bool tr_go = false;
+            (void)tr_n; (void)tr_go;
+            unsigned it = 0, a_cnt = 0, lc = 0, c_par = 0;  // c_par: bit cb = phase parity of bar_c(cb) to wait for next
             const uint32_t a_hi0 = smem_u32(sAhi), a_lo0 = smem_u32(sAlo);
             for (long long ti = 0; ti < tile_iters; ++ti) {
+                tr_go = blockIdx.x == 0 && p.trace != nullptr && ti >= TRACE_FROM && ti < TRACE_TO;
                 for (int l = 1; l <= L - 2; ++l) {
                     const int K = net.Hp[l - 1], Nn = net.Hp[l];
                     const uint32_t idesc = umma_idesc(Nn);
                     const uint32_t b_lbo = (uint32_t)Nn * 16u, b_sbo = 128u;  // K halves N*16 B apart, 8-row groups 128 B
                     const uint32_t a_lbo = 2048u, a_sbo = 128u;
-                    mbar_wait(bar_a, a_cnt & 1u, p.error_flag);
-                    ++a_cnt;
+#if D4S_EXP & 64
+                    if (l == 1)
+#endif
+                    {
+                        mbar_wait(bar_a, a_cnt & 1u, p.error_flag);
+                        ++a_cnt;
+                    }
+                    TRACE(50 + l);
 #if D4S_EXP & 16
                     // early layer 0: this layer's accumulator is the region the previous (TS-form) layer reads its A operand
                     // from; wait until that layer has completed before overwriting it
@@ -436,7 +485,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     (void)dprev;
                     const long long mma_t0 = (p.prof && blockIdx.x == 0) ? clock64() : 0;
                     ++lc;
-                    for (int ks = 0; ks < K / 16; ++ks, ++it) {
+                    for (int i = 0; i < K / 16; ++i, ++it) {
+#if D4S_EXP & 64
+                        const int ks = (l > 1) ? ks_of(i, K / 64) : i;
+                        if (l > 1 && (i & 3) == 0) {  // block i / 4 of the previous layer's epilogue is in tensor memory
+                            mbar_wait(bar_c(i >> 2), (c_par >> (i >> 2)) & 1u, p.error_flag);
+                            c_par ^= 1u << (i >> 2);  // (layers of different widths use different numbers of block barriers)
+                            tc_fence_after();
+                        }
+#else
+                        const int ks = i;
+#endif
                         const int s = it % TC_NSTG;
                         const uint32_t ph = (it / TC_NSTG) & 1u;
                         mbar_wait(bar_full(s), ph, p.error_flag);
@@ -447,7 +506,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
 #if D4S_EXP & 8
                         if (l > 1) {  // A = the previous layer's accumulator region, converted in place by the epilogue
                             const uint32_t a_t = dprev + (uint32_t)ks * 16u;  // K-step ks: hi in columns 16 ks .. +7, lo in +8 .. +15
-                            tc_mma_bf16_ts(dacc, a_t, b_hi, idesc, ks > 0 ? 1u : 0u);
+                            tc_mma_bf16_ts(dacc, a_t, b_hi, idesc, i > 0 ? 1u : 0u);
                             tc_mma_bf16_ts(dacc, a_t + 8u, b_hi, idesc, 1u);
                             tc_mma_bf16_ts(dacc, a_t, b_lo, idesc, 1u);
                         } else
@@ -455,12 +514,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         {
                             const uint64_t a_hi = umma_desc(a_hi0 + ks * 4096, a_lbo, a_sbo);
                             const uint64_t a_lo = umma_desc(a_lo0 + ks * 4096, a_lbo, a_sbo);
-                            tc_mma_bf16(dacc, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
+                            tc_mma_bf16(dacc, a_hi, b_hi, idesc, i > 0 ? 1u : 0u);
                             tc_mma_bf16(dacc, a_lo, b_hi, idesc, 1u);
                             tc_mma_bf16(dacc, a_hi, b_lo, idesc, 1u);
                         }
                         tc_commit(bar_empty(s));  // ring slot is free once these MMAs have read it
+                        if (i == 0) TRACE(30 + l);
                     }
+                    TRACE(40 + l);
                     tc_commit(bar_dn(lc - 1u));  // accumulator complete
                     if (p.prof && blockIdx.x == 0) {  // profiling: duration of this layer's MMAs (slots 8 / 9: first / last layer)
                         mbar_wait(bar_dn(lc - 1u), ((lc - 1u) >> 1) & 1u, p.error_flag);
@@ -561,6 +622,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
         const int row = 32 * q + lane;           // the TMEM lane / tile row this thread owns in the epilogues
         unsigned d_cnt = 0;
         const bool prof_on = (p.prof != nullptr) && blockIdx.x == 0 && tid == 0;
+        int tr_n = 0;
+        bool tr_go = false;
+        (void)tr_n; (void)tr_go;
         long long prof_t = prof_on ? clock64() : 0;
         const int nkg = H0 / 8;
 #if D4S_EXP & 1
@@ -952,6 +1016,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
         };
 
         const int Lh = L - 2;  // hidden layers on the tensor core
+        // Layer 0 reads, per thread, 16 floats of obs_feat (its observation = lane, its two k-groups): with the whole observation set
+        // in one tile of <= 32 observations per sample they are the SAME 16 floats for every item of the trajectory -> loaded once.
+        // (Per-item loads were 30 KB per item through a 28 KB L1 that also has to hold the local-memory lines.)
+        const bool obs_in_regs = p.C == 1 && p.OC <= 32 && p.fin.ctx_samples == 0;
+        float4 upre[2][2];
+        if (obs_in_regs) l0_load(upre, 0, min(p.OC, p.n), lane);
         for (int gk = 0; gk < my_groups;) {
             const int ngr = (pairing && gk + 1 < my_groups) ? 2 : 1;
             // Two groups interleaved: the last epilogue / scores of a pass run while the tensor core is on layer 1 of the
@@ -960,16 +1030,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
             const bool defer = (ngr == 2);
             const int total = ngr * n_steps;
             const int total_p = total * p.C;  // passes (defer => C == 1)
-            int i0g[2], nsg[2];
-#pragma unroll
-            for (int gi = 0; gi < 2; ++gi) {
-                i0g[gi] = (blockIdx.x + (gk + min(gi, ngr - 1)) * (int)gridDim.x) * p.SG;
-                nsg[gi] = min(p.SG, p.N - i0g[gi]);
-            }
+            // (scalars + selects, not arrays indexed by the group: those would live in local memory, and a local-memory miss
+            // costs an L2 round trip here -- the L1 is almost entirely carved out as shared memory)
+            const int i0g0 = (blockIdx.x + gk * (int)gridDim.x) * p.SG;
+            const int i0g1 = (blockIdx.x + (gk + ngr - 1) * (int)gridDim.x) * p.SG;
+            const int nsg0 = min(p.SG, p.N - i0g0), nsg1 = min(p.SG, p.N - i0g1);
+            auto i0g = [&](int gi) { return gi ? i0g1 : i0g0; };
+            auto nsg = [&](int gi) { return gi ? nsg1 : nsg0; };
             for (int e = tid; e < ngr * TC_SG_MAX * MMAX; e += TC_CT) {
                 const int gi = e / (TC_SG_MAX * MMAX), r = e - gi * TC_SG_MAX * MMAX;
                 const int si = r / MMAX, k = r - si * MMAX;
-                sTheta[e] = (si < nsg[gi] && k < m) ? p.theta[(size_t)(i0g[gi] + si) * m + k] : 0.f;
+                sTheta[e] = (si < nsg(gi) && k < m) ? p.theta[(size_t)(i0g(gi) + si) * m + k] : 0.f;
             }
             compute_bar();
             if (total > 0) bar_arrive(2, NB23);  // theta of item 0 is final: the helper warp may start on it
@@ -979,6 +1050,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 compute_bar();
             }
             for (int ps = 0; ps <= total_p; ++ps) {  // one extra iteration finishes the last pass
+                tr_go = blockIdx.x == 0 && p.trace != nullptr && ps >= TRACE_FROM && ps < TRACE_TO;
+                TRACE(20);
                 const bool have = ps < total_p, prev = ps > 0;
                 const int it = ps / p.C, chunk = ps - it * p.C;
                 const int gi = defer ? (it & 1) : 0;
@@ -991,19 +1064,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 float4 bcur[4];
                 float inv_sigma_prev = 0.f;
                 uint32_t dacc_prev = 0;
-                float4 upre[2][2];
                 // layer 0 of this pass goes first when it does not depend on the previous pass: interleaved groups, or a
                 // later observation chunk of the same item (its sample part was recomputed at the end of the last pass)
                 const bool early = have && (defer || chunk > 0);
 #if D4S_EXP & 16
-                const bool have_pre = early && (ps == 0 || Lh < 2) && lane < p.OC && p.fin.ctx_samples == 0;
+                const bool have_pre = !obs_in_regs && early && (ps == 0 || Lh < 2) && lane < p.OC && p.fin.ctx_samples == 0;
 #else
-                const bool have_pre = early && lane < p.OC && p.fin.ctx_samples == 0;
+                const bool have_pre = !obs_in_regs && early && lane < p.OC && p.fin.ctx_samples == 0;
 #endif
                 if (have_pre) l0_load(upre, j0, nobs, lane);  // layer 0 follows the wait directly: hide its global loads
                 if (prev) {  // the last layer of the previous pass: once it is done the operand images are free again
                     inv_sigma_prev = __ldg(p.sched + (size_t)step_of(pit) * D4S_SCHED_STRIDE + D4S_S_INV_SIGMA);
                     dacc_prev = tmem_d + ((d_cnt & 1u) ? 256u : 0u);
+                    TRACE(21);
                     mbar_wait(bar_dn(d_cnt), (d_cnt >> 1) & 1u, p.error_flag);
                     ++d_cnt;
                     tc_fence_after();
@@ -1015,23 +1088,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
 #else
                 if (early) {
 #endif
-                    do_layer0(i0g[gi], nsg[gi], j0, nobs, upre, have_pre);
+                    do_layer0(i0g(gi), nsg(gi), j0, nobs, upre, have_pre || obs_in_regs);
                     PROF_MARK(1);  // layer 0
                 }
-                if (prev) do_last_epilogue(dacc_prev, inv_sigma_prev, pj0, pnobs, i0g[pgi], nsg[pgi], pchunk == 0);
+                if (prev) do_last_epilogue(dacc_prev, inv_sigma_prev, pj0, pnobs, i0g(pgi), nsg(pgi), pchunk == 0);
                 if (!defer) {
                     if (prev) {
-                        if (!fused_sums) do_sums(nsg[pgi], pj0, pnobs, pchunk == 0);
+                        if (!fused_sums) do_sums(nsg(pgi), pj0, pnobs, pchunk == 0);
                         compute_bar();
                         PROF_MARK(6);  // inv(Sigma) s + sums over observations
                         if (pchunk == p.C - 1) {
                             bar_sync(3, NB23);  // schedule/matrix rows, prior terms and noise of this step are in smem
                             PROF_MARK(2);       // (time spent waiting for the helper warp, normally zero)
                             if (p.part_out) {
-                                for (int e = tid; e < nsg[pgi] * 2 * m; e += TC_CT) p.part_out[(size_t)i0g[pgi] * 2 * m + e] = sAcc[e];
+                                for (int e = tid; e < nsg(pgi) * 2 * m; e += TC_CT) p.part_out[(size_t)i0g(pgi) * 2 * m + e] = sAcc[e];
                             } else {
-                                if (p.xg.world > 0) xchg_group_sums(p.xg, sAcc, p.N, m, n_groups, p.SG, step_of(pit), i0g[pgi], nsg[pgi], tid, p.error_flag);
-                                do_tail(pth, nsg[pgi]);
+                                if (p.xg.world > 0) xchg_group_sums(p.xg, sAcc, p.N, m, n_groups, p.SG, step_of(pit), i0g(pgi), nsg(pgi), tid, p.error_flag);
+                                do_tail(pth, nsg(pgi));
                             }
                             compute_bar();
                             if (have) bar_arrive(2, NB23);
@@ -1042,7 +1115,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         do_base(th, true, 0, step_of(it + 1));
                         compute_bar();
                         PROF_MARK(0);  // per-sample layer-0 part
-                        do_layer0(i0g[gi], nsg[gi], j0, nobs, upre, false);
+                        do_layer0(i0g(gi), nsg(gi), j0, nobs, upre, obs_in_regs);
                         PROF_MARK(1);  // layer 0
                     }
                 }
@@ -1054,6 +1127,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
 #pragma unroll
                         for (int e = 0; e < 4; ++e) bcur[e] = __ldg(reinterpret_cast<const float4*>(bias_l) + e);  // hidden behind the MMA
                         const uint32_t dacc = tmem_d + ((d_cnt & 1u) ? 256u : 0u);
+                        TRACE(22);
                         mbar_wait(bar_dn(d_cnt), (d_cnt >> 1) & 1u, p.error_flag);
                         ++d_cnt;
                         tc_fence_after();
@@ -1080,6 +1154,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                                     split8_regs(v, w + 4 * k8, w + 8 + 4 * k8);
                                 }
                                 tc_st16(dacc + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, w);
+#if D4S_EXP & 64
+                                tc_wait_st();
+                                tc_fence_before();
+                                mbar_arrive(bar_c(cb));
+#endif
                             }
 #else
 #pragma unroll
@@ -1095,6 +1174,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                                 for (int e = 0; e < 4; ++e) bcur[e] = bnxt[e];
                             }
                         }
+#if !(D4S_EXP & 64)
 #if D4S_EXP & 8
                         tc_wait_st();
 #else
@@ -1102,6 +1182,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
 #endif
                         tc_fence_before();
                         mbar_arrive(bar_a);
+#endif
                         PROF_MARK(4);  // epilogues
                     }
                 }
@@ -1112,26 +1193,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
 #if D4S_EXP & 16
                     if (l0_early) {  // its layer 0 now, under the last tensor-core layer of this chunk
                         const int nj0 = (chunk + 1) * p.OC;
-                        do_layer0(i0g[gi], nsg[gi], nj0, min(p.OC, p.n - nj0), upre, false);
+                        do_layer0(i0g(gi), nsg(gi), nj0, min(p.OC, p.n - nj0), upre, false);
                         PROF_MARK(1);
                     }
 #endif
                 }
                 if (defer) {
 #if D4S_EXP & 16
-                    const bool pre_next = l0_early && ps + 1 < total_p && lane < p.OC && p.fin.ctx_samples == 0;
+                    const bool pre_next = !obs_in_regs && l0_early && ps + 1 < total_p && lane < p.OC && p.fin.ctx_samples == 0;
+                    TRACE(23);
                     if (pre_next) l0_load(upre, 0, min(p.OC, p.n), lane);  // obs_feat rows of the next item's layer 0: latency hidden
 #endif
+                    TRACE(24);
                     if (prev) {
-                        if (!fused_sums) do_sums(nsg[pgi], 0, pnobs, true);
+                        if (!fused_sums) do_sums(nsg(pgi), 0, pnobs, true);
+                        TRACE(25);
 #if !(D4S_EXP & 4)
                         compute_bar();  // (redundant: every compute thread also takes part in barrier 3 below)
 #endif
                         PROF_MARK(6);
                         bar_sync(3, NB23);  // schedule / matrix rows, prior terms and noise of the previous item are in smem
                         PROF_MARK(2);  // (time spent waiting for the helper warp)
-                        if (p.xg.world > 0) xchg_group_sums(p.xg, sAcc, p.N, m, n_groups, p.SG, step_of(pit), i0g[pgi], nsg[pgi], tid, p.error_flag);
-                        do_tail(pth, nsg[pgi]);
+                        if (p.xg.world > 0) xchg_group_sums(p.xg, sAcc, p.N, m, n_groups, p.SG, step_of(pit), i0g(pgi), nsg(pgi), tid, p.error_flag);
+                        do_tail(pth, nsg(pgi));
                         PROF_MARK(10);  // tail proper (the barrier wait below stays in slot 6)
                         compute_bar();
                         if (have) bar_arrive(2, NB23);  // helper warp: buffers are free, go on with this item
@@ -1143,7 +1227,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         PROF_MARK(0);
 #if D4S_EXP & 16
                         if (l0_early) {  // layer 0 of the next item now, under the last tensor-core layer of this one
-                            do_layer0(i0g[gi ^ 1], nsg[gi ^ 1], 0, min(p.OC, p.n), upre, pre_next);
+                            do_layer0(i0g(gi ^ 1), nsg(gi ^ 1), 0, min(p.OC, p.n), upre, pre_next || obs_in_regs);
                             PROF_MARK(1);
                         }
 #endif
@@ -1154,7 +1238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 for (int e = tid; e < ngr * TC_SG_MAX * MMAX; e += TC_CT) {
                     const int gi = e / (TC_SG_MAX * MMAX), r = e - gi * TC_SG_MAX * MMAX;
                     const int si = r / MMAX, k = r - si * MMAX;
-                    if (si < nsg[gi] && k < m) p.theta[(size_t)(i0g[gi] + si) * m + k] = sTheta[e];
+                    if (si < nsg(gi) && k < m) p.theta[(size_t)(i0g(gi) + si) * m + k] = sTheta[e];
                 }
             }
             compute_bar();
@@ -1184,6 +1268,26 @@ cudaError_t launch_traj_tc(const TrajParams& p, int n_ctas, cudaStream_t stream)
         if (fa.numRegs < 96) return cudaErrorLaunchOutOfResources;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
+#ifdef D4S_TRACE
+    static long long* trace_buf = nullptr;
+    const size_t trace_bytes = (size_t)(TC_THREADS / 32) * TRACE_MAX * 2 * sizeof(long long);
+    if (const char* path = getenv("D4S_TRACE_FILE")) {
+        if (!trace_buf) cudaMalloc(&trace_buf, trace_bytes);
+        cudaMemsetAsync(trace_buf, 0, trace_bytes, stream);
+        TrajParams q = p;
+        q.trace = trace_buf;
+        traj_tc_kernel<<<n_ctas, TC_THREADS, TC_SMEM_BYTES, stream>>>(q);
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return e;
+        std::vector<long long> host(trace_bytes / sizeof(long long));
+        cudaMemcpy(host.data(), trace_buf, trace_bytes, cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(path, "wb")) {
+            fwrite(host.data(), 1, trace_bytes, f);
+            fclose(f);
+        }
+        return cudaGetLastError();
+    }
+#endif
     traj_tc_kernel<<<n_ctas, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
 }

@@ -37,10 +37,15 @@ def build(force=False, verbose=False, extra_flags=(), out=None, obj_dir=None):
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + list(extra_flags)
     if obj_dir:
         os.makedirs(obj_dir, exist_ok=True)
-    for src in SOURCES:
+    def compile_one(src):
         obj = os.path.join(obj_dir or CSRC, src.replace(".cu", ".o"))
         cmd = [_nvcc(), *flags, "-Xptxas", "-v" if verbose else "-warn-spills", "-c", os.path.join(CSRC, src), "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:  # one nvcc per source, side by side
+        results = list(pool.map(compile_one, SOURCES))
+    for src, obj, r in results:
         if verbose or r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
         if r.returncode:
