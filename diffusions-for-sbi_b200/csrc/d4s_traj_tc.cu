@@ -31,7 +31,7 @@
 #include "d4s_tc_common.cuh"
 
 #ifndef D4S_EXP
-#define D4S_EXP 57  // feature bit mask (A/B builds: -DD4S_EXP=..., tests/gpu_ab.py; round-2 measurements in profiles/r02_tc_notes.md): 1 base on 16 warps, 2 Wout prefetch, 4 one barrier less,
+#define D4S_EXP 121  // feature bit mask (A/B builds: -DD4S_EXP=..., tests/gpu_ab.py; round-2 measurements in profiles/r02_tc_notes.md): 1 base on 16 warps, 2 Wout prefetch, 4 one barrier less,
                    // 8 A operand of the layers >= 2 in tensor memory (TS form), written in place over the accumulator,
                    // 16 (needs 8) layer 0 of the next pass is written while the last tensor-core layer of this one runs,
                    // 32 per-sample sums straight from the output-layer partials (no per-row scores in shared memory)
@@ -317,6 +317,10 @@ __device__ __noinline__ void xchg_group_sums(const XchgDev& xg, float* s_acc, in
     compute_bar();
 }
 
+// MT: theta_dim as a compile-time constant (0 = read it from the net).  With a runtime theta_dim every small loop of the kernel
+// (layer-0 sample part, Q_j products, sums, tail) is a chain of predicated steps over MMAX = 10 slots; the instantiations for the
+// benchmark tasks' dimensions unroll them exactly.
+template <int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_constant__ TrajParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sAhi = smem + OFF_AHI;
@@ -354,7 +358,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
 
     const NetDev& net = p.net;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m = net.m, L = net.L;
+    const int m = MT > 0 ? MT : net.m, L = net.L;
     const int H0 = net.Hp[0];
     const bool a_in_smem = (m <= MMAX / 2);
     // sBase holds SG <= 8 rows of 256 floats, and its first 1280 floats double as scratch of the scores phase; with
@@ -1222,6 +1226,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         PROF_MARK(6);
                     }
                     if (ps + 1 < total_p) {
+                        // first pass of a block: nothing since layer 0 of item 0 has synchronised the compute warps (later passes
+                        // go through the barriers of the last epilogue / tail) -- warps without layer-0 work (narrow first layer)
+                        // would overwrite the sample part while the others still read it
+                        if (!prev) compute_bar();
                         do_base(sTheta + (gi ^ 1) * TC_SG_MAX * MMAX, true, 0, step_of(it + 2));
                         compute_bar();
                         PROF_MARK(0);
@@ -1252,18 +1260,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     }
 }
 
-cudaError_t launch_traj_tc(const TrajParams& p, int n_ctas, cudaStream_t stream) {
+template <int MT>
+static cudaError_t launch_traj_tc_m(const TrajParams& p, int n_ctas, cudaStream_t stream) {
     // the attribute is per device: keep one flag per device ordinal (a process may drive several GPUs)
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(traj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(traj_tc_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         // setmaxnreg moves registers inside the CTA's launch allocation: with fewer than 96 registers per thread at launch
         // the compute warps' `inc` could never be served (the kernel would hang), so refuse to launch instead
         cudaFuncAttributes fa;
-        e = cudaFuncGetAttributes(&fa, traj_tc_kernel);
+        e = cudaFuncGetAttributes(&fa, traj_tc_kernel<MT>);
         if (e != cudaSuccess) return e;
         if (fa.numRegs < 96) return cudaErrorLaunchOutOfResources;
         if (dev >= 0 && dev < 64) configured[dev] = true;
@@ -1276,7 +1285,7 @@ cudaError_t launch_traj_tc(const TrajParams& p, int n_ctas, cudaStream_t stream)
         cudaMemsetAsync(trace_buf, 0, trace_bytes, stream);
         TrajParams q = p;
         q.trace = trace_buf;
-        traj_tc_kernel<<<n_ctas, TC_THREADS, TC_SMEM_BYTES, stream>>>(q);
+        traj_tc_kernel<MT><<<n_ctas, TC_THREADS, TC_SMEM_BYTES, stream>>>(q);
         cudaError_t e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) return e;
         std::vector<long long> host(trace_bytes / sizeof(long long));
@@ -1288,8 +1297,17 @@ cudaError_t launch_traj_tc(const TrajParams& p, int n_ctas, cudaStream_t stream)
         return cudaGetLastError();
     }
 #endif
-    traj_tc_kernel<<<n_ctas, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
+    traj_tc_kernel<MT><<<n_ctas, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
+}
+
+cudaError_t launch_traj_tc(const TrajParams& p, int n_ctas, cudaStream_t stream) {
+    switch (p.net.m) {  // theta_dim of the benchmark tasks: SIR 2, Lotka-Volterra / JR-NMM 4, SLCP 5; anything else: generic
+        case 2: return launch_traj_tc_m<2>(p, n_ctas, stream);
+        case 4: return launch_traj_tc_m<4>(p, n_ctas, stream);
+        case 5: return launch_traj_tc_m<5>(p, n_ctas, stream);
+        default: return launch_traj_tc_m<0>(p, n_ctas, stream);
+    }
 }
 
 int traj_tc_smem_bytes() { return TC_SMEM_BYTES; }
