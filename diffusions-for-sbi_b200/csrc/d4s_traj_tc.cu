@@ -30,18 +30,6 @@
 #include "d4s_finalize_core.cuh"
 #include "d4s_tc_common.cuh"
 
-#ifndef D4S_EXP
-#define D4S_EXP 121  // feature bit mask (A/B builds: -DD4S_EXP=..., tests/gpu_ab.py; round-2 measurements in profiles/r02_tc_notes.md): 1 base on 16 warps, 2 Wout prefetch, 4 one barrier less,
-                   // 8 A operand of the layers >= 2 in tensor memory (TS form), written in place over the accumulator,
-                   // 16 (needs 8) layer 0 of the next pass is written while the last tensor-core layer of this one runs,
-                   // 32 per-sample sums straight from the output-layer partials (no per-row scores in shared memory)
-                   // 64 (needs 8) the mid epilogue hands its 16-column blocks to the MMA warp one by one (one mbarrier per block index,
-                   //    K-steps of the TS-form layers issued in block order): the next layer starts after the first block
-#endif
-#if (D4S_EXP & 64) && !(D4S_EXP & 8)
-#error "D4S_EXP bit 64 needs bit 8"
-#endif
-
 namespace d4s {
 
 constexpr int TC_THREADS = (TC_CW + 4) * 32;   // 640: + TMA producer, MMA issuer, scalar helper, one idle warp (full warpgroup)
@@ -346,7 +334,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     const uint32_t bar0 = smem_u32(smem + OFF_BAR);
     auto bar_full = [&](int s) { return bar0 + 8u * s; };
     auto bar_empty = [&](int s) { return bar0 + 8u * (TC_NSTG + s); };
-    const uint32_t bar_a = bar0 + 8u * (2 * TC_NSTG);      // A operand (and TMEM D) ready for the MMA warp
+    const uint32_t bar_a = bar0 + 8u * (2 * TC_NSTG);      // layer-0 A operand (and TMEM D) ready for the MMA warp
+    // (handing layer 0 over in two K halves, like the mid epilogue below, measured -3 % .. -5 %: a second fence.proxy.async per
+    // pass, and the early MMAs compete with the rest of layer 0 for the shared-memory pipe)
     // accumulator ready for the epilogue: two barriers used alternately, layer by layer (the MMA warp may complete two layers
     // -- the last layer of an item and the first layer of the next one -- before the compute warps look at the first)
     auto bar_dn = [&](unsigned n) { return bar0 + 8u * (2 * TC_NSTG + 1 + (n & 1u)); };
@@ -367,13 +357,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     // (row stride odd: lanes = observations read Q_j[r][k] at the same (r, k), an even stride would be a 16-way bank conflict)
     const int qstr = (m * m) | 1;
     const bool q_in_smem = p.obs_prec != nullptr && p.C == 1 && p.SG <= 5 && p.n * qstr <= 768 && p.fin.ctx_samples == 0;
-#if D4S_EXP & 32
     // needs the aligned tile layout (row stride RS of a sample = power of two <= 32, chosen by the host when it costs no rows)
     const bool fused_sums = m <= 5 && (p.obs_prec == nullptr || q_in_smem) && p.fin.ctx_samples == 0 && p.C == 1 &&
                             p.RS <= 32 && (p.RS & (p.RS - 1)) == 0;
-#else
-    constexpr bool fused_sums = false;
-#endif
     const int n_groups = (p.N + p.SG - 1) / p.SG;
     const int mats_floats = 2 * m * m + m;
     constexpr int NB23 = TC_CT + 32;  // participants of named barriers 2 and 3
@@ -439,11 +425,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     const uint32_t bytes = (uint32_t)Nn * 64u;
                     const uint8_t* src = net.wimg[l];
                     for (int i = 0; i < K / 16; ++i, ++it) {
-#if D4S_EXP & 64
                         const int ks = (l > 1) ? ks_of(i, K / 64) : i;  // the order the MMA warp consumes them in
-#else
-                        const int ks = i;
-#endif
                         const int s = it % TC_NSTG;
                         const uint32_t ph = (it / TC_NSTG) & 1u;
                         mbar_wait(bar_empty(s), ph ^ 1u, p.error_flag);
@@ -470,19 +452,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     const uint32_t idesc = umma_idesc(Nn);
                     const uint32_t b_lbo = (uint32_t)Nn * 16u, b_sbo = 128u;  // K halves N*16 B apart, 8-row groups 128 B
                     const uint32_t a_lbo = 2048u, a_sbo = 128u;
-#if D4S_EXP & 64
                     if (l == 1)
-#endif
                     {
                         mbar_wait(bar_a, a_cnt & 1u, p.error_flag);
                         ++a_cnt;
                     }
                     TRACE(50 + l);
-#if D4S_EXP & 16
                     // early layer 0: this layer's accumulator is the region the previous (TS-form) layer reads its A operand
                     // from; wait until that layer has completed before overwriting it
                     if (l == 1 && lc > 0 && L - 2 >= 2) mbar_wait(bar_dn(lc - 1u), ((lc - 1u) >> 1) & 1u, p.error_flag);
-#endif
                     tc_fence_after();
                     const uint32_t dacc = tmem_d + ((lc & 1u) ? 256u : 0u);  // the other accumulator may still be read by an epilogue
                     const uint32_t dprev = tmem_d + ((lc & 1u) ? 0u : 256u);  // accumulator of the previous layer (TS form: its A operand)
@@ -490,16 +468,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     const long long mma_t0 = (p.prof && blockIdx.x == 0) ? clock64() : 0;
                     ++lc;
                     for (int i = 0; i < K / 16; ++i, ++it) {
-#if D4S_EXP & 64
                         const int ks = (l > 1) ? ks_of(i, K / 64) : i;
                         if (l > 1 && (i & 3) == 0) {  // block i / 4 of the previous layer's epilogue is in tensor memory
                             mbar_wait(bar_c(i >> 2), (c_par >> (i >> 2)) & 1u, p.error_flag);
                             c_par ^= 1u << (i >> 2);  // (layers of different widths use different numbers of block barriers)
                             tc_fence_after();
                         }
-#else
-                        const int ks = i;
-#endif
                         const int s = it % TC_NSTG;
                         const uint32_t ph = (it / TC_NSTG) & 1u;
                         mbar_wait(bar_full(s), ph, p.error_flag);
@@ -507,14 +481,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         const uint32_t wb = smem_u32(smem + OFF_RING + s * TC_STAGE_BYTES);
                         const uint64_t b_hi = umma_desc(wb, b_lbo, b_sbo);
                         const uint64_t b_lo = umma_desc(wb + (uint32_t)Nn * 32u, b_lbo, b_sbo);
-#if D4S_EXP & 8
                         if (l > 1) {  // A = the previous layer's accumulator region, converted in place by the epilogue
                             const uint32_t a_t = dprev + (uint32_t)ks * 16u;  // K-step ks: hi in columns 16 ks .. +7, lo in +8 .. +15
                             tc_mma_bf16_ts(dacc, a_t, b_hi, idesc, i > 0 ? 1u : 0u);
                             tc_mma_bf16_ts(dacc, a_t + 8u, b_hi, idesc, 1u);
                             tc_mma_bf16_ts(dacc, a_t, b_lo, idesc, 1u);
                         } else
-#endif
                         {
                             const uint64_t a_hi = umma_desc(a_hi0 + ks * 4096, a_lbo, a_sbo);
                             const uint64_t a_lo = umma_desc(a_lo0 + ks * 4096, a_lbo, a_sbo);
@@ -631,12 +603,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
         (void)tr_n; (void)tr_go;
         long long prof_t = prof_on ? clock64() : 0;
         const int nkg = H0 / 8;
-#if D4S_EXP & 1
         const int bcol = tid & 255, bhalf = tid >> 8;  // layer-0 sample part: column, and which half of the samples
         float tf_next = (bcol < H0 && n_steps > 0) ? __ldg(p.time_feat + (size_t)p.step_begin * H0 + bcol) : 0.f;
-#else
-        float tf_next = (tid < H0 && n_steps > 0) ? __ldg(p.time_feat + (size_t)p.step_begin * H0 + tid) : 0.f;
-#endif
         // ---- phases shared by the two schedules (one group after the other / two groups interleaved) ----------------------
         // layer-0 per-sample part of an item: base[si][col] = time_feat[col] + sum_k A[k][col] theta[si][k]
         auto do_base = [&](const float* th, bool fresh, int step, int next_step) {
@@ -653,7 +621,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 theta_embed_base(net, th, sS, sQS, sBase, p.SG, H0, t0e, tid);
                 return;
             }
-#if D4S_EXP & 1
             if (bcol < H0) {  // all 16 compute warps: thread = (column, half of the group's samples)
                 float t0;
                 if (fresh) {
@@ -674,28 +641,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     sBase[si * 256 + bcol] = z;
                 }
             }
-#else
-            if (tid < H0) {
-                float t0;
-                if (fresh) {
-                    t0 = tf_next;
-                    tf_next = __ldg(p.time_feat + (size_t)next_step * H0 + tid);  // consumed one item later: latency hidden
-                } else {
-                    t0 = __ldg(p.time_feat + (size_t)step * H0 + tid);  // (later observation chunks of the same step)
-                }
-                float ak[MMAX];  // column tid of the layer-0 theta block
-#pragma unroll
-                for (int k = 0; k < MMAX; ++k)
-                    ak[k] = (k < m) ? (a_in_smem ? sA[k * 256 + tid] : __ldg(net.A + (size_t)k * H0 + tid)) : 0.f;
-                for (int si = 0; si < p.SG; ++si) {
-                    float z = t0;
-#pragma unroll
-                    for (int k = 0; k < MMAX; ++k)
-                        if (k < m) z = fmaf(ak[k], th[si * MMAX + k], z);
-                    sBase[si * 256 + tid] = z;
-                }
-            }
-#endif
         };
         // per-sample sums over the chunk's observations.  item = (sample si, component c < 2m): S1[c] = sum_j s_ij[c]
         // (c < m), S2[c-m] = sum_j (inv(Sigma_j) s_ij)[c-m] (rows of sQS); a warp takes one item at a time, its lanes run over the
@@ -835,81 +780,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
             const int Nn = net.Hp[L - 2];
             const int qcols = Nn >> 2, nblk = qcols / 16;
             const float* bias_l = net.bias[L - 2] + cq * qcols;
-            float po[MMAX];  // output-layer partial dot products of this thread's row / column quarter
+            // output-layer partial dot products of this thread's row / column quarter, as packed pairs (even | odd columns): the
+            // products run as FFMA2 over column pairs, po[o] = po2[o].x + po2[o].y at the end
+            float2 po2[MMAX];
 #pragma unroll
-            for (int o = 0; o < MMAX; ++o) po[o] = 0.f;
+            for (int o = 0; o < MMAX; ++o) po2[o] = make_float2(0.f, 0.f);
+            auto load_w = [&](float4 (&w)[4], int o, int col0) {  // Wout[o][col0 .. col0 + 15] (smem, broadcast reads)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) w[e] = *reinterpret_cast<const float4*>(sWout + o * 256 + col0 + 4 * e);
+            };
             for (int cb = 0; cb < nblk; ++cb) {
                 const int col0 = cq * qcols + 16 * cb;
                 float4 bb[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bias_l + 16 * cb) + e);
-                float a[16];
-                ld_act(dacc, col0, bb, a);
-                // po[o] += sum_c act[c] * Wout[o][c]   (Wout in smem, broadcast reads)
-                // (five outputs at a time: their weight loads are independent and issued together)
-#if D4S_EXP & 2
-                // software pipeline over the 4-column groups: the weights of group e + 1 are loaded before the FMAs of group e
+                // The weight loads of output o + 1 are issued before the products of output o, those of output 0 before the wait for
+                // the accumulator block: a shared-memory load issued right before its use waited ~40 % of this phase's cycles (the
+                // MMA operand reads and the TMA writes of the other item's layer keep the shared-memory pipe busy).
+                uint32_t d[16];
+                tc_ld16(dacc + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, d);
+                float4 wn[4];
+                load_w(wn, 0, col0);
+                tc_wait_ld();
+                float2 a2[8];
 #pragma unroll
-                for (int oh = 0; oh < MMAX; oh += 5) {
-                    if (oh < m) {
-                        float4 wc[5], wn[5];
+                for (int e = 0; e < 4; ++e) {
+                    a2[2 * e] = make_float2(fmaxf(__uint_as_float(d[4 * e]) + bb[e].x, 0.f), fmaxf(__uint_as_float(d[4 * e + 1]) + bb[e].y, 0.f));
+                    a2[2 * e + 1] = make_float2(fmaxf(__uint_as_float(d[4 * e + 2]) + bb[e].z, 0.f), fmaxf(__uint_as_float(d[4 * e + 3]) + bb[e].w, 0.f));
+                }
 #pragma unroll
-                        for (int o = 0; o < 5; ++o) wc[o] = *reinterpret_cast<const float4*>(sWout + (oh + o) * 256 + col0);
+                for (int o = 0; o < MMAX; ++o) {
+                    if (o < m) {
+                        float4 wc[4];
 #pragma unroll
-                        for (int e = 0; e < 16; e += 4) {
-                            if (e + 4 < 16) {
+                        for (int e = 0; e < 4; ++e) wc[e] = wn[e];
+                        if (o + 1 < m) load_w(wn, o + 1, col0);
+                        float2 acc = po2[o];
 #pragma unroll
-                                for (int o = 0; o < 5; ++o)
-                                    wn[o] = *reinterpret_cast<const float4*>(sWout + (oh + o) * 256 + col0 + e + 4);
-                            }
-#pragma unroll
-                            for (int o = 0; o < 5; ++o) {
-                                float acc = po[oh + o];
-                                acc = fmaf(a[e], wc[o].x, acc);
-                                acc = fmaf(a[e + 1], wc[o].y, acc);
-                                acc = fmaf(a[e + 2], wc[o].z, acc);
-                                acc = fmaf(a[e + 3], wc[o].w, acc);
-                                po[oh + o] = acc;
-                            }
-                            if (e + 4 < 16) {
-#pragma unroll
-                                for (int o = 0; o < 5; ++o) wc[o] = wn[o];
-                            }
+                        for (int e = 0; e < 4; ++e) {
+                            acc = __ffma2_rn(a2[2 * e], make_float2(wc[e].x, wc[e].y), acc);
+                            acc = __ffma2_rn(a2[2 * e + 1], make_float2(wc[e].z, wc[e].w), acc);
                         }
+                        po2[o] = acc;
                     }
                 }
-#else
-#pragma unroll
-                for (int oh = 0; oh < MMAX; oh += 5) {
-                    if (oh < m) {
-#pragma unroll
-                        for (int e = 0; e < 16; e += 4) {
-                            float4 w4[5];
-#pragma unroll
-                            for (int o = 0; o < 5; ++o)
-                                w4[o] = *reinterpret_cast<const float4*>(sWout + (oh + o) * 256 + col0 + e);  // rows >= m: unused, in bounds
-#pragma unroll
-                            for (int o = 0; o < 5; ++o) {
-                                float acc = po[oh + o];
-                                acc = fmaf(a[e], w4[o].x, acc);
-                                acc = fmaf(a[e + 1], w4[o].y, acc);
-                                acc = fmaf(a[e + 2], w4[o].z, acc);
-                                acc = fmaf(a[e + 3], w4[o].w, acc);
-                                po[oh + o] = acc;
-                            }
-                        }
-                    }
-                }
-#endif
             }
+            float po[MMAX];
+#pragma unroll
+            for (int o = 0; o < MMAX; ++o) po[o] = po2[o].x + po2[o].y;
             PROF_MARK(4);  // epilogues
-#if D4S_EXP & 32
             if (fused_sums) {
                 // The sums over the observations are LINEAR in the output-layer partials: S1 = -1/sigma sum_rows sum_quarters (po + b),
                 // S2 = -1/sigma sum_rows Q_j sum_quarters (po + b).  Every thread applies inv(Sigma_j) to its own partial (bias added by
-                // quarter 0), the lanes of one sample are reduced with a segmented shuffle tree, the segment heads park 10 floats per
-                // (warp, sample) and a fixed-order sum over at most (quarters x lane quarters) slots finishes -- no per-row scores in
-                // shared memory, one barrier instead of four.
+                // quarter 0), the lanes of one sample are reduced with shuffles, 10 floats per (warp, sample) are parked and a
+                // fixed-order sum over the column quarters finishes -- no per-row scores in shared memory, one barrier instead of four.
                 const int si = sRowSi[row], oj = sRowOj[row];
                 const bool in_tile = si != 255;
                 float val[10];
@@ -934,19 +858,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         }
                     }
                 }
-                const int reach = in_tile ? min(31 - lane, p.OC - 1 - oj) : 0;  // lanes after this one that hold the same sample
+                // Sum over the RS lanes of a sample (an aligned power-of-two segment of the warp; padding rows hold zeros) by recursive
+                // halving: at distance d the lower lanes keep the lower half of the value slots and receive the partner's, the upper
+                // lanes the upper half -- 8 + 4 + 2 + 1 (+ 1) shuffles for 16 slots (10 used) instead of 10 per tree level, and the
+                // order depends only on a row's offset inside its segment (=> independent of the sample's slot in the tile).
+                float v[16];
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
+                for (int e = 0; e < 16; ++e) v[e] = e < 10 ? val[e] : 0.f;
+                int prefix = 0, cnt = 16;  // this lane ends up with slots prefix * cnt .. prefix * cnt + cnt - 1
 #pragma unroll
-                    for (int e = 0; e < 10; ++e) {
-                        const float t = __shfl_down_sync(0xffffffffu, val[e], off);
-                        if (off <= reach) val[e] += t;
+                for (int k = 0; k < 4; ++k) {
+                    const int dist = p.RS >> (k + 1);
+                    if (dist > 0) {
+                        const bool upper = (lane & dist) != 0;
+#pragma unroll
+                        for (int i = 0; i < (8 >> k); ++i) {
+                            const float send = upper ? v[i] : v[(8 >> k) + i];
+                            const float keep = upper ? v[(8 >> k) + i] : v[i];
+                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, dist);
+                        }
+                        prefix = 2 * prefix + (upper ? 1 : 0);
+                        cnt = 8 >> k;
                     }
                 }
-                if (in_tile && (oj == 0 || lane == 0)) {  // head of a segment: sample si, lane quarter q, column quarter cq
-                    float* dst = sS + (((q * 4 + cq) * TC_SG_MAX) + (si - (32 * q) / p.RS)) * 10;
+                if (p.RS == 32) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);  // (one slot per lane pair left)
+                // (the lane that ends up with a slot may be a padding row of its sample: what counts is the segment, not the lane)
+                const int seg = lane / p.RS;  // segment of this lane inside the warp = sample (32 q) / RS + seg of the tile
+                if ((32 * q) / p.RS + seg < p.SG && (p.RS < 32 || (lane & 1) == 0)) {  // lane quarter q, column quarter cq
+                    float* dst = sS + (((q * 4 + cq) * TC_SG_MAX) + seg) * 10;
 #pragma unroll
-                    for (int e = 0; e < 10; ++e) dst[e] = val[e];
+                    for (int j = 0; j < 16; ++j) {
+                        const int e = prefix * cnt + j;
+                        if (j < cnt && e < 10) dst[e] = v[j];
+                    }
                 }
                 tc_fence_before();
                 PROF_MARK(11);  // per-thread contributions + segmented shuffle tree (the barrier wait below stays in slot 5)
@@ -966,7 +910,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 PROF_MARK(5);
                 return;
             }
-#endif
             // ---- scores: the column quarters 1..3 park their partial dot products in sS / sQS / sBase (free here), quarter 0
             // adds them up as (q0 + q1) + (q2 + q3), s = -(eps + b) / sigma, and applies inv(Sigma_j) to its row's score.
             // (when layer 0 of the next pass ran just before this epilogue, other warps may still be reading sBase there:
@@ -1071,11 +1014,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 // layer 0 of this pass goes first when it does not depend on the previous pass: interleaved groups, or a
                 // later observation chunk of the same item (its sample part was recomputed at the end of the last pass)
                 const bool early = have && (defer || chunk > 0);
-#if D4S_EXP & 16
                 const bool have_pre = !obs_in_regs && early && (ps == 0 || Lh < 2) && lane < p.OC && p.fin.ctx_samples == 0;
-#else
-                const bool have_pre = !obs_in_regs && early && lane < p.OC && p.fin.ctx_samples == 0;
-#endif
                 if (have_pre) l0_load(upre, j0, nobs, lane);  // layer 0 follows the wait directly: hide its global loads
                 if (prev) {  // the last layer of the previous pass: once it is done the operand images are free again
                     inv_sigma_prev = __ldg(p.sched + (size_t)step_of(pit) * D4S_SCHED_STRIDE + D4S_S_INV_SIGMA);
@@ -1086,12 +1025,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     tc_fence_after();
                     PROF_MARK(3);  // waiting for the tensor core
                 }
-#if D4S_EXP & 16
                 const bool l0_early = Lh >= 2;  // the operand image in shared memory is free once layer 1 has completed
                 if (early && (ps == 0 || !l0_early)) {
-#else
-                if (early) {
-#endif
                     do_layer0(i0g(gi), nsg(gi), j0, nobs, upre, have_pre || obs_in_regs);
                     PROF_MARK(1);  // layer 0
                 }
@@ -1146,7 +1081,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                             }
                             float a[16];
                             ld_act(dacc, col0, bcur, a);
-#if D4S_EXP & 8
                             {   // next layer's A operand goes back to TENSOR MEMORY, in place over the 16 accumulator columns just
                                 // read: columns col0 .. +7 = bf16 hi of K elements col0 .. col0 + 15, columns +8 .. +15 = lo
                                 uint32_t w[16];
@@ -1158,35 +1092,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                                     split8_regs(v, w + 4 * k8, w + 8 + 4 * k8);
                                 }
                                 tc_st16(dacc + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, w);
-#if D4S_EXP & 64
                                 tc_wait_st();
                                 tc_fence_before();
                                 mbar_arrive(bar_c(cb));
-#endif
                             }
-#else
-#pragma unroll
-                            for (int k8 = 0; k8 < 2; ++k8) {
-                                float v[8];
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) v[e] = a[8 * k8 + e];
-                                store_split8(v, sAhi, sAlo, a_off(row, (col0 >> 3) + k8));
-                            }
-#endif
                             if (cb + 1 < nblk) {
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) bcur[e] = bnxt[e];
                             }
                         }
-#if !(D4S_EXP & 64)
-#if D4S_EXP & 8
-                        tc_wait_st();
-#else
-                        fence_proxy_async();
-#endif
-                        tc_fence_before();
-                        mbar_arrive(bar_a);
-#endif
                         PROF_MARK(4);  // epilogues
                     }
                 }
@@ -1194,27 +1108,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     do_base(th, false, step_of(it), 0);
                     compute_bar();
                     PROF_MARK(0);
-#if D4S_EXP & 16
                     if (l0_early) {  // its layer 0 now, under the last tensor-core layer of this chunk
                         const int nj0 = (chunk + 1) * p.OC;
                         do_layer0(i0g(gi), nsg(gi), nj0, min(p.OC, p.n - nj0), upre, false);
                         PROF_MARK(1);
                     }
-#endif
                 }
                 if (defer) {
-#if D4S_EXP & 16
                     const bool pre_next = !obs_in_regs && l0_early && ps + 1 < total_p && lane < p.OC && p.fin.ctx_samples == 0;
                     TRACE(23);
                     if (pre_next) l0_load(upre, 0, min(p.OC, p.n), lane);  // obs_feat rows of the next item's layer 0: latency hidden
-#endif
                     TRACE(24);
                     if (prev) {
                         if (!fused_sums) do_sums(nsg(pgi), 0, pnobs, true);
                         TRACE(25);
-#if !(D4S_EXP & 4)
                         compute_bar();  // (redundant: every compute thread also takes part in barrier 3 below)
-#endif
                         PROF_MARK(6);
                         bar_sync(3, NB23);  // schedule / matrix rows, prior terms and noise of the previous item are in smem
                         PROF_MARK(2);  // (time spent waiting for the helper warp)
@@ -1233,12 +1141,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         do_base(sTheta + (gi ^ 1) * TC_SG_MAX * MMAX, true, 0, step_of(it + 2));
                         compute_bar();
                         PROF_MARK(0);
-#if D4S_EXP & 16
                         if (l0_early) {  // layer 0 of the next item now, under the last tensor-core layer of this one
                             do_layer0(i0g(gi ^ 1), nsg(gi ^ 1), 0, min(p.OC, p.n), upre, pre_next || obs_in_regs);
                             PROF_MARK(1);
                         }
-#endif
                     }
                 }
             }  // passes

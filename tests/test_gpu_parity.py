@@ -327,7 +327,11 @@ def test_full_size_trajectory_properties(dev):
                                    (4, 6, (128, 256), 12, 1190, "gaussian"), (10, 10, (256, 256), 30, 700, "gaussian"),
                                    # one short tensor-core layer, 8 samples per tile: the shape that exposed a shared-memory
                                    # race between layer 0 of the next item and the scores scratch of the previous one
-                                   (3, 8, (64, 64), 9, 1500, "gaussian")],
+                                   (3, 8, (64, 64), 9, 1500, "gaussian"),
+                                   # fused per-sample sums with padding rows inside a sample's 32-row block: the lane that ends up
+                                   # with a result slot of the shuffle reduction is a padding row (n = 17, 18), or not (n = 26)
+                                   (5, 8, (256, 256), 17, 600, "uniform"), (4, 6, (128, 256), 18, 700, "gaussian"),
+                                   (5, 8, (256, 128), 26, 900, "uniform")],
                          ids=lambda s: f"m{s[0]}_n{s[3]}_N{s[4]}_{s[5]}")
 def test_tc_group_schedules_agree(shape, dev):
     """The tcgen05 trajectory kernel interleaves two sample groups per CTA when a CTA owns several (N > 148 groups):
