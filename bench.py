@@ -76,8 +76,9 @@ def parse():
     ap.add_argument("--stress-n-obs", type=int, default=10000)
     ap.add_argument("--no-obs-sharded", action="store_true", help="skip the observation-sharded stress record")
     ap.add_argument("--no-sweep", action="store_true", help="skip the n_obs sweep and the JAC sub-record (1 GPU only)")
-    ap.add_argument("--jac-tc", action="store_true",
-                    help="JAC steps on the opt-in tcgen05 score + Jacobian kernel (fp16x3) instead of the fp32 SIMT kernel")
+    ap.add_argument("--jac-simt", action="store_true",
+                    help="JAC steps on the fp32 SIMT kernel instead of the default tcgen05 score + Jacobian kernel (fp16x3)")
+    ap.add_argument("--jac-tc", action="store_true", help="(accepted for older scripts: the tcgen05 JAC kernel is the default)")
     return ap.parse_args()
 
 
@@ -167,7 +168,7 @@ def config_dict(args, w, world):
                         f"samples per GPU, DDIM {w['ddim_steps']} steps eta={w['eta']}, {args.cov_mode}, "
                         f"{w['prior_kind']} prior; one bench step = one full trajectory",
             "n_obs": w["n"], "samples_per_gpu": args.samples, "ddim_steps": w["ddim_steps"], "cov_mode": args.cov_mode,
-            "jac_kernel": ("tcgen05 fp16x3 (opt-in)" if getattr(args, "jac_tc", False) else "fp32 SIMT") if args.cov_mode == "JAC" else None,
+            "jac_kernel": ("fp32 SIMT (--jac-simt)" if getattr(args, "jac_simt", False) else "tcgen05 fp16x3") if args.cov_mode == "JAC" else None,
             "parallelism": f"samples sharded over {world} GPU(s), no collective",
             "l2": "256 MiB buffer written between timed trajectories (L2 flush)"}
 
@@ -617,8 +618,19 @@ def jac_record(args, dev, peaks):
     flops = float(N) * w["n_units"] * flops_per_pair(w) * ((1 + m) * gate + (w["ddim_steps"] - gate))
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     ach = flops / (ms * 1e-3) / 1e12
+    from d4s import _cabi as abi
+    simt_rate = None
+    if not getattr(args, "jac_simt", False):  # the same trajectory with the Jacobian steps on the fp32 SIMT kernel, for comparison
+        abi.set_option("jac_tc", 0)
+        try:
+            simt_rate = trajectory_rate(args, dev, args.n_obs, "JAC", reps=1)[0]
+        finally:
+            abi.set_option("jac_tc", 1)
     rec = {"value": rate, "unit": "samples/s", "ms_per_trajectory": ms, "ddim_steps": w["ddim_steps"], "eta": w["eta"],
            "gpu_launches_per_trajectory": launches, "jacobian_steps": gate,
+           "jac_kernel": "fp32 SIMT (--jac-simt)" if getattr(args, "jac_simt", False) else
+                         "jac_tc_kernel (tcgen05 kind::f16, fp16x3 split, cross terms accumulated first, forward-mode tangent rows)",
+           "fp32_simt_jac_kernel_samples_per_s": simt_rate,
            "e2e": {"value": e2e_rate, "unit": "samples/s"},
            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                         "flops_per_trajectory": flops,
@@ -654,8 +666,8 @@ def run_ours(args):
 
     w = workload(args)
     N, m, n = args.samples, w["m"], w["n"]
-    if getattr(args, "jac_tc", False):
-        abi.set_option("jac_tc", 1)
+    if getattr(args, "jac_simt", False):
+        abi.set_option("jac_tc", 0)
     nse = build_nse(w, dev)
     # host (pinned) copies of the inputs for the e2e leg
     x_h = torch.as_tensor(w["x"]).pin_memory()
@@ -812,7 +824,7 @@ def run_ours(args):
             roofline = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                         "traffic": None,
                         "kernel": ("jac_tc_kernel (tcgen05 kind::f16, fp16x3 split, forward-mode tangent rows)"
-                                   if (args.cov_mode == "JAC" and getattr(args, "jac_tc", False))
+                                   if (args.cov_mode == "JAC" and not getattr(args, "jac_simt", False))
                                    else "score_simt_kernel (fp32 SIMT; forward-mode tangents in JAC)"),
                         "peak_source": src, "flops_per_launch": flops_step, "launch_ms": k1_ms,
                         "finalize_launch_ms": k3_ms,

@@ -21,7 +21,7 @@ static int g_opt_path = 0;      // 0 auto, 1 SIMT per-step kernels only, 2 requi
 static int g_opt_tc_steps = 0;  // > 0: DDIM steps per tcgen05 launch (0 = whole trajectory in one launch)
 static int* g_err_flag = nullptr;
 static int g_opt_profile = 0;
-static int g_opt_jac_tc = 0;      // 1: JAC steps on the tcgen05 score + Jacobian kernel (fp16x3; faster, looser parity)
+static int g_opt_jac_tc = 1;      // 1 (default): JAC steps on the tcgen05 score + Jacobian kernel where eligible (fp16x3 split); 0: fp32 SIMT kernel
 static int g_opt_tc_pairing = 1;  // interleave two sample groups per CTA in the tcgen05 kernel (0 = one after the other)
 static long long* g_prof = nullptr;
 

@@ -21,6 +21,10 @@
 #include "d4s_finalize_core.cuh"
 #include "d4s_tc_common.cuh"
 
+#ifndef JT_TWO_PASS
+#define JT_TWO_PASS 1
+#endif
+
 namespace d4s {
 
 constexpr int JT_THREADS = (TC_CW + 4) * 32;  // 640: 16 compute warps + TMA producer + MMA issuer + 2 idle (full warpgroup)
@@ -48,7 +52,8 @@ constexpr int JOFF_PAIR = JOFF_H + TC_CW * 8 * 16 * 4;        // float [32][m + 
 constexpr int JOFF_TH = JOFF_PAIR + JT_PMAX * JT_WMAX * 4;    // float [2][32][m] theta of the pair's sample
 constexpr int JOFF_PI = JOFF_TH + 2 * JT_PMAX * JT_MMAX * 4;  // int [2][32] sample of the pair (-1: empty slot)
 constexpr int JOFF_PJ = JOFF_PI + 2 * JT_PMAX * 4;            // int [2][32] observation of the pair
-constexpr int JOFF_BOUT = JOFF_PJ + 2 * JT_PMAX * 4;          // float [8]
+constexpr int JOFF_PS = JOFF_PJ + 2 * JT_PMAX * 4;            // float [2][32] power-of-two scale of the pair's primal row
+constexpr int JOFF_BOUT = JOFF_PS + 2 * JT_PMAX * 4;          // float [8]
 constexpr int JOFF_BAR = JOFF_BOUT + 32;                      // mbarriers
 constexpr int JOFF_TMEM = JOFF_BAR + (2 * JT_NSTG + 2) * 8;
 constexpr int JT_SMEM_BYTES = JOFF_TMEM + 16;
@@ -99,6 +104,7 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
     float* sTh = reinterpret_cast<float*>(smem + JOFF_TH);
     int* sPI = reinterpret_cast<int*>(smem + JOFF_PI);
     int* sPJ = reinterpret_cast<int*>(smem + JOFF_PJ);
+    float* sPS = reinterpret_cast<float*>(smem + JOFF_PS);
     float* sBout = reinterpret_cast<float*>(smem + JOFF_BOUT);
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem + JOFF_TMEM);
     const uint32_t bar0 = smem_u32(smem + JOFF_BAR);
@@ -178,12 +184,16 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                     const int K = net.Hp[l - 1], Nn = net.Hp[l];
                     const uint32_t bytes = (uint32_t)Nn * 64u;
                     const uint8_t* src = net.wimg16[l];  // fp16 hi | lo
-                    for (int ks = 0; ks < K / 16; ++ks, ++it) {
-                        const int s = it % JT_NSTG;
-                        const uint32_t ph = (it / JT_NSTG) & 1u;
-                        mbar_wait(bar_empty(s), ph ^ 1u, p.error_flag);
-                        mbar_expect_tx(bar_full(s), bytes);
-                        tma_bulk_g2s(smem_u32(smem + JOFF_RING + s * TC_STAGE_BYTES), src + (size_t)ks * bytes, bytes, bar_full(s));
+                    // two passes over K (see the MMA issuer): cross terms first (hi | lo images), then the main terms (hi image only)
+                    for (int pass = 0; pass < (JT_TWO_PASS ? 2 : 1); ++pass) {
+                        const uint32_t nb = (JT_TWO_PASS && pass == 1) ? bytes / 2 : bytes;
+                        for (int ks = 0; ks < K / 16; ++ks, ++it) {
+                            const int s = it % JT_NSTG;
+                            const uint32_t ph = (it / JT_NSTG) & 1u;
+                            mbar_wait(bar_empty(s), ph ^ 1u, p.error_flag);
+                            mbar_expect_tx(bar_full(s), nb);
+                            tma_bulk_g2s(smem_u32(smem + JOFF_RING + s * TC_STAGE_BYTES), src + (size_t)ks * bytes, nb, bar_full(s));
+                        }
                     }
                 }
             }
@@ -208,20 +218,28 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                     tc_fence_after();
                     const uint32_t dacc = tmem_d + ((lc & 1u) ? 256u : 0u);
                     ++lc;
-                    for (int ks = 0; ks < K / 16; ++ks, ++it) {
-                        const int s = it % JT_NSTG;
-                        const uint32_t ph = (it / JT_NSTG) & 1u;
-                        mbar_wait(bar_full(s), ph, p.error_flag);
-                        tc_fence_after();
-                        const uint32_t wb = smem_u32(smem + JOFF_RING + s * TC_STAGE_BYTES);
-                        const uint64_t b_hi = umma_desc(wb, b_lbo, b_sbo);
-                        const uint64_t b_lo = umma_desc(wb + (uint32_t)Nn * 32u, b_lbo, b_sbo);
-                        const uint64_t a_hi = umma_desc(a_hi0 + ks * 4096, a_lbo, a_sbo);
-                        const uint64_t a_lo = umma_desc(a_lo0 + ks * 4096, a_lbo, a_sbo);
-                        tc_mma_bf16(dacc, a_lo, b_hi, idesc, ks > 0 ? 1u : 0u);  // small terms first
-                        tc_mma_bf16(dacc, a_hi, b_lo, idesc, 1u);
-                        tc_mma_bf16(dacc, a_hi, b_hi, idesc, 1u);
-                        tc_commit(bar_empty(s));
+                    // The tensor core truncates when it adds into the accumulator: every accumulating instruction loses a fraction of an
+                    // ulp of the RUNNING SUM.  All cross terms (2^-11 of the result) are therefore summed first, while the accumulator
+                    // is still small, and the K / 16 main-term instructions follow: a third as many truncations at full magnitude (the
+                    // remaining, now uniform, deficit is what acc_debias() corrects in the epilogues).  Costs one more pass of the hi images.
+                    for (int pass = 0; pass < (JT_TWO_PASS ? 2 : 1); ++pass) {
+                        for (int ks = 0; ks < K / 16; ++ks, ++it) {
+                            const int s = it % JT_NSTG;
+                            const uint32_t ph = (it / JT_NSTG) & 1u;
+                            mbar_wait(bar_full(s), ph, p.error_flag);
+                            tc_fence_after();
+                            const uint32_t wb = smem_u32(smem + JOFF_RING + s * TC_STAGE_BYTES);
+                            const uint64_t b_hi = umma_desc(wb, b_lbo, b_sbo);
+                            const uint64_t b_lo = umma_desc(wb + (uint32_t)Nn * 32u, b_lbo, b_sbo);
+                            const uint64_t a_hi = umma_desc(a_hi0 + ks * 4096, a_lbo, a_sbo);
+                            const uint64_t a_lo = umma_desc(a_lo0 + ks * 4096, a_lbo, a_sbo);
+                            if (!JT_TWO_PASS || pass == 0) {
+                                tc_mma_bf16(dacc, a_lo, b_hi, idesc, ks > 0 ? 1u : 0u);
+                                tc_mma_bf16(dacc, a_hi, b_lo, idesc, 1u);
+                            }
+                            if (!JT_TWO_PASS || pass == 1) tc_mma_bf16(dacc, a_hi, b_hi, idesc, 1u);
+                            tc_commit(bar_empty(s));
+                        }
                     }
                     tc_commit(bar_d);
                 }
@@ -256,6 +274,19 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                 }
                 sPI[buf * JT_PMAX + tid] = i;
                 sPJ[buf * JT_PMAX + tid] = j;
+                // The fp16 operands hold |value| < 65504 / 2^4.  A primal row is positively homogeneous in its activations (ReLU;
+                // biases scaled alongside), so a sample far outside the usual range of normalised parameters (max |theta_k| > 16:
+                // diverged trajectories of untrained nets) runs with its primal row scaled by a power of two and is unscaled
+                // after the output layer; tangent rows are derivatives and do not scale.  |theta| <= 16: scale 1, nothing changes.
+                float mx = 0.f;
+                if (i >= 0)
+                    for (int k = 0; k < m; ++k) mx = fmaxf(mx, fabsf(__ldg(p.theta + (size_t)i * m + k)));
+                int ex = 0;
+                if (mx > 16.f && mx < 3.0e38f) {
+                    (void)frexpf(mx, &ex);  // mx = f 2^ex, f in [0.5, 1)
+                    ex -= 4;
+                }
+                sPS[buf * JT_PMAX + tid] = ldexpf(1.f, -ex);
             }
             for (int e = tid; e < PT * m; e += TC_CT) {
                 const int pp = e / m, k = e - pp * m;
@@ -272,6 +303,7 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
             const int pp = lane;
             const int i = (pp < PT) ? sPI[buf * JT_PMAX + pp] : -1;
             if (i >= 0) {
+                const float psc = sPS[buf * JT_PMAX + pp];
                 const int j = sPJ[buf * JT_PMAX + pp];
                 const int prow = 32 * (pp / PW) + (pp % PW) * R;  // tile row of the pair's primal
                 const float* up = p.obs_feat + (size_t)j * H0;
@@ -315,7 +347,7 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                             mw[e] = (z[2 * e] > 0.f ? 0x0000FFFFu : 0u) | (z[2 * e + 1] > 0.f ? 0xFFFF0000u : 0u);
                         float v[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = fmaxf(z[e], 0.f);
+                        for (int e = 0; e < 8; ++e) v[e] = fmaxf(z[e], 0.f) * psc;
                         store_split8_f16(v, sAhi, sAlo, a_off(prow, kg));
 #pragma unroll
                         for (int k = 0; k < JT_MMAX; ++k) {
@@ -347,7 +379,7 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
         };
         // one 16-column block of an accumulator row.  Primal: x = d + bias, a = relu(x).  Tangent: a = d * [x_primal > 0].
         // `hval` = what the indicator holds for an active unit: 2^-sw16[l] (operand of the next layer) or 1 (last layer).
-        auto ld_act = [&](uint32_t dacc, int col0, const float* bias16, float hval, float (&a)[16]) {
+        auto ld_act = [&](uint32_t dacc, int col0, const float* bias16, float hval, float deb, float psb, float (&a)[16]) {
             uint32_t d[16];
             tc_ld16(dacc + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, d);
             float4 bb[4];
@@ -357,10 +389,10 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
             float x[16];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                x[4 * e] = fmaf(bb[e].x, bsel, __uint_as_float(d[4 * e]));
-                x[4 * e + 1] = fmaf(bb[e].y, bsel, __uint_as_float(d[4 * e + 1]));
-                x[4 * e + 2] = fmaf(bb[e].z, bsel, __uint_as_float(d[4 * e + 2]));
-                x[4 * e + 3] = fmaf(bb[e].w, bsel, __uint_as_float(d[4 * e + 3]));
+                x[4 * e] = fmaf(bb[e].x, psb, __uint_as_float(d[4 * e]) * deb);
+                x[4 * e + 1] = fmaf(bb[e].y, psb, __uint_as_float(d[4 * e + 1]) * deb);
+                x[4 * e + 2] = fmaf(bb[e].z, psb, __uint_as_float(d[4 * e + 2]) * deb);
+                x[4 * e + 3] = fmaf(bb[e].w, psb, __uint_as_float(d[4 * e + 3]) * deb);
             }
             __syncwarp();  // the previous block's indicators have been read by every lane
             if (bsel != 0.f) {
@@ -382,18 +414,21 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
         };
         // epilogue of the last hidden layer + output layer (fp32) -> sOut[row][o]: score of the primal row, column k of
         // d eps / d theta for tangent row k
-        auto do_last_epilogue = [&](uint32_t dacc) {
+        auto do_last_epilogue = [&](uint32_t dacc, int buf) {
+            const float prs = rvalid ? sPS[buf * JT_PMAX + q * PW + pl] : 1.f;  // scale of this row's pair (primal rows use it)
+            const float psb = bsel * prs, inv_prs = 1.f / prs;
             const int Nn = net.Hp[L - 2];
             const int qcols = Nn >> 2, nblk = qcols / 16;
             const float* bias_l = net.bias16[L - 2] + cq * qcols;
             const float uns = exp2f(-(float)(D4S_ACT_SHIFT16 + net.sw16[L - 2]));  // accumulator scale of the last hidden layer
+            const float deb_last = acc_debias(net.Hp[L - 3]);  // (truncating accumulation of the tensor core, d4s_tc_common.cuh)
             float po[JT_MMAX];
 #pragma unroll
             for (int o = 0; o < JT_MMAX; ++o) po[o] = 0.f;
             for (int cb = 0; cb < nblk; ++cb) {
                 const int col0 = cq * qcols + 16 * cb;
                 float a[16];
-                ld_act(dacc, col0, bias_l + 16 * cb, 1.f, a);
+                ld_act(dacc, col0, bias_l + 16 * cb, 1.f, deb_last, psb, a);
 #pragma unroll
                 for (int e = 0; e < 16; e += 4) {
                     float4 w4[JT_MMAX];
@@ -424,7 +459,7 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                         const float v = uns * ((po[o] + sRed[row * JT_MMAX + o]) +
                                                (sRed[(TC_M + row) * JT_MMAX + o] + sRed[(2 * TC_M + row) * JT_MMAX + o]));
                         // primal: score = -(eps + b) / sigma (nse.py:166); tangent k: d eps_o / d theta_k
-                        sOut[row * m + o] = (rc == 0) ? -(v + sBout[o]) * inv_sigma : v;
+                        sOut[row * m + o] = (rc == 0) ? -(v * inv_prs + sBout[o]) * inv_sigma : v;
                     }
                 }
             }
@@ -482,13 +517,15 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                 tc_fence_after();
             }
             if (have) do_layer0(buf);
-            if (prev) do_last_epilogue(dacc_prev);
+            if (prev) do_last_epilogue(dacc_prev, buf ^ 1);
             if (have) {
                 for (int l = 1; l < Lh; ++l) {  // hidden layers that feed another tensor-core layer
                     const int Nn = net.Hp[l];
                     const int qcols = Nn >> 2, nblk = qcols / 16;
                     const float* bias_l = net.bias16[l] + cq * qcols;
                     const float hval = exp2f(-(float)net.sw16[l]);
+                    const float deb_l = acc_debias(net.Hp[l - 1]);
+                    const float psb_cur = bsel * (rvalid ? sPS[buf * JT_PMAX + q * PW + pl] : 1.f);
                     const uint32_t dacc = tmem_d + ((d_cnt & 1u) ? 256u : 0u);
                     mbar_wait(bar_d, d_cnt & 1u, p.error_flag);
                     ++d_cnt;
@@ -496,7 +533,7 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                     for (int cb = 0; cb < nblk; ++cb) {
                         const int col0 = cq * qcols + 16 * cb;
                         float a[16];
-                        ld_act(dacc, col0, bias_l + 16 * cb, hval, a);
+                        ld_act(dacc, col0, bias_l + 16 * cb, hval, deb_l, psb_cur, a);
 #pragma unroll
                         for (int k8 = 0; k8 < 2; ++k8) {
                             float v[8];

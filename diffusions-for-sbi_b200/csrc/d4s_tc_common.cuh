@@ -211,6 +211,19 @@ __device__ __forceinline__ void store_split8_f16(const float (&v)[8], uint8_t* a
     *reinterpret_cast<uint4*>(a_lo + byte_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// The tensor core accumulates by TRUNCATION: every tcgen05.mma that adds into an fp32 accumulator loses, on average, a fixed
+// fraction of an ulp of the running sum, always towards zero -- a systematic relative deficit of the result that grows with the
+// number of accumulating instructions at full magnitude.  Measured on the JAC fixtures, where inv(I - sigma J) amplifies it: the
+// error of the Jacobian sums is linear in a correction factor c and vanishes at c = +600 .. +900 ppb (K = 256) when the three
+// products of a K-step are accumulated together (48 instructions per layer), at c = +250 ppb when only the K / 16 main-term
+// instructions run at full magnitude (d4s_jac_tc.cu; profiles/r02_jac_tc_notes.md).  The JAC kernel's epilogues multiply the
+// accumulator by 1 + c K / 256; the GAUSS trajectory kernel does not (its error is the bf16x3 product truncation, the correction
+// changes nothing measurable there).
+#ifndef D4S_ACC_DEBIAS_PPB
+#define D4S_ACC_DEBIAS_PPB 250
+#endif
+__device__ __forceinline__ float acc_debias(int K) { return 1.f + (1e-9f * D4S_ACC_DEBIAS_PPB / 256.f) * (float)K; }
+
 // byte offset of (row r, k-group kg of 8 columns) inside an A image: K16 step = kg/2, half = kg%2
 __device__ __forceinline__ int a_off(int r, int kg) { return (kg >> 1) * 4096 + (kg & 1) * 2048 + r * 16; }
 

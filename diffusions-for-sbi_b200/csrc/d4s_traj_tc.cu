@@ -419,7 +419,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
         // ================= TMA producer: streams the weight images in consumption order ===========================
         if (lane == 0) {
             unsigned it = 0;
+            int tr_n = 0;
+            bool tr_go = false;
+            (void)tr_n; (void)tr_go;
             for (long long ti = 0; ti < tile_iters; ++ti) {
+                tr_go = blockIdx.x == 0 && p.trace != nullptr && ti >= TRACE_FROM && ti < TRACE_TO;
                 for (int l = 1; l <= L - 2; ++l) {
                     const int K = net.Hp[l - 1], Nn = net.Hp[l];
                     const uint32_t bytes = (uint32_t)Nn * 64u;
@@ -429,6 +433,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         const int s = it % TC_NSTG;
                         const uint32_t ph = (it / TC_NSTG) & 1u;
                         mbar_wait(bar_empty(s), ph ^ 1u, p.error_flag);
+                        TRACE(60 + l);  // ring slot free = the MMAs of the K-step 4 stages back have completed
                         mbar_expect_tx(bar_full(s), bytes);
                         tma_bulk_g2s(smem_u32(smem + OFF_RING + s * TC_STAGE_BYTES), src + (size_t)ks * bytes, bytes,
                                      bar_full(s));

@@ -164,9 +164,9 @@ def load():
             fn.argtypes = args
         if lib.d4s_abi_version() != ABI_VERSION:
             raise D4sError(f"libd4s ABI {lib.d4s_abi_version()} != binding {ABI_VERSION}: rebuild the library")
-        if os.environ.get("D4S_JAC_TC", "0") == "1":  # opt in to the tensor-core JAC kernel for the whole process
-            lib.d4s_set_option(b"jac_tc", 1)
-            _options["jac_tc"] = 1
+        if os.environ.get("D4S_JAC_TC", "1") == "0":  # opt out of the tensor-core JAC kernel for the whole process (fp32 SIMT instead)
+            lib.d4s_set_option(b"jac_tc", 0)
+            _options["jac_tc"] = 0
         _lib = lib
     return _lib
 

@@ -53,6 +53,12 @@ for e in range(nev):
     print(f"  {names.get(tag, str(tag)):12s} min {min(ts):7d}  max {max(ts):7d}  warp0 {ts[0]:7d}  spread {max(ts) - min(ts):6d}  "
           f"(+{max(ts) - prev_max:6d} after the previous event's slowest warp; slowest = warp {cw[int(np.argmax(ts))]})")
     prev_max = max(ts)
+w = 16
+print("TMA warp: ring slot freed (= MMAs of the K-step 4 stages back completed), deltas in cycles:")
+ts = [int(tr[w, e, 1]) - t0 for e in range(int((tr[w, :, 1] > 0).sum()))]
+tg = [int(tr[w, e, 0]) % 10 for e in range(len(ts))]
+for i in range(0, len(ts), 16):
+    print("  layer", tg[i], "first at", ts[i], " deltas:", " ".join(str(ts[j] - ts[j - 1]) for j in range(max(i, 1), min(i + 16, len(ts)))))
 w = 17
 print("MMA warp:")
 for e in range(int((tr[w, :, 1] > 0).sum())):
