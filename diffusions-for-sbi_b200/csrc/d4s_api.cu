@@ -23,6 +23,10 @@ static int* g_err_flag = nullptr;
 static int g_opt_profile = 0;
 static int g_opt_jac_tc = 1;      // 1 (default): JAC steps on the tcgen05 score + Jacobian kernel where eligible (fp16x3 split); 0: fp32 SIMT kernel
 static int g_opt_tc_pairing = 1;  // interleave two sample groups per CTA in the tcgen05 kernel (0 = one after the other)
+static int g_opt_tc_cta_pair = [] {  // trajectory kernel as CTA pairs (cta_group::2, clusters of 2) where eligible; D4S_TC_CTA_PAIR=0/1
+    const char* e = getenv("D4S_TC_CTA_PAIR");
+    return e ? atoi(e) : 0;
+}();
 static long long* g_prof = nullptr;
 
 static int fail(int code, const std::string& msg) {
@@ -257,7 +261,7 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
     const size_t off_WoutT = reserve((size_t)m * Hp[L - 2]);
     for (int o = 0; o < m; ++o)
         for (int k = 0; k < Kl; ++k) h[off_WoutT + (size_t)o * Hp[L - 2] + k] = d->weight[L - 1][(size_t)o * Kl + k];
-    std::vector<size_t> off_img(L, 0), off_img16(L, 0), off_b16(L, 0);
+    std::vector<size_t> off_img(L, 0), off_img16(L, 0), off_b16(L, 0), off_img2(L, 0);
     std::vector<int> sw16(L, 0);
     for (int l = 1; l <= L - 2; ++l) {
         const int K = d->dims[l], Ho = d->dims[l + 1], Kp = Hp[l - 1], Np = Hp[l];
@@ -279,6 +283,8 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
         const size_t bytes = (size_t)(Kp / 16) * Np * 64;
         off_img[l] = reserve(bytes / 4);
         off_img16[l] = reserve(bytes / 4);
+        off_img2[l] = reserve(bytes / 4);
+        uint16_t* img2 = reinterpret_cast<uint16_t*>(h.data() + off_img2[l]);
         uint16_t* img = reinterpret_cast<uint16_t*>(h.data() + off_img[l]);
         uint16_t* img16 = reinterpret_cast<uint16_t*>(h.data() + off_img16[l]);
         for (int ks = 0; ks < Kp / 16; ++ks)
@@ -293,6 +299,12 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
                         const size_t idx = (size_t)hf * Np * 8 + (size_t)nn * 8 + e;
                         img[base + idx] = hi;
                         img[base + (size_t)Np * 16 + idx] = lo;
+                        {   // CTA-pair image: the K-step split by output rows, [rank][hi | lo][2 K halves][Np / 2 rows][8]
+                            const int hn = Np / 2, rk = nn / hn;
+                            const size_t idx2 = (size_t)rk * Np * 16 + (size_t)hf * hn * 8 + (size_t)(nn - rk * hn) * 8 + e;
+                            img2[base + idx2] = hi;
+                            img2[base + (size_t)hn * 16 + idx2] = lo;
+                        }
                         const float ws = w * wsc;
                         const __half h16 = __float2half_rn(ws);  // fp16 hi / lo: 22 significant bits (JAC kernel)
                         img16[base + idx] = __half_as_ushort(h16);
@@ -348,6 +360,7 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
         nd.emb_bias[l] = net->blob + off_eb[l];
     }
     for (int l = 1; l <= L - 2; ++l) nd.wimg[l] = reinterpret_cast<const uint8_t*>(net->blob + off_img[l]);
+    for (int l = 1; l <= L - 2; ++l) nd.wimg2[l] = reinterpret_cast<const uint8_t*>(net->blob + off_img2[l]);
     for (int l = 1; l <= L - 2; ++l) {
         nd.wimg16[l] = reinterpret_cast<const uint8_t*>(net->blob + off_img16[l]);
         nd.sw16[l] = sw16[l];
@@ -394,7 +407,7 @@ int64_t d4s_workspace_floats(const D4sNet* net, const D4sProblem* pb) {
 // Fills the parameter block of the fused tcgen05 kernel (tile geometry, tables, finalize constants).
 static int fill_traj_params(const D4sNet* net, const D4sProblem* pb, const float* sched, const float* tf, const float* mats,
                             const float* noise, float* theta, TrajParams* out, int* n_ctas, cudaStream_t stream,
-                            int sg_cap = 0) {
+                            int sg_cap = 0, bool allow_pair = false) {
     const NetDev& nd = net->dev;
     TrajParams& p = *out;
     memset(&p, 0, sizeof(p));
@@ -470,6 +483,20 @@ static int fill_traj_params(const D4sNet* net, const D4sProblem* pb, const float
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int groups = (p.N + p.SG - 1) / p.SG;
     *n_ctas = groups < sms ? groups : sms;
+    // CTA pairs (cta_group::2): both CTAs of a pair must run the same number of items, which an even number of sample groups on
+    // an even grid guarantees (group g -> CTA g mod grid); plain fused mode only (whole observation set in one tile, in-kernel
+    // tail: the callers that export partial sums or exchange them between ranks do not allow it); instantiated for the
+    // benchmark tasks' theta_dim; every hidden layer a multiple of 32 wide (N / 2 per CTA, multiple of 16).
+    p.cta_pair = 0;
+    if (allow_pair && g_opt_tc_cta_pair && groups >= 2 && groups % 2 == 0 && p.C == 1 &&
+        (nd.m == 2 || nd.m == 4 || nd.m == 5)) {
+        bool widths_ok = true;
+        for (int l = 1; l <= nd.L - 2; ++l) widths_ok = widths_ok && nd.Hp[l] % 32 == 0 && nd.Hp[l] <= 256;
+        if (widths_ok) {
+            p.cta_pair = 1;
+            *n_ctas &= ~1;
+        }
+    }
     return D4S_OK;
 }
 
@@ -671,7 +698,7 @@ static int enqueue_steps(const D4sNet* net, const D4sProblem* pb0, int steps, co
             if (e - k >= 2 && tc_eligible(net, pb)) {
                 TrajParams tp;
                 int ctas = 0;
-                int rc = fill_traj_params(net, pb, sched, tf, mats, noise, theta, &tp, &ctas, stream);
+                int rc = fill_traj_params(net, pb, sched, tf, mats, noise, theta, &tp, &ctas, stream, 0, true);
                 if (rc) return rc;
                 tp.step_begin = k;
                 tp.step_end = e;
@@ -713,7 +740,7 @@ static int try_traj_tc(const D4sNet* net, const D4sProblem* pb, int steps, const
     }
     TrajParams p;
     int ctas = 0;
-    int rc = fill_traj_params(net, pb, sched, tf, mats, noise, theta, &p, &ctas, stream);
+    int rc = fill_traj_params(net, pb, sched, tf, mats, noise, theta, &p, &ctas, stream, 0, true);
     if (rc) return rc;
     const int per = g_opt_tc_steps > 0 ? g_opt_tc_steps : steps;
     for (int s0 = 0; s0 < steps; s0 += per) {
@@ -767,7 +794,7 @@ int d4s_ddim_run(const D4sNet* net, const D4sProblem* pb, int32_t steps, const f
     key.theta = theta_dev;
     key.affine = affine_dev;
     key.mode_hash = 1469598103934665603ull;
-    for (int v : {g_opt_path, g_opt_tc_steps, g_opt_profile, g_opt_tc_pairing, g_opt_jac_tc})  // a captured graph froze the options it was built with
+    for (int v : {g_opt_path, g_opt_tc_steps, g_opt_profile, g_opt_tc_pairing, g_opt_jac_tc, g_opt_tc_cta_pair})  // a captured graph froze the options it was built with
         key.mode_hash = (key.mode_hash ^ (uint64_t)(uint32_t)v) * 1099511628211ull;
     if (step_mode)
         for (int k = 0; k < steps; ++k) key.mode_hash = (key.mode_hash ^ (uint64_t)(step_mode[k] + 1)) * 1099511628211ull;
@@ -954,6 +981,7 @@ int d4s_set_option(const char* key, int32_t value) {
     else if (k == "profile") g_opt_profile = value;
     else if (k == "tc_pairing") g_opt_tc_pairing = value;
     else if (k == "jac_tc") g_opt_jac_tc = value;
+    else if (k == "tc_cta_pair") g_opt_tc_cta_pair = value;
     else return fail(D4S_ERR_ARG, "unknown option: " + k);
     return D4S_OK;
 }

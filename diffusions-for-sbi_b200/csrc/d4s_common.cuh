@@ -39,6 +39,7 @@ struct NetDev {
     const float* emb_Wt[D4S_MAX_LAYERS];    // [in][out]
     const float* emb_bias[D4S_MAX_LAYERS];  // [out]
     const uint8_t* wimg[D4S_MAX_LAYERS];  // l = 1 .. L-2: bf16 hi/lo UMMA images, [Hp[l-1]/16][hi | lo][2][Hp[l]][8]
+    const uint8_t* wimg2[D4S_MAX_LAYERS];  // the bf16 images again, every K-step split by output rows for a CTA pair: [Hp[l-1]/16][rank][hi | lo][2][Hp[l]/2][8]
     const uint8_t* wimg16[D4S_MAX_LAYERS];  // same layout, fp16 hi / lo of 2^sw16[l] W_l (JAC kernel: fp16x3 split)
     int sw16[D4S_MAX_LAYERS];               // power-of-two weight scale that keeps the fp16 lo parts out of the subnormals
     const float* bias16[D4S_MAX_LAYERS];    // 2^(D4S_ACT_SHIFT16 + sw16[l]) bias_l: the JAC kernel's accumulators are scaled
@@ -109,6 +110,7 @@ struct TrajParams {
     int RS;                  // tile row of (sample si, observation oj) = si * RS + oj; RS == OC, or OC rounded up to a power of two
     int step_begin, step_end;
     int pairing;             // 1: a CTA that owns >= 2 sample groups interleaves them step by step (software pipeline)
+    int cta_pair;            // 1: launched as clusters of 2 CTAs sharing one cta_group::2 MMA stream (traj_tc_kernel<MT, true>)
     const float* obs_feat;   // [n][Hp0]
     const float* obs_prec;   // [n][m][m] or NULL
     const float* obs_weight; // [n] or NULL

@@ -34,6 +34,13 @@ namespace d4s {
 
 constexpr int TC_THREADS = (TC_CW + 4) * 32;   // 640: + TMA producer, MMA issuer, scalar helper, one idle warp (full warpgroup)
 constexpr int TC_NSTG = 4;                     // weight ring stages
+#ifndef D4S_PAIR_NSTG
+#define D4S_PAIR_NSTG 7
+#endif
+// CTA-pair instantiation: a CTA streams half of every weight tile (<= 8 KB per K-step), so the same 64 KB hold 7 half-size
+// stages + one spare half-stage for the ring's mbarriers and the leader's peer barriers
+constexpr int TC_NSTG_PAIR = D4S_PAIR_NSTG;
+static_assert(TC_NSTG_PAIR >= 2 && TC_NSTG_PAIR <= 7, "pair ring: 2..7 half-size stages");
 constexpr int TC_SG_MAX = 8;                   // samples per tile (warp w < SG sums sample w)
 constexpr int TC_EMB_STRIDE = (TC_M * MMAX) / TC_SG_MAX;  // 160: widest theta-embedding layer (ping-pong in sS / sQS)
 constexpr int TC_MATS_MAX = 2 * MMAX * MMAX + MMAX + 2;
@@ -308,7 +315,17 @@ __device__ __noinline__ void xchg_group_sums(const XchgDev& xg, float* s_acc, in
 // MT: theta_dim as a compile-time constant (0 = read it from the net).  With a runtime theta_dim every small loop of the kernel
 // (layer-0 sample part, Q_j products, sums, tail) is a chain of predicated steps over MMAX = 10 slots; the instantiations for the
 // benchmark tasks' dimensions unroll them exactly.
-template <int MT>
+//
+// PAIR: the CTA runs as one half of a CTA pair (cluster of 2, `cta_group::2`).  Both CTAs keep their own sample groups, operand
+// images, tensor memory and compute / helper warps exactly as in the single-CTA kernel; what is shared is the tensor-core
+// instruction stream: the leader (cluster rank 0) issues every tcgen05.mma over M = 256 rows (its own tile + the peer's), each CTA
+// streams only HALF of every weight tile (rows [rank N/2, (rank+1) N/2) of the K-major image) into its ring.  Per SM that halves
+// the bytes pulled from L2 and the B-operand reads of shared memory, the two things the MMA phases of the single-CTA kernel are
+// bound by (profiles/r02_tc_notes.md).  Protocol: the peer's compute warps arrive on the LEADER's "peer" copies of bar_a /
+// bar_c (remote mbarrier arrive), the peer's otherwise idle MMA warp forwards its ring's full barriers to the leader, and the
+// leader's tcgen05.commit arrives on bar_empty / bar_dn of BOTH CTAs (multicast).  Needs the same number of items on both CTAs
+// (the host only selects it for an even number of sample groups) and the plain fused mode (no export, no exchange, C == 1).
+template <int MT, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_constant__ TrajParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sAhi = smem + OFF_AHI;
@@ -332,8 +349,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     uint8_t* sRowOj = smem + OFF_ROWS + 128;
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
     const uint32_t bar0 = smem_u32(smem + OFF_BAR);
-    auto bar_full = [&](int s) { return bar0 + 8u * s; };
-    auto bar_empty = [&](int s) { return bar0 + 8u * (TC_NSTG + s); };
+    constexpr int NSTG = PAIR ? TC_NSTG_PAIR : TC_NSTG;                      // ring stages
+    constexpr int STG_BYTES = PAIR ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES;    // bytes per stage
+    // CTA pair: the ring's barriers and the leader's copies for the peer CTA's arrivals live in the spare half-stage
+    const uint32_t barp0 = smem_u32(smem + OFF_RING + 7 * (TC_STAGE_BYTES / 2));
+    auto bar_full = [&](int s) { return PAIR ? barp0 + 8u * s : bar0 + 8u * s; };
+    auto bar_empty = [&](int s) { return PAIR ? barp0 + 8u * (NSTG + s) : bar0 + 8u * (TC_NSTG + s); };
     const uint32_t bar_a = bar0 + 8u * (2 * TC_NSTG);      // layer-0 A operand (and TMEM D) ready for the MMA warp
     // (handing layer 0 over in two K halves, like the mid epilogue below, measured -3 % .. -5 %: a second fence.proxy.async per
     // pass, and the early MMAs compete with the rest of layer 0 for the shared-memory pipe)
@@ -343,6 +364,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     // block cb of a mid epilogue is in tensor memory (every compute warp has converted its cb-th 16-column block): K-steps
     // {cq * nblk + cb, cq = 0..3} of the next layer may be issued
     auto bar_c = [&](int cb) { return bar0 + 8u * (2 * TC_NSTG + 3 + cb); };
+    // CTA pair: the leader's copies of the barriers the peer CTA arrives on
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = crank == 0u;
+    auto bar_fullp = [&](int s) { return barp0 + 8u * (2 * NSTG + s); };
+    const uint32_t bar_ap = barp0 + 8u * (3 * NSTG);
+    auto bar_cp = [&](int cb) { return barp0 + 8u * (3 * NSTG + 1 + cb); };
+    // what the compute warps arrive on: their own CTA's barrier (leader, single-CTA kernel) or the leader's peer copy
+    const uint32_t arr_a = (PAIR && !leader) ? mapa_shared(bar_ap, 0u) : bar_a;
+    auto arrive_a = [&]() {
+        if (PAIR && !leader) mbar_arrive_cluster(arr_a);
+        else mbar_arrive(bar_a);
+    };
+    auto arrive_c = [&](int cb) {
+        if (PAIR && !leader) mbar_arrive_cluster(mapa_shared(bar_cp(cb), 0u));
+        else mbar_arrive(bar_c(cb));
+    };
     // i-th K-step of a TS-form layer in issue order (K = 64 nblk): block index first, column quarter second
     auto ks_of = [](int i, int nblk) { return (i & 3) * nblk + (i >> 2); };
 
@@ -365,7 +402,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     constexpr int NB23 = TC_CT + 32;  // participants of named barriers 2 and 3
 
     if (tid == 0) {
-        for (int s = 0; s < TC_NSTG; ++s) {
+        for (int s = 0; s < NSTG; ++s) {
             mbar_init(bar_full(s), 1);
             mbar_init(bar_empty(s), 1);
         }
@@ -373,11 +410,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
         mbar_init(bar_dn(0), 1);
         mbar_init(bar_dn(1), 1);
         for (int cb = 0; cb < 4; ++cb) mbar_init(bar_c(cb), TC_CW * 32);
+        if (PAIR) {
+            for (int s = 0; s < NSTG; ++s) mbar_init(bar_fullp(s), 1);
+            mbar_init(bar_ap, TC_CW * 32);
+            for (int cb = 0; cb < 4; ++cb) mbar_init(bar_cp(cb), TC_CW * 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC_CW + 1) {  // TMEM: two 256-column fp32 accumulators, used alternately layer by layer
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        if (PAIR) {  // (the same warp of both CTAs of the pair)
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
     }
     // constant tables: output layer, its bias, row -> (sample, observation) maps, zeroed operand images
     for (int e = tid; e < 2 * TC_A_BYTES / 16; e += TC_THREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
@@ -399,6 +446,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_d = *sTmem;
 
@@ -430,13 +478,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                     const uint8_t* src = net.wimg[l];
                     for (int i = 0; i < K / 16; ++i, ++it) {
                         const int ks = (l > 1) ? ks_of(i, K / 64) : i;  // the order the MMA warp consumes them in
-                        const int s = it % TC_NSTG;
-                        const uint32_t ph = (it / TC_NSTG) & 1u;
+                        const int s = it % NSTG;
+                        const uint32_t ph = (it / NSTG) & 1u;
                         mbar_wait(bar_empty(s), ph ^ 1u, p.error_flag);
                         TRACE(60 + l);  // ring slot free = the MMAs of the K-step 4 stages back have completed
-                        mbar_expect_tx(bar_full(s), bytes);
-                        tma_bulk_g2s(smem_u32(smem + OFF_RING + s * TC_STAGE_BYTES), src + (size_t)ks * bytes, bytes,
-                                     bar_full(s));
+                        if (PAIR) {
+                            // this CTA's half of the tile: rows [rank N/2, (rank+1) N/2) of the K-step, hi | lo, contiguous in
+                            // the pair image
+                            mbar_expect_tx(bar_full(s), bytes / 2);
+                            tma_bulk_g2s(smem_u32(smem + OFF_RING + s * STG_BYTES),
+                                         net.wimg2[l] + (size_t)ks * bytes + crank * (bytes / 2), bytes / 2, bar_full(s));
+                        } else {
+                            mbar_expect_tx(bar_full(s), bytes);
+                            tma_bulk_g2s(smem_u32(smem + OFF_RING + s * TC_STAGE_BYTES), src + (size_t)ks * bytes, bytes,
+                                         bar_full(s));
+                        }
                     }
                 }
             }
@@ -444,6 +500,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     } else if (warp == TC_CW + 1) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ================= MMA issuer ===================================================================================
+        if (PAIR && !leader) {
+            // peer CTA of a pair: no instructions to issue.  Lane 0 forwards "ring stage full" to the leader, in the order the
+            // leader consumes the stages (the leader's MMAs read this CTA's half of every weight tile).
+            if (lane == 0) {
+                unsigned it = 0;
+                const uint32_t fwd0 = mapa_shared(bar_fullp(0), 0u);
+                for (long long ti = 0; ti < tile_iters; ++ti)
+                    for (int l = 1; l <= L - 2; ++l)
+                        for (int i = 0; i < net.Hp[l - 1] / 16; ++i, ++it) {
+                            const int s = it % NSTG;
+                            mbar_wait(bar_full(s), (it / NSTG) & 1u, p.error_flag);
+                            mbar_arrive_cluster(fwd0 + 8u * s);
+                        }
+            }
+        } else
         if (lane == 0) {
             int tr_n = 0;
             bool tr_go = false;
@@ -454,12 +525,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 tr_go = blockIdx.x == 0 && p.trace != nullptr && ti >= TRACE_FROM && ti < TRACE_TO;
                 for (int l = 1; l <= L - 2; ++l) {
                     const int K = net.Hp[l - 1], Nn = net.Hp[l];
-                    const uint32_t idesc = umma_idesc(Nn);
-                    const uint32_t b_lbo = (uint32_t)Nn * 16u, b_sbo = 128u;  // K halves N*16 B apart, 8-row groups 128 B
+                    const uint32_t idesc = umma_idesc(Nn, PAIR ? 256 : TC_M);
+                    const int Nb = PAIR ? Nn / 2 : Nn;                        // B rows held by this CTA
+                    const uint32_t b_lbo = (uint32_t)Nb * 16u, b_sbo = 128u;  // K halves Nb*16 B apart, 8-row groups 128 B
                     const uint32_t a_lbo = 2048u, a_sbo = 128u;
                     if (l == 1)
                     {
                         mbar_wait(bar_a, a_cnt & 1u, p.error_flag);
+                        if (PAIR) mbar_wait(bar_ap, a_cnt & 1u, p.error_flag);  // the peer's layer 0
                         ++a_cnt;
                     }
                     TRACE(50 + l);
@@ -476,34 +549,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                         const int ks = (l > 1) ? ks_of(i, K / 64) : i;
                         if (l > 1 && (i & 3) == 0) {  // block i / 4 of the previous layer's epilogue is in tensor memory
                             mbar_wait(bar_c(i >> 2), (c_par >> (i >> 2)) & 1u, p.error_flag);
+                            if (PAIR) mbar_wait(bar_cp(i >> 2), (c_par >> (i >> 2)) & 1u, p.error_flag);
                             c_par ^= 1u << (i >> 2);  // (layers of different widths use different numbers of block barriers)
                             tc_fence_after();
                         }
-                        const int s = it % TC_NSTG;
-                        const uint32_t ph = (it / TC_NSTG) & 1u;
+                        const int s = it % NSTG;
+                        const uint32_t ph = (it / NSTG) & 1u;
                         mbar_wait(bar_full(s), ph, p.error_flag);
+                        if (PAIR) mbar_wait(bar_fullp(s), ph, p.error_flag);  // the peer's half of the tile
                         tc_fence_after();
-                        const uint32_t wb = smem_u32(smem + OFF_RING + s * TC_STAGE_BYTES);
+                        const uint32_t wb = smem_u32(smem + OFF_RING + s * STG_BYTES);
                         const uint64_t b_hi = umma_desc(wb, b_lbo, b_sbo);
-                        const uint64_t b_lo = umma_desc(wb + (uint32_t)Nn * 32u, b_lbo, b_sbo);
+                        const uint64_t b_lo = umma_desc(wb + (uint32_t)Nb * 32u, b_lbo, b_sbo);
                         if (l > 1) {  // A = the previous layer's accumulator region, converted in place by the epilogue
                             const uint32_t a_t = dprev + (uint32_t)ks * 16u;  // K-step ks: hi in columns 16 ks .. +7, lo in +8 .. +15
-                            tc_mma_bf16_ts(dacc, a_t, b_hi, idesc, i > 0 ? 1u : 0u);
-                            tc_mma_bf16_ts(dacc, a_t + 8u, b_hi, idesc, 1u);
-                            tc_mma_bf16_ts(dacc, a_t, b_lo, idesc, 1u);
+                            if (PAIR) {
+                                tc_mma2_bf16_ts(dacc, a_t, b_hi, idesc, i > 0 ? 1u : 0u);
+                                tc_mma2_bf16_ts(dacc, a_t + 8u, b_hi, idesc, 1u);
+                                tc_mma2_bf16_ts(dacc, a_t, b_lo, idesc, 1u);
+                            } else {
+                                tc_mma_bf16_ts(dacc, a_t, b_hi, idesc, i > 0 ? 1u : 0u);
+                                tc_mma_bf16_ts(dacc, a_t + 8u, b_hi, idesc, 1u);
+                                tc_mma_bf16_ts(dacc, a_t, b_lo, idesc, 1u);
+                            }
                         } else
                         {
                             const uint64_t a_hi = umma_desc(a_hi0 + ks * 4096, a_lbo, a_sbo);
                             const uint64_t a_lo = umma_desc(a_lo0 + ks * 4096, a_lbo, a_sbo);
-                            tc_mma_bf16(dacc, a_hi, b_hi, idesc, i > 0 ? 1u : 0u);
-                            tc_mma_bf16(dacc, a_lo, b_hi, idesc, 1u);
-                            tc_mma_bf16(dacc, a_hi, b_lo, idesc, 1u);
+                            if (PAIR) {
+                                tc_mma2_bf16(dacc, a_hi, b_hi, idesc, i > 0 ? 1u : 0u);
+                                tc_mma2_bf16(dacc, a_lo, b_hi, idesc, 1u);
+                                tc_mma2_bf16(dacc, a_hi, b_lo, idesc, 1u);
+                            } else {
+                                tc_mma_bf16(dacc, a_hi, b_hi, idesc, i > 0 ? 1u : 0u);
+                                tc_mma_bf16(dacc, a_lo, b_hi, idesc, 1u);
+                                tc_mma_bf16(dacc, a_hi, b_lo, idesc, 1u);
+                            }
                         }
-                        tc_commit(bar_empty(s));  // ring slot is free once these MMAs have read it
+                        // ring slot is free once these MMAs have read it (pair: the slot of both CTAs)
+                        if (PAIR) tc_commit2(bar_empty(s));
+                        else tc_commit(bar_empty(s));
                         if (i == 0) TRACE(30 + l);
                     }
                     TRACE(40 + l);
-                    tc_commit(bar_dn(lc - 1u));  // accumulator complete
+                    // accumulator complete (pair: in the tensor memory of both CTAs)
+                    if (PAIR) tc_commit2(bar_dn(lc - 1u));
+                    else tc_commit(bar_dn(lc - 1u));
                     if (p.prof && blockIdx.x == 0) {  // profiling: duration of this layer's MMAs (slots 8 / 9: first / last layer)
                         mbar_wait(bar_dn(lc - 1u), ((lc - 1u) >> 1) & 1u, p.error_flag);
                         p.prof[(l == L - 2) ? 9 : 8] += clock64() - mma_t0;
@@ -725,7 +816,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                 layer0_contexts(p.obs_feat, sBase, sAhi, sAlo, H0, p.OC, p.SG, nsamp, p.n, j0, nobs, p.fin.ctx_samples, i0, warp, lane);  // (RS == OC there)
                 fence_proxy_async();
                 tc_fence_before();
-                mbar_arrive(bar_a);
+                arrive_a();
                 return;
             }
             // ---- layer 0: act0[r][col] = relu(base[si][col] + obs_feat[j][col]) -> bf16 hi/lo A images -----------
@@ -765,7 +856,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
             }
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(bar_a);
+            arrive_a();
         };
         // one 16-column block of an accumulator row: bias + ReLU
         auto ld_act = [&](uint32_t dacc, int col0, const float4 (&bb)[4], float (&a)[16]) {
@@ -1099,7 +1190,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
                                 tc_st16(dacc + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, w);
                                 tc_wait_st();
                                 tc_fence_before();
-                                mbar_arrive(bar_c(cb));
+                                arrive_c(cb);
                             }
                             if (cb + 1 < nblk) {
 #pragma unroll
@@ -1166,24 +1257,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while the other may still use its shared memory
     if (warp == TC_CW + 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512));
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512));
     }
 }
 
-template <int MT>
+// plain launch, or a cluster of 2 CTAs (the two SMs of a TPC) for the CTA-pair instantiation
+template <int MT, bool PAIR>
+static cudaError_t launch_kernel(const TrajParams& p, int n_ctas, cudaStream_t stream) {
+    if (!PAIR) {
+        traj_tc_kernel<MT, false><<<n_ctas, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n_ctas, 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, traj_tc_kernel<MT, PAIR>, p);
+}
+
+template <int MT, bool PAIR>
 static cudaError_t launch_traj_tc_m(const TrajParams& p, int n_ctas, cudaStream_t stream) {
     // the attribute is per device: keep one flag per device ordinal (a process may drive several GPUs)
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(traj_tc_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(traj_tc_kernel<MT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         // setmaxnreg moves registers inside the CTA's launch allocation: with fewer than 96 registers per thread at launch
         // the compute warps' `inc` could never be served (the kernel would hang), so refuse to launch instead
         cudaFuncAttributes fa;
-        e = cudaFuncGetAttributes(&fa, traj_tc_kernel<MT>);
+        e = cudaFuncGetAttributes(&fa, traj_tc_kernel<MT, PAIR>);
         if (e != cudaSuccess) return e;
         if (fa.numRegs < 96) return cudaErrorLaunchOutOfResources;
         if (dev >= 0 && dev < 64) configured[dev] = true;
@@ -1196,8 +1311,9 @@ static cudaError_t launch_traj_tc_m(const TrajParams& p, int n_ctas, cudaStream_
         cudaMemsetAsync(trace_buf, 0, trace_bytes, stream);
         TrajParams q = p;
         q.trace = trace_buf;
-        traj_tc_kernel<MT><<<n_ctas, TC_THREADS, TC_SMEM_BYTES, stream>>>(q);
-        cudaError_t e = cudaStreamSynchronize(stream);
+        cudaError_t e = launch_kernel<MT, PAIR>(q, n_ctas, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) return e;
         std::vector<long long> host(trace_bytes / sizeof(long long));
         cudaMemcpy(host.data(), trace_buf, trace_bytes, cudaMemcpyDeviceToHost);
@@ -1208,16 +1324,23 @@ static cudaError_t launch_traj_tc_m(const TrajParams& p, int n_ctas, cudaStream_
         return cudaGetLastError();
     }
 #endif
-    traj_tc_kernel<MT><<<n_ctas, TC_THREADS, TC_SMEM_BYTES, stream>>>(p);
-    return cudaGetLastError();
+    return launch_kernel<MT, PAIR>(p, n_ctas, stream);
 }
 
 cudaError_t launch_traj_tc(const TrajParams& p, int n_ctas, cudaStream_t stream) {
+    if (p.cta_pair) {  // (chosen by the host only for the instantiated dimensions and an even grid)
+        switch (p.net.m) {
+            case 2: return launch_traj_tc_m<2, true>(p, n_ctas, stream);
+            case 4: return launch_traj_tc_m<4, true>(p, n_ctas, stream);
+            case 5: return launch_traj_tc_m<5, true>(p, n_ctas, stream);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (p.net.m) {  // theta_dim of the benchmark tasks: SIR 2, Lotka-Volterra / JR-NMM 4, SLCP 5; anything else: generic
-        case 2: return launch_traj_tc_m<2>(p, n_ctas, stream);
-        case 4: return launch_traj_tc_m<4>(p, n_ctas, stream);
-        case 5: return launch_traj_tc_m<5>(p, n_ctas, stream);
-        default: return launch_traj_tc_m<0>(p, n_ctas, stream);
+        case 2: return launch_traj_tc_m<2, false>(p, n_ctas, stream);
+        case 4: return launch_traj_tc_m<4, false>(p, n_ctas, stream);
+        case 5: return launch_traj_tc_m<5, false>(p, n_ctas, stream);
+        default: return launch_traj_tc_m<0, false>(p, n_ctas, stream);
     }
 }
 

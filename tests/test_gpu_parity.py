@@ -364,6 +364,44 @@ def test_tc_group_schedules_agree(shape, dev):
     assert err < TRAJ_TOL, err
 
 
+@pytest.mark.parametrize("shape", [(5, 8, (256, 256, 256), 30, 1000, "uniform"), (5, 8, (256, 256, 256), 30, 80, "uniform"),
+                                   (4, 6, (128, 256), 12, 1184, "gaussian"), (2, 3, (64, 64), 9, 1504, "gaussian"),
+                                   (5, 8, (256, 128), 26, 904, "uniform")],
+                         ids=lambda s: f"m{s[0]}_n{s[3]}_N{s[4]}_{s[5]}")
+def test_tc_cta_pairs_agree(shape, dev):
+    """`tc_cta_pair` (opt-in): the trajectory kernel launched as clusters of two CTAs that share one cta_group::2 tensor-core
+    stream (M = 256 per instruction, each CTA streams half of every weight tile).  Every row still goes through the same
+    products in the same order, so the result must be bit-identical to the single-CTA kernel (even numbers of sample groups:
+    the host only selects the pair kernel then)."""
+    from d4s import _cabi as abi
+    from d4s import engine
+    from d4s_helpers import nse_from_oracle
+    m, d, hidden, n, N, pkind = shape
+    onet, x, cov, theta, oprior = _problem(m, d, hidden, n, N, pkind, seed=5)
+    nse = nse_from_oracle(onet, dev)
+    prior, fn = _d4s_prior(oprior, nse, dev)
+    steps = 6
+    rng = np.random.default_rng(2)
+    z0, z = rng.standard_normal((N, m)), rng.standard_normal((steps, N, m))
+    kw = dict(steps=steps, eta=1.0, prior=prior, prior_type=pkind, prior_score_fn=fn, dist_cov_est=_t(cov, dev),
+              cov_mode="GAUSS", _noise=(torch.as_tensor(z0, dtype=torch.float32), torch.as_tensor(z, dtype=torch.float32)))
+    abi.set_option("path", 2)
+    try:
+        abi.set_option("tc_cta_pair", 0)
+        out = nse.ddim((N,), _t(x, dev), **kw)
+        n0 = engine.launch_count()
+        abi.set_option("tc_cta_pair", 1)
+        out_pair = nse.ddim((N,), _t(x, dev), **kw)
+        assert engine.launch_count() - n0 == 1  # still one launch per trajectory
+        for _ in range(2):
+            assert torch.equal(nse.ddim((N,), _t(x, dev), **kw), out_pair)
+    finally:
+        abi.set_option("tc_cta_pair", 0)
+        abi.set_option("path", 0)
+    assert torch.isfinite(out_pair).all()
+    assert torch.equal(out, out_pair)
+
+
 @pytest.mark.parametrize("shape", [(5, 8, (256, 256, 256), 30, 1000), (4, 6, (128, 256), 7, 333), (2, 3, (64, 64), 40, 150),
                                    (3, 5, (256, 96, 128), 1, 500), (1, 2, (64, 128), 11, 77)],
                          ids=lambda s: f"m{s[0]}_n{s[3]}_N{s[4]}")
