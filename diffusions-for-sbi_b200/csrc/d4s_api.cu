@@ -23,6 +23,10 @@ static int* g_err_flag = nullptr;
 static int g_opt_profile = 0;
 static int g_opt_jac_tc = 1;      // 1 (default): JAC steps on the tcgen05 score + Jacobian kernel where eligible (fp16x3 split); 0: fp32 SIMT kernel
 static int g_opt_tc_pairing = 1;  // interleave two sample groups per CTA in the tcgen05 kernel (0 = one after the other)
+static int g_opt_jac_cta_pair = [] {  // JAC step kernel as CTA pairs; D4S_JAC_CTA_PAIR=0/1
+    const char* e = getenv("D4S_JAC_CTA_PAIR");
+    return e ? atoi(e) : 0;
+}();
 static int g_opt_tc_cta_pair = [] {  // trajectory kernel as CTA pairs (cta_group::2, clusters of 2) where eligible; D4S_TC_CTA_PAIR=0/1
     const char* e = getenv("D4S_TC_CTA_PAIR");
     return e ? atoi(e) : 0;
@@ -261,7 +265,7 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
     const size_t off_WoutT = reserve((size_t)m * Hp[L - 2]);
     for (int o = 0; o < m; ++o)
         for (int k = 0; k < Kl; ++k) h[off_WoutT + (size_t)o * Hp[L - 2] + k] = d->weight[L - 1][(size_t)o * Kl + k];
-    std::vector<size_t> off_img(L, 0), off_img16(L, 0), off_b16(L, 0), off_img2(L, 0);
+    std::vector<size_t> off_img(L, 0), off_img16(L, 0), off_b16(L, 0), off_img2(L, 0), off_img16p(L, 0);
     std::vector<int> sw16(L, 0);
     for (int l = 1; l <= L - 2; ++l) {
         const int K = d->dims[l], Ho = d->dims[l + 1], Kp = Hp[l - 1], Np = Hp[l];
@@ -284,7 +288,9 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
         off_img[l] = reserve(bytes / 4);
         off_img16[l] = reserve(bytes / 4);
         off_img2[l] = reserve(bytes / 4);
+        off_img16p[l] = reserve(bytes / 4);
         uint16_t* img2 = reinterpret_cast<uint16_t*>(h.data() + off_img2[l]);
+        uint16_t* img16p = reinterpret_cast<uint16_t*>(h.data() + off_img16p[l]);
         uint16_t* img = reinterpret_cast<uint16_t*>(h.data() + off_img[l]);
         uint16_t* img16 = reinterpret_cast<uint16_t*>(h.data() + off_img16[l]);
         for (int ks = 0; ks < Kp / 16; ++ks)
@@ -309,6 +315,12 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
                         const __half h16 = __float2half_rn(ws);  // fp16 hi / lo: 22 significant bits (JAC kernel)
                         img16[base + idx] = __half_as_ushort(h16);
                         img16[base + (size_t)Np * 16 + idx] = __half_as_ushort(__float2half_rn(ws - __half2float(h16)));
+                        {
+                            const int hn = Np / 2, rk = nn / hn;
+                            const size_t idx2 = (size_t)rk * Np * 16 + (size_t)hf * hn * 8 + (size_t)(nn - rk * hn) * 8 + e;
+                            img16p[base + idx2] = img16[base + idx];
+                            img16p[base + (size_t)hn * 16 + idx2] = img16[base + (size_t)Np * 16 + idx];
+                        }
                     }
     }
 
@@ -363,6 +375,7 @@ int d4s_net_create(D4sNet** out, const D4sNetDesc* d, void* stream_) {
     for (int l = 1; l <= L - 2; ++l) nd.wimg2[l] = reinterpret_cast<const uint8_t*>(net->blob + off_img2[l]);
     for (int l = 1; l <= L - 2; ++l) {
         nd.wimg16[l] = reinterpret_cast<const uint8_t*>(net->blob + off_img16[l]);
+        nd.wimg16p[l] = reinterpret_cast<const uint8_t*>(net->blob + off_img16p[l]);
         nd.sw16[l] = sw16[l];
         nd.bias16[l] = net->blob + off_b16[l];
     }
@@ -547,10 +560,26 @@ static int score_partials_impl(const D4sNet* net, const D4sProblem* pb, const D4
             cudaMemset(g_err_flag, 0, sizeof(int));
         }
         jp.error_flag = g_err_flag;
+        if (g_opt_profile) {  // (counters accumulate over the launches since the last reset by a trajectory-kernel launch)
+            if (!g_prof) {
+                if (cudaMalloc(&g_prof, 16 * sizeof(long long)) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaMalloc(prof)");
+                cudaMemsetAsync(g_prof, 0, 16 * sizeof(long long), stream);
+            }
+            jp.prof = g_prof;
+        }
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaError_t e = launch_jac_tc(jp, jp.n_tiles < sms ? jp.n_tiles : sms, stream);
+        int ctas = jp.n_tiles < sms ? jp.n_tiles : sms;
+        {   // CTA pairs (cta_group::2): an even grid; a tile index past the end is an empty tile
+            bool widths_ok = true;
+            for (int l = 1; l <= net->dev.L - 2; ++l) widths_ok = widths_ok && net->dev.Hp[l] % 32 == 0 && net->dev.Hp[l] <= 256;
+            if (g_opt_jac_cta_pair && widths_ok && sms % 2 == 0 && jp.n_tiles >= 2) {
+                jp.cta_pair = 1;
+                ctas = (ctas + 1) & ~1;
+            }
+        }
+        cudaError_t e = launch_jac_tc(jp, ctas, stream);
         if (e != cudaSuccess) return cuda_fail(e, "tcgen05 JAC kernel launch");
         ++g_launches;
         return D4S_OK;
@@ -794,7 +823,7 @@ int d4s_ddim_run(const D4sNet* net, const D4sProblem* pb, int32_t steps, const f
     key.theta = theta_dev;
     key.affine = affine_dev;
     key.mode_hash = 1469598103934665603ull;
-    for (int v : {g_opt_path, g_opt_tc_steps, g_opt_profile, g_opt_tc_pairing, g_opt_jac_tc, g_opt_tc_cta_pair})  // a captured graph froze the options it was built with
+    for (int v : {g_opt_path, g_opt_tc_steps, g_opt_profile, g_opt_tc_pairing, g_opt_jac_tc, g_opt_tc_cta_pair, g_opt_jac_cta_pair})  // a captured graph froze the options it was built with
         key.mode_hash = (key.mode_hash ^ (uint64_t)(uint32_t)v) * 1099511628211ull;
     if (step_mode)
         for (int k = 0; k < steps; ++k) key.mode_hash = (key.mode_hash ^ (uint64_t)(step_mode[k] + 1)) * 1099511628211ull;
@@ -982,6 +1011,7 @@ int d4s_set_option(const char* key, int32_t value) {
     else if (k == "tc_pairing") g_opt_tc_pairing = value;
     else if (k == "jac_tc") g_opt_jac_tc = value;
     else if (k == "tc_cta_pair") g_opt_tc_cta_pair = value;
+    else if (k == "jac_cta_pair") g_opt_jac_cta_pair = value;
     else return fail(D4S_ERR_ARG, "unknown option: " + k);
     return D4S_OK;
 }

@@ -40,6 +40,7 @@ struct NetDev {
     const float* emb_bias[D4S_MAX_LAYERS];  // [out]
     const uint8_t* wimg[D4S_MAX_LAYERS];  // l = 1 .. L-2: bf16 hi/lo UMMA images, [Hp[l-1]/16][hi | lo][2][Hp[l]][8]
     const uint8_t* wimg2[D4S_MAX_LAYERS];  // the bf16 images again, every K-step split by output rows for a CTA pair: [Hp[l-1]/16][rank][hi | lo][2][Hp[l]/2][8]
+    const uint8_t* wimg16p[D4S_MAX_LAYERS];  // the fp16 images split by output rows for a CTA pair (layout of wimg2)
     const uint8_t* wimg16[D4S_MAX_LAYERS];  // same layout, fp16 hi / lo of 2^sw16[l] W_l (JAC kernel: fp16x3 split)
     int sw16[D4S_MAX_LAYERS];               // power-of-two weight scale that keeps the fp16 lo parts out of the subnormals
     const float* bias16[D4S_MAX_LAYERS];    // 2^(D4S_ACT_SHIFT16 + sw16[l]) bias_l: the JAC kernel's accumulators are scaled
@@ -135,6 +136,7 @@ struct JacTcParams {
     NetDev net;
     int N, n, C, OC, UT, PW;
     int n_tiles;
+    int cta_pair;             // 1: clusters of 2 CTAs sharing one cta_group::2 MMA stream (jac_tc_kernel<true>)
     const float* theta;       // [N][m]
     const float* obs_feat;    // [n][Hp0]
     const float* time_feat;   // [Hp0] row of this step
@@ -142,6 +144,7 @@ struct JacTcParams {
     const float* obs_weight;  // [n] or NULL
     float* part;              // [N][C][m + m^2] sums over the chunk's observations of P s | P
     int* error_flag;
+    long long* prof;          // optional [16] cycle counters of CTA 0 (d4s_set_option("profile", 1); tests/gpu_debug_jac_prof.py)
 };
 cudaError_t launch_jac_tc(const JacTcParams& p, int n_ctas, cudaStream_t stream);
 

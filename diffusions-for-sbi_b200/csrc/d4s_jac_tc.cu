@@ -56,7 +56,11 @@ constexpr int JOFF_PS = JOFF_PJ + 2 * JT_PMAX * 4;            // float [2][32] p
 constexpr int JOFF_BOUT = JOFF_PS + 2 * JT_PMAX * 4;          // float [8]
 constexpr int JOFF_BAR = JOFF_BOUT + 32;                      // mbarriers
 constexpr int JOFF_TMEM = JOFF_BAR + (2 * JT_NSTG + 2) * 8;
-constexpr int JT_SMEM_BYTES = JOFF_TMEM + 16;
+// CTA-pair instantiation: the ring region holds 6 half-size stages (a CTA streams half of every weight tile); its barriers and
+// the leader's copies for the peer's arrivals: full[6] | empty[6] | fullp[6] | ap
+constexpr int JT_NSTG_PAIR = 6;
+constexpr int JOFF_BARP = JOFF_TMEM + 16;
+constexpr int JT_SMEM_BYTES = JOFF_BARP + (3 * JT_NSTG_PAIR + 1) * 8;
 static_assert(JT_SMEM_BYTES <= 232448, "shared memory budget (227 KB per CTA) exceeded");
 static_assert(JOFF_BAR % 8 == 0 && JOFF_AIMG % 16 == 0 && JOFF_H % 16 == 0, "alignment");
 
@@ -89,6 +93,12 @@ __device__ __forceinline__ void jac_pair_col_dispatch(int m, const float* out_ro
     }
 }
 
+// PAIR: clusters of two CTAs share one cta_group::2 tensor-core stream, exactly like traj_tc_kernel<MT, true> (d4s_traj_tc.cu):
+// the leader issues every tcgen05.mma over M = 256 rows (its tile + the peer's), each CTA streams half of every weight tile from
+// the row-split fp16 image.  This kernel needs it more than the trajectory kernel does: two passes over the hi images make it
+// pull 384 KB per layer and tile through a 3-stage ring (40 B/clk at the tensor core's pace), which is what bounded its MMA
+// phases (15-17k cycles per layer against ~9.7k for the instructions themselves, profiles/r02_jac_tc_notes.md).
+template <bool PAIR>
 __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sAhi = smem + JOFF_AHI;
@@ -108,10 +118,23 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
     float* sBout = reinterpret_cast<float*>(smem + JOFF_BOUT);
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem + JOFF_TMEM);
     const uint32_t bar0 = smem_u32(smem + JOFF_BAR);
-    auto bar_full = [&](int s) { return bar0 + 8u * s; };
-    auto bar_empty = [&](int s) { return bar0 + 8u * (JT_NSTG + s); };
+    constexpr int NSTG = PAIR ? JT_NSTG_PAIR : JT_NSTG;
+    constexpr int STG_BYTES = PAIR ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES;
+    const uint32_t barp0 = smem_u32(smem + JOFF_BARP);
+    auto bar_full = [&](int s) { return PAIR ? barp0 + 8u * s : bar0 + 8u * s; };
+    auto bar_empty = [&](int s) { return PAIR ? barp0 + 8u * (NSTG + s) : bar0 + 8u * (JT_NSTG + s); };
     const uint32_t bar_a = bar0 + 8u * (2 * JT_NSTG);      // A operand ready for the MMA warp
     const uint32_t bar_d = bar0 + 8u * (2 * JT_NSTG + 1);  // accumulator ready for the epilogue
+    // CTA pair: the leader's copies of the barriers the peer CTA arrives on
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = crank == 0u;
+    auto bar_fullp = [&](int s) { return barp0 + 8u * (2 * NSTG + s); };
+    const uint32_t bar_ap = barp0 + 8u * (3 * NSTG);
+    const uint32_t arr_a = (PAIR && !leader) ? mapa_shared(bar_ap, 0u) : bar_a;
+    auto arrive_a = [&]() {
+        if (PAIR && !leader) mbar_arrive_cluster(arr_a);
+        else mbar_arrive(bar_a);
+    };
 
     const NetDev& net = p.net;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -123,17 +146,24 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
     const int W = m + m * m;
 
     if (tid == 0) {
-        for (int s = 0; s < JT_NSTG; ++s) {
+        for (int s = 0; s < NSTG; ++s) {
             mbar_init(bar_full(s), 1);
             mbar_init(bar_empty(s), 1);
+            if (PAIR) mbar_init(bar_fullp(s), 1);
         }
         mbar_init(bar_a, TC_CW * 32);
+        if (PAIR) mbar_init(bar_ap, TC_CW * 32);
         mbar_init(bar_d, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC_CW + 1) {  // TMEM: two 256-column fp32 accumulators, used alternately layer by layer
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        if (PAIR) {  // (the same warp of both CTAs of the pair)
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
     }
     // constant tables; operand images zeroed once (rows that belong to no pair are never written again)
     for (int e = tid; e < 2 * TC_A_BYTES / 16; e += JT_THREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
@@ -165,11 +195,13 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_d = *sTmem;
 
+    // (pair: both CTAs run the leader's number of tiles -- a tile index past the end has no valid pair slot and writes nothing)
     int my_tiles = 0;
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) ++my_tiles;
+    for (int t = PAIR ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x; t < p.n_tiles; t += gridDim.x) ++my_tiles;
 
     // setmaxnreg: launched with 96 registers per thread; the service warpgroup keeps 32, the compute warps grow to 112
     if (warp >= TC_CW + 2) {
@@ -183,16 +215,18 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                 for (int l = 1; l <= Lh; ++l) {
                     const int K = net.Hp[l - 1], Nn = net.Hp[l];
                     const uint32_t bytes = (uint32_t)Nn * 64u;
-                    const uint8_t* src = net.wimg16[l];  // fp16 hi | lo
+                    // fp16 hi | lo; pair: the image split by output rows, this CTA's half of a K-step contiguous (hi | lo)
+                    const uint8_t* src = PAIR ? net.wimg16p[l] + crank * (bytes / 2) : net.wimg16[l];
+                    const uint32_t mine = PAIR ? bytes / 2 : bytes;
                     // two passes over K (see the MMA issuer): cross terms first (hi | lo images), then the main terms (hi image only)
                     for (int pass = 0; pass < (JT_TWO_PASS ? 2 : 1); ++pass) {
-                        const uint32_t nb = (JT_TWO_PASS && pass == 1) ? bytes / 2 : bytes;
+                        const uint32_t nb = (JT_TWO_PASS && pass == 1) ? mine / 2 : mine;
                         for (int ks = 0; ks < K / 16; ++ks, ++it) {
-                            const int s = it % JT_NSTG;
-                            const uint32_t ph = (it / JT_NSTG) & 1u;
+                            const int s = it % NSTG;
+                            const uint32_t ph = (it / NSTG) & 1u;
                             mbar_wait(bar_empty(s), ph ^ 1u, p.error_flag);
                             mbar_expect_tx(bar_full(s), nb);
-                            tma_bulk_g2s(smem_u32(smem + JOFF_RING + s * TC_STAGE_BYTES), src + (size_t)ks * bytes, nb, bar_full(s));
+                            tma_bulk_g2s(smem_u32(smem + JOFF_RING + s * STG_BYTES), src + (size_t)ks * bytes, nb, bar_full(s));
                         }
                     }
                 }
@@ -201,6 +235,20 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
     } else if (warp == TC_CW + 1) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         // ================= MMA issuer ===================================================================================
+        if (PAIR && !leader) {
+            // peer CTA of a pair: lane 0 forwards "ring stage full" to the leader in consumption order
+            if (lane == 0) {
+                unsigned it = 0;
+                const uint32_t fwd0 = mapa_shared(bar_fullp(0), 0u);
+                for (int ti = 0; ti < my_tiles; ++ti)
+                    for (int l = 1; l <= Lh; ++l)
+                        for (int i = 0; i < (JT_TWO_PASS ? 2 : 1) * (net.Hp[l - 1] / 16); ++i, ++it) {
+                            const int s = it % NSTG;
+                            mbar_wait(bar_full(s), (it / NSTG) & 1u, p.error_flag);
+                            mbar_arrive_cluster(fwd0 + 8u * s);
+                        }
+            }
+        } else
         if (lane == 0) {
             unsigned it = 0, a_cnt = 0, lc = 0;
             const uint32_t a_hi0 = smem_u32(sAhi), a_lo0 = smem_u32(sAlo);
@@ -210,11 +258,20 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                     // fp16x3: a w ~= a_lo w_hi + a_hi w_lo + a_hi w_hi with fp16 hi / lo parts (~2^-22 per product; the bf16x3
                     // split of the GAUSS kernel is not enough here: the Jacobian goes through inv(I - sigma J), which
                     // amplifies the GEMM error by its condition number)
-                    const uint32_t idesc = umma_idesc_fmt(Nn, false, false);
-                    const uint32_t b_lbo = (uint32_t)Nn * 16u, b_sbo = 128u;
+                    const uint32_t idesc = umma_idesc_fmt(Nn, false, false, PAIR ? 256 : TC_M);
+                    const int Nb = PAIR ? Nn / 2 : Nn;  // B rows held by this CTA
+                    const uint32_t b_lbo = (uint32_t)Nb * 16u, b_sbo = 128u;
                     const uint32_t a_lbo = 2048u, a_sbo = 128u;
+                    const bool prof_on = p.prof != nullptr && blockIdx.x == 0;
+                    long long pt0 = prof_on ? clock64() : 0;
                     mbar_wait(bar_a, a_cnt & 1u, p.error_flag);
+                    if (PAIR) mbar_wait(bar_ap, a_cnt & 1u, p.error_flag);  // the peer's operand image
                     ++a_cnt;
+                    long long pt1 = 0, pfull = 0;
+                    if (prof_on) {
+                        pt1 = clock64();
+                        p.prof[0] += pt1 - pt0;  // MMA warp: waiting for the operand image
+                    }
                     tc_fence_after();
                     const uint32_t dacc = tmem_d + ((lc & 1u) ? 256u : 0u);
                     ++lc;
@@ -224,24 +281,45 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                     // remaining, now uniform, deficit is what acc_debias() corrects in the epilogues).  Costs one more pass of the hi images.
                     for (int pass = 0; pass < (JT_TWO_PASS ? 2 : 1); ++pass) {
                         for (int ks = 0; ks < K / 16; ++ks, ++it) {
-                            const int s = it % JT_NSTG;
-                            const uint32_t ph = (it / JT_NSTG) & 1u;
+                            const int s = it % NSTG;
+                            const uint32_t ph = (it / NSTG) & 1u;
+                            const long long pf0 = prof_on ? clock64() : 0;
                             mbar_wait(bar_full(s), ph, p.error_flag);
+                            if (PAIR) mbar_wait(bar_fullp(s), ph, p.error_flag);  // the peer's half of the tile
+                            if (prof_on) pfull += clock64() - pf0;
                             tc_fence_after();
-                            const uint32_t wb = smem_u32(smem + JOFF_RING + s * TC_STAGE_BYTES);
+                            const uint32_t wb = smem_u32(smem + JOFF_RING + s * STG_BYTES);
                             const uint64_t b_hi = umma_desc(wb, b_lbo, b_sbo);
-                            const uint64_t b_lo = umma_desc(wb + (uint32_t)Nn * 32u, b_lbo, b_sbo);
+                            const uint64_t b_lo = umma_desc(wb + (uint32_t)Nb * 32u, b_lbo, b_sbo);
                             const uint64_t a_hi = umma_desc(a_hi0 + ks * 4096, a_lbo, a_sbo);
                             const uint64_t a_lo = umma_desc(a_lo0 + ks * 4096, a_lbo, a_sbo);
-                            if (!JT_TWO_PASS || pass == 0) {
-                                tc_mma_bf16(dacc, a_lo, b_hi, idesc, ks > 0 ? 1u : 0u);
-                                tc_mma_bf16(dacc, a_hi, b_lo, idesc, 1u);
+                            if (PAIR) {
+                                if (!JT_TWO_PASS || pass == 0) {
+                                    tc_mma2_bf16(dacc, a_lo, b_hi, idesc, ks > 0 ? 1u : 0u);
+                                    tc_mma2_bf16(dacc, a_hi, b_lo, idesc, 1u);
+                                }
+                                if (!JT_TWO_PASS || pass == 1) tc_mma2_bf16(dacc, a_hi, b_hi, idesc, 1u);
+                                tc_commit2(bar_empty(s));
+                            } else {
+                                if (!JT_TWO_PASS || pass == 0) {
+                                    tc_mma_bf16(dacc, a_lo, b_hi, idesc, ks > 0 ? 1u : 0u);
+                                    tc_mma_bf16(dacc, a_hi, b_lo, idesc, 1u);
+                                }
+                                if (!JT_TWO_PASS || pass == 1) tc_mma_bf16(dacc, a_hi, b_hi, idesc, 1u);
+                                tc_commit(bar_empty(s));
                             }
-                            if (!JT_TWO_PASS || pass == 1) tc_mma_bf16(dacc, a_hi, b_hi, idesc, 1u);
-                            tc_commit(bar_empty(s));
                         }
                     }
-                    tc_commit(bar_d);
+                    if (PAIR) tc_commit2(bar_d);
+                    else tc_commit(bar_d);
+                    if (prof_on) {  // profiling only: drain, so that slot 3 is issue -> complete of this layer
+                        const long long pt2 = clock64();
+                        mbar_wait(bar_d, (lc - 1u) & 1u, p.error_flag);
+                        p.prof[1] += pfull;                 // waiting for ring stages
+                        p.prof[2] += pt2 - pt1;             // issue loop (including those waits)
+                        p.prof[3] += clock64() - pt1;       // operand ready -> accumulator complete
+                        p.prof[4] += 1;                     // layers
+                    }
                 }
             }
         }
@@ -375,7 +453,7 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
             }
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(bar_a);
+            arrive_a();
         };
         // one 16-column block of an accumulator row.  Primal: x = d + bias, a = relu(x).  Tangent: a = d * [x_primal > 0].
         // `hval` = what the indicator holds for an active unit: 2^-sw16[l] (operand of the next layer) or 1 (last layer).
@@ -505,6 +583,16 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
 
         if (my_tiles > 0) prepare_meta(blockIdx.x, 0);
         compute_bar();
+        const bool cprof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
+        long long ct = cprof ? clock64() : 0;
+#define JPROF(slot)                            \
+    do {                                       \
+        if (cprof) {                           \
+            const long long now_ = clock64();  \
+            p.prof[slot] += now_ - ct;         \
+            ct = now_;                         \
+        }                                      \
+    } while (0)
         for (int ps = 0; ps <= my_tiles; ++ps) {  // one extra iteration finishes the last tile
             const bool have = ps < my_tiles, prev = ps > 0;
             const int tile = blockIdx.x + ps * (int)gridDim.x;
@@ -516,8 +604,11 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                 ++d_cnt;
                 tc_fence_after();
             }
+            JPROF(5);  // waiting for the last layer of the previous tile
             if (have) do_layer0(buf);
+            JPROF(6);
             if (prev) do_last_epilogue(dacc_prev, buf ^ 1);
+            JPROF(7);
             if (have) {
                 for (int l = 1; l < Lh; ++l) {  // hidden layers that feed another tensor-core layer
                     const int Nn = net.Hp[l];
@@ -530,6 +621,7 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                     mbar_wait(bar_d, d_cnt & 1u, p.error_flag);
                     ++d_cnt;
                     tc_fence_after();
+                    JPROF(8);  // waiting for a hidden layer
                     for (int cb = 0; cb < nblk; ++cb) {
                         const int col0 = cq * qcols + 16 * cb;
                         float a[16];
@@ -544,39 +636,67 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                     }
                     fence_proxy_async();
                     tc_fence_before();
-                    mbar_arrive(bar_a);
+                    arrive_a();
+                    JPROF(9);  // mid epilogue
                 }
             }
             if (prev) do_pairs(tile - (int)gridDim.x, buf ^ 1);
+            JPROF(10);
             if (ps + 1 < my_tiles) prepare_meta(tile + (int)gridDim.x, buf ^ 1);
+            JPROF(11);
             compute_bar();
+            JPROF(12);
         }
+#undef JPROF
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while the other may still use its shared memory
     if (warp == TC_CW + 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512));
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512));
     }
 }
 
-cudaError_t launch_jac_tc(const JacTcParams& p, int n_ctas, cudaStream_t stream) {
+template <bool PAIR>
+static cudaError_t launch_jac_tc_t(const JacTcParams& p, int n_ctas, cudaStream_t stream) {
     // the attribute is per device: keep one flag per device ordinal (a process may drive several GPUs)
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(jac_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JT_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(jac_tc_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, JT_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         // setmaxnreg moves registers inside the CTA's launch allocation: with fewer than 96 registers per thread at launch
         // the compute warps' `inc` could never be served (the kernel would hang), so refuse to launch instead
         cudaFuncAttributes fa;
-        e = cudaFuncGetAttributes(&fa, jac_tc_kernel);
+        e = cudaFuncGetAttributes(&fa, jac_tc_kernel<PAIR>);
         if (e != cudaSuccess) return e;
         if (fa.numRegs < 96) return cudaErrorLaunchOutOfResources;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    jac_tc_kernel<<<n_ctas, JT_THREADS, JT_SMEM_BYTES, stream>>>(p);
-    return cudaGetLastError();
+    if (!PAIR) {
+        jac_tc_kernel<false><<<n_ctas, JT_THREADS, JT_SMEM_BYTES, stream>>>(p);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n_ctas, 1, 1);
+    cfg.blockDim = dim3(JT_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = JT_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, jac_tc_kernel<true>, p);
+}
+
+// p.cta_pair: clusters of 2 CTAs (n_ctas even)
+cudaError_t launch_jac_tc(const JacTcParams& p, int n_ctas, cudaStream_t stream) {
+    return p.cta_pair ? launch_jac_tc_t<true>(p, n_ctas, stream) : launch_jac_tc_t<false>(p, n_ctas, stream);
 }
 
 }  // namespace d4s

@@ -187,9 +187,9 @@ __device__ __forceinline__ uint32_t umma_idesc(int n, int m_rows = TC_M) {  // m
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m_rows >> 4) << 24);
 }
 // same with the operand formats chosen per instruction: bit 7 / bit 10 set = A / B is bf16, clear = fp16
-__device__ __forceinline__ uint32_t umma_idesc_fmt(int n, bool a_bf16, bool b_bf16) {
+__device__ __forceinline__ uint32_t umma_idesc_fmt(int n, bool a_bf16, bool b_bf16, int m_rows = TC_M) {
     return (1u << 4) | (a_bf16 ? (1u << 7) : 0u) | (b_bf16 ? (1u << 10) : 0u) | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(TC_M >> 4) << 24);
+           ((uint32_t)(m_rows >> 4) << 24);
 }
 
 // named barriers: 1 = compute warps only; 2 = theta of the step is final (compute arrive, helper sync);

@@ -403,6 +403,37 @@ def test_tc_cta_pairs_agree(shape, dev):
 
 
 @pytest.mark.parametrize("shape", [(5, 8, (256, 256, 256), 30, 1000), (4, 6, (128, 256), 7, 333), (2, 3, (64, 64), 40, 150),
+                                   (1, 2, (64, 128), 11, 77)], ids=lambda s: f"m{s[0]}_n{s[3]}_N{s[4]}")
+def test_jac_cta_pairs_agree(shape, dev):
+    """`jac_cta_pair` (opt-in): the JAC step kernel launched as clusters of two CTAs on one cta_group::2 stream; the partial
+    sums must be bit-identical to the single-CTA kernel (odd tile counts: the last pair's second CTA runs an empty tile)."""
+    import ctypes as C
+    from d4s import _cabi as abi
+    from d4s import engine
+    from d4s_helpers import nse_from_oracle
+    m, d, hidden, n, N = shape
+    rng = np.random.default_rng(11)
+    onet = orc.random_net(rng, m, d, hidden=hidden)
+    nse = nse_from_oracle(onet, dev)
+    xt = _t(rng.standard_normal((n, d)), dev)
+    th = _t(rng.standard_normal((N, m)), dev)
+    t = torch.tensor([0.3], dtype=torch.float32)
+    outs = []
+    try:
+        for pair in (0, 1, 1):
+            abi.set_option("jac_cta_pair", pair)
+            setup = engine.build_setup(nse, xt, N, t, None, 0.0, engine.PriorSpec(abi.PRIOR_NONE), "JAC", None)
+            engine.score_partials(setup, th, 0)
+            torch.cuda.synchronize()
+            nf = abi.load().d4s_partials_floats(setup.pn.handle, C.byref(setup.prob))
+            outs.append(setup.keep[4][:nf].clone())
+    finally:
+        abi.set_option("jac_cta_pair", 0)
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+
+
+@pytest.mark.parametrize("shape", [(5, 8, (256, 256, 256), 30, 1000), (4, 6, (128, 256), 7, 333), (2, 3, (64, 64), 40, 150),
                                    (3, 5, (256, 96, 128), 1, 500), (1, 2, (64, 128), 11, 77)],
                          ids=lambda s: f"m{s[0]}_n{s[3]}_N{s[4]}")
 def test_jac_tc_partial_sums(shape, dev):
