@@ -876,54 +876,91 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
             const int Nn = net.Hp[L - 2];
             const int qcols = Nn >> 2, nblk = qcols / 16;
             const float* bias_l = net.bias[L - 2] + cq * qcols;
-            // output-layer partial dot products of this thread's row / column quarter, as packed pairs (even | odd columns): the
-            // products run as FFMA2 over column pairs, po[o] = po2[o].x + po2[o].y at the end
-            float2 po2[MMAX];
+            float po[MMAX];  // output-layer partial dot products of this thread's row / column quarter
+            if constexpr (MT == 0 || MT > MMAX / 2) {
+                // wide theta (and the generic instantiation): plain FMAs, five outputs at a time -- the packed / pipelined form
+                // below needs 2 x MMAX accumulators + two weight sets and spills at the kernel's 96 registers (stress shape,
+                // theta_dim = 10: +6 % per step, profiles/r02_tc_notes.md)
 #pragma unroll
-            for (int o = 0; o < MMAX; ++o) po2[o] = make_float2(0.f, 0.f);
-            auto load_w = [&](float4 (&w)[4], int o, int col0) {  // Wout[o][col0 .. col0 + 15] (smem, broadcast reads)
+                for (int o = 0; o < MMAX; ++o) po[o] = 0.f;
+                for (int cb = 0; cb < nblk; ++cb) {
+                    const int col0 = cq * qcols + 16 * cb;
+                    float4 bb[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) w[e] = *reinterpret_cast<const float4*>(sWout + o * 256 + col0 + 4 * e);
-            };
-            for (int cb = 0; cb < nblk; ++cb) {
-                const int col0 = cq * qcols + 16 * cb;
-                float4 bb[4];
+                    for (int e = 0; e < 4; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bias_l + 16 * cb) + e);
+                    float a[16];
+                    ld_act(dacc, col0, bb, a);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bias_l + 16 * cb) + e);
-                // The weight loads of output o + 1 are issued before the products of output o, those of output 0 before the wait for
-                // the accumulator block: a shared-memory load issued right before its use waited ~40 % of this phase's cycles (the
-                // MMA operand reads and the TMA writes of the other item's layer keep the shared-memory pipe busy).
-                uint32_t d[16];
-                tc_ld16(dacc + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, d);
-                float4 wn[4];
-                load_w(wn, 0, col0);
-                tc_wait_ld();
-                float2 a2[8];
+                    for (int oh = 0; oh < MMAX; oh += 5) {
+                        if (oh < m) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    a2[2 * e] = make_float2(fmaxf(__uint_as_float(d[4 * e]) + bb[e].x, 0.f), fmaxf(__uint_as_float(d[4 * e + 1]) + bb[e].y, 0.f));
-                    a2[2 * e + 1] = make_float2(fmaxf(__uint_as_float(d[4 * e + 2]) + bb[e].z, 0.f), fmaxf(__uint_as_float(d[4 * e + 3]) + bb[e].w, 0.f));
-                }
+                            for (int e = 0; e < 16; e += 4) {
+                                float4 w4[5];
 #pragma unroll
-                for (int o = 0; o < MMAX; ++o) {
-                    if (o < m) {
-                        float4 wc[4];
+                                for (int o = 0; o < 5; ++o)
+                                    w4[o] = *reinterpret_cast<const float4*>(sWout + (oh + o) * 256 + col0 + e);  // rows >= m: unused, in bounds
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) wc[e] = wn[e];
-                        if (o + 1 < m) load_w(wn, o + 1, col0);
-                        float2 acc = po2[o];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            acc = __ffma2_rn(a2[2 * e], make_float2(wc[e].x, wc[e].y), acc);
-                            acc = __ffma2_rn(a2[2 * e + 1], make_float2(wc[e].z, wc[e].w), acc);
+                                for (int o = 0; o < 5; ++o) {
+                                    float acc = po[oh + o];
+                                    acc = fmaf(a[e], w4[o].x, acc);
+                                    acc = fmaf(a[e + 1], w4[o].y, acc);
+                                    acc = fmaf(a[e + 2], w4[o].z, acc);
+                                    acc = fmaf(a[e + 3], w4[o].w, acc);
+                                    po[oh + o] = acc;
+                                }
+                            }
                         }
-                        po2[o] = acc;
                     }
                 }
-            }
-            float po[MMAX];
+            } else {
+                // output-layer partial dot products of this thread's row / column quarter, as packed pairs (even | odd columns): the
+                // products run as FFMA2 over column pairs, po[o] = po2[o].x + po2[o].y at the end
+                float2 po2[MMAX];
 #pragma unroll
-            for (int o = 0; o < MMAX; ++o) po[o] = po2[o].x + po2[o].y;
+                for (int o = 0; o < MMAX; ++o) po2[o] = make_float2(0.f, 0.f);
+                auto load_w = [&](float4 (&w)[4], int o, int col0) {  // Wout[o][col0 .. col0 + 15] (smem, broadcast reads)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) w[e] = *reinterpret_cast<const float4*>(sWout + o * 256 + col0 + 4 * e);
+                };
+                for (int cb = 0; cb < nblk; ++cb) {
+                    const int col0 = cq * qcols + 16 * cb;
+                    float4 bb[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) bb[e] = __ldg(reinterpret_cast<const float4*>(bias_l + 16 * cb) + e);
+                    // The weight loads of output o + 1 are issued before the products of output o, those of output 0 before the wait for
+                    // the accumulator block: a shared-memory load issued right before its use waited ~40 % of this phase's cycles (the
+                    // MMA operand reads and the TMA writes of the other item's layer keep the shared-memory pipe busy).
+                    uint32_t d[16];
+                    tc_ld16(dacc + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, d);
+                    float4 wn[4];
+                    load_w(wn, 0, col0);
+                    tc_wait_ld();
+                    float2 a2[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        a2[2 * e] = make_float2(fmaxf(__uint_as_float(d[4 * e]) + bb[e].x, 0.f), fmaxf(__uint_as_float(d[4 * e + 1]) + bb[e].y, 0.f));
+                        a2[2 * e + 1] = make_float2(fmaxf(__uint_as_float(d[4 * e + 2]) + bb[e].z, 0.f), fmaxf(__uint_as_float(d[4 * e + 3]) + bb[e].w, 0.f));
+                    }
+#pragma unroll
+                    for (int o = 0; o < MMAX; ++o) {
+                        if (o < m) {
+                            float4 wc[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) wc[e] = wn[e];
+                            if (o + 1 < m) load_w(wn, o + 1, col0);
+                            float2 acc = po2[o];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                acc = __ffma2_rn(a2[2 * e], make_float2(wc[e].x, wc[e].y), acc);
+                                acc = __ffma2_rn(a2[2 * e + 1], make_float2(wc[e].z, wc[e].w), acc);
+                            }
+                            po2[o] = acc;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 0; o < MMAX; ++o) po[o] = po2[o].x + po2[o].y;
+            }
             PROF_MARK(4);  // epilogues
             if (fused_sums) {
                 // The sums over the observations are LINEAR in the output-layer partials: S1 = -1/sigma sum_rows sum_quarters (po + b),
@@ -1062,7 +1099,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) traj_tc_kernel(const __grid_con
         // Layer 0 reads, per thread, 16 floats of obs_feat (its observation = lane, its two k-groups): with the whole observation set
         // in one tile of <= 32 observations per sample they are the SAME 16 floats for every item of the trajectory -> loaded once.
         // (Per-item loads were 30 KB per item through a 28 KB L1 that also has to hold the local-memory lines.)
-        const bool obs_in_regs = p.C == 1 && p.OC <= 32 && p.fin.ctx_samples == 0;
+        // (instantiations for theta_dim <= 5 only: the generic / wide ones are short of registers, 16 more live values cost the tall
+        // stress shape 9 % per step)
+        const bool obs_in_regs = (MT != 0 && MT <= MMAX / 2) && p.C == 1 && p.OC <= 32 && p.fin.ctx_samples == 0;
         float4 upre[2][2];
         if (obs_in_regs) l0_load(upre, 0, min(p.OC, p.n), lane);
         for (int gk = 0; gk < my_groups;) {
@@ -1340,6 +1379,7 @@ cudaError_t launch_traj_tc(const TrajParams& p, int n_ctas, cudaStream_t stream)
         case 2: return launch_traj_tc_m<2, false>(p, n_ctas, stream);
         case 4: return launch_traj_tc_m<4, false>(p, n_ctas, stream);
         case 5: return launch_traj_tc_m<5, false>(p, n_ctas, stream);
+        case 10: return launch_traj_tc_m<10, false>(p, n_ctas, stream);  // the tall-data stress shape (BASELINE config 5)
         default: return launch_traj_tc_m<0, false>(p, n_ctas, stream);
     }
 }
