@@ -49,18 +49,19 @@ constexpr int JOFF_RED = JOFF_TF + 256 * 4;                   // float [3][128][
 constexpr int JOFF_OUT = JOFF_RED + 3 * TC_M * JT_MMAX * 4;   // float [128][m] row outputs: score (primal) / J column
 constexpr int JOFF_H = JOFF_OUT + TC_M * JT_MMAX * 4;         // float [16 warps][8 pairs][16] ReLU indicators
 constexpr int JOFF_PAIR = JOFF_H + TC_CW * 8 * 16 * 4;        // float [32][m + m^2] per-pair P s | P
-constexpr int JOFF_TH = JOFF_PAIR + JT_PMAX * JT_WMAX * 4;    // float [2][32][m] theta of the pair's sample
-constexpr int JOFF_PI = JOFF_TH + 2 * JT_PMAX * JT_MMAX * 4;  // int [2][32] sample of the pair (-1: empty slot)
-constexpr int JOFF_PJ = JOFF_PI + 2 * JT_PMAX * 4;            // int [2][32] observation of the pair
-constexpr int JOFF_PS = JOFF_PJ + 2 * JT_PMAX * 4;            // float [2][32] power-of-two scale of the pair's primal row
-constexpr int JOFF_BOUT = JOFF_PS + 2 * JT_PMAX * 4;          // float [8]
-constexpr int JOFF_BAR = JOFF_BOUT + 32;                      // mbarriers
-constexpr int JOFF_TMEM = JOFF_BAR + (2 * JT_NSTG + 2) * 8;
+constexpr int JT_MBUF = 3;  // pair tables of the tiles t - 1 (being finished), t and t + 1 (prepared ahead)
+constexpr int JOFF_TH = JOFF_PAIR + JT_PMAX * JT_WMAX * 4;          // float [3][32][m] theta of the pair's sample
+constexpr int JOFF_PI = JOFF_TH + JT_MBUF * JT_PMAX * JT_MMAX * 4;  // int [3][32] sample of the pair (-1: empty slot)
+constexpr int JOFF_PJ = JOFF_PI + JT_MBUF * JT_PMAX * 4;            // int [3][32] observation of the pair
+constexpr int JOFF_PS = JOFF_PJ + JT_MBUF * JT_PMAX * 4;            // float [3][32] power-of-two scale of the pair's primal row
+constexpr int JOFF_BOUT = JOFF_PS + JT_MBUF * JT_PMAX * 4;          // float [8]
+constexpr int JOFF_BAR = JOFF_BOUT + 32;                            // mbarriers: full[3] | empty[3] | a | dn[2] | c[4]
+constexpr int JOFF_TMEM = JOFF_BAR + (2 * JT_NSTG + 3 + 4) * 8;
 // CTA-pair instantiation: the ring region holds 6 half-size stages (a CTA streams half of every weight tile); its barriers and
-// the leader's copies for the peer's arrivals: full[6] | empty[6] | fullp[6] | ap
+// the leader's copies for the peer's arrivals: full[6] | empty[6] | fullp[6] | ap | cp[4]
 constexpr int JT_NSTG_PAIR = 6;
 constexpr int JOFF_BARP = JOFF_TMEM + 16;
-constexpr int JT_SMEM_BYTES = JOFF_BARP + (3 * JT_NSTG_PAIR + 1) * 8;
+constexpr int JT_SMEM_BYTES = JOFF_BARP + (3 * JT_NSTG_PAIR + 1 + 4) * 8;
 static_assert(JT_SMEM_BYTES <= 232448, "shared memory budget (227 KB per CTA) exceeded");
 static_assert(JOFF_BAR % 8 == 0 && JOFF_AIMG % 16 == 0 && JOFF_H % 16 == 0, "alignment");
 
@@ -124,13 +125,25 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
     auto bar_full = [&](int s) { return PAIR ? barp0 + 8u * s : bar0 + 8u * s; };
     auto bar_empty = [&](int s) { return PAIR ? barp0 + 8u * (NSTG + s) : bar0 + 8u * (JT_NSTG + s); };
     const uint32_t bar_a = bar0 + 8u * (2 * JT_NSTG);      // A operand ready for the MMA warp
-    const uint32_t bar_d = bar0 + 8u * (2 * JT_NSTG + 1);  // accumulator ready for the epilogue
+    // accumulator ready for the epilogue: two barriers used alternately, layer by layer (the MMA warp may complete the last layer
+    // of a tile and the first layer of the next one before the compute warps look at the first)
+    auto bar_dn = [&](unsigned n) { return bar0 + 8u * (2 * JT_NSTG + 1 + (n & 1u)); };
+    // block cb of a mid epilogue is in tensor memory (every compute warp has converted its cb-th 16-column block): K-steps
+    // {cq * nblk + cb, cq = 0..3} of the next layer may be issued
+    auto bar_c = [&](int cb) { return bar0 + 8u * (2 * JT_NSTG + 3 + cb); };
+    // i-th K-step of a TS-form layer in issue order (K = 64 nblk): block index first, column quarter second
+    auto ks_of = [](int i, int nblk) { return (i & 3) * nblk + (i >> 2); };
     // CTA pair: the leader's copies of the barriers the peer CTA arrives on
     const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = crank == 0u;
     auto bar_fullp = [&](int s) { return barp0 + 8u * (2 * NSTG + s); };
     const uint32_t bar_ap = barp0 + 8u * (3 * NSTG);
+    auto bar_cp = [&](int cb) { return barp0 + 8u * (3 * NSTG + 1 + cb); };
     const uint32_t arr_a = (PAIR && !leader) ? mapa_shared(bar_ap, 0u) : bar_a;
+    auto arrive_c = [&](int cb) {
+        if (PAIR && !leader) mbar_arrive_cluster(mapa_shared(bar_cp(cb), 0u));
+        else mbar_arrive(bar_c(cb));
+    };
     auto arrive_a = [&]() {
         if (PAIR && !leader) mbar_arrive_cluster(arr_a);
         else mbar_arrive(bar_a);
@@ -153,7 +166,12 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
         }
         mbar_init(bar_a, TC_CW * 32);
         if (PAIR) mbar_init(bar_ap, TC_CW * 32);
-        mbar_init(bar_d, 1);
+        mbar_init(bar_dn(0), 1);
+        mbar_init(bar_dn(1), 1);
+        for (int cb = 0; cb < 4; ++cb) {
+            mbar_init(bar_c(cb), TC_CW * 32);
+            if (PAIR) mbar_init(bar_cp(cb), TC_CW * 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC_CW + 1) {  // TMEM: two 256-column fp32 accumulators, used alternately layer by layer
@@ -221,7 +239,8 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                     // two passes over K (see the MMA issuer): cross terms first (hi | lo images), then the main terms (hi image only)
                     for (int pass = 0; pass < (JT_TWO_PASS ? 2 : 1); ++pass) {
                         const uint32_t nb = (JT_TWO_PASS && pass == 1) ? mine / 2 : mine;
-                        for (int ks = 0; ks < K / 16; ++ks, ++it) {
+                        for (int i = 0; i < K / 16; ++i, ++it) {
+                            const int ks = (l > 1) ? ks_of(i, K / 64) : i;  // the order the MMA warp consumes them in
                             const int s = it % NSTG;
                             const uint32_t ph = (it / NSTG) & 1u;
                             mbar_wait(bar_empty(s), ph ^ 1u, p.error_flag);
@@ -250,7 +269,7 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
             }
         } else
         if (lane == 0) {
-            unsigned it = 0, a_cnt = 0, lc = 0;
+            unsigned it = 0, a_cnt = 0, lc = 0, c_par = 0;  // c_par: bit cb = phase parity of bar_c(cb) to wait for next
             const uint32_t a_hi0 = smem_u32(sAhi), a_lo0 = smem_u32(sAlo);
             for (int ti = 0; ti < my_tiles; ++ti) {
                 for (int l = 1; l <= Lh; ++l) {
@@ -264,9 +283,13 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                     const uint32_t a_lbo = 2048u, a_sbo = 128u;
                     const bool prof_on = p.prof != nullptr && blockIdx.x == 0;
                     long long pt0 = prof_on ? clock64() : 0;
-                    mbar_wait(bar_a, a_cnt & 1u, p.error_flag);
-                    if (PAIR) mbar_wait(bar_ap, a_cnt & 1u, p.error_flag);  // the peer's operand image
-                    ++a_cnt;
+                    if (l == 1) {  // layer 0 of the tile is in shared memory (layers l > 1 take their operand from tensor memory)
+                        mbar_wait(bar_a, a_cnt & 1u, p.error_flag);
+                        if (PAIR) mbar_wait(bar_ap, a_cnt & 1u, p.error_flag);  // the peer's operand image
+                        ++a_cnt;
+                        // this layer's accumulator is the region the previous tile's last (TS-form) layer reads its A operand from
+                        if (lc > 0 && Lh >= 2) mbar_wait(bar_dn(lc - 1u), ((lc - 1u) >> 1) & 1u, p.error_flag);
+                    }
                     long long pt1 = 0, pfull = 0;
                     if (prof_on) {
                         pt1 = clock64();
@@ -274,13 +297,22 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                     }
                     tc_fence_after();
                     const uint32_t dacc = tmem_d + ((lc & 1u) ? 256u : 0u);
+                    const uint32_t dprev = tmem_d + ((lc & 1u) ? 0u : 256u);  // accumulator of the previous layer = TS-form A operand
                     ++lc;
                     // The tensor core truncates when it adds into the accumulator: every accumulating instruction loses a fraction of an
                     // ulp of the RUNNING SUM.  All cross terms (2^-11 of the result) are therefore summed first, while the accumulator
                     // is still small, and the K / 16 main-term instructions follow: a third as many truncations at full magnitude (the
                     // remaining, now uniform, deficit is what acc_debias() corrects in the epilogues).  Costs one more pass of the hi images.
                     for (int pass = 0; pass < (JT_TWO_PASS ? 2 : 1); ++pass) {
-                        for (int ks = 0; ks < K / 16; ++ks, ++it) {
+                        for (int i = 0; i < K / 16; ++i, ++it) {
+                            const int ks = (l > 1) ? ks_of(i, K / 64) : i;
+                            if (l > 1 && pass == 0 && (i & 3) == 0) {  // block i / 4 of the previous layer's epilogue is in tensor memory
+                                mbar_wait(bar_c(i >> 2), (c_par >> (i >> 2)) & 1u, p.error_flag);
+                                if (PAIR) mbar_wait(bar_cp(i >> 2), (c_par >> (i >> 2)) & 1u, p.error_flag);
+                                c_par ^= 1u << (i >> 2);
+                                tc_fence_after();
+                            }
+                            const bool first = pass == 0 && i == 0;  // first instruction of the layer overwrites the accumulator
                             const int s = it % NSTG;
                             const uint32_t ph = (it / NSTG) & 1u;
                             const long long pf0 = prof_on ? clock64() : 0;
@@ -293,28 +325,47 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                             const uint64_t b_lo = umma_desc(wb + (uint32_t)Nb * 32u, b_lbo, b_sbo);
                             const uint64_t a_hi = umma_desc(a_hi0 + ks * 4096, a_lbo, a_sbo);
                             const uint64_t a_lo = umma_desc(a_lo0 + ks * 4096, a_lbo, a_sbo);
+                            // layers l > 1: A = the previous layer's accumulator region, converted in place by the mid epilogue
+                            // (K-step ks: fp16 hi parts in columns 16 ks .. +7, lo parts in +8 .. +15)
+                            const uint32_t a_t = dprev + (uint32_t)ks * 16u;
                             if (PAIR) {
                                 if (!JT_TWO_PASS || pass == 0) {
-                                    tc_mma2_bf16(dacc, a_lo, b_hi, idesc, ks > 0 ? 1u : 0u);
-                                    tc_mma2_bf16(dacc, a_hi, b_lo, idesc, 1u);
+                                    if (l > 1) {
+                                        tc_mma2_bf16_ts(dacc, a_t + 8u, b_hi, idesc, first ? 0u : 1u);
+                                        tc_mma2_bf16_ts(dacc, a_t, b_lo, idesc, 1u);
+                                    } else {
+                                        tc_mma2_bf16(dacc, a_lo, b_hi, idesc, first ? 0u : 1u);
+                                        tc_mma2_bf16(dacc, a_hi, b_lo, idesc, 1u);
+                                    }
                                 }
-                                if (!JT_TWO_PASS || pass == 1) tc_mma2_bf16(dacc, a_hi, b_hi, idesc, 1u);
+                                if (!JT_TWO_PASS || pass == 1) {
+                                    if (l > 1) tc_mma2_bf16_ts(dacc, a_t, b_hi, idesc, 1u);
+                                    else tc_mma2_bf16(dacc, a_hi, b_hi, idesc, 1u);
+                                }
                                 tc_commit2(bar_empty(s));
                             } else {
                                 if (!JT_TWO_PASS || pass == 0) {
-                                    tc_mma_bf16(dacc, a_lo, b_hi, idesc, ks > 0 ? 1u : 0u);
-                                    tc_mma_bf16(dacc, a_hi, b_lo, idesc, 1u);
+                                    if (l > 1) {
+                                        tc_mma_bf16_ts(dacc, a_t + 8u, b_hi, idesc, first ? 0u : 1u);
+                                        tc_mma_bf16_ts(dacc, a_t, b_lo, idesc, 1u);
+                                    } else {
+                                        tc_mma_bf16(dacc, a_lo, b_hi, idesc, first ? 0u : 1u);
+                                        tc_mma_bf16(dacc, a_hi, b_lo, idesc, 1u);
+                                    }
                                 }
-                                if (!JT_TWO_PASS || pass == 1) tc_mma_bf16(dacc, a_hi, b_hi, idesc, 1u);
+                                if (!JT_TWO_PASS || pass == 1) {
+                                    if (l > 1) tc_mma_bf16_ts(dacc, a_t, b_hi, idesc, 1u);
+                                    else tc_mma_bf16(dacc, a_hi, b_hi, idesc, 1u);
+                                }
                                 tc_commit(bar_empty(s));
                             }
                         }
                     }
-                    if (PAIR) tc_commit2(bar_d);
-                    else tc_commit(bar_d);
+                    if (PAIR) tc_commit2(bar_dn(lc - 1u));
+                    else tc_commit(bar_dn(lc - 1u));
                     if (prof_on) {  // profiling only: drain, so that slot 3 is issue -> complete of this layer
                         const long long pt2 = clock64();
-                        mbar_wait(bar_d, (lc - 1u) & 1u, p.error_flag);
+                        mbar_wait(bar_dn(lc - 1u), ((lc - 1u) >> 1) & 1u, p.error_flag);
                         p.prof[1] += pfull;                 // waiting for ring stages
                         p.prof[2] += pt2 - pt1;             // issue loop (including those waits)
                         p.prof[3] += clock64() - pt1;       // operand ready -> accumulator complete
@@ -581,7 +632,18 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
             compute_bar();  // the pair tables of this buffer are rewritten next
         };
 
+        // Schedule (one tile = layer 0 -> tensor-core layers 1 .. Lh -> fp32 output layer -> pair algebra).  The tensor core is the
+        // critical resource, so everything else runs underneath it:
+        //   while layer 1 of tile t runs:        last epilogue + output layer + pair algebra of tile t - 1
+        //   mid epilogue of tile t:               converted IN PLACE in tensor memory (the next layer takes its A operand from there,
+        //                                         TS form), handed over block by block: the next layer starts after the first block
+        //   while the last layer of tile t runs:  layer 0 of tile t + 1 into the shared-memory images (free since layer 1 completed),
+        //                                         pair tables of tile t + 2
+        // so layer 1 of tile t + 1 starts the moment the last layer of tile t has completed.
         if (my_tiles > 0) prepare_meta(blockIdx.x, 0);
+        compute_bar();
+        if (my_tiles > 0) do_layer0(0);
+        if (my_tiles > 1) prepare_meta(blockIdx.x + (int)gridDim.x, 1);
         compute_bar();
         const bool cprof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
         long long ct = cprof ? clock64() : 0;
@@ -593,59 +655,72 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
             ct = now_;                         \
         }                                      \
     } while (0)
-        for (int ps = 0; ps <= my_tiles; ++ps) {  // one extra iteration finishes the last tile
-            const bool have = ps < my_tiles, prev = ps > 0;
+        auto wait_layer = [&]() -> uint32_t {  // next tensor-core layer in issue order; returns its accumulator
+            const uint32_t dacc = tmem_d + ((d_cnt & 1u) ? 256u : 0u);
+            mbar_wait(bar_dn(d_cnt), (d_cnt >> 1) & 1u, p.error_flag);
+            ++d_cnt;
+            tc_fence_after();
+            return dacc;
+        };
+        uint32_t dacc_last = 0;  // accumulator of the last layer of the previous tile
+        for (int ps = 0; ps < my_tiles; ++ps) {
             const int tile = blockIdx.x + ps * (int)gridDim.x;
-            const int buf = ps & 1;
-            uint32_t dacc_prev = 0;
-            if (prev) {  // the last layer of the previous tile: once it is done the operand images are free again
-                dacc_prev = tmem_d + ((d_cnt & 1u) ? 256u : 0u);
-                mbar_wait(bar_d, d_cnt & 1u, p.error_flag);
-                ++d_cnt;
-                tc_fence_after();
+            const int buf = ps % JT_MBUF, pbuf = (ps + JT_MBUF - 1) % JT_MBUF;
+            if (ps > 0) {
+                do_last_epilogue(dacc_last, pbuf);
+                JPROF(7);
+                do_pairs(tile - (int)gridDim.x, pbuf);
+                JPROF(10);
             }
-            JPROF(5);  // waiting for the last layer of the previous tile
-            if (have) do_layer0(buf);
-            JPROF(6);
-            if (prev) do_last_epilogue(dacc_prev, buf ^ 1);
-            JPROF(7);
-            if (have) {
-                for (int l = 1; l < Lh; ++l) {  // hidden layers that feed another tensor-core layer
-                    const int Nn = net.Hp[l];
-                    const int qcols = Nn >> 2, nblk = qcols / 16;
-                    const float* bias_l = net.bias16[l] + cq * qcols;
-                    const float hval = exp2f(-(float)net.sw16[l]);
-                    const float deb_l = acc_debias(net.Hp[l - 1]);
-                    const float psb_cur = bsel * (rvalid ? sPS[buf * JT_PMAX + q * PW + pl] : 1.f);
-                    const uint32_t dacc = tmem_d + ((d_cnt & 1u) ? 256u : 0u);
-                    mbar_wait(bar_d, d_cnt & 1u, p.error_flag);
-                    ++d_cnt;
-                    tc_fence_after();
-                    JPROF(8);  // waiting for a hidden layer
-                    for (int cb = 0; cb < nblk; ++cb) {
-                        const int col0 = cq * qcols + 16 * cb;
-                        float a[16];
-                        ld_act(dacc, col0, bias_l + 16 * cb, hval, deb_l, psb_cur, a);
+            for (int l = 1; l < Lh; ++l) {  // hidden layers that feed another tensor-core layer
+                const int Nn = net.Hp[l];
+                const int qcols = Nn >> 2, nblk = qcols / 16;
+                const float* bias_l = net.bias16[l] + cq * qcols;
+                const float hval = exp2f(-(float)net.sw16[l]);
+                const float deb_l = acc_debias(net.Hp[l - 1]);
+                const float psb_cur = bsel * (rvalid ? sPS[buf * JT_PMAX + q * PW + pl] : 1.f);
+                const uint32_t dacc = wait_layer();
+                JPROF(8);  // waiting for a hidden layer
+                for (int cb = 0; cb < nblk; ++cb) {
+                    const int col0 = cq * qcols + 16 * cb;
+                    float a[16];
+                    ld_act(dacc, col0, bias_l + 16 * cb, hval, deb_l, psb_cur, a);
+                    // the next layer's A operand goes back to TENSOR MEMORY, in place over the 16 accumulator columns just read:
+                    // columns col0 .. +7 = fp16 hi parts of K elements col0 .. col0 + 15, columns +8 .. +15 = lo parts
+                    uint32_t w[16];
 #pragma unroll
-                        for (int k8 = 0; k8 < 2; ++k8) {
-                            float v[8];
+                    for (int k8 = 0; k8 < 2; ++k8) {
+                        float v[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = a[8 * k8 + e];
-                            store_split8_f16(v, sAhi, sAlo, a_off(row, (col0 >> 3) + k8));
-                        }
+                        for (int e = 0; e < 8; ++e) v[e] = a[8 * k8 + e];
+                        split8_regs_f16(v, w + 4 * k8, w + 8 + 4 * k8);
                     }
-                    fence_proxy_async();
+                    tc_st16(dacc + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, w);
+                    tc_wait_st();
                     tc_fence_before();
-                    arrive_a();
-                    JPROF(9);  // mid epilogue
+                    arrive_c(cb);
                 }
+                JPROF(9);  // mid epilogue
             }
-            if (prev) do_pairs(tile - (int)gridDim.x, buf ^ 1);
-            JPROF(10);
-            if (ps + 1 < my_tiles) prepare_meta(tile + (int)gridDim.x, buf ^ 1);
+            if (Lh < 2) {  // a single tensor-core layer: the shared-memory images are free once it has completed
+                dacc_last = wait_layer();
+                JPROF(5);
+            }
+            if (ps + 1 < my_tiles) do_layer0((ps + 1) % JT_MBUF);
+            JPROF(6);
+            if (ps + 2 < my_tiles) prepare_meta(tile + 2 * (int)gridDim.x, (ps + 2) % JT_MBUF);
             JPROF(11);
             compute_bar();
             JPROF(12);
+            if (Lh >= 2) {
+                dacc_last = wait_layer();  // the last layer of this tile
+                JPROF(5);
+            }
+        }
+        if (my_tiles > 0) {
+            const int pbuf = (my_tiles - 1) % JT_MBUF;
+            do_last_epilogue(dacc_last, pbuf);
+            do_pairs(blockIdx.x + (my_tiles - 1) * (int)gridDim.x, pbuf);
         }
 #undef JPROF
     }

@@ -260,6 +260,21 @@ __device__ __forceinline__ void store_split8_f16(const float (&v)[8], uint8_t* a
     *reinterpret_cast<uint4*>(a_lo + byte_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// the same split into registers: hi[e] / lo[e] = packed fp16 pair of elements (2e, 2e + 1)
+__device__ __forceinline__ void split8_regs_f16(const float (&v)[8], uint32_t* hi, uint32_t* lo) {
+    const float2 k = make_float2(8193.0f, 8193.0f), neg1 = make_float2(-1.0f, -1.0f);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 x = make_float2(v[2 * e], v[2 * e + 1]);
+        const float2 c = __fmul2_rn(x, k);
+        const float2 d = __ffma2_rn(x, neg1, c);
+        const float2 h = __ffma2_rn(d, neg1, c);
+        const float2 l = __ffma2_rn(h, neg1, x);
+        hi[e] = pack_f16x2_sat(h.x, h.y);
+        lo[e] = pack_f16x2_sat(l.x, l.y);
+    }
+}
+
 // The tensor core accumulates by TRUNCATION: every tcgen05.mma that adds into an fp32 accumulator loses, on average, a fixed
 // fraction of an ulp of the running sum, always towards zero -- a systematic relative deficit of the result that grows with the
 // number of accumulating instructions at full magnitude.  Measured on the JAC fixtures, where inv(I - sigma J) amplifies it: the
