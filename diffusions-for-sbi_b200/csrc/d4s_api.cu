@@ -92,9 +92,11 @@ static bool tc_eligible(const D4sNet* net, const D4sProblem* pb) {
 }
 
 static bool jac_tc_eligible(const D4sNet* net, const D4sProblem* pb) {
-    return g_opt_path != 1 && g_opt_jac_tc != 0 && pb->cov_mode == D4S_COV_JAC && !pb->paired && net->dev.L >= 3 && net->dev.emb_L == 0 &&
+    return g_opt_path != 1 && g_opt_jac_tc != 0 && pb->cov_mode == D4S_COV_JAC && !pb->paired && net->dev.L >= 3 &&
            net->dev.out_act == 0 && net->dev.out_scale == 1.f && pb->obs_raw == nullptr && net->dev.m <= 5 &&
-           pb->ctx_samples == 0;
+           // (batched contexts of an embedding net stay on the fp32 SIMT kernel: on the JR-NMM contexts fixture 2 of 15 JAC
+           // trajectories leave the reference's path instead of 1 -- per-call parity holds, JAC trajectories are chaotic)
+           (pb->ctx_samples == 0 || net->dev.emb_L == 0);
 }
 
 // Units (sample, chunk of OC observations) packed UT per tile of PT pairs: pick the chunking that wastes the fewest
@@ -549,12 +551,23 @@ static int score_partials_impl(const D4sNet* net, const D4sProblem* pb, const D4
         const long long tiles = (units + t.jUT - 1) / t.jUT;
         if (tiles > 2147483647LL) return fail(D4S_ERR_ARG, "too many tiles");
         jp.n_tiles = (int)tiles;
+        jp.ctx_samples = pb->ctx_samples;
         jp.theta = theta;
         jp.obs_feat = pb->obs_feat;
         jp.time_feat = st->time_feat;
         jp.sched = st->sched;
         jp.obs_weight = pb->obs_weight;
         jp.part = pb->workspace;
+        if (net->dev.emb_L > 0) {  // kernel 0: embedded theta -> layer-0 sample part + tangent seeds (behind the partial sums)
+            const int64_t part = (int64_t)pb->n_samples * (t.C > t.Cws ? t.C : t.Cws) * t.W;
+            float* base_pre = pb->workspace + part;
+            float* tan_pre = base_pre + (size_t)pb->n_samples * net->dev.Hp[0];
+            cudaError_t e0 = launch_theta_embed(net->dev, theta, pb->n_samples, 1, base_pre, tan_pre, stream);
+            if (e0 != cudaSuccess) return cuda_fail(e0, "theta embedding kernel launch");
+            ++g_launches;
+            jp.base_pre = base_pre;
+            jp.tan_pre = tan_pre;
+        }
         if (!g_err_flag) {
             if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaMalloc(flag)");
             cudaMemset(g_err_flag, 0, sizeof(int));

@@ -137,12 +137,15 @@ struct JacTcParams {
     int N, n, C, OC, UT, PW;
     int n_tiles;
     int cta_pair;             // 1: clusters of 2 CTAs sharing one cta_group::2 MMA stream (jac_tc_kernel<true>)
+    int ctx_samples;          // batched contexts (D4sProblem.ctx_samples): > 0 = samples per context, obs_feat is [B n][Hp0]
     const float* theta;       // [N][m]
     const float* obs_feat;    // [n][Hp0]
     const float* time_feat;   // [Hp0] row of this step
     const float* sched;       // [16] row of this step
     const float* obs_weight;  // [n] or NULL
     float* part;              // [N][C][m + m^2] sums over the chunk's observations of P s | P
+    const float* base_pre;    // nets with a theta-embedding MLP: [N][Hp0] A e(theta_i) and
+    const float* tan_pre;     //   [N][m][Hp0] A d e / d theta_k from theta_embed_kernel (NULL otherwise)
     int* error_flag;
     long long* prof;          // optional [16] cycle counters of CTA 0 (d4s_set_option("profile", 1); tests/gpu_debug_jac_prof.py)
 };

@@ -189,11 +189,13 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
         const int Kout = net.Hp[L - 2];
         for (int e = tid; e < m * Kout; e += JT_THREADS) sWout[(e / Kout) * 256 + (e % Kout)] = __ldg(net.WoutT + e);
         // the operands carry 2^4 x activation (ACT_SC), see the note at store_split8_f16: layer 0 is built in that scale
-        for (int e = tid; e < m * H0; e += JT_THREADS) sA[(e / H0) * 256 + (e % H0)] = ACT_SC * __ldg(net.A + e);
+        // (nets with a theta-embedding MLP: the layer-0 sample part and its tangents come per sample from theta_embed_kernel)
+        const bool emb = p.base_pre != nullptr;
+        for (int e = tid; e < (emb ? 0 : m * H0); e += JT_THREADS) sA[(e / H0) * 256 + (e % H0)] = ACT_SC * __ldg(net.A + e);
         for (int e = tid; e < H0; e += JT_THREADS) sTf[e] = ACT_SC * __ldg(p.time_feat + e);
         if (tid < 8) sBout[tid] = (tid < m) ? __ldg(net.bout + tid) : 0.f;
         // fp16 hi / lo K-groups of the theta block (the layer-0 tangents are masked copies of them)
-        for (int e = tid; e < m * (H0 / 8); e += JT_THREADS) {
+        for (int e = tid; e < (emb ? 0 : m * (H0 / 8)); e += JT_THREADS) {
             const int k = e / (H0 / 8), kg = e - k * (H0 / 8);
             uint32_t hi[4], lo[4];
 #pragma unroll
@@ -400,6 +402,9 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                     const int ii = (int)(gu / p.C), ch = (int)(gu - (long long)ii * p.C);
                     j = ch * p.OC + o;
                     if (j < p.n) i = ii;
+                    // batched contexts: sample ii belongs to context ii / ctx_samples, whose observation block starts at row
+                    // (ii / ctx_samples) * n of obs_feat
+                    if (p.ctx_samples > 0) j += (ii / p.ctx_samples) * p.n;
                 }
                 sPI[buf * JT_PMAX + tid] = i;
                 sPJ[buf * JT_PMAX + tid] = j;
@@ -459,15 +464,25 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                         z[2] = fmaf(u[jj][0].z, ACT_SC, t0.z); z[3] = fmaf(u[jj][0].w, ACT_SC, t0.w);
                         z[4] = fmaf(u[jj][1].x, ACT_SC, t1.x); z[5] = fmaf(u[jj][1].y, ACT_SC, t1.y);
                         z[6] = fmaf(u[jj][1].z, ACT_SC, t1.z); z[7] = fmaf(u[jj][1].w, ACT_SC, t1.w);
+                        if (p.base_pre) {  // embedding net: A e(theta_i), precomputed per sample
+                            const float* bp = p.base_pre + (size_t)i * H0 + 8 * kg;
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
+                            z[0] = fmaf(b0.x, ACT_SC, z[0]); z[1] = fmaf(b0.y, ACT_SC, z[1]);
+                            z[2] = fmaf(b0.z, ACT_SC, z[2]); z[3] = fmaf(b0.w, ACT_SC, z[3]);
+                            z[4] = fmaf(b1.x, ACT_SC, z[4]); z[5] = fmaf(b1.y, ACT_SC, z[5]);
+                            z[6] = fmaf(b1.z, ACT_SC, z[6]); z[7] = fmaf(b1.w, ACT_SC, z[7]);
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < JT_MMAX; ++k) {
-                            if (k < m) {
-                                const float4 a0 = *reinterpret_cast<const float4*>(sA + k * 256 + 8 * kg);
-                                const float4 a1 = *reinterpret_cast<const float4*>(sA + k * 256 + 8 * kg + 4);
-                                z[0] = fmaf(a0.x, th[k], z[0]); z[1] = fmaf(a0.y, th[k], z[1]);
-                                z[2] = fmaf(a0.z, th[k], z[2]); z[3] = fmaf(a0.w, th[k], z[3]);
-                                z[4] = fmaf(a1.x, th[k], z[4]); z[5] = fmaf(a1.y, th[k], z[5]);
-                                z[6] = fmaf(a1.z, th[k], z[6]); z[7] = fmaf(a1.w, th[k], z[7]);
+                            for (int k = 0; k < JT_MMAX; ++k) {
+                                if (k < m) {
+                                    const float4 a0 = *reinterpret_cast<const float4*>(sA + k * 256 + 8 * kg);
+                                    const float4 a1 = *reinterpret_cast<const float4*>(sA + k * 256 + 8 * kg + 4);
+                                    z[0] = fmaf(a0.x, th[k], z[0]); z[1] = fmaf(a0.y, th[k], z[1]);
+                                    z[2] = fmaf(a0.z, th[k], z[2]); z[3] = fmaf(a0.w, th[k], z[3]);
+                                    z[4] = fmaf(a1.x, th[k], z[4]); z[5] = fmaf(a1.y, th[k], z[5]);
+                                    z[6] = fmaf(a1.z, th[k], z[6]); z[7] = fmaf(a1.w, th[k], z[7]);
+                                }
                             }
                         }
                         uint32_t mw[4];  // 16-bit lane masks of the bf16 pairs
@@ -478,13 +493,27 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] = fmaxf(z[e], 0.f) * psc;
                         store_split8_f16(v, sAhi, sAlo, a_off(prow, kg));
+                        if (p.tan_pre) {  // embedding net: tangent k of the layer-0 input = A d e / d theta_k of this sample, masked
+                            for (int k = 0; k < m; ++k) {
+                                const float* tp = p.tan_pre + ((size_t)i * m + k) * H0 + 8 * kg;
+                                const float4 t0 = __ldg(reinterpret_cast<const float4*>(tp));
+                                const float4 t1 = __ldg(reinterpret_cast<const float4*>(tp + 4));
+                                float tv[8];
+                                tv[0] = z[0] > 0.f ? ACT_SC * t0.x : 0.f; tv[1] = z[1] > 0.f ? ACT_SC * t0.y : 0.f;
+                                tv[2] = z[2] > 0.f ? ACT_SC * t0.z : 0.f; tv[3] = z[3] > 0.f ? ACT_SC * t0.w : 0.f;
+                                tv[4] = z[4] > 0.f ? ACT_SC * t1.x : 0.f; tv[5] = z[5] > 0.f ? ACT_SC * t1.y : 0.f;
+                                tv[6] = z[6] > 0.f ? ACT_SC * t1.z : 0.f; tv[7] = z[7] > 0.f ? ACT_SC * t1.w : 0.f;
+                                store_split8_f16(tv, sAhi, sAlo, a_off(prow + 1 + k, kg));
+                            }
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < JT_MMAX; ++k) {
-                            if (k < m) {
-                                const uint4 hi = sAimg[(k * 32 + kg) * 2], lo = sAimg[(k * 32 + kg) * 2 + 1];
-                                const int off = a_off(prow + 1 + k, kg);
-                                *reinterpret_cast<uint4*>(sAhi + off) = make_uint4(hi.x & mw[0], hi.y & mw[1], hi.z & mw[2], hi.w & mw[3]);
-                                *reinterpret_cast<uint4*>(sAlo + off) = make_uint4(lo.x & mw[0], lo.y & mw[1], lo.z & mw[2], lo.w & mw[3]);
+                            for (int k = 0; k < JT_MMAX; ++k) {
+                                if (k < m) {
+                                    const uint4 hi = sAimg[(k * 32 + kg) * 2], lo = sAimg[(k * 32 + kg) * 2 + 1];
+                                    const int off = a_off(prow + 1 + k, kg);
+                                    *reinterpret_cast<uint4*>(sAhi + off) = make_uint4(hi.x & mw[0], hi.y & mw[1], hi.z & mw[2], hi.w & mw[3]);
+                                    *reinterpret_cast<uint4*>(sAlo + off) = make_uint4(lo.x & mw[0], lo.y & mw[1], lo.z & mw[2], lo.w & mw[3]);
+                                }
                             }
                         }
                     }
@@ -622,7 +651,8 @@ __global__ void __launch_bounds__(JT_THREADS, 1) jac_tc_kernel(const JacTcParams
                     for (int o = 0; o < p.OC; ++o) {
                         const int pp = u * p.OC + o;
                         if (sPI[buf * JT_PMAX + pp] >= 0) {
-                            const float wj = p.obs_weight ? __ldg(p.obs_weight + sPJ[buf * JT_PMAX + pp]) : 1.f;
+                            const int pj = sPJ[buf * JT_PMAX + pp];
+                            const float wj = p.obs_weight ? __ldg(p.obs_weight + (p.ctx_samples > 0 ? pj % p.n : pj)) : 1.f;
                             acc = fmaf(wj, sPair[pp * W + w], acc);
                         }
                     }
