@@ -819,6 +819,14 @@ int d4s_ddim_run(const D4sNet* net, const D4sProblem* pb, int32_t steps, const f
         const int tc = try_traj_tc(net, pb, steps, sched_dev, time_feat_dev, mats_dev, noise_dev, theta_dev, step_mode, stream);
         if (tc <= 0) return tc;  // 0 = launched on the tcgen05 path, < 0 = error
     }
+    {   // A graph pays when the per-step kernels are shorter than their launches.  Its key holds the seed, so a fresh trajectory
+        // captures and instantiates 2 x steps nodes again (~9 us per node: 7 ms of an 85 ms Lotka-Volterra JAC trajectory);
+        // with >= 32k grid rows per step every kernel runs for tens of microseconds and plain stream launches stay ahead of the
+        // GPU.
+        const long long rows = (long long)pb->n_samples * (pb->paired ? 1 : pb->n_obs) *
+                               (pb->cov_mode == D4S_COV_JAC || step_mode ? 1 + net->dev.m : 1);
+        if (rows >= 32768) use_graph = 0;
+    }
     if (!use_graph)
         return enqueue_steps(net, pb, steps, sched_dev, time_feat_dev, mats_dev, noise_dev, theta_dev, step_mode, affine_dev,
                              stream);
