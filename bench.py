@@ -44,10 +44,10 @@ SHAPES = {  # BASELINE.json configs
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE traj_tc_kernel launch (a whole 1000-step trajectory) of the default
-# workload, from the ncu --set full capture summarised in profiles/r02_ncu_full_traj_tc.txt (3.123 MB + 0.194 MB): weights,
+# workload, from the ncu --set full capture summarised in profiles/r02_ncu_full_traj_tc.txt (3.126 MB + 0.129 MB): weights,
 # observation features and per-step tables are read once and stay in L2; the kernel is not HBM-bound.  NOT measured in the
 # bench run itself (a number printed under a profiler is never a bench value): the roofline record names this source.
-TRAJ_TC_DRAM_BYTES = 3122688 + 194048
+TRAJ_TC_DRAM_BYTES = 3125760 + 128768
 
 
 def is_default_workload(args, w) -> bool:
