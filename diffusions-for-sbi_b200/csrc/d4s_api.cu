@@ -23,6 +23,7 @@ static int* g_err_flag = nullptr;
 static int g_opt_profile = 0;
 static int g_opt_jac_tc = 1;      // 1 (default): JAC steps on the tcgen05 score + Jacobian kernel where eligible (fp16x3 split); 0: fp32 SIMT kernel
 static int g_opt_tc_pairing = 1;  // interleave two sample groups per CTA in the tcgen05 kernel (0 = one after the other)
+static int g_opt_paired_tc = 1;  // paired mode (covariance pre-pass) on its tcgen05 trajectory kernel; 0: fp32 SIMT kernels
 static int g_opt_jac_cta_pair = [] {  // JAC step kernel as CTA pairs; D4S_JAC_CTA_PAIR=0/1
     const char* e = getenv("D4S_JAC_CTA_PAIR");
     return e ? atoi(e) : 0;
@@ -171,7 +172,8 @@ static int check_problem(const D4sNet* net, const D4sProblem* pb) {
     if (pb->theta_dim != net->dev.m) return fail(D4S_ERR_ARG, "problem.theta_dim != net output dim");
     if (pb->n_samples < 1 || pb->n_obs < 1) return fail(D4S_ERR_ARG, "n_samples and n_obs must be >= 1");
     if (pb->cov_mode != D4S_COV_GAUSS && pb->cov_mode != D4S_COV_JAC) return fail(D4S_ERR_ARG, "bad cov_mode");
-    if (pb->paired && pb->n_obs != pb->n_samples) return fail(D4S_ERR_ARG, "paired mode needs n_obs == n_samples");
+    if (pb->paired < 0 || (pb->paired && (long long)pb->n_obs != (pb->n_samples + pb->paired - 1) / pb->paired))
+        return fail(D4S_ERR_ARG, "paired mode (k samples per observation row) needs n_obs == ceil(n_samples / k)");
     if (!pb->obs_feat) return fail(D4S_ERR_ARG, "obs_feat is null");
     if (pb->prior_kind == D4S_PRIOR_UNIFORM && (!pb->prior_low || !pb->prior_high))
         return fail(D4S_ERR_ARG, "uniform prior needs prior_low/prior_high");
@@ -768,6 +770,47 @@ static int enqueue_steps(const D4sNet* net, const D4sProblem* pb0, int steps, co
     return D4S_OK;
 }
 
+// Paired mode (row i = sample i with its own observation: nse.py:253-254, the covariance pre-pass) on its own tcgen05 trajectory
+// kernel (d4s_paired_tc.cu).  Returns 0 when enqueued, 1 when not eligible, < 0 on error.
+static int try_paired_tc(const D4sNet* net, const D4sProblem* pb, int steps, const float* sched, const float* tf,
+                         const float* noise, float* theta, cudaStream_t stream) {
+    const NetDev& nd = net->dev;
+    bool ok = g_opt_path != 1 && g_opt_paired_tc != 0 && pb->paired && nd.L >= 3 && nd.emb_L == 0 && nd.out_act == 0 &&
+              nd.out_scale == 1.f && pb->obs_raw == nullptr && pb->obs_weight == nullptr && nd.m <= 5 && pb->ctx_samples == 0 &&
+              pb->prior_kind == D4S_PRIOR_NONE && nd.Hp[0] % 8 == 0;
+    for (int l = 0; l <= nd.L - 2 && ok; ++l) ok = nd.Hp[l] <= 256 && nd.Hp[l] % 64 == 0;
+    if (!ok) return 1;
+    PairedTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.net = nd;
+    p.N = pb->n_samples;
+    p.obs_div = pb->paired;
+    p.step_begin = 0;
+    p.step_end = steps;
+    p.obs_feat = pb->obs_feat;
+    p.time_feat = tf;
+    p.sched = sched;
+    p.noise = noise;
+    p.theta = theta;
+    p.seed = pb->seed;
+    p.sample_offset = pb->sample_offset;
+    p.clip_lo = pb->clip_lo;
+    p.clip_hi = pb->clip_hi;
+    if (!g_err_flag) {
+        if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaMalloc(flag)");
+        cudaMemset(g_err_flag, 0, sizeof(int));
+    }
+    p.error_flag = g_err_flag;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (p.N + 127) / 128;
+    cudaError_t e = launch_paired_tc(p, (int)(tiles < sms ? tiles : sms), stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tcgen05 paired trajectory kernel launch");
+    ++g_launches;
+    return 0;
+}
+
 // Returns 0 when the trajectory was enqueued on the fused tcgen05 kernel, 1 when the problem is not eligible
 // (caller falls back to the per-step SIMT kernels), < 0 on error.
 static int try_traj_tc(const D4sNet* net, const D4sProblem* pb, int steps, const float* sched, const float* tf,
@@ -816,6 +859,10 @@ int d4s_ddim_run(const D4sNet* net, const D4sProblem* pb, int32_t steps, const f
     }
     if (affine_dev && (!pb->obs_raw || pb->x_dim < 1)) return fail(D4S_ERR_ARG, "affine table needs obs_raw and x_dim");
     if (!affine_dev) {
+        if (pb->paired) {
+            const int pr = try_paired_tc(net, pb, steps, sched_dev, time_feat_dev, noise_dev, theta_dev, stream);
+            if (pr <= 0) return pr;
+        }
         const int tc = try_traj_tc(net, pb, steps, sched_dev, time_feat_dev, mats_dev, noise_dev, theta_dev, step_mode, stream);
         if (tc <= 0) return tc;  // 0 = launched on the tcgen05 path, < 0 = error
     }
@@ -1033,6 +1080,7 @@ int d4s_set_option(const char* key, int32_t value) {
     else if (k == "jac_tc") g_opt_jac_tc = value;
     else if (k == "tc_cta_pair") g_opt_tc_cta_pair = value;
     else if (k == "jac_cta_pair") g_opt_jac_cta_pair = value;
+    else if (k == "paired_tc") g_opt_paired_tc = value;
     else return fail(D4S_ERR_ARG, "unknown option: " + k);
     return D4S_OK;
 }

@@ -151,6 +151,24 @@ struct JacTcParams {
 };
 cudaError_t launch_jac_tc(const JacTcParams& p, int n_ctas, cudaStream_t stream);
 
+// tcgen05 trajectory kernel of the paired mode (d4s_paired_tc.cu): row i = (sample i, observation i / obs_div), plain score
+struct PairedTcParams {
+    NetDev net;
+    long long N;              // rows = posterior samples
+    int obs_div;              // row i reads obs_feat[i / obs_div] (1: one observation row per sample)
+    int step_begin, step_end;
+    const float* obs_feat;    // [ceil(N / obs_div)][Hp0]
+    const float* time_feat;   // [steps][Hp0]
+    const float* sched;       // [steps][16]
+    const float* noise;       // [steps][N][m] or NULL (Philox)
+    float* theta;             // [N][m] in/out
+    unsigned long long seed;
+    long long sample_offset;
+    float clip_lo, clip_hi;
+    int* error_flag;
+};
+cudaError_t launch_paired_tc(const PairedTcParams& p, int n_ctas, cudaStream_t stream);
+
 // generic path (d4s_generic.cu): kernel 3b + 4 for theta_dim <= D4S_MAX_THETA_WIDE
 struct WideParams {
     long long N;

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(NT, 2) score_simt_kernel(const ScoreParams p) 
             sSamp[r] = si;
             // batched contexts: the sample's context owns observations [c n, (c + 1) n)
             const int ctx0 = p.ctx_samples > 0 ? (min(i0 + si, p.N - 1) / p.ctx_samples) * p.n : 0;
-            sObs[r] = p.paired ? min(i0 + si, p.n - 1) : ctx0 + min(j0 + oj, p.n - 1);
+            sObs[r] = p.paired ? min((i0 + si) / p.paired, p.n - 1) : ctx0 + min(j0 + oj, p.n - 1);  // paired = samples per observation row
         }
     }
     for (int e = tid; e < p.SG * m; e += NT) {

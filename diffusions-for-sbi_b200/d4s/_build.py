@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB = os.path.join(HERE, "libd4s.so")
-SOURCES = ["d4s_api.cu", "d4s_score_simt.cu", "d4s_finalize.cu", "d4s_traj_tc.cu", "d4s_jac_tc.cu", "d4s_generic.cu"]
+SOURCES = ["d4s_api.cu", "d4s_score_simt.cu", "d4s_finalize.cu", "d4s_traj_tc.cu", "d4s_jac_tc.cu", "d4s_paired_tc.cu", "d4s_generic.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
               "-cudart", "static"]

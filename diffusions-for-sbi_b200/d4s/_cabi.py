@@ -13,7 +13,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("D4S_LIB_PATH") or os.path.join(HERE, "libd4s.so")  # (override: A/B builds of the kernels)
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 MAX_LAYERS = 8
 MAX_THETA = 10
 MAX_THETA_WIDE = 32

@@ -476,6 +476,9 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
     """`obs_slice` restricts the kernels to a shard of the observations (observation sharding over ranks):
     (1-n) and Lambda still use the total n, the partial sums are all-reduced by the caller.
 
+    `paired = k >= 1` (True == 1): every sample has its own observation, row i // k of `x`, and the plain score is used
+    (nse.py:253); k = S with x[B, d] is the covariance pre-pass (S draws from each of B single-observation posteriors).
+
     `contexts = B > 0`: B independent tall problems in one launch (replaces `vmap(sampler)` over calibration sets,
     jrnnm_posterior_estimation.py:286-294).  `x` is [B * n, d] and `dist_cov_est` [B * n, m, m], context-major;
     samples [c S, (c+1) S) with S = n_samples / B belong to context c."""
@@ -565,7 +568,7 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
     prob.theta_dim = m
     prob.cov_mode = abi.COV_JAC if cov_jac else abi.COV_GAUSS
     prob.prior_kind = prior.kind
-    prob.paired = 1 if paired else 0
+    prob.paired = int(paired)  # k >= 1: samples per observation row (True == 1: one row per sample)
     prob.obs_chunk = obs_chunk
     prob.n_obs_total = n_total
     prob.obs_feat = of_dev.data_ptr()

@@ -213,11 +213,10 @@ class NSE(nn.Module):
         t, t_prev = grid[:-1], grid[:-1].to(torch.float64) - 1.0 / steps
         if seed is None:
             seed = self._draw_seed()
-        if x.ndim == 2 or x.shape[1] == 1:  # one observation per context: plain score, row i pairs with context i // S
-            x_rows = x.reshape(B, -1).repeat_interleave(S, dim=0).contiguous()
-            setup = engine.build_setup(self, x_rows, N, t, t_prev, float(eta), engine.PriorSpec(abi.PRIOR_NONE),
-                                       opts["cov_mode"], None, paired=True, clip=theta_clipping_range, seed=seed,
-                                       sample_offset=sample_offset, weighted=False)
+        if x.ndim == 2 or x.shape[1] == 1:  # one observation per context: plain score, sample i reads observation row i // S
+            setup = engine.build_setup(self, x.reshape(B, -1).contiguous(), N, t, t_prev, float(eta),
+                                       engine.PriorSpec(abi.PRIOR_NONE), opts["cov_mode"], None, paired=S,
+                                       clip=theta_clipping_range, seed=seed, sample_offset=sample_offset, weighted=False)
         else:
             n = x.shape[1]
             prior = engine.prior_spec(opts["prior_type"], opts["prior"], opts["prior_score_fn"], m)

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define D4S_ABI_VERSION 14
+#define D4S_ABI_VERSION 15
 
 #define D4S_OK 0
 #define D4S_ERR_ARG -1      /* bad argument / unsupported shape */
@@ -114,7 +114,10 @@ typedef struct {
     int32_t theta_dim;       /* m */
     int32_t cov_mode;        /* D4S_COV_* */
     int32_t prior_kind;      /* D4S_PRIOR_* */
-    int32_t paired;          /* 1: observation j == sample i (nse.py:253 `x.shape[0] == shape[0]`), n_obs == N */
+    int32_t paired;          /* k >= 1: sample i has its OWN observation, row i / k of obs_feat, and the plain score is used (no
+                                factorisation); n_obs = ceil(N / k).  k = 1: nse.py:253 `x.shape[0] == shape[0]`; k = S: the
+                                covariance pre-pass vmap(ddim) over the observations, S samples each
+                                (sbibm_posterior_estimation.py:306-314) (ABI v15: k > 1) */
     int32_t obs_chunk;       /* observations per tile (0 = library default) */
     int32_t n_obs_total;     /* n used in (1-n) and in Lambda (== n_obs unless observations are sharded over ranks) */
     const float* obs_feat;   /* [n_obs, H1p] layer-1 partial of observation j: W1[:, x-block] e_x(x_j) (+ one-hot block) */
