@@ -586,6 +586,32 @@ def per_call_record(args, dev):
     return out
 
 
+def prepass_record(args, dev):
+    """Covariance pre-pass of the GAUSS pipeline (sbibm_posterior_estimation.py:306-314: `vmap(ddim)` over the observations,
+    1000 draws each, 100 steps, eta 0.5, then `torch.cov`) through `NSE.estimate_dist_cov`: one launch of the paired-mode
+    tcgen05 trajectory kernel; wall time per call, host tables included."""
+    import torch
+    from d4s.engine import launch_count
+    w = workload(args)
+    nse = build_nse(w, dev)
+    x = torch.as_tensor(w["x"]).to(dev)
+    for _ in range(2):
+        nse.estimate_dist_cov(x, nsamples=1000, steps=100, eta=0.5, _seed=11)
+    torch.cuda.synchronize()
+    reps = 5
+    l0 = launch_count()
+    t0 = time.perf_counter()
+    for k in range(reps):
+        cov = nse.estimate_dist_cov(x, nsamples=1000, steps=100, eta=0.5, _seed=12 + k)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    return {"ms_per_call": ms, "n_obs": int(x.shape[0]), "samples_per_observation": 1000, "ddim_steps": 100, "eta": 0.5,
+            "samples_per_s": x.shape[0] * 1000 / (ms * 1e-3), "launches_per_call": (launch_count() - l0) / reps,
+            "finite": bool(torch.isfinite(cov).all()),
+            "note": "NSE.estimate_dist_cov = vmap(ddim) over the observations + torch.cov; paired_tc_kernel (tcgen05), one launch "
+                    "per trajectory + the Philox initial draw; wall clock per call incl. host tables"}
+
+
 def n_obs_sweep(args, dev):
     """samples/s of complete trajectories for n_obs in {1, 8, 14, 22, 30} x {GAUSS (1000 steps, eta 1), JAC (400 steps,
     eta 0.8)} on the default task's shape, N = --samples (sbibm_posterior_estimation.py:21, 330-334, 617-619)."""
@@ -850,6 +876,7 @@ def run_ours(args):
             line["sweep"] = n_obs_sweep(args, dev)
             line["jac"] = jac_record(args, dev, peaks)
             line["per_call_us"] = per_call_record(args, dev)
+            line["prepass"] = prepass_record(args, dev)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_record(args, w)
         print(json.dumps(line))
