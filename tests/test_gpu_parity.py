@@ -605,6 +605,66 @@ def test_estimate_dist_cov_prepass(dev):
         assert np.abs(cov[j].cpu().numpy() - np.cov(ref.T)).max() < 1e-3 * max(1.0, np.abs(np.cov(ref.T)).max())
 
 
+@pytest.mark.parametrize("shape", [(5, 8, (256, 256, 256), 148 * 128 * 2 + 77, 1), (4, 6, (128, 256), 3 * 128 + 1, 1),
+                                   (2, 3, (64, 64), 500, 1), (5, 8, (256, 256, 256), 37 * 1100, 1100), (3, 4, (64, 128, 64), 9 * 130, 130)],
+                         ids=lambda s: f"m{s[0]}_L{len(s[2])}_N{s[3]}_k{s[4]}")
+def test_paired_tc_kernel(shape, dev):
+    """`paired_tc_kernel` (row = sample with its own observation, nse.py:253-254; k samples per observation row = the covariance
+    pre-pass): against the fp32 SIMT kernels on every row and against the fp64 oracle on a few, under replayed noise; several
+    tiles per CTA (items of different tiles overlap), a single tile per CTA (program order), ragged last tile, 1 .. 3 tensor-core
+    layers, clipping, and the Philox path (deterministic, independent of the kernel)."""
+    from d4s import _cabi as abi
+    from d4s import engine
+    from d4s_helpers import nse_from_oracle
+    m, d, hidden, N, k = shape
+    rng = np.random.default_rng(21)
+    onet = orc.random_net(rng, m, d, hidden=hidden)
+    nse = nse_from_oracle(onet, dev)
+    steps, eta = 6, 0.5
+    B = N // k
+    x = 0.5 * rng.standard_normal((B, d))
+    z0, z = rng.standard_normal((N, m)).astype(np.float32), rng.standard_normal((steps, N, m)).astype(np.float32)
+    noise = (torch.as_tensor(z0), torch.as_tensor(z))
+
+    def run(**kw):
+        if k == 1:
+            return nse.ddim((N,), _t(x, dev), steps=steps, eta=eta, **kw)
+        return nse.ddim_contexts((k,), _t(x, dev), steps=steps, eta=eta, **kw).reshape(N, m)
+
+    try:
+        abi.set_option("paired_tc", 0)
+        n0 = engine.launch_count()
+        simt = run(_noise=noise)
+        simt_launches = engine.launch_count() - n0
+        abi.set_option("paired_tc", 1)
+        n0 = engine.launch_count()
+        tc = run(_noise=noise)
+        assert engine.launch_count() - n0 == 1 and simt_launches >= 2 * steps  # one launch per trajectory
+        clip_tc = run(_noise=noise, theta_clipping_range=(-0.7, 0.9))
+        abi.set_option("paired_tc", 0)
+        clip_simt = run(_noise=noise, theta_clipping_range=(-0.7, 0.9))
+        abi.set_option("paired_tc", 1)
+        ph = [run(_seed=5), run(_seed=5), run(_seed=6)]
+        abi.set_option("paired_tc", 0)
+        ph_simt = run(_seed=5)
+    finally:
+        abi.set_option("paired_tc", 1)
+    scale = max(1.0, float(simt.abs().max()))
+    assert torch.isfinite(tc).all()
+    assert float((tc - simt).abs().max()) < TRAJ_TOL * scale, float((tc - simt).abs().max())
+    # (a random-init net gives no contraction: the scores are ~`scale` large, so the unclipped coordinates of a clipped run carry
+    # the same relative tolerance as the unclipped run)
+    assert float((clip_tc - clip_simt).abs().max()) < TRAJ_TOL * scale and float(clip_tc.max()) <= 0.9 and float(clip_tc.min()) >= -0.7
+    assert torch.equal(ph[0], ph[1]) and not torch.equal(ph[0], ph[2])
+    assert float((ph[0] - ph_simt).abs().max()) < TRAJ_TOL * max(1.0, float(ph_simt.abs().max()))  # same noise stream as kernel 4
+    rows = sorted({0, 1, 127, 128, N // 2, N - 2, N - 1})
+    xr = x[[r // k for r in rows]]
+    ref = orc.ddim_single(onet, xr, z0[rows].astype(np.float64), z[:, rows].astype(np.float64), steps, eta)
+    err = np.abs(tc[rows].cpu().numpy() - ref).max() / max(1.0, np.abs(ref).max())
+    print(f"{shape}: max |tc - simt| = {float((tc - simt).abs().max()):.2e}, |tc - oracle| (rel) = {err:.2e}")
+    assert err < TRAJ_TOL, err
+
+
 def test_jac_trajectory_fuses_plain_sum_steps(dev):
     """A JAC trajectory only needs the Jacobian inside the alpha-gate (nse.py:643).  The run of plain-sum steps before it
     goes through the fused tcgen05 trajectory kernel in one launch; the result must follow the per-step fp32 SIMT
