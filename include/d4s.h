@@ -238,9 +238,12 @@ D4S_API int d4s_xchg_close(void* peer_ptr);
  * kernel (bf16x3 split on the tensor cores; GAUSS, tall grid); "tc_steps_per_launch" = DDIM steps per tcgen05
  * launch (0 = whole trajectory in one launch); "profile" = 1 enables the in-kernel phase timers; "tc_pairing" = 1
  * (default) lets a CTA that owns two sample groups interleave them step by step, 0 runs them one after the other
- * (same arithmetic, bit-identical results); "jac_tc" = 1 runs JAC steps (theta_dim <= 5) on the tcgen05 score +
- * Jacobian kernel (fp16x3 products, ~5x faster than the fp32 SIMT kernel; the tensor core's truncating accumulation
- * costs about one decimal digit where inv(I - sigma J) is ill-conditioned, so it is off by default). */
+ * (same arithmetic, bit-identical results); "jac_tc" = 1 (default) runs JAC steps (theta_dim <= 5) on the tcgen05 score +
+ * Jacobian kernel (fp16x3 products, cross terms accumulated first, accumulator debias: same tolerance as the fp32 SIMT
+ * kernel, ~5x faster), 0 = fp32 SIMT kernel; "paired_tc" = 1 (default) runs the paired mode (D4sProblem.paired) on its
+ * tcgen05 trajectory kernel, 0 = fp32 SIMT kernels; "tc_cta_pair" / "jac_cta_pair" = 1 launch the trajectory kernel / the
+ * JAC step kernel as clusters of two CTAs on one cta_group::2 instruction stream (default 0: bit-identical, measured
+ * slower). */
 D4S_API int d4s_set_option(const char* key, int32_t value);
 /* "profile" = 1 makes CTA 0 of the tcgen05 kernel accumulate clock64() cycles per phase; this call synchronises and
  * copies the 16 counters of the last launch: 0 layer-0 sample part, 1 layer 0, 2 prior+noise, 3 tensor-core wait,
