@@ -151,8 +151,10 @@ class NSE(nn.Module):
         """DDIM sampler adapted to n context observations (nse.py:223-267); returns theta[shape[0], m] on x.device.
 
         The whole `steps`-long loop is enqueued by one C-ABI call (`d4s_ddim_run`): ONE launch of the fused tcgen05
-        trajectory kernel for GAUSS-type runs; JAC steps inside the alpha-gate (nse.py:643) and the toy nets run two
-        kernels per step, captured in a CUDA graph.
+        trajectory kernel for GAUSS-type runs (and for the runs of plain-sum steps of a JAC trajectory), ONE launch of the
+        paired-mode tcgen05 kernel when every sample has its own observation; JAC steps inside the alpha-gate (nse.py:643)
+        run the tcgen05 score + Jacobian kernel and kernel 3/4 per step, toy nets the fp32 SIMT kernels (captured in a
+        CUDA graph when the steps are short).
         """
         self._require_cuda(x)
         opts, noise, seed, sample_offset = self._split_kwargs(kwargs)
