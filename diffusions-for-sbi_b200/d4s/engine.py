@@ -494,8 +494,8 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
     x2 = x if x.ndim > 1 else x[None]
     n_total = x2.shape[0]
     if contexts:
-        if paired or cfg is not None or obs_slice is not None or n_sizes is not None:
-            raise NotImplementedError("batched contexts with paired / classifier-free guidance / sharded / PF_NSE inputs")
+        if paired or cfg is not None or obs_slice is not None:
+            raise NotImplementedError("batched contexts with paired / classifier-free guidance / sharded inputs")
         if x2.shape[0] % contexts or n_samples % contexts:
             raise ValueError("batched contexts: x must be [B * n, d] and n_samples a multiple of B")
         n_total = x2.shape[0] // contexts  # observations of ONE context: the n of (1 - n) and of Lambda

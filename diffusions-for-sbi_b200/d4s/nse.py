@@ -206,8 +206,8 @@ class NSE(nn.Module):
         Returns theta[B, shape[0], m].  Same keyword contract as `ddim`; `_noise` is (z0[B*S, m], z[steps, B*S, m])."""
         self._require_cuda(x)
         opts, noise, seed, sample_offset = self._split_kwargs(kwargs)
-        if opts["clf_free_guidance"] or opts["n_sizes"] is not None:
-            raise NotImplementedError("ddim_contexts: classifier-free guidance / PF_NSE subsets are not batched")
+        if opts["clf_free_guidance"]:
+            raise NotImplementedError("ddim_contexts: classifier-free guidance is not batched")
         S, m = int(shape[0]), self.zeros.shape[0]
         B = x.shape[0]
         N = B * S
@@ -215,9 +215,12 @@ class NSE(nn.Module):
         t, t_prev = grid[:-1], grid[:-1].to(torch.float64) - 1.0 / steps
         if seed is None:
             seed = self._draw_seed()
-        if x.ndim == 2 or x.shape[1] == 1:  # one observation per context: plain score, sample i reads observation row i // S
-            setup = engine.build_setup(self, x.reshape(B, -1).contiguous(), N, t, t_prev, float(eta),
+        pf = opts["n_sizes"] is not None  # PF_NSE: x is [B, K, n_max, d], `n` the subset sizes [B, K, 1]
+        if x.ndim == 2 or x.shape[1] == 1:  # one observation (PF_NSE: one subset) per context: plain score, sample i reads row i // S
+            xr = x.reshape((B,) + tuple(x.shape[2:])) if pf else x.reshape(B, -1)
+            setup = engine.build_setup(self, xr.contiguous(), N, t, t_prev, float(eta),
                                        engine.PriorSpec(abi.PRIOR_NONE), opts["cov_mode"], None, paired=S,
+                                       n_sizes=opts["n_sizes"].reshape(B, 1) if pf else None,
                                        clip=theta_clipping_range, seed=seed, sample_offset=sample_offset, weighted=False)
         else:
             n = x.shape[1]
@@ -225,7 +228,10 @@ class NSE(nn.Module):
             cov = opts["dist_cov_est"]
             if cov is not None:
                 cov = cov.reshape(B * n, m, m)
-            setup = engine.build_setup(self, x.reshape(B * n, -1), N, t, t_prev, float(eta), prior, opts["cov_mode"], cov,
+            # PF_NSE: a subset is one "observation" of its context
+            xs = x.reshape((B * n,) + tuple(x.shape[2:])) if pf else x.reshape(B * n, -1)
+            ns = opts["n_sizes"].reshape(B * n, 1) if pf else None
+            setup = engine.build_setup(self, xs, N, t, t_prev, float(eta), prior, opts["cov_mode"], cov, n_sizes=ns,
                                        clip=theta_clipping_range, seed=seed, sample_offset=sample_offset, contexts=B)
         if noise is not None:
             z0, z = noise

@@ -89,6 +89,19 @@ class PF_NSE(NSE):
         return super().ddim(shape=shape, x=xs, steps=steps, eta=eta, verbose=verbose,
                             theta_clipping_range=theta_clipping_range, n=ns, **kwargs)
 
+    def ddim_contexts(self, shape: Size, x: Tensor, steps: int = 64, eta: float = 1.0, verbose: bool = False,
+                      theta_clipping_range=(None, None), **kwargs) -> Tensor:
+        """`vmap(lambda x_c, cov_c: self.ddim(shape, x_c, ..., dist_cov_est=cov_c))(x, dist_cov_est)` as one trajectory launch
+        (see `NSE.ddim_contexts`): x[B, n, d] -> every context is split into its K = ceil(n / n_max) subsets like `ddim` does
+        (pf_nse.py:169-197); dist_cov_est is [B, K, m, m] (one covariance per subset, as for `ddim`)."""
+        if x.ndim != 3:
+            raise ValueError("PF_NSE.ddim_contexts: x must be [B, n, d]")
+        parts = [self._create_pf_data(xc) for xc in x]
+        xs = torch.stack([p[0] for p in parts])  # [B, K, n_max, d]
+        ns = torch.stack([p[1] for p in parts])  # [B, K, 1]
+        return super().ddim_contexts(shape=shape, x=xs, steps=steps, eta=eta, verbose=verbose,
+                                     theta_clipping_range=theta_clipping_range, n=ns, **kwargs)
+
     def predictor_corrector(self, shape: Size, x: Tensor, steps: int = 64, verbose: bool = False,
                             predictor_type="ddim", corrector_type="langevin", theta_clipping_range=(None, None),
                             **kwargs) -> Tensor:

@@ -587,6 +587,41 @@ def test_ddim_contexts_random_shapes(seed, dev):
         abi.set_option("path", 0)
 
 
+@pytest.mark.parametrize("case", [(3, 7, 3, 40, "uniform"), (4, 30, 3, 17, "gaussian"), (5, 3, 3, 130, "uniform")],
+                         ids=lambda c: f"B{c[0]}_n{c[1]}_nmax{c[2]}_S{c[3]}_{c[4]}")
+def test_pf_nse_ddim_contexts(case, dev):
+    """`PF_NSE.ddim_contexts`: every context split into its K = ceil(n / n_max) subsets (pf_nse.py:169-197), all contexts in one
+    launch == B separate `PF_NSE.ddim` calls under the same noise; K = 1 (n <= n_max) is the plain-score single-subset case."""
+    from d4s_helpers import nse_from_oracle
+    B, n, n_max, S, pkind = case
+    m, d, steps = 4, 5, 5
+    rng = np.random.default_rng(31)
+    onet = orc.random_net(rng, m, d, hidden=(128, 256), n_max=n_max, pf=True)
+    pf = nse_from_oracle(onet, dev)
+    K = -(-n // n_max)
+    x = 0.5 * rng.standard_normal((B, n, d))
+    a = 0.2 * rng.standard_normal((B, K, m, m))
+    cov = a @ a.transpose(0, 1, 3, 2) + 0.05 * np.eye(m)
+    if pkind == "uniform":
+        oprior = orc.UniformPrior(np.full(m, -3.46), np.full(m, 3.46))
+    else:
+        b = 0.3 * rng.standard_normal((m, m))
+        oprior = orc.GaussianPrior(0.1 * rng.standard_normal(m), b @ b.T + np.eye(m))
+    prior, fn = _d4s_prior(oprior, pf, dev)
+    z0, z = rng.standard_normal((B * S, m)), rng.standard_normal((steps, B * S, m))
+    kw = dict(steps=steps, eta=0.8, prior=prior, prior_type=pkind, prior_score_fn=fn, cov_mode="GAUSS")
+    out = pf.ddim_contexts((S,), _t(x, dev), dist_cov_est=_t(cov, dev),
+                           _noise=(torch.as_tensor(z0, dtype=torch.float32), torch.as_tensor(z, dtype=torch.float32)), **kw)
+    assert out.shape == (B, S, m) and torch.isfinite(out).all()
+    for c in range(B):
+        sl = slice(c * S, (c + 1) * S)
+        one = pf.ddim((S,), _t(x[c], dev), dist_cov_est=_t(cov[c], dev),
+                      _noise=(torch.as_tensor(z0[sl], dtype=torch.float32), torch.as_tensor(z[:, sl], dtype=torch.float32)), **kw)
+        scale = max(1.0, float(one.abs().max()))
+        rel = float((out[c] - one).abs().max()) / scale
+        assert rel < 1e-4, (case, c, rel)
+
+
 def test_estimate_dist_cov_prepass(dev):
     """sbibm_posterior_estimation.py:306-314: vmap(ddim) over the observations + torch.cov, as one launch."""
     from d4s_helpers import nse_from_oracle
