@@ -774,12 +774,26 @@ def run_ours(args):
     barrier()
     launches = engine.launch_count() - l0
     ms_e2e = []
+    prof = None
+    if os.environ.get("D4S_BENCH_PROFILE_E2E"):  # host-side profile of the end-to-end steps, to stderr
+        import cProfile
+        prof = cProfile.Profile()
     for k in range(args.steps):
         flush.fill_(float(k))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        if prof:
+            prof.enable()
         e2e_step(k)
+        if prof:
+            prof.disable()
         ms_e2e.append((time.perf_counter() - t0) * 1e3)
+    if prof and rank == 0:
+        import io
+        import pstats
+        buf = io.StringIO()
+        pstats.Stats(prof, stream=buf).sort_stats("cumulative").print_stats(25)
+        sys.stderr.write(f"e2e ms per step: {ms_e2e}\n" + buf.getvalue()[:5000])
     barrier()
     clk = clocks.stop()
     assert torch.isfinite(theta).all(), "non-finite samples"
@@ -866,7 +880,8 @@ def run_ours(args):
                 "config": config_dict(args, w, world),
                 "clocks": clk,
                 "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(N * m * 4), "ms_per_step": tot_dev[1] / args.steps},
+                        "d2h_bytes_per_step": int(N * m * 4), "ms_per_step": tot_dev[1] / args.steps,
+                        "ms_steps_rank0": [round(v, 3) for v in ms_e2e]},
                 "gpu_launches": int(launches),
                 "roofline": roofline,
                 "us_per_ddim_step": ms_step * 1e3 / w["ddim_steps"]}

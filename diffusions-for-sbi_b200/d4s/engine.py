@@ -407,11 +407,37 @@ _qinv_cache = _LRU(8)     # dist_cov_est -> inv (fp64, host)
 _obsfeat_cache = _LRU(8)  # (packed net, x, n_sizes) -> layer-0 observation partials (fp64, host)
 _dev_cache = _LRU(64)     # host fp64 table -> fp32 device copy (keyed by the host tensor's identity)
 _setup_cache = _LRU(1200)  # whole per-call setups (NSE.factorized_score with the same inputs and the same t)
+_tables_cache = _LRU(8)    # VALUES of everything the schedule / step matrices depend on -> their device copies
 
 
 def clear_caches():
-    for c in (_qinv_cache, _obsfeat_cache, _dev_cache, _setup_cache):
+    for c in (_qinv_cache, _obsfeat_cache, _dev_cache, _setup_cache, _tables_cache):
         c.clear()
+
+
+def _bytes(v) -> Optional[bytes]:
+    return None if v is None else torch.as_tensor(v).detach().to("cpu", torch.float64).contiguous().numpy().tobytes()
+
+
+def _sched_mats_dev(nse, t, t_prev, eta, n_total, comb, coef, prior: PriorSpec, cov_jac, sum_q, m, w_sum, device):
+    """Device copies of the schedule rows and the per-step matrices of a trajectory.  A `ddim` call on fresh input tensors
+    (new x / dist_cov_est every call) still repeats these tables whenever the grid, eta, n, the prior and sum_j inv(Sigma_j) are
+    the same; building them is most of the host time of a call.  The key holds the VALUES they depend on -- alpha / sigma are
+    evaluated on the grid every time (callers monkey-patch them), the prior's parameters and sum_q enter as bytes -- never a
+    tensor identity, so a hit cannot be stale."""
+    t64 = t.to(torch.float64)
+    key = (_bytes(_scalar64(nse.alpha, t64)), _bytes(_scalar64(nse.sigma, t64)),
+           None if t_prev is None else _bytes(_scalar64(nse.alpha, t_prev.to(torch.float64))), _bytes(t64), float(eta), int(n_total),
+           tuple(int(c) for c in comb), None if not coef else tuple((k, _bytes(v)) for k, v in sorted(coef.items())),
+           prior.kind, _bytes(prior.low), _bytes(prior.high), _bytes(prior.mean), _bytes(prior.cov), _bytes(prior.cov_prec),
+           bool(cov_jac), _bytes(sum_q), int(m), None if w_sum is None else float(w_sum), str(device))
+    hit = _tables_cache.get(key)
+    if hit is None:
+        rows = schedule_rows(nse, t, t_prev, eta, n_total, comb, coef)
+        mats = mats_table(rows, prior, cov_jac, n_total, sum_q, m, w_sum)
+        hit = (_dev32(rows, device), _dev32(mats, device))
+        _tables_cache.put(key, hit, ())
+    return hit
 
 
 def _inv_cov64(cov: torch.Tensor) -> torch.Tensor:
@@ -535,9 +561,8 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
     comb = torch.where(sa > 0.5, c_hi, c_lo).tolist()
     if cfg is not None and weighted:  # nse.py:622-625: always the weighted solve
         comb = [abi.COMBINE_PER_SAMPLE if cov_jac else abi.COMBINE_SHARED] * len(comb)
-    rows = schedule_rows(nse, t, None if t_prev is None else t_prev.detach().to("cpu").reshape(-1), eta, n_total, comb,
-                         coef)
-    mats = mats_table(rows, prior, cov_jac, n_total, sum_q, m, None if w64 is None else float(w64.sum()))
+    sched_dev, mats_dev = _sched_mats_dev(nse, t, None if t_prev is None else t_prev.detach().to("cpu").reshape(-1), eta, n_total,
+                                          comb, coef, prior, cov_jac, sum_q, m, None if w64 is None else float(w64.sum()), device)
     tf = time_feat_table(nse, pn, t)
     of = _obs_feat_cached(nse, pn, x2, n_sizes)
     of_cached = cfg is None and obs_slice is None
@@ -604,7 +629,7 @@ def build_setup(nse, x: torch.Tensor, n_samples: int, t: torch.Tensor, t_prev: O
             x_raw = x_raw[obs_slice].contiguous()
         prob.obs_raw = x_raw.data_ptr()
         prob.x_dim = x_raw.shape[-1]
-    return TallSetup(pn, prob, _dev32(rows, device), _dev32(tf, device), _dev32(mats, device), step_modes,
+    return TallSetup(pn, prob, sched_dev, _dev32_cached(tf, device), mats_dev, step_modes,
                      (of_dev, q_dev, low_dev, high_dev, ws, x_raw, w_dev, qsum_dev), t.numel(), affine_dev)
 
 
