@@ -185,3 +185,48 @@ def test_driver_normalisation_wrappers_cpu():
     s = torch.randn(5, 2, generator=g)
     assert torch.allclose(io.unnormalize_samples(s, tm, ts, theta_log_space=True), torch.exp(s * ts + tm))
     assert torch.allclose(io.unnormalize_samples(s, tm, ts), s * ts + tm)
+
+
+def test_schedule_and_matrix_tables_are_cached_by_value():
+    """engine._sched_mats_dev: the device copies of the schedule rows / step matrices are reused when everything they depend
+    on has the same VALUES (fresh tensors with equal contents: hit), and rebuilt when any of it changes -- a monkey-patched
+    alpha, another eta, another prior parameter, another sum of precisions (never a stale hit)."""
+    rng = np.random.default_rng(0)
+    onet = orc.random_net(rng, 3, 4, hidden=(64, 64))
+    nse = nse_from_oracle(onet, "cpu")
+    m, n, steps = 3, 7, 20
+    grid = engine.time_grid(steps)
+    t, t_prev = grid[:-1], grid[:-1].to(torch.float64) - 1.0 / steps
+    comb = [abi.COMBINE_SHARED] * steps
+    b = rng.standard_normal((m, m))
+    cov0 = torch.as_tensor(b @ b.T + np.eye(m))
+    sum_q = torch.as_tensor(np.eye(m) * 5.0)
+
+    def spec(scale=1.0):
+        return engine.PriorSpec(abi.PRIOR_GAUSSIAN, mean=torch.zeros(m, dtype=torch.float64), cov=scale * cov0.clone())
+
+    def tables(**over):
+        kw = dict(eta=1.0, prior=spec(), sum_q=sum_q.clone())
+        kw.update(over)
+        return engine._sched_mats_dev(nse, t.clone(), t_prev.clone(), kw["eta"], n, list(comb), None, kw["prior"], False,
+                                      kw["sum_q"], m, None, "cpu")
+
+    engine.clear_caches()
+    s0, m0 = tables()
+    s1, m1 = tables()
+    assert s1 is s0 and m1 is m0  # equal values in fresh tensors: the same device copies
+    rows = engine.schedule_rows(nse, t, t_prev, 1.0, n, comb)
+    assert torch.equal(s0, rows.to(torch.float32))
+    assert torch.equal(m0, engine.mats_table(rows, spec(), False, n, sum_q, m).to(torch.float32))
+    for over in (dict(eta=0.5), dict(prior=spec(1.5)), dict(sum_q=sum_q * 2.0)):
+        s2, m2 = tables(**over)
+        assert s2 is not s0 and (not torch.equal(s2, s0) or not torch.equal(m2, m0)), over
+    old_alpha = nse.alpha
+    try:
+        nse.alpha = lambda tt: old_alpha(tt) ** 1.1  # callers monkey-patch the schedule (BASELINE.md section 4)
+        s3, _ = tables()
+        assert s3 is not s0 and not torch.equal(s3, s0)
+    finally:
+        del nse.alpha
+    s4, m4 = tables()
+    assert torch.equal(s4, s0) and torch.equal(m4, m0)
