@@ -247,7 +247,17 @@ __device__ __noinline__ void theta_embed_base(const NetDev& net, const float* th
         for (int idx = tid; idx < SG * Nn; idx += TC_CT) {
             const int si = idx / Nn, o = idx - si * Nn;
             float acc = __ldg(net.emb_bias[l] + o);
-            for (int k = 0; k < K; ++k) acc = fmaf(__ldg(Wt + (size_t)k * Nn + o), in[si * in_stride + k], acc);
+            // (eight weight loads in flight per step of the dependent FMA chain: one load per FMA left the chain waiting a
+            // cache round trip per term; same summation order)
+            int k = 0;
+            for (; k + 8 <= K; k += 8) {
+                float w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] = __ldg(Wt + (size_t)(k + j) * Nn + o);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc = fmaf(w[j], in[si * in_stride + k + j], acc);
+            }
+            for (; k < K; ++k) acc = fmaf(__ldg(Wt + (size_t)k * Nn + o), in[si * in_stride + k], acc);
             out[si * TC_EMB_STRIDE + o] = relu ? fmaxf(acc, 0.f) : acc;
         }
         compute_bar();
@@ -258,7 +268,18 @@ __device__ __noinline__ void theta_embed_base(const NetDev& net, const float* th
         float z[TC_SG_MAX];
 #pragma unroll
         for (int si = 0; si < TC_SG_MAX; ++si) z[si] = t0;
-        for (int f = 0; f < net.theta_cols; ++f) {
+        int f = 0;
+        for (; f + 8 <= net.theta_cols; f += 8) {
+            float a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = __ldg(net.A + (size_t)(f + j) * H0 + tid);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                for (int si = 0; si < TC_SG_MAX; ++si) z[si] = fmaf(a[j], in[si * TC_EMB_STRIDE + f + j], z[si]);
+            }
+        }
+        for (; f < net.theta_cols; ++f) {
             const float a = __ldg(net.A + (size_t)f * H0 + tid);
 #pragma unroll
             for (int si = 0; si < TC_SG_MAX; ++si) z[si] = fmaf(a, in[si * TC_EMB_STRIDE + f], z[si]);
